@@ -1,0 +1,188 @@
+"""Runs the UNMODIFIED reference modules from /root/reference on CPU -- TEST
+INFRASTRUCTURE, authoring container only (the GPU box has no /root/reference; nothing
+under tests/ -m gpu, smoke() or bench.py imports this file).
+
+Three gaps are filled so that lib/models/{tepose,spin,smpl}.py and
+lib/utils/geometry.py import as they are:
+  1. ``yacs`` is not installed  -> a minimal ``yacs.config.CfgNode`` stub
+     (lib/core/config.py:19 only builds defaults with it);
+  2. ``smplx`` is not installed / not vendored (requirements.txt:7) -> a stand-in
+     module exposing ``SMPL``, ``body_models.SMPLOutput`` and ``lbs.vertices2joints``
+     (the three names lib/models/smpl.py:7-9 imports) implemented with the oracle's
+     restated LBS.  This is why the SMPL part of the goldens is "parity unpinned";
+  3. licensed assets are absent -> synthetic ``data/base_data`` in a temp cwd
+     (paths are cwd-relative: lib/core/config.py:31).
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+import pickle
+import sys
+import tempfile
+import types
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import synth, torch_ref
+
+REFERENCE_ROOT = "/root/reference"
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "lib", "models", "tepose.py"))
+
+
+def _install_yacs_stub():
+    if "yacs.config" in sys.modules:
+        return
+
+    class CfgNode(dict):
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError as e:
+                raise AttributeError(k) from e
+
+        def __setattr__(self, k, v):
+            self[k] = v
+
+        def clone(self):
+            import copy
+            return copy.deepcopy(self)
+
+        def merge_from_file(self, path):
+            raise NotImplementedError("yacs stub")
+
+    yacs = types.ModuleType("yacs")
+    cfgmod = types.ModuleType("yacs.config")
+    cfgmod.CfgNode = CfgNode
+    yacs.config = cfgmod
+    sys.modules["yacs"] = yacs
+    sys.modules["yacs.config"] = cfgmod
+
+
+def _install_smplx_standin():
+    if "smplx" in sys.modules and getattr(sys.modules["smplx"], "_tepose_b200_standin", False):
+        return
+    SMPLOutput = namedtuple("SMPLOutput", ["vertices", "joints", "full_pose", "betas",
+                                           "global_orient", "body_pose"])
+    SMPLOutput.__new__.__defaults__ = (None,) * 6
+
+    class SMPL(torch.nn.Module):
+        """smplx.SMPL stand-in: same constructor keywords the reference uses
+        (lib/models/spin.py:226-230, evaluate.py:130-135), same buffers / Parameters
+        (SURVEY.md App. A.1), forward restated in oracle/torch_ref.py:smpl_lbs."""
+
+        def __init__(self, model_path, batch_size=1, create_transl=True, gender="neutral", **kw):
+            super().__init__()
+            fn = os.path.join(model_path, f"SMPL_{gender.upper()}.pkl") if os.path.isdir(model_path) else model_path
+            with open(fn, "rb") as fh:
+                data = pickle.load(fh, encoding="latin1")
+            m = torch_ref.SmplModel(data, {"J_regressor_extra": np.zeros((9, 6890), np.float32),
+                                           "J_regressor_h36m": np.zeros((17, 6890), np.float32)})
+            self._m = m
+            self.faces = m.faces
+            self.register_buffer("faces_tensor", torch.as_tensor(m.faces))
+            self.register_buffer("v_template", m.v_template)
+            self.register_buffer("shapedirs", m.shapedirs)
+            self.register_buffer("J_regressor", m.J_regressor)
+            self.register_buffer("posedirs", m.posedirs)
+            self.register_buffer("parents", m.parents)
+            self.register_buffer("lbs_weights", m.lbs_weights)
+            self.betas = torch.nn.Parameter(torch.zeros(batch_size, 10))
+            self.global_orient = torch.nn.Parameter(torch.zeros(batch_size, 3))
+            self.body_pose = torch.nn.Parameter(torch.zeros(batch_size, 69))
+
+        def forward(self, betas=None, body_pose=None, global_orient=None, transl=None,
+                    return_verts=True, return_full_pose=False, pose2rot=True, **kw):
+            m = self._m
+            if pose2rot:
+                full = torch.cat([global_orient.reshape(-1, 3), body_pose.reshape(-1, 69)], dim=1)
+                R = torch_ref.batch_rodrigues_smplx(full.reshape(-1, 3)).reshape(-1, 24, 3, 3)
+            else:
+                full = torch.cat([global_orient.reshape(-1, 1, 3, 3), body_pose.reshape(-1, 23, 3, 3)], dim=1)
+                R = full
+            verts, posed_J = torch_ref.smpl_lbs(m, betas, R)
+            joints = torch.cat([posed_J, verts[:, m.extra_vertex_ids]], dim=1)
+            return SMPLOutput(vertices=verts, joints=joints, full_pose=full, betas=betas,
+                              global_orient=global_orient, body_pose=body_pose)
+
+    def vertices2joints(J_regressor, vertices):
+        return torch.einsum("bik,ji->bjk", vertices, J_regressor)
+
+    smplx = types.ModuleType("smplx")
+    smplx._tepose_b200_standin = True
+    smplx.SMPL = SMPL
+    bm = types.ModuleType("smplx.body_models")
+    bm.SMPLOutput = SMPLOutput
+    lbs = types.ModuleType("smplx.lbs")
+    lbs.vertices2joints = vertices2joints
+    smplx.body_models, smplx.lbs = bm, lbs
+    sys.modules.update({"smplx": smplx, "smplx.body_models": bm, "smplx.lbs": lbs})
+
+
+def _install_lib_packages():
+    """Register ``lib``, ``lib.models`` ... as bare namespace packages so that
+    lib/models/__init__.py (which drags in the discriminator) is not executed; the
+    hot-path module files themselves are imported unmodified."""
+    for name in ("lib", "lib.core", "lib.models", "lib.utils"):
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            mod.__path__ = [os.path.join(REFERENCE_ROOT, *name.split("."))]
+            sys.modules[name] = mod
+
+
+@contextlib.contextmanager
+def reference_env(seed: int = 0):
+    """cwd = temp dir holding synthetic data/base_data; yields the reference modules."""
+    if not available():
+        raise RuntimeError("/root/reference is not present on this box")
+    _install_yacs_stub()
+    _install_smplx_standin()
+    _install_lib_packages()
+    old = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        synth.write_base_data(os.path.join(tmp, "data", "base_data"), seed)
+        os.chdir(tmp)
+        try:
+            import importlib
+            mods = types.SimpleNamespace(
+                tepose=importlib.import_module("lib.models.tepose"),
+                spin=importlib.import_module("lib.models.spin"),
+                smpl=importlib.import_module("lib.models.smpl"),
+                geometry=importlib.import_module("lib.utils.geometry"),
+            )
+            yield mods
+        finally:
+            os.chdir(old)
+
+
+def build_reference_model(mods, sd_np: dict, seqlen: int, n_layers: int, hidden: int):
+    """lib.models.TePose with our synthetic parameters loaded (strict on everything
+    that make_state_dict provides; regressor.smpl.* keeps what the constructor read)."""
+    model = mods.tepose.TePose(seqlen=seqlen, n_layers=n_layers, hidden_size=hidden, pretrained="")
+    own = model.state_dict()
+    for k, v in sd_np.items():
+        assert k in own and tuple(own[k].shape) == tuple(v.shape), k
+        own[k] = torch.as_tensor(v)
+    missing = [k for k in own if k not in sd_np and not k.startswith("regressor.smpl.")]
+    assert not missing, missing
+    model.load_state_dict(own, strict=True)
+    return model.eval()
+
+
+def run_reference(seed, batch, seqlen, n_layers, hidden, is_train=False, use_h36m=False, x=None):
+    sd = synth.make_state_dict(seed, n_layers, hidden)
+    if x is None:
+        x = synth.make_input(seed, batch, seqlen)
+    with reference_env(seed) as mods:
+        model = build_reference_model(mods, sd, seqlen, n_layers, hidden)
+        Jr = None
+        if use_h36m:
+            Jr = torch.from_numpy(np.load(os.path.join("data", "base_data", "J_regressor_h36m.npy"))).float()
+        with torch.no_grad():
+            out = model(torch.from_numpy(x), is_train=is_train, J_regressor=Jr)[-1]
+    return {k: v.detach().numpy().copy() for k, v in out.items()}
