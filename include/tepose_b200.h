@@ -1,0 +1,200 @@
+/*
+ * tepose_b200 -- C ABI of the B200 (sm_100a) implementation of TePose's per-sequence
+ * inference hot path.
+ *
+ * The reference (ostadabbas/TePose) is pure Python/PyTorch and has no FFI of its own;
+ * the boundary it exposes is the Python module API of lib.models.  The
+ * entry points below are what a reference-side ctypes binding for that path calls:
+ * each comment names the reference code the entry point replaces (paths relative to
+ * the reference repository).  See INTEGRATION.md for the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host"; the library never
+ *     allocates or frees caller memory (scratch comes in through `workspace`);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), no host
+ *     synchronisation, safe to capture in a CUDA graph;
+ *   - return value: 0 = ok, <0 = error (see TP_ERR_*); tp_last_error() gives the text
+ *     for the calling thread;
+ *   - matrices are row-major float32 unless stated; `ld*` are row strides in ELEMENTS.
+ */
+#ifndef TEPOSE_B200_H
+#define TEPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TP_API __attribute__((visibility("default")))
+#else
+#define TP_API
+#endif
+
+#define TP_OK 0
+#define TP_ERR_INVALID (-1)     /* bad argument (null pointer, misaligned, bad size)   */
+#define TP_ERR_UNSUPPORTED (-2) /* shape / device not supported by this build           */
+#define TP_ERR_CUDA (-3)        /* a CUDA runtime / driver call failed                  */
+
+#define TP_PRECISION_FP32 0 /* fp32 operands, FFMA, fp32 accumulate (strict parity mode)   */
+#define TP_PRECISION_BF16 1 /* bf16 operands on tensor cores, fp32 accumulate + fp32 state */
+
+#define TP_POSE_ROTMAT 0     /* [n,24,3,3]  (smplx pose2rot=False, lib/models/spin.py:265-270) */
+#define TP_POSE_AXIS_ANGLE 1 /* [n,72]      (smplx pose2rot=True,  lib/utils/eval_utils.py:168) */
+#define TP_POSE_ROT6D 2      /* [n,144]     (rot6d_to_rotmat fused, lib/models/spin.py:263)     */
+
+#define TP_RODRIGUES_SMPLX 0 /* smplx.lbs.batch_rodrigues                         */
+#define TP_RODRIGUES_QUAT 1  /* lib/utils/geometry.py:22-65 (quaternion form)     */
+
+/* joint source codes for tp_smpl_forward (composition of lib/models/smpl.py:75-77 and
+ * lib/models/spin.py:275-278): */
+#define TP_JSRC_POSED(j) (j)            /* 0..23  : posed kinematic-chain joint          */
+#define TP_JSRC_REGRESSED(r) (100 + (r)) /* row r of the caller-supplied joint regressor  */
+#define TP_JSRC_VERTEX(v) (1000 + (v))   /* mesh vertex v (smplx vertex_joint_selector)   */
+
+TP_API int tp_version(void);
+TP_API const char* tp_last_error(void);
+/* host out-params; any may be NULL */
+TP_API int tp_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_per_block_optin);
+
+/* ------------------------------------------------------------------ rotation utilities
+ * lib/utils/geometry.py:330-343  rot6d_to_rotmat          x [n,6]   -> R [n,3,3]          */
+TP_API int tp_rot6d_to_rotmat(const float* x, float* R, int64_t n, void* stream);
+/* lib/utils/geometry.py:68-233   rotation_matrix_to_angle_axis   R [n,3,3] -> aa [n,3]   */
+TP_API int tp_rotmat_to_angle_axis(const float* R, float* aa, int64_t n, void* stream);
+/* smplx.lbs.batch_rodrigues / lib/utils/geometry.py:22-65   aa [n,3] -> R [n,3,3]        */
+TP_API int tp_batch_rodrigues(const float* aa, float* R, int64_t n, int form, void* stream);
+/* lib/models/spin.py:307-351  projection   joints [n,nj,3], cam [n,3] -> kp2d [n,nj,2]   */
+TP_API int tp_projection(const float* joints, const float* cam, float* kp2d, int n, int nj, void* stream);
+
+/* ------------------------------------------------------------------ operand packing
+ * Gathers a [rows_b, rows_t, k] fp32 tensor (element (b,t,c) at src[b*stride_b + t*stride_t + c])
+ * into a dense, zero-padded [rows_t*rows_b, kp] matrix whose row index is t*rows_b + b
+ * (time-major, what the recurrence consumes), as fp32 (dst_precision 0) or bf16 (1).
+ * Replaces x.permute(1,0,2) (lib/models/tepose.py:73,76).  kp >= k, kp % 8 == 0.        */
+TP_API int tp_pack_rows(const float* src, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t, int k,
+                 void* dst, int kp, int dst_precision, int relu, void* stream);
+
+/* ------------------------------------------------------------------ GEMMs (torch.nn.Linear / GRU input projection)
+ * C[M,N] = alpha * ( act(A)[M,K] . W[N,K]^T + bias[N] ) + beta * Cin[M,N]
+ * fp32 FFMA path.  bias / Cin may be NULL; Cin may alias C.  K % 4 == 0, lda/ldw % 4 == 0,
+ * A and W 16-byte aligned.  relu_a applies max(.,0) to A on load (F.relu before Linear,
+ * lib/models/tepose.py:79-80).                                                           */
+TP_API int tp_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                const float* Cin, int64_t ldcin, float* C, int64_t ldc,
+                int M, int N, int K, float alpha, float beta, int relu_a, void* stream);
+
+/* One segment of a tensor-core GEMM launch: rows [m_start, m_start+m_rows) of A against rows
+ * [n_start, n_start+n_cols) of W;  out[(m-m_start)*ldc + (n-n_start)] = dot + bias[n-n_start]. */
+typedef struct tp_gemm_seg {
+  int32_t m_start, m_rows;
+  int32_t n_start, n_cols; /* n_cols % 16 == 0 */
+  float* out;
+  int64_t ldc;
+  const float* bias; /* [n_cols] or NULL */
+} tp_gemm_seg;
+
+/* tcgen05 / TMEM GEMM fed by TMA (GRU input projection over all timesteps, K1):
+ * A [a_rows, kp] bf16 and W [w_rows, kp] bf16, both K-major, kp % 64 == 0, 16-byte aligned.
+ * `segs` is a HOST array (nseg <= 8).  Requires an sm_100 device.                        */
+TP_API int tp_gemm_bf16_tc(const void* A, int a_rows, const void* W, int w_rows, int kp,
+                    const tp_gemm_seg* segs, int nseg, void* stream);
+
+/* ------------------------------------------------------------------ GRU recurrence (K2)
+ * One direction of one torch.nn.GRU layer (lib/models/tepose.py:53-64,73,76) given the
+ * input projections gi = x.W_ih^T + b_ih.  Step s (0-based) reads gi row block
+ * (t_in0 + s*t_in_step) and writes outputs at time index (t_out0 + s*t_out_step).          */
+typedef struct tp_gru_job {
+  const float* gi;   /* [T, B, ldg] fp32, columns ordered r|z|n (3H wide)                  */
+  int64_t ldg;
+  const void* w_hh;  /* fp32: [3H,H] row-major.  bf16: [3H,H] row-major bf16               */
+  const float* b_hh; /* [3H]                                                                */
+  const float* h0;   /* [B,H] (ld = H) initial state, or NULL for zeros                     */
+  float* y;          /* optional [T,B,ldy] fp32 sequence output, or NULL                    */
+  int64_t ldy;
+  void* y_lp;        /* optional bf16 copy of the sequence output [T,B,ldy_lp], or NULL     */
+  int64_t ldy_lp;
+  float* h_final;    /* optional [B,ld_hf] state after the last step, or NULL               */
+  int64_t ld_hf;
+  int32_t steps;
+  int32_t t_in0, t_in_step;
+  int32_t t_out0, t_out_step;
+} tp_gru_job;
+
+/* bytes of scratch tp_gru_recurrence needs for (njobs, B, H) */
+TP_API size_t tp_gru_workspace_bytes(int njobs, int B, int H);
+/* Runs up to 4 independent jobs (directions) concurrently in ONE persistent cooperative
+ * kernel that grid-synchronises once per timestep.  `jobs` is a HOST array.  B <= 64.
+ * H % 32 == 0.  workspace must be 256-byte aligned.                                        */
+TP_API int tp_gru_recurrence(const tp_gru_job* jobs, int njobs, int B, int H, int precision,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ Regressor (K3)
+ * Linear heads of the encoder (lib/models/tepose.py:79-85):
+ *   is_train = 0: feat [B,2048]   = (linear_fwd(relu(h_fwd)) + linear_rec(relu(h_rec))) / 2
+ *   is_train = 1: feat [B,2,2048] = stack(linear_fwd(..), linear_rec(..))
+ * h_fwd [B, ld_hf] is y[-1] of gru_fwd (H wide), h_rec [B, ld_hr] is y_rec[0] (2H wide).
+ * w_fwd [2048,H], w_rec [2048,2H] row-major fp32 (nn.Linear layout).                     */
+TP_API int tp_encoder_heads(const float* w_fwd, const float* b_fwd, const float* w_rec, const float* b_rec,
+                     const float* h_fwd, int64_t ld_hf, const float* h_rec, int64_t ld_hr,
+                     int B, int H, int is_train, float* feat, void* stream);
+
+/* 3-iteration IEF loop (lib/models/spin.py:250-261).  fc1 is split into its feature columns
+ * (w1x, iteration-invariant) and its [pose|shape|cam] columns (w1p, zero-padded 157 -> 160);
+ * decpose/decshape/deccam are stacked into one [160,1024] matrix.                         */
+typedef struct tp_ief_weights {
+  const float* w1x;  /* [1024, 2048] fc1.weight[:, :2048] */
+  const float* b1;   /* [1024] */
+  const float* w1p;  /* [1024, 160]  fc1.weight[:, 2048:2205] zero-padded */
+  const float* w2;   /* [1024, 1024] */
+  const float* b2;   /* [1024] */
+  const float* wdec; /* [160, 1024]  rows: decpose(144) | decshape(10) | deccam(3) | 0(3) */
+  const float* bdec; /* [160] */
+} tp_ief_weights;
+
+TP_API size_t tp_ief_workspace_bytes(int n_rows);
+/* feat [n_rows,2048]; init [init_rows,160] = pose6d(144)|shape(10)|cam(3)|0(3) with
+ * init_rows == 1 (broadcast, the init_* buffers) or n_rows; psc [n_rows,160] receives the
+ * refined pose6d | shape | cam | pad.                                                      */
+TP_API int tp_ief_forward(const tp_ief_weights* w, const float* feat, int n_rows, const float* init, int init_rows,
+                   int n_iter, float* psc, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ SMPL forward (K4 + K5)
+ * Packed, device-resident body-model constants (built once by the host, see
+ * tepose_b200/smpl.py:pack_smpl_model).                                                    */
+typedef struct tp_smpl_model {
+  const float* blend;    /* [218][3][vp]: rows 0..206 posedirs, 207..216 shapedirs, 217 v_template;
+                            plane c of row k holds coordinate c of every vertex (padded to vp)  */
+  const float* j_template; /* [24,3]     J_regressor . v_template                               */
+  const float* j_shapedirs;/* [24,3,10]  J_regressor . shapedirs                                 */
+  const int32_t* parents;  /* [24], parents[0] = -1, parents[i] < i                              */
+  const int32_t* skin_idx; /* [vp, ks] joint index of each retained skinning weight             */
+  const float* skin_w;     /* [vp, ks]                                                           */
+  int32_t ks;              /* retained weights per vertex (4 for SMPL; up to 24)                */
+  int32_t n_verts;         /* 6890 */
+  int32_t vp;              /* n_verts rounded up to a multiple of 128 */
+} tp_smpl_model;
+
+TP_API size_t tp_smpl_workspace_bytes(const tp_smpl_model* m, int n, int nreg);
+/* smplx.SMPL.forward + lbs (restated third-party code), the wrapper
+ * lib/models/smpl.py:72-84, the optional H36M regression lib/models/spin.py:275-278, the
+ * projection spin.py:280 and the theta assembly spin.py:282-285 in three launches:
+ * verts never round-trip HBM between stages.
+ *   pose      : per pose_kind, row stride ld_pose   betas : [n,10] (row stride ld_betas)
+ *   cam       : [n,3] or NULL (then kp2d/theta are not produced)
+ *   jreg      : [nreg, vp] dense joint regressor rows (zero padded to vp), nreg <= 32
+ *   joint_src : [nj] device array of TP_JSRC_* codes
+ * outputs (any may be NULL; verts is required when nj > 0): verts [n,n_verts,3], joints [n,nj,3], kp2d [n,nj,2],
+ *   rotmat [n,24,3,3], theta [n,85] = cam | axis-angle(72) | betas(10).                    */
+TP_API int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose, int64_t ld_pose, int pose_kind,
+                    const float* betas, int64_t ld_betas, const float* cam, int64_t ld_cam,
+                    const float* jreg, int nreg, const int32_t* joint_src, int nj,
+                    float* verts, float* joints, float* kp2d, float* rotmat, float* theta,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEPOSE_B200_H */

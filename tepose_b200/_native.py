@@ -1,0 +1,126 @@
+"""ctypes binding of the C-ABI library declared in include/tepose_b200.h.
+
+There is deliberately NO fallback: if libtepose_b200.so is missing, or a call is made
+without a CUDA device, this raises -- the product never routes through torch ops or the
+CPU oracle for the hot path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtepose_b200.so")
+
+PRECISION_FP32, PRECISION_BF16 = 0, 1
+POSE_ROTMAT, POSE_AXIS_ANGLE, POSE_ROT6D = 0, 1, 2
+RODRIGUES_SMPLX, RODRIGUES_QUAT = 0, 1
+PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16}
+
+# every symbol include/tepose_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "tp_version", "tp_last_error", "tp_device_info",
+    "tp_rot6d_to_rotmat", "tp_rotmat_to_angle_axis", "tp_batch_rodrigues", "tp_projection",
+    "tp_pack_rows", "tp_gemm_f32", "tp_gemm_bf16_tc",
+    "tp_gru_workspace_bytes", "tp_gru_recurrence",
+    "tp_encoder_heads", "tp_ief_workspace_bytes", "tp_ief_forward",
+    "tp_smpl_workspace_bytes", "tp_smpl_forward",
+]
+
+vp, i32, i64, f32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+
+class GemmSeg(C.Structure):
+    _fields_ = [("m_start", i32), ("m_rows", i32), ("n_start", i32), ("n_cols", i32),
+                ("out", vp), ("ldc", i64), ("bias", vp)]
+
+
+class GruJob(C.Structure):
+    _fields_ = [("gi", vp), ("ldg", i64), ("w_hh", vp), ("b_hh", vp), ("h0", vp),
+                ("y", vp), ("ldy", i64), ("y_lp", vp), ("ldy_lp", i64),
+                ("h_final", vp), ("ld_hf", i64), ("steps", i32),
+                ("t_in0", i32), ("t_in_step", i32), ("t_out0", i32), ("t_out_step", i32)]
+
+
+class IefWeights(C.Structure):
+    _fields_ = [(n, vp) for n in ("w1x", "b1", "w1p", "w2", "b2", "wdec", "bdec")]
+
+
+class SmplModel(C.Structure):
+    _fields_ = [("blend", vp), ("j_template", vp), ("j_shapedirs", vp), ("parents", vp),
+                ("skin_idx", vp), ("skin_w", vp), ("ks", i32), ("n_verts", i32), ("vp", i32)]
+
+
+_SIGNATURES = {
+    "tp_version": (C.c_int, []),
+    "tp_last_error": (C.c_char_p, []),
+    "tp_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(sz)]),
+    "tp_rot6d_to_rotmat": (C.c_int, [vp, vp, i64, vp]),
+    "tp_rotmat_to_angle_axis": (C.c_int, [vp, vp, i64, vp]),
+    "tp_batch_rodrigues": (C.c_int, [vp, vp, i64, C.c_int, vp]),
+    "tp_projection": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp]),
+    "tp_pack_rows": (C.c_int, [vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "tp_gemm_f32": (C.c_int, [vp, i64, vp, i64, vp, vp, i64, vp, i64, C.c_int, C.c_int, C.c_int, f32, f32, C.c_int, vp]),
+    "tp_gemm_bf16_tc": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.POINTER(GemmSeg), C.c_int, vp]),
+    "tp_gru_workspace_bytes": (sz, [C.c_int, C.c_int, C.c_int]),
+    "tp_gru_recurrence": (C.c_int, [C.POINTER(GruJob), C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, vp]),
+    "tp_encoder_heads": (C.c_int, [vp, vp, vp, vp, vp, i64, vp, i64, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "tp_ief_workspace_bytes": (sz, [C.c_int]),
+    "tp_ief_forward": (C.c_int, [C.POINTER(IefWeights), vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, sz, vp]),
+    "tp_smpl_workspace_bytes": (sz, [C.POINTER(SmplModel), C.c_int, C.c_int]),
+    "tp_smpl_forward": (C.c_int, [C.POINTER(SmplModel), C.c_int, vp, i64, C.c_int, vp, i64, vp, i64,
+                                  vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, sz, vp]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads the native library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m tepose_b200.build` "
+                "(or __graft_entry__.build()).  tepose_b200 has no CPU / torch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().tp_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"tepose_b200 native call {what} failed (code {rc}): {msg}")
+
+
+def require_cuda(t: torch.Tensor, name: str = "tensor") -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"tepose_b200: {name} must live on a CUDA device (got {t.device}); "
+                           "there is no CPU path")
+
+
+def ptr(t, dtype=None) -> vp:
+    """Device pointer of a contiguous CUDA tensor (or NULL for None)."""
+    if t is None:
+        return vp(0)
+    require_cuda(t)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return vp(t.data_ptr())
+
+
+def stream() -> vp:
+    return vp(torch.cuda.current_stream().cuda_stream)
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """256-byte aligned scratch (torch's caching allocator aligns to 512 B)."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

@@ -1,0 +1,49 @@
+// Library-level entry points: version, error text, device query.
+#include "common.cuh"
+#include <string.h>
+
+namespace tp {
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+}  // namespace tp
+
+extern "C" int tp_version(void) { return 100; }
+
+extern "C" const char* tp_last_error(void) { return tp::g_err; }
+
+extern "C" int tp_device_info(int device, int* sm_count, int* cc_major, int* cc_minor,
+                              size_t* smem_per_block_optin) {
+  cudaDeviceProp p;
+  TP_CUDA(cudaGetDeviceProperties(&p, device));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (smem_per_block_optin) *smem_per_block_optin = p.sharedMemPerBlockOptin;
+  return TP_OK;
+}

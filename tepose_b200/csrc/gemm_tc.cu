@@ -1,0 +1,293 @@
+// K1 -- GRU input projection on the 5th-gen tensor cores:  out = A . W^T + bias
+// (replaces the input GEMM inside cuDNN's GRU / the x.W_ih^T half of torch.nn.GRU,
+// reference lib/models/tepose.py:53-64,73,76).
+//
+//   * operands bf16, K-major, moved by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a
+//     6-stage shared-memory ring guarded by mbarriers;
+//   * one elected thread issues tcgen05.mma (cta_group::1, M=128, N=128, K=16) with the fp32
+//     accumulator in TMEM (128 lanes x 128 columns);
+//   * tcgen05.commit releases ring slots / signals the epilogue; four warps read the
+//     accumulator back with tcgen05.ld (32 lanes x 32 columns per instruction), add the bias
+//     and store fp32.
+// One 128x128 output tile per CTA; tiles that share a W tile are adjacent in launch order so
+// the W tile is fetched from HBM once and re-served from L2.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace tp {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 6;
+constexpr int TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK * 2;   // 32 KB
+constexpr int TC_MAX_SEGS = 8;
+constexpr int TC_THREADS = 128;
+
+struct TcParams {
+  tp_gemm_seg seg[TC_MAX_SEGS];
+  int tile_begin[TC_MAX_SEGS + 1];
+  int nseg, kblocks;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}\n" : "+r"(pred) : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+          "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major operand tile, 128-byte swizzle: 8-row groups are 1024 B apart (SBO), LBO unused (=1),
+// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29).
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // carve: [stages][A 16KB | W 16KB] (1024-aligned), then barriers
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile decode
+  int s = 0;
+#pragma unroll
+  for (int q = 1; q < TC_MAX_SEGS; ++q)
+    if (q < p.nseg && (int)blockIdx.x >= p.tile_begin[q]) s = q;
+  const tp_gemm_seg sg = p.seg[s];
+  const int local = blockIdx.x - p.tile_begin[s];
+  const int m_tiles = (sg.m_rows + TC_BM - 1) / TC_BM;
+  const int n_tile = local / m_tiles, m_tile = local - n_tile * m_tiles;
+  const int m0 = m_tile * TC_BM, n0 = n_tile * TC_BN;   // segment-local
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TC_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {  // ===== TMA producer =====
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        const int st = kb % TC_STAGES;
+        const uint32_t ph = (kb / TC_STAGES) & 1;
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        unsigned char* a_dst = smem + st * TC_STAGE_BYTES;
+        unsigned char* w_dst = a_dst + TC_BM * TC_BK * 2;
+        mbar_expect_tx(&full_bar[st], TC_STAGE_BYTES);
+        tma_load_2d(a_dst, &map_a, &full_bar[st], kb * TC_BK, sg.m_start + m0);
+        tma_load_2d(w_dst, &map_w, &full_bar[st], kb * TC_BK, sg.n_start + n0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {  // ===== MMA issuer =====
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        const int st = kb % TC_STAGES;
+        const uint32_t ph = (kb / TC_STAGES) & 1;
+        mbar_wait(&full_bar[st], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t a_addr = smem_u32(smem + st * TC_STAGE_BYTES);
+        const uint32_t w_addr = a_addr + TC_BM * TC_BK * 2;
+        const uint64_t da = umma_desc_sw128(a_addr), db = umma_desc_sw128(w_addr);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in 16-byte units
+          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[st]);   // slot reusable once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);      // accumulator complete
+    }
+    __syncwarp();
+  }
+
+  // ===== epilogue: all four warps, warp w owns TMEM lanes 32w..32w+31 =====
+  mbar_wait(tmem_full_bar, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const int row = m0 + warp * 32 + lane;                 // segment-local output row
+  const bool row_ok = row < sg.m_rows;
+  float* out_row = sg.out + (int64_t)row * sg.ldc;
+  const bool vec_ok = ((sg.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(sg.out) & 15) == 0);
+#pragma unroll 1
+  for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+    if (row_ok) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int n = n0 + c0 + q * 4;
+        if (n >= sg.n_cols) break;
+        float4 o;
+        o.x = __uint_as_float(v[q * 4 + 0]); o.y = __uint_as_float(v[q * 4 + 1]);
+        o.z = __uint_as_float(v[q * 4 + 2]); o.w = __uint_as_float(v[q * 4 + 3]);
+        if (n + 3 < sg.n_cols && vec_ok) {
+          if (sg.bias) {
+            const float4 bb = *reinterpret_cast<const float4*>(sg.bias + n);
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+          }
+          *reinterpret_cast<float4*>(out_row + n) = o;
+        } else {
+          const float e[4] = {o.x, o.y, o.z, o.w};
+          for (int i = 0; i < 4; ++i)
+            if (n + i < sg.n_cols) out_row[n + i] = e[i] + (sg.bias ? sg.bias[n + i] : 0.0f);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)TC_BN));
+  }
+}
+
+// ---- host side: tensor maps through the driver entry point (no libcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, int rows, int kp, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(TP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return TP_OK;
+}
+
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" int tp_gemm_bf16_tc(const void* A, int a_rows, const void* W, int w_rows, int kp,
+                               const tp_gemm_seg* segs, int nseg, void* stream) {
+  TP_CHECK_ARG(A && W && segs, "tp_gemm_bf16_tc: null pointer");
+  TP_CHECK_ARG(nseg >= 1 && nseg <= TC_MAX_SEGS, "tp_gemm_bf16_tc: nseg=%d out of range", nseg);
+  TP_CHECK_ARG(kp > 0 && kp % TC_BK == 0, "tp_gemm_bf16_tc: kp=%d must be a positive multiple of %d", kp, TC_BK);
+  TP_CHECK_ARG(a_rows > 0 && w_rows > 0, "tp_gemm_bf16_tc: empty operand");
+  TP_CHECK_ARG(aligned16(A) && aligned16(W), "tp_gemm_bf16_tc: operands must be 16-byte aligned");
+  int dev = 0, major = 0;
+  TP_CUDA(cudaGetDevice(&dev));
+  TP_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail(TP_ERR_UNSUPPORTED, "tp_gemm_bf16_tc needs an sm_100 device (found sm_%d)", major);
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.nseg = nseg;
+  p.kblocks = kp / TC_BK;
+  int tiles = 0;
+  for (int i = 0; i < nseg; ++i) {
+    const tp_gemm_seg& sg = segs[i];
+    TP_CHECK_ARG(sg.out && sg.m_rows > 0 && sg.n_cols > 0, "tp_gemm_bf16_tc: segment %d is empty / has no output", i);
+    TP_CHECK_ARG(sg.m_start >= 0 && sg.m_start + sg.m_rows <= a_rows, "tp_gemm_bf16_tc: segment %d rows out of range", i);
+    TP_CHECK_ARG(sg.n_start >= 0 && sg.n_start + sg.n_cols <= w_rows, "tp_gemm_bf16_tc: segment %d cols out of range", i);
+    p.seg[i] = sg;
+    p.tile_begin[i] = tiles;
+    tiles += (int)(ceil_div(sg.m_rows, TC_BM) * ceil_div(sg.n_cols, TC_BN));
+  }
+  for (int i = nseg; i <= TC_MAX_SEGS; ++i) p.tile_begin[i] = tiles;
+  CUtensorMap map_a, map_w;
+  int rc = make_map(&map_a, A, a_rows, kp, TC_BM);
+  if (rc != TP_OK) return rc;
+  rc = make_map(&map_w, W, w_rows, kp, TC_BN);
+  if (rc != TP_OK) return rc;
+  const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  TP_CUDA(cudaFuncSetAttribute(k_gemm_bf16_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_gemm_bf16_tc<<<(unsigned)tiles, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, p);
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}

@@ -1,0 +1,383 @@
+// K2 -- GRU recurrence as ONE persistent cooperative kernel (replaces the cuDNN / ATen
+// GRU time loop behind torch.nn.GRU, reference lib/models/tepose.py:53-64,73,76).
+//
+// Work decomposition: every job (= one direction of one layer) is cut into items of U
+// hidden units; an item owns the 3U rows {r,z,n} x U of W_hh, computes
+// gh = W_hh[rows,:] . h_prev^T for the whole batch tile, applies the gate math and publishes
+// its U columns of h_t.  All items of all jobs advance one timestep, then the grid
+// synchronises (h_t must be complete before anybody starts t+1).
+//
+//   fp32 : FFMA, W_hh / h_prev staged K-major through shared memory with cp.async.
+//   bf16 : mma.sync m16n8k16 (batch <= 32 makes this a weight-streaming problem, not a
+//          tensor-throughput one); W_hh fragments are loaded straight from global/L2 with
+//          128-bit loads in a permuted-K order, h_prev (bf16) is staged once per step in
+//          shared memory, 8 warps split K (x M) and reduce through shared memory.
+//          State, gates and accumulation stay fp32.
+#include "common.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace tp {
+
+constexpr int kMaxJobs = 4;
+constexpr int kGruThreads = 256;
+
+struct GruParams {
+  tp_gru_job jobs[kMaxJobs];
+  int item_begin[kMaxJobs + 1];
+  int njobs, B, H, U, max_steps, total_items, any_h0;
+  float* hbuf;              // [njobs][2][B][H]  fp32 state ping-pong
+  __nv_bfloat16* hbuf_lp;   // [njobs][2][B][H]  bf16 copy (MMA operand of the next step)
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ void cp_async16_z(void* smem, const void* gmem, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void mma_bf16(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Gate math of torch.nn.GRU for one (batch b, hidden unit u): acc_* are W_h* . h_prev.
+__device__ __forceinline__ void gru_finalize(const GruParams& p, int j, int s, int b, int u,
+                                             float acc_r, float acc_z, float acc_n) {
+  const tp_gru_job& jb = p.jobs[j];
+  const int H = p.H, B = p.B;
+  const int t_in = jb.t_in0 + s * jb.t_in_step;
+  const float* gi = jb.gi + ((int64_t)t_in * B + b) * jb.ldg;
+  float hp = 0.0f;
+  const bool have_prev = (s > 0) || (jb.h0 != nullptr);
+  const float* hprev = p.hbuf + ((int64_t)(j * 2 + ((s + 1) & 1)) * B) * H;
+  if (have_prev) hp = __ldcg(hprev + (int64_t)b * H + u);
+  float r = sigmoidf_(gi[u] + (acc_r + jb.b_hh[u]));
+  float z = sigmoidf_(gi[H + u] + (acc_z + jb.b_hh[H + u]));
+  float n = tanhf(gi[2 * H + u] + r * (acc_n + jb.b_hh[2 * H + u]));
+  float h = (1.0f - z) * n + z * hp;
+  const int64_t slot = ((int64_t)(j * 2 + (s & 1)) * B + b) * H + u;
+  p.hbuf[slot] = h;
+  p.hbuf_lp[slot] = __float2bfloat16_rn(h);
+  const int t_out = jb.t_out0 + s * jb.t_out_step;
+  if (jb.y) jb.y[((int64_t)t_out * B + b) * jb.ldy + u] = h;
+  if (jb.y_lp) reinterpret_cast<__nv_bfloat16*>(jb.y_lp)[((int64_t)t_out * B + b) * jb.ldy_lp + u] = __float2bfloat16_rn(h);
+  if (jb.h_final && s == jb.steps - 1) jb.h_final[(int64_t)b * jb.ld_hf + u] = h;
+}
+
+__device__ __forceinline__ void locate_item(const GruParams& p, int item, int& j, int& u0) {
+  j = 0;
+#pragma unroll
+  for (int q = 1; q < kMaxJobs; ++q)
+    if (q < p.njobs && item >= p.item_begin[q]) j = q;
+  u0 = (item - p.item_begin[j]) * p.U;
+}
+
+// h0 -> state slot 1 (the "previous" slot of step 0), fp32 and bf16.
+__device__ void seed_h0(const GruParams& p) {
+  const int64_t per = (int64_t)p.B * p.H;
+  for (int j = 0; j < p.njobs; ++j) {
+    const float* h0 = p.jobs[j].h0;
+    if (!h0) continue;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
+      float v = h0[i];
+      p.hbuf[(int64_t)(j * 2 + 1) * per + i] = v;
+      p.hbuf_lp[(int64_t)(j * 2 + 1) * per + i] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ fp32
+// U = 32 units per item, batch tile 32: thread (u = tid/8, bq = tid%8) owns gates r,z,n of
+// unit u for batches bq + 8i.  Rows are staged K-major (pitch 36 floats) so the float4 reads
+// along K are conflict free.
+__global__ void __launch_bounds__(kGruThreads, 1) k_gru_f32(const GruParams p) {
+  constexpr int U = 32, BT = 32, BK = 32, LD = BK + 4, STAGES = 3;
+  extern __shared__ __align__(16) float smem_f[];
+  float* Ws = smem_f;                          // [STAGES][3U][LD]
+  float* Hs = smem_f + STAGES * 3 * U * LD;    // [STAGES][BT][LD]
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x, u = tid >> 3, bq = tid & 7;
+  const int H = p.H, B = p.B;
+
+  if (p.any_h0) { seed_h0(p); grid.sync(); }
+
+  for (int s = 0; s < p.max_steps; ++s) {
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int j, u0;
+      locate_item(p, item, j, u0);
+      const tp_gru_job& jb = p.jobs[j];
+      if (s >= jb.steps) continue;
+      const bool have_prev = (s > 0) || (jb.h0 != nullptr);
+      const float* W = reinterpret_cast<const float*>(jb.w_hh);
+      const float* hprev = p.hbuf + ((int64_t)(j * 2 + ((s + 1) & 1)) * B) * H;
+      for (int b0 = 0; b0 < B; b0 += BT) {
+        float acc[3][4];
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[g][i] = 0.0f;
+        if (have_prev) {
+          const int nkt = H / BK;
+          auto load_stage = [&](int stage, int kt) {
+            const int k0 = kt * BK;
+            for (int c = tid; c < (3 * U + BT) * (BK / 4); c += kGruThreads) {
+              int r = c >> 3, q = c & 7;
+              if (r < 3 * U) {
+                int g = r >> 5, uu = r & 31;
+                cp_async16_z(&Ws[(stage * 3 * U + r) * LD + q * 4],
+                             W + ((int64_t)g * H + u0 + uu) * H + k0 + q * 4, true);
+              } else {
+                int bb = r - 3 * U;
+                bool ok = (b0 + bb) < B;
+                cp_async16_z(&Hs[(stage * BT + bb) * LD + q * 4],
+                             ok ? (hprev + (int64_t)(b0 + bb) * H + k0 + q * 4) : hprev, ok);
+              }
+            }
+          };
+#pragma unroll
+          for (int st = 0; st < STAGES - 1; ++st) {
+            if (st < nkt) load_stage(st, st);
+            cp_commit();
+          }
+          for (int kt = 0; kt < nkt; ++kt) {
+            cp_wait<STAGES - 2>();
+            __syncthreads();
+            int nk = kt + STAGES - 1;
+            if (nk < nkt) load_stage(nk % STAGES, nk);
+            cp_commit();
+            const float* ws = Ws + (kt % STAGES) * 3 * U * LD;
+            const float* hs = Hs + (kt % STAGES) * BT * LD;
+#pragma unroll
+            for (int q = 0; q < BK / 4; ++q) {
+              float4 w[3], hv[4];
+#pragma unroll
+              for (int g = 0; g < 3; ++g) w[g] = *reinterpret_cast<const float4*>(&ws[(g * U + u) * LD + q * 4]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) hv[i] = *reinterpret_cast<const float4*>(&hs[(bq + 8 * i) * LD + q * 4]);
+#pragma unroll
+              for (int g = 0; g < 3; ++g)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  acc[g][i] = fmaf(w[g].x, hv[i].x, acc[g][i]);
+                  acc[g][i] = fmaf(w[g].y, hv[i].y, acc[g][i]);
+                  acc[g][i] = fmaf(w[g].z, hv[i].z, acc[g][i]);
+                  acc[g][i] = fmaf(w[g].w, hv[i].w, acc[g][i]);
+                }
+            }
+          }
+          cp_wait<0>();
+          __syncthreads();  // smem ring is reused by the next batch tile / item
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int b = b0 + bq + 8 * i;
+          if (b < B) gru_finalize(p, j, s, b, u0 + u, acc[0][i], acc[1][i], acc[2][i]);
+        }
+      }
+    }
+    if (s + 1 < p.max_steps) grid.sync();
+  }
+}
+
+// ------------------------------------------------------------------------------------ bf16
+// NT = batch-tile / 8 (1 or 4), MG = U / 16 (1 or 2).  Warp w -> (kg = w / MG, mg = w % MG):
+// K is split over KG = 8/MG warp groups, each warp owns 3 m-tiles (one per gate, 16 units).
+template <int NT, int MG>
+__global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) {
+  constexpr int KG = 8 / MG, U = 16 * MG, NB = NT * 8, RP = U + 4;
+  extern __shared__ __align__(16) unsigned char smem_b[];
+  const int H = p.H, B = p.B;
+  const int HP = H + 32;                                     // bf16 row pitch of the staged h
+  __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(smem_b);          // [NB][HP]
+  float* red = reinterpret_cast<float*>(smem_b + (size_t)NB * HP * 2);   // [KG][3][NB][RP]
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int kg = warp / MG, mg = warp % MG;
+
+  if (p.any_h0) { seed_h0(p); grid.sync(); }
+
+  for (int s = 0; s < p.max_steps; ++s) {
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int j, u0;
+      locate_item(p, item, j, u0);
+      const tp_gru_job& jb = p.jobs[j];
+      if (s >= jb.steps) continue;
+      const bool have_prev = (s > 0) || (jb.h0 != nullptr);
+      const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(jb.w_hh);
+      const __nv_bfloat16* hprev = p.hbuf_lp + ((int64_t)(j * 2 + ((s + 1) & 1)) * B) * H;
+      for (int b0 = 0; b0 < B; b0 += NB) {
+        if (have_prev) {
+          // stage h_prev[b0 : b0+NB, :] (bf16) into shared memory
+          const int chunks = H / 8;
+          for (int c = tid; c < NB * chunks; c += kGruThreads) {
+            int bb = c / chunks, q = c - bb * chunks;
+            bool ok = (b0 + bb) < B;
+            cp_async16_z(hs + (size_t)bb * HP + q * 8, ok ? (hprev + (int64_t)(b0 + bb) * H + q * 8) : hprev, ok);
+          }
+          cp_commit();
+          float acc[3][NT][4];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc[i][n][e] = 0.0f;
+          const int nblk = H / 32;
+          const int blk_lo = (kg * nblk) / KG, blk_hi = ((kg + 1) * nblk) / KG;
+          const __nv_bfloat16* wrow[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) wrow[i] = W + ((int64_t)i * H + u0 + mg * 16 + g) * H + 8 * t;
+          uint4 a_lo[3], a_hi[3];
+          if (blk_lo < blk_hi) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              a_lo[i] = ldg_stream(wrow[i] + blk_lo * 32);
+              a_hi[i] = ldg_stream(wrow[i] + (int64_t)8 * H + blk_lo * 32);
+            }
+          }
+          cp_wait<0>();
+          __syncthreads();
+          for (int blk = blk_lo; blk < blk_hi; ++blk) {
+            uint4 n_lo[3], n_hi[3];
+            if (blk + 1 < blk_hi) {
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                n_lo[i] = ldg_stream(wrow[i] + (blk + 1) * 32);
+                n_hi[i] = ldg_stream(wrow[i] + (int64_t)8 * H + (blk + 1) * 32);
+              }
+            }
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+              uint4 bv = *reinterpret_cast<const uint4*>(hs + (size_t)(n * 8 + g) * HP + blk * 32 + 8 * t);
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                mma_bf16(acc[i][n], a_lo[i].x, a_hi[i].x, a_lo[i].y, a_hi[i].y, bv.x, bv.y);
+                mma_bf16(acc[i][n], a_lo[i].z, a_hi[i].z, a_lo[i].w, a_hi[i].w, bv.z, bv.w);
+              }
+            }
+            if (blk + 1 < blk_hi) {
+#pragma unroll
+              for (int i = 0; i < 3; ++i) { a_lo[i] = n_lo[i]; a_hi[i] = n_hi[i]; }
+            }
+          }
+          // partial sums -> red[kg][gate][n][unit]
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+              float* r0 = red + ((size_t)(kg * 3 + i) * NB + n * 8 + 2 * t) * RP + mg * 16 + g;
+              r0[0] = acc[i][n][0];
+              r0[RP] = acc[i][n][1];
+              r0[8] = acc[i][n][2];
+              r0[RP + 8] = acc[i][n][3];
+            }
+          __syncthreads();
+        }
+        for (int idx = tid; idx < NB * U; idx += kGruThreads) {
+          int bb = idx / U, uu = idx - bb * U;
+          if (b0 + bb >= B) continue;
+          float ar = 0.f, az = 0.f, an = 0.f;
+          if (have_prev) {
+#pragma unroll
+            for (int k = 0; k < KG; ++k) {
+              ar += red[((size_t)(k * 3 + 0) * NB + bb) * RP + uu];
+              az += red[((size_t)(k * 3 + 1) * NB + bb) * RP + uu];
+              an += red[((size_t)(k * 3 + 2) * NB + bb) * RP + uu];
+            }
+          }
+          gru_finalize(p, j, s, b0 + bb, u0 + uu, ar, az, an);
+        }
+        __syncthreads();  // hs / red are reused by the next batch tile / item
+      }
+    }
+    if (s + 1 < p.max_steps) grid.sync();
+  }
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" size_t tp_gru_workspace_bytes(int njobs, int B, int H) {
+  size_t per = (size_t)njobs * 2 * B * H;
+  return align_up(per * sizeof(float), 256) + align_up(per * sizeof(__nv_bfloat16), 256);
+}
+
+template <typename KernelT>
+static int launch_coop(KernelT kfn, const GruParams& p, size_t smem, cudaStream_t st) {
+  TP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  TP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kGruThreads, smem));
+  if (per_sm < 1) return fail(TP_ERR_UNSUPPORTED, "tp_gru_recurrence: kernel does not fit on an SM (smem=%zu)", smem);
+  int grid = p.total_items < sm_count() ? p.total_items : sm_count();
+  void* args[] = {(void*)&p};
+  TP_CUDA(cudaLaunchCooperativeKernel((const void*)kfn, dim3(grid), dim3(kGruThreads), args, smem, st));
+  return TP_OK;
+}
+
+extern "C" int tp_gru_recurrence(const tp_gru_job* jobs, int njobs, int B, int H, int precision,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  TP_CHECK_ARG(jobs && njobs >= 1 && njobs <= kMaxJobs, "tp_gru_recurrence: njobs=%d out of range [1,%d]", njobs, kMaxJobs);
+  TP_CHECK_ARG(B >= 1 && H >= 32 && H % 32 == 0, "tp_gru_recurrence: need B>=1 and H a multiple of 32 (B=%d H=%d)", B, H);
+  TP_CHECK_ARG(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "tp_gru_recurrence: workspace must be 256-byte aligned");
+  TP_CHECK_ARG(workspace_bytes >= tp_gru_workspace_bytes(njobs, B, H), "tp_gru_recurrence: workspace too small");
+  TP_CHECK_ARG(precision == TP_PRECISION_FP32 || precision == TP_PRECISION_BF16, "tp_gru_recurrence: bad precision");
+  GruParams p;
+  memset(&p, 0, sizeof(p));
+  p.njobs = njobs; p.B = B; p.H = H;
+  int units_total = njobs * H;
+  int U = 32;
+  if (precision == TP_PRECISION_BF16 && units_total / 16 <= sm_count()) U = 16;
+  p.U = U;
+  int items = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const tp_gru_job& jb = jobs[j];
+    TP_CHECK_ARG(jb.gi && jb.w_hh && jb.b_hh && jb.steps >= 1, "tp_gru_recurrence: job %d has null gi/w_hh/b_hh or steps<1", j);
+    TP_CHECK_ARG(aligned16(jb.w_hh), "tp_gru_recurrence: job %d w_hh must be 16-byte aligned", j);
+    p.jobs[j] = jb;
+    p.item_begin[j] = items;
+    items += H / U;
+    if (jb.steps > p.max_steps) p.max_steps = jb.steps;
+    if (jb.h0) p.any_h0 = 1;
+  }
+  for (int j = njobs; j <= kMaxJobs; ++j) p.item_begin[j] = items;
+  p.total_items = items;
+  size_t per = (size_t)njobs * 2 * B * H;
+  p.hbuf = reinterpret_cast<float*>(workspace);
+  p.hbuf_lp = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(workspace) + align_up(per * sizeof(float), 256));
+  cudaStream_t st = (cudaStream_t)stream;
+
+  if (precision == TP_PRECISION_FP32) {
+    size_t smem = (size_t)3 * (3 * 32 + 32) * 36 * sizeof(float);
+    return launch_coop(k_gru_f32, p, smem, st);
+  }
+  const int NB = (B <= 8) ? 8 : 32;
+  const int KG = (U == 16) ? 8 : 4;
+  size_t smem = (size_t)NB * (H + 32) * 2 + (size_t)KG * 3 * NB * (U + 4) * sizeof(float);
+  if (smem > 227 * 1024) return fail(TP_ERR_UNSUPPORTED, "tp_gru_recurrence(bf16): H=%d needs %zu B of shared memory", H, smem);
+  if (NB == 8) {
+    if (U == 16) return launch_coop(k_gru_bf16<1, 1>, p, smem, st);
+    return launch_coop(k_gru_bf16<1, 2>, p, smem, st);
+  }
+  if (U == 16) return launch_coop(k_gru_bf16<4, 1>, p, smem, st);
+  return launch_coop(k_gru_bf16<4, 2>, p, smem, st);
+}

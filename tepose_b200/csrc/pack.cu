@@ -1,0 +1,38 @@
+// Operand packing: [B,T,K] fp32 -> time-major, zero-padded [T*B, Kp] fp32 / bf16.
+#include "common.cuh"
+
+namespace tp {
+
+template <typename OutT>
+__global__ void k_pack_rows(const float* __restrict__ src, int64_t stride_b, int64_t stride_t,
+                            int rows_b, int rows_t, int k, OutT* __restrict__ dst, int kp, int relu) {
+  int row = blockIdx.x;               // t * rows_b + b
+  int t = row / rows_b, b = row - t * rows_b;
+  const float* s = src + (int64_t)b * stride_b + (int64_t)t * stride_t;
+  OutT* d = dst + (int64_t)row * kp;
+  for (int c = threadIdx.x; c < kp; c += blockDim.x) {
+    float v = (c < k) ? s[c] : 0.0f;
+    if (relu) v = fmaxf(v, 0.0f);
+    if constexpr (sizeof(OutT) == 2) d[c] = __float2bfloat16_rn(v); else d[c] = v;
+  }
+}
+
+}  // namespace tp
+
+extern "C" int tp_pack_rows(const float* src, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t,
+                            int k, void* dst, int kp, int dst_precision, int relu, void* stream) {
+  using namespace tp;
+  TP_CHECK_ARG(rows_b >= 0 && rows_t >= 0 && k >= 0 && kp >= k, "tp_pack_rows: bad sizes");
+  TP_CHECK_ARG(kp % 8 == 0, "tp_pack_rows: kp=%d must be a multiple of 8", kp);
+  if (rows_b == 0 || rows_t == 0 || kp == 0) return TP_OK;
+  TP_CHECK_ARG(src && dst, "tp_pack_rows: null pointer");
+  unsigned grid = (unsigned)(rows_b * rows_t);
+  if (dst_precision == TP_PRECISION_BF16)
+    k_pack_rows<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, stride_b, stride_t, rows_b, rows_t, k,
+                                                                      (__nv_bfloat16*)dst, kp, relu);
+  else
+    k_pack_rows<float><<<grid, 256, 0, (cudaStream_t)stream>>>(src, stride_b, stride_t, rows_b, rows_t, k,
+                                                              (float*)dst, kp, relu);
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}

@@ -1,0 +1,65 @@
+// K3 -- encoder linear heads + IEF Regressor (reference lib/models/tepose.py:79-85 and
+// lib/models/spin.py:250-261).  v1: a fixed sequence of fp32 FFMA GEMM launches on one
+// stream (graph-capturable); fc1 is evaluated as  x.W1x^T (once)  +  [pose|shape|cam].W1p^T
+// (per iteration) -- algebraically identical to fc1(cat[x, pose, shape, cam]).
+#include "common.cuh"
+
+namespace tp {
+
+__global__ void k_broadcast_rows(const float* __restrict__ src, float* __restrict__ dst, int rows, int width, int src_rows) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * width) dst[i] = (src_rows == 1) ? src[i % width] : src[i];
+}
+
+static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+
+}  // namespace tp
+
+using namespace tp;
+
+#define TP_TRY(x) do { int _rc = (x); if (_rc != TP_OK) return _rc; } while (0)
+
+extern "C" int tp_encoder_heads(const float* w_fwd, const float* b_fwd, const float* w_rec, const float* b_rec,
+                                const float* h_fwd, int64_t ld_hf, const float* h_rec, int64_t ld_hr,
+                                int B, int H, int is_train, float* feat, void* stream) {
+  TP_CHECK_ARG(w_fwd && b_fwd && w_rec && b_rec && h_fwd && h_rec && feat, "tp_encoder_heads: null pointer");
+  TP_CHECK_ARG(B >= 1 && H >= 4 && H % 4 == 0, "tp_encoder_heads: bad sizes B=%d H=%d", B, H);
+  if (!is_train) {
+    // (linear_fwd(relu(hF)) + linear_rec(relu(hR))) / 2  -- halving each term first is exact in fp32
+    TP_TRY(tp_gemm_f32(h_fwd, ld_hf, w_fwd, H, b_fwd, nullptr, 0, feat, 2048, B, 2048, H, 0.5f, 0.f, 1, stream));
+    TP_TRY(tp_gemm_f32(h_rec, ld_hr, w_rec, 2 * H, b_rec, feat, 2048, feat, 2048, B, 2048, 2 * H, 0.5f, 1.f, 1, stream));
+  } else {
+    // stacked [B,2,2048]: row b holds the fwd features then the rec features
+    TP_TRY(tp_gemm_f32(h_fwd, ld_hf, w_fwd, H, b_fwd, nullptr, 0, feat, 4096, B, 2048, H, 1.f, 0.f, 1, stream));
+    TP_TRY(tp_gemm_f32(h_rec, ld_hr, w_rec, 2 * H, b_rec, nullptr, 0, feat + 2048, 4096, B, 2048, 2 * H, 1.f, 0.f, 1, stream));
+  }
+  return TP_OK;
+}
+
+extern "C" size_t tp_ief_workspace_bytes(int n_rows) {
+  return 3 * al256((size_t)(n_rows > 0 ? n_rows : 0) * 1024 * sizeof(float));
+}
+
+extern "C" int tp_ief_forward(const tp_ief_weights* w, const float* feat, int n_rows, const float* init, int init_rows,
+                              int n_iter, float* psc, void* workspace, size_t workspace_bytes, void* stream) {
+  TP_CHECK_ARG(w && feat && init && psc, "tp_ief_forward: null pointer");
+  TP_CHECK_ARG(n_rows >= 1 && n_iter >= 0, "tp_ief_forward: bad sizes n_rows=%d n_iter=%d", n_rows, n_iter);
+  TP_CHECK_ARG(init_rows == 1 || init_rows == n_rows, "tp_ief_forward: init_rows must be 1 or n_rows");
+  TP_CHECK_ARG(w->w1x && w->b1 && w->w1p && w->w2 && w->b2 && w->wdec && w->bdec, "tp_ief_forward: null weight");
+  TP_CHECK_ARG(workspace && workspace_bytes >= tp_ief_workspace_bytes(n_rows), "tp_ief_forward: workspace too small");
+  TP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "tp_ief_forward: workspace must be 256-byte aligned");
+  const int N = n_rows;
+  const size_t slab = al256((size_t)N * 1024 * sizeof(float));
+  float* base = reinterpret_cast<float*>(workspace);
+  float* u1 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + slab);
+  float* u2 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 2 * slab);
+  TP_TRY(tp_gemm_f32(feat, 2048, w->w1x, 2048, w->b1, nullptr, 0, base, 1024, N, 1024, 2048, 1.f, 0.f, 0, stream));
+  k_broadcast_rows<<<(unsigned)ceil_div((int64_t)N * 160, 256), 256, 0, (cudaStream_t)stream>>>(init, psc, N, 160, init_rows);
+  TP_LAUNCH_CHECK();
+  for (int it = 0; it < n_iter; ++it) {
+    TP_TRY(tp_gemm_f32(psc, 160, w->w1p, 160, nullptr, base, 1024, u1, 1024, N, 1024, 160, 1.f, 1.f, 0, stream));
+    TP_TRY(tp_gemm_f32(u1, 1024, w->w2, 1024, w->b2, nullptr, 0, u2, 1024, N, 1024, 1024, 1.f, 0.f, 0, stream));
+    TP_TRY(tp_gemm_f32(u2, 1024, w->wdec, 1024, w->bdec, psc, 160, psc, 160, N, 160, 1024, 1.f, 1.f, 0, stream));
+  }
+  return TP_OK;
+}

@@ -1,0 +1,416 @@
+// K4 + K5 -- SMPL body-model forward in three launches (replaces ~40 ATen/cuBLAS launches of
+// smplx.SMPL.forward / smplx.lbs.lbs (third-party, restated: SURVEY.md App. A.6), the wrapper
+// lib/models/smpl.py:72-84, the H36M regression lib/models/spin.py:275-278, projection
+// spin.py:280 and the theta assembly spin.py:282-285).
+//
+//  k_smpl_prepare  one warp per body, lane = joint: pose -> R (rot6d / Rodrigues / pass-through),
+//                  J from betas (J_regressor folded into a 24x3x10 table at pack time),
+//                  warp-shuffle kinematic-chain scan (level-synchronous over the tree depth),
+//                  A_j = [W_R | W_t - W_R J_j], blend coefficients, R -> axis-angle, theta.
+//  k_smpl_verts    thread = vertex, NB = 8 bodies per thread in registers: one 218-term
+//                  contraction gives template + shape blend + pose blend (K4), then top-k
+//                  skinning (K5).  Vertices are written once (coalesced, staged in shared
+//                  memory) and the joint regressors are applied to the tile while it is still
+//                  on chip -- vertices never round-trip HBM.
+//  k_smpl_finalize per body: reduce regressor partials, compose the output joint set, project.
+#include "rotations.cuh"
+
+namespace tp {
+
+constexpr int kJ = 24;          // SMPL joints
+constexpr int kCoef = 218;      // 207 pose-blend + 10 shape + 1 template
+constexpr int kCoefLd = 224;    // row pitch of the coefficient scratch
+constexpr int kVT = 128;        // vertices per tile (= threads per CTA in k_smpl_verts)
+constexpr int kNB = 8;          // bodies per CTA in k_smpl_verts
+constexpr int kMaxReg = 32;     // max rows of the caller's joint regressor
+
+__device__ __forceinline__ void project_point_(const float* X, const float* cam, float* kp) {
+  // lib/models/spin.py:307-351 (same operation order, see geometry.cu)
+  float tz = 2.0f * 5000.0f / (224.0f * cam[0] + 1e-9f);
+  float px = X[0] + cam[1], py = X[1] + cam[2], pz = X[2] + tz;
+  px = px / pz; py = py / pz;
+  kp[0] = (5000.0f * px) / 112.0f;
+  kp[1] = (5000.0f * py) / 112.0f;
+}
+
+struct PrepArgs {
+  const float* pose; int64_t ld_pose; int pose_kind;
+  const float* betas; int64_t ld_betas;
+  const float* cam; int64_t ld_cam;
+  float* A;        // [n][24][12]
+  float* posedJ;   // [n][24][3]
+  float* coef;     // [n][kCoefLd]
+  float* rotmat;   // [n][24][9] or null
+  float* theta;    // [n][85] or null
+};
+
+__global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int n, const PrepArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= n) return;                       // whole warp exits together
+  const int j = lane < kJ ? lane : kJ - 1;  // idle lanes shadow joint 23 (never written)
+  const bool active = lane < kJ;
+
+  float R[9];
+  if (a.pose_kind == TP_POSE_ROTMAT) {
+    const float* p = a.pose + (int64_t)b * a.ld_pose + j * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = p[k];
+  } else if (a.pose_kind == TP_POSE_AXIS_ANGLE) {
+    const float* p = a.pose + (int64_t)b * a.ld_pose + j * 3;
+    float r[3] = {p[0], p[1], p[2]};
+    rodrigues_smplx(r, R);
+  } else {
+    const float* p = a.pose + (int64_t)b * a.ld_pose + j * 6;
+    float x[6] = {p[0], p[1], p[2], p[3], p[4], p[5]};
+    rot6d_to_rotmat(x, R);
+  }
+  float beta[10];
+#pragma unroll
+  for (int l = 0; l < 10; ++l) beta[l] = a.betas[(int64_t)b * a.ld_betas + l];
+
+  // rest-pose joint location: J = J_regressor.(v_template + shapedirs.beta), regressor pre-applied
+  float Jx[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float s = m.j_template[j * 3 + c];
+#pragma unroll
+    for (int l = 0; l < 10; ++l) s = fmaf(m.j_shapedirs[(j * 3 + c) * 10 + l], beta[l], s);
+    Jx[c] = s;
+  }
+  const int parent = m.parents[j];
+  int depth = 0;
+  for (int p = parent; p >= 0; p = m.parents[p]) ++depth;
+  int maxd = depth;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+  const int src = parent < 0 ? 0 : parent;
+
+  // world transform W = [WR | Wt]; root: G_0 = [R_0 | J_0]
+  float WR[9], Wt[3], rel[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float pj = __shfl_sync(0xffffffffu, Jx[c], src);
+    rel[c] = parent < 0 ? Jx[c] : Jx[c] - pj;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) WR[k] = R[k];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) Wt[c] = rel[c];
+  for (int d = 1; d <= maxd; ++d) {
+    float PR[9], Pt[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) PR[k] = __shfl_sync(0xffffffffu, WR[k], src);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Pt[c] = __shfl_sync(0xffffffffu, Wt[c], src);
+    if (depth == d) {  // W_i = W_parent @ G_i
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          WR[r * 3 + c] = PR[r * 3 + 0] * R[0 * 3 + c] + PR[r * 3 + 1] * R[1 * 3 + c] + PR[r * 3 + 2] * R[2 * 3 + c];
+        Wt[r] = PR[r * 3 + 0] * rel[0] + PR[r * 3 + 1] * rel[1] + PR[r * 3 + 2] * rel[2] + Pt[r];
+      }
+    }
+  }
+  if (!active) return;
+
+  float* Ab = a.A + ((int64_t)b * kJ + j) * 12;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    Ab[r * 4 + 0] = WR[r * 3 + 0];
+    Ab[r * 4 + 1] = WR[r * 3 + 1];
+    Ab[r * 4 + 2] = WR[r * 3 + 2];
+    Ab[r * 4 + 3] = Wt[r] - (WR[r * 3 + 0] * Jx[0] + WR[r * 3 + 1] * Jx[1] + WR[r * 3 + 2] * Jx[2]);
+    a.posedJ[((int64_t)b * kJ + j) * 3 + r] = Wt[r];
+  }
+  float* cf = a.coef + (int64_t)b * kCoefLd;
+  if (j >= 1) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) cf[(j - 1) * 9 + k] = R[k] - ((k == 0 || k == 4 || k == 8) ? 1.0f : 0.0f);
+  } else {
+#pragma unroll
+    for (int l = 0; l < 10; ++l) cf[207 + l] = beta[l];
+    cf[217] = 1.0f;
+    for (int k = kCoef; k < kCoefLd; ++k) cf[k] = 0.0f;
+  }
+  if (a.rotmat) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.rotmat[((int64_t)b * kJ + j) * 9 + k] = R[k];
+  }
+  if (a.theta) {
+    float aa[3];
+    rotmat_to_angle_axis(R, aa);
+    float* th = a.theta + (int64_t)b * 85;
+    th[3 + j * 3 + 0] = aa[0]; th[3 + j * 3 + 1] = aa[1]; th[3 + j * 3 + 2] = aa[2];
+    if (j == 0) {
+#pragma unroll
+      for (int l = 0; l < 10; ++l) th[75 + l] = beta[l];
+      if (a.cam) { th[0] = a.cam[(int64_t)b * a.ld_cam]; th[1] = a.cam[(int64_t)b * a.ld_cam + 1]; th[2] = a.cam[(int64_t)b * a.ld_cam + 2]; }
+      else { th[0] = th[1] = th[2] = 0.0f; }
+    }
+  }
+}
+
+// shared-memory carve-up of k_smpl_verts (floats)
+constexpr int kAPitch = 13;                              // joint stride in A_s (12 + 1: conflict-free gathers)
+constexpr int kVsPitch = 28;                             // per-vertex stride of the transposed tile
+constexpr int kSmCoef = kCoef * kNB;                     // coef_s[k][b]
+constexpr int kSmA = kNB * kJ * kAPitch;                 // A_s[b][j][13]
+constexpr int kSmVsT = kVT * kVsPitch;                   // vsT[v][c*NB + b]
+constexpr int kSmVout = kNB * kVT * 3;                   // vout[b][v*3 + c]
+constexpr int kSmPart = 4 * kMaxReg * kNB * 3;           // part[q][r][c*NB + b]
+constexpr int kSmVertsFloats = kSmCoef + kSmA + kSmVsT + kSmVout + kSmPart;
+
+__global__ void __launch_bounds__(kVT) k_smpl_verts(const tp_smpl_model m, int n, const float* __restrict__ coef,
+                                                    const float* __restrict__ A, const float* __restrict__ jreg,
+                                                    int nreg, float* __restrict__ verts, float* __restrict__ jpart,
+                                                    int nsplit, int tiles_per_split, int ntiles) {
+  extern __shared__ __align__(16) float sm[];
+  float* coef_s = sm;
+  float* A_s = coef_s + kSmCoef;
+  float* vsT = A_s + kSmA;
+  float* vout = vsT + kSmVsT;
+  float* part = vout + kSmVout;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int body0 = blockIdx.x * kNB;
+  const int split = blockIdx.y;
+  const int vp = m.vp;
+
+  for (int i = tid; i < kCoef * kNB; i += kVT) {
+    int k = i / kNB, b = i - k * kNB;
+    coef_s[i] = (body0 + b < n) ? coef[(int64_t)(body0 + b) * kCoefLd + k] : 0.0f;
+  }
+  for (int i = tid; i < kNB * kJ * 12; i += kVT) {
+    int b = i / (kJ * 12), r = i - b * (kJ * 12), j = r / 12, e = r - j * 12;
+    A_s[(b * kJ + j) * kAPitch + e] = (body0 + b < n) ? A[(int64_t)(body0 + b) * kJ * 12 + r] : 0.0f;
+  }
+  __syncthreads();
+
+  float accj[kNB * 3];
+#pragma unroll
+  for (int i = 0; i < kNB * 3; ++i) accj[i] = 0.0f;
+
+  const int tile_lo = split * tiles_per_split;
+  const int tile_hi = min(ntiles, tile_lo + tiles_per_split);
+  for (int tile = tile_lo; tile < tile_hi; ++tile) {
+    const int v = tile * kVT + tid;  // < vp always (blend / skin tables are padded to vp)
+    float acc[kNB][3];
+#pragma unroll
+    for (int b = 0; b < kNB; ++b) acc[b][0] = acc[b][1] = acc[b][2] = 0.0f;
+    const float* bl = m.blend + v;
+#pragma unroll 2
+    for (int k = 0; k < kCoef; ++k) {
+      float d0 = __ldg(bl + (int64_t)(k * 3 + 0) * vp);
+      float d1 = __ldg(bl + (int64_t)(k * 3 + 1) * vp);
+      float d2 = __ldg(bl + (int64_t)(k * 3 + 2) * vp);
+      const float4 c0 = *reinterpret_cast<const float4*>(&coef_s[k * kNB]);
+      const float4 c1 = *reinterpret_cast<const float4*>(&coef_s[k * kNB + 4]);
+      const float cc[kNB] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+      for (int b = 0; b < kNB; ++b) {
+        acc[b][0] = fmaf(cc[b], d0, acc[b][0]);
+        acc[b][1] = fmaf(cc[b], d1, acc[b][1]);
+        acc[b][2] = fmaf(cc[b], d2, acc[b][2]);
+      }
+    }
+    // linear blend skinning with the retained (top-k) weights of this vertex
+    float T[kNB][12];
+#pragma unroll
+    for (int b = 0; b < kNB; ++b)
+#pragma unroll
+      for (int e = 0; e < 12; ++e) T[b][e] = 0.0f;
+    for (int i = 0; i < m.ks; ++i) {
+      const int jj = m.skin_idx[(int64_t)v * m.ks + i];
+      const float w = m.skin_w[(int64_t)v * m.ks + i];
+#pragma unroll
+      for (int b = 0; b < kNB; ++b) {
+        const float* Aj = &A_s[(b * kJ + jj) * kAPitch];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) T[b][e] = fmaf(w, Aj[e], T[b][e]);
+      }
+    }
+    const bool vvalid = v < m.n_verts;
+    float o[kNB][3];
+#pragma unroll
+    for (int b = 0; b < kNB; ++b) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        float val = T[b][r * 4 + 0] * acc[b][0] + T[b][r * 4 + 1] * acc[b][1] + T[b][r * 4 + 2] * acc[b][2] + T[b][r * 4 + 3];
+        o[b][r] = vvalid ? val : 0.0f;
+        vout[(b * kVT + tid) * 3 + r] = o[b][r];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      *reinterpret_cast<float4*>(&vsT[tid * kVsPitch + c * kNB]) = make_float4(o[0][c], o[1][c], o[2][c], o[3][c]);
+      *reinterpret_cast<float4*>(&vsT[tid * kVsPitch + c * kNB + 4]) = make_float4(o[4][c], o[5][c], o[6][c], o[7][c]);
+    }
+    __syncthreads();
+    if (verts) {
+      const int64_t nv3 = (int64_t)m.n_verts * 3;
+      const int64_t base = (int64_t)tile * kVT * 3;
+#pragma unroll
+      for (int b = 0; b < kNB; ++b) {
+        if (body0 + b >= n) break;
+        float* dst = verts + (int64_t)(body0 + b) * nv3 + base;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          int idx = tid + i * kVT;
+          if (base + idx < nv3) dst[idx] = vout[b * kVT * 3 + idx];
+        }
+      }
+    }
+    if (lane < nreg) {  // joint regressors on the on-chip tile: lane = regressor row, warp = vertex quarter
+      const float* jr = jreg + (int64_t)lane * vp + tile * kVT + warp * 32;
+      for (int vv = 0; vv < 32; ++vv) {
+        const float w = __ldg(jr + vv);
+        const float* vs = &vsT[(warp * 32 + vv) * kVsPitch];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const float4 x = *reinterpret_cast<const float4*>(vs + q * 4);
+          accj[q * 4 + 0] = fmaf(w, x.x, accj[q * 4 + 0]);
+          accj[q * 4 + 1] = fmaf(w, x.y, accj[q * 4 + 1]);
+          accj[q * 4 + 2] = fmaf(w, x.z, accj[q * 4 + 2]);
+          accj[q * 4 + 3] = fmaf(w, x.w, accj[q * 4 + 3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (nreg > 0) {
+    if (lane < nreg) {
+#pragma unroll
+      for (int i = 0; i < kNB * 3; ++i) part[(warp * kMaxReg + lane) * kNB * 3 + i] = accj[i];
+    }
+    __syncthreads();
+    for (int i = tid; i < nreg * kNB * 3; i += kVT) {
+      int r = i / (kNB * 3), rem = i - r * (kNB * 3), c = rem / kNB, b = rem - c * kNB;
+      if (body0 + b >= n) continue;
+      float s = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s += part[(q * kMaxReg + r) * kNB * 3 + rem];
+      jpart[(((int64_t)(body0 + b) * nsplit + split) * nreg + r) * 3 + c] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_smpl_finalize(int n, int n_verts, const float* __restrict__ posedJ,
+                                                       const float* __restrict__ jpart, int nsplit, int nreg,
+                                                       const float* __restrict__ verts, const int32_t* __restrict__ joint_src,
+                                                       int nj, const float* __restrict__ cam, int64_t ld_cam,
+                                                       float* __restrict__ joints, float* __restrict__ kp2d) {
+  __shared__ float Jr[kMaxReg * 3];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < nreg * 3; i += blockDim.x) {
+    float s = 0.0f;
+    for (int sp = 0; sp < nsplit; ++sp) s += jpart[((int64_t)b * nsplit + sp) * nreg * 3 + i];
+    Jr[i] = s;
+  }
+  __syncthreads();
+  for (int o = tid; o < nj; o += blockDim.x) {
+    const int code = joint_src[o];
+    float X[3];
+    if (code >= 1000) {
+      const float* p = verts + ((int64_t)b * n_verts + (code - 1000)) * 3;
+      X[0] = p[0]; X[1] = p[1]; X[2] = p[2];
+    } else if (code >= 100) {
+      X[0] = Jr[(code - 100) * 3]; X[1] = Jr[(code - 100) * 3 + 1]; X[2] = Jr[(code - 100) * 3 + 2];
+    } else {
+      const float* p = posedJ + ((int64_t)b * kJ + code) * 3;
+      X[0] = p[0]; X[1] = p[1]; X[2] = p[2];
+    }
+    if (joints) {
+      float* d = joints + ((int64_t)b * nj + o) * 3;
+      d[0] = X[0]; d[1] = X[1]; d[2] = X[2];
+    }
+    if (kp2d && cam) {
+      float c[3] = {cam[(int64_t)b * ld_cam], cam[(int64_t)b * ld_cam + 1], cam[(int64_t)b * ld_cam + 2]}, kp[2];
+      project_point_(X, c, kp);
+      kp2d[((int64_t)b * nj + o) * 2] = kp[0];
+      kp2d[((int64_t)b * nj + o) * 2 + 1] = kp[1];
+    }
+  }
+}
+
+static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+
+struct SmplPlan { int ntiles, nsplit, tiles_per_split, ngroups; size_t off_A, off_J, off_coef, off_part, total; };
+
+static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg) {
+  SmplPlan p;
+  p.ntiles = m->vp / kVT;
+  p.ngroups = (n + kNB - 1) / kNB;
+  int want = (2 * sm_count() + p.ngroups - 1) / p.ngroups;   // aim for >= 2 CTAs per SM
+  if (want < 1) want = 1;
+  if (want > p.ntiles) want = p.ntiles;
+  p.tiles_per_split = (p.ntiles + want - 1) / want;
+  p.nsplit = (p.ntiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  size_t o = 0;
+  p.off_A = o; o += al256((size_t)n * kJ * 12 * 4);
+  p.off_J = o; o += al256((size_t)n * kJ * 3 * 4);
+  p.off_coef = o; o += al256((size_t)n * kCoefLd * 4);
+  p.off_part = o; o += al256((size_t)n * p.nsplit * (nreg > 0 ? nreg : 1) * 3 * 4);
+  p.total = o;
+  return p;
+}
+
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" size_t tp_smpl_workspace_bytes(const tp_smpl_model* m, int n, int nreg) {
+  if (!m || n <= 0 || m->vp <= 0) return 0;
+  return make_plan(m, n, nreg).total;
+}
+
+extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose, int64_t ld_pose, int pose_kind,
+                               const float* betas, int64_t ld_betas, const float* cam, int64_t ld_cam,
+                               const float* jreg, int nreg, const int32_t* joint_src, int nj,
+                               float* verts, float* joints, float* kp2d, float* rotmat, float* theta,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  TP_CHECK_ARG(m != nullptr, "tp_smpl_forward: null model");
+  TP_CHECK_ARG(n >= 0, "tp_smpl_forward: n=%d", n);
+  if (n == 0) return TP_OK;
+  TP_CHECK_ARG(m->blend && m->j_template && m->j_shapedirs && m->parents && m->skin_idx && m->skin_w,
+               "tp_smpl_forward: model has null tables");
+  TP_CHECK_ARG(m->vp % kVT == 0 && m->n_verts > 0 && m->n_verts <= m->vp, "tp_smpl_forward: bad n_verts/vp (%d/%d)", m->n_verts, m->vp);
+  TP_CHECK_ARG(m->ks >= 1 && m->ks <= kJ, "tp_smpl_forward: ks=%d out of range", m->ks);
+  TP_CHECK_ARG(pose && betas, "tp_smpl_forward: null pose/betas");
+  TP_CHECK_ARG(pose_kind >= 0 && pose_kind <= 2, "tp_smpl_forward: bad pose_kind %d", pose_kind);
+  TP_CHECK_ARG(nreg >= 0 && nreg <= kMaxReg && (nreg == 0 || jreg), "tp_smpl_forward: nreg=%d (max %d) / null jreg", nreg, kMaxReg);
+  TP_CHECK_ARG(nj >= 0 && (nj == 0 || joint_src), "tp_smpl_forward: null joint_src");
+  TP_CHECK_ARG(aligned16(m->blend), "tp_smpl_forward: blend table must be 16-byte aligned");
+  SmplPlan pl = make_plan(m, n, nreg);
+  TP_CHECK_ARG(workspace && workspace_bytes >= pl.total, "tp_smpl_forward: workspace too small (%zu < %zu)", workspace_bytes, pl.total);
+  TP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "tp_smpl_forward: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  PrepArgs pa;
+  pa.pose = pose; pa.ld_pose = ld_pose; pa.pose_kind = pose_kind;
+  pa.betas = betas; pa.ld_betas = ld_betas; pa.cam = cam; pa.ld_cam = ld_cam;
+  pa.A = reinterpret_cast<float*>(ws + pl.off_A);
+  pa.posedJ = reinterpret_cast<float*>(ws + pl.off_J);
+  pa.coef = reinterpret_cast<float*>(ws + pl.off_coef);
+  pa.rotmat = rotmat; pa.theta = theta;
+  float* jpart = reinterpret_cast<float*>(ws + pl.off_part);
+
+  k_smpl_prepare<<<(unsigned)ceil_div(n, 4), 128, 0, st>>>(*m, n, pa);
+  TP_LAUNCH_CHECK();
+  const bool need_verts_pass = verts != nullptr || nreg > 0;
+  if (need_verts_pass) {
+    constexpr size_t smem = (size_t)kSmVertsFloats * sizeof(float);
+    TP_CUDA(cudaFuncSetAttribute(k_smpl_verts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)pl.ngroups, (unsigned)pl.nsplit);
+    k_smpl_verts<<<grid, kVT, smem, st>>>(*m, n, pa.coef, pa.A, jreg, nreg, verts, jpart, pl.nsplit,
+                                          pl.tiles_per_split, pl.ntiles);
+    TP_LAUNCH_CHECK();
+  }
+  if (nj > 0 && (joints || kp2d)) {
+    TP_CHECK_ARG(verts != nullptr, "tp_smpl_forward: verts is required when joints are requested (vertex picks read it)");
+    k_smpl_finalize<<<(unsigned)n, 128, 0, st>>>(n, m->n_verts, pa.posedJ, jpart, pl.nsplit, nreg, verts, joint_src,
+                                                nj, cam, ld_cam, joints, kp2d);
+    TP_LAUNCH_CHECK();
+  }
+  return TP_OK;
+}

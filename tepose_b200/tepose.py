@@ -1,0 +1,294 @@
+"""TePose with the reference's module API (lib/models/tepose.py:44-147) on sm_100a kernels.
+
+  TemporalEncoder(n_layers=1, seq_len=16, hidden_size=2048)
+  TePose(seqlen, batch_size=64, n_layers=1, hidden_size=2048, pretrained=..., precision='fp32')
+  TePose.forward(input [B,T,2133], is_train=False, J_regressor=None) -> [ {theta, verts, kp_2d, kp_3d, rotmat} ]
+
+The nn.GRU / nn.Linear members are PARAMETER CONTAINERS only (same state_dict keys and
+default init as the reference); their forward is never called.  The
+arithmetic is: K1 input-projection GEMM (tcgen05 in bf16 mode, FFMA in fp32 mode), K2
+persistent GRU recurrence, K3 linear heads + IEF, K4/K5 fused SMPL.
+
+Encoder schedule: with x_rec = flip(x), gru_rec's backward direction runs
+over x in ORIGINAL order and only its final state is consumed; its forward direction is
+consumed only at x_rec index 0 -- one step from h0 = 0 for the last layer.
+"""
+from __future__ import annotations
+
+import os
+import os.path as osp
+
+import torch
+import torch.nn as nn
+
+from . import _native as nv
+from .smpl import BASE_DATA_DIR
+from .spin import Regressor
+
+INPUT_SIZE = 2133
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class TemporalEncoder(nn.Module):
+    def __init__(self, n_layers=1, seq_len=16, hidden_size=2048, precision="fp32"):
+        super().__init__()
+        self.gru_fwd = nn.GRU(input_size=INPUT_SIZE, hidden_size=hidden_size, bidirectional=False, num_layers=n_layers)
+        self.gru_rec = nn.GRU(input_size=INPUT_SIZE, hidden_size=hidden_size, bidirectional=True, num_layers=n_layers)
+        self.mid_frame = int(seq_len / 2)
+        self.hidden_size = hidden_size
+        self.n_layers = n_layers
+        self.linear_fwd = nn.Linear(hidden_size, 2048)
+        self.linear_rec = nn.Linear(hidden_size * 2, 2048)
+        self.precision = precision
+        self._pack = None
+        self._pack_key = None
+        if hidden_size % 32 != 0:
+            raise ValueError("tepose_b200 needs hidden_size to be a multiple of 32")
+
+    # ------------------------------------------------------------------ packing
+    def _key(self):
+        ts = list(self.gru_fwd.parameters()) + list(self.gru_rec.parameters()) + \
+            list(self.linear_fwd.parameters()) + list(self.linear_rec.parameters())
+        return (self.precision,) + tuple((t.device, t.data_ptr(), t._version) for t in ts)
+
+    def packed(self):
+        key = self._key()
+        if self._pack is not None and self._pack_key == key:
+            return self._pack
+        w0 = self.gru_fwd.weight_ih_l0
+        nv.require_cuda(w0, "encoder parameters (call .cuda() first)")
+        dev, H, Ln = w0.device, self.hidden_size, self.n_layers
+        lp = self.precision == "bf16"
+        wdt = torch.bfloat16 if lp else torch.float32
+        f = lambda t: t.detach().to(dev, torch.float32)
+        g = lambda mod, name: f(getattr(mod, name))
+
+        def pad_k(w, kp):
+            out = torch.zeros(w.shape[0], kp, device=dev, dtype=wdt)
+            out[:, :w.shape[1]] = w.to(wdt)
+            return out
+
+        layers = []
+        for l in range(Ln):
+            in_f = INPUT_SIZE if l == 0 else H
+            in_r = INPUT_SIZE if l == 0 else 2 * H
+            kpf, kpr = _round_up(in_f, 64), _round_up(in_r, 64)
+            wf = g(self.gru_fwd, f"weight_ih_l{l}")
+            wr = g(self.gru_rec, f"weight_ih_l{l}")
+            wb = g(self.gru_rec, f"weight_ih_l{l}_reverse")
+            d = {"kpf": kpf, "kpr": kpr}
+            if l == 0:
+                # all three directions read the same packed x: stack [fwd | rec-backward | rec-forward]
+                d["w_ih"] = torch.cat([pad_k(wf, kpf), pad_k(wb, kpf), pad_k(wr, kpf)], dim=0).contiguous()
+                d["b_ih"] = torch.cat([g(self.gru_fwd, "bias_ih_l0"), g(self.gru_rec, "bias_ih_l0_reverse"),
+                                       g(self.gru_rec, "bias_ih_l0")]).contiguous()
+            else:
+                d["w_ih_f"] = pad_k(wf, kpf).contiguous()
+                d["b_ih_f"] = g(self.gru_fwd, f"bias_ih_l{l}").contiguous()
+                d["w_ih_r"] = torch.cat([pad_k(wb, kpr), pad_k(wr, kpr)], dim=0).contiguous()   # [backward | forward]
+                d["b_ih_r"] = torch.cat([g(self.gru_rec, f"bias_ih_l{l}_reverse"), g(self.gru_rec, f"bias_ih_l{l}")]).contiguous()
+            d["w_hh"] = [g(self.gru_fwd, f"weight_hh_l{l}").to(wdt).contiguous(),
+                         g(self.gru_rec, f"weight_hh_l{l}_reverse").to(wdt).contiguous(),
+                         g(self.gru_rec, f"weight_hh_l{l}").to(wdt).contiguous()]
+            d["b_hh"] = [g(self.gru_fwd, f"bias_hh_l{l}").contiguous(),
+                         g(self.gru_rec, f"bias_hh_l{l}_reverse").contiguous(),
+                         g(self.gru_rec, f"bias_hh_l{l}").contiguous()]
+            layers.append(d)
+        pk = {"layers": layers,
+              "w_fwd": g(self.linear_fwd, "weight").contiguous(), "b_fwd": g(self.linear_fwd, "bias").contiguous(),
+              "w_rec": g(self.linear_rec, "weight").contiguous(), "b_rec": g(self.linear_rec, "bias").contiguous()}
+        self._pack, self._pack_key = pk, key
+        return pk
+
+    # ------------------------------------------------------------------ kernels
+    def _input_proj(self, A, a_rows, W, kp, bias, segs, outs):
+        """K1: outs[i] = A[m-range] . W[n-range]^T + bias[n-range]."""
+        L = nv.lib()
+        if self.precision == "bf16":
+            arr = (nv.GemmSeg * len(segs))()
+            for i, ((m0, mr, n0, nc), out) in enumerate(zip(segs, outs)):
+                arr[i] = nv.GemmSeg(m0, mr, n0, nc, nv.ptr(out), out.shape[1], nv.vp(bias.data_ptr() + 4 * n0))
+            nv.check(L.tp_gemm_bf16_tc(nv.ptr(A), a_rows, nv.ptr(W), W.shape[0], kp, arr, len(segs), nv.stream()),
+                     "tp_gemm_bf16_tc")
+        else:
+            for (m0, mr, n0, nc), out in zip(segs, outs):
+                nv.check(L.tp_gemm_f32(nv.vp(A.data_ptr() + 4 * m0 * kp), kp, nv.vp(W.data_ptr() + 4 * n0 * kp), kp,
+                                       nv.vp(bias.data_ptr() + 4 * n0), nv.vp(0), 0, nv.ptr(out), out.shape[1],
+                                       mr, nc, kp, 1.0, 0.0, 0, nv.stream()), "tp_gemm_f32")
+
+    def _recurrence(self, jobs, B):
+        L = nv.lib()
+        H = self.hidden_size
+        arr = (nv.GruJob * len(jobs))(*jobs)
+        ws = nv.workspace(L.tp_gru_workspace_bytes(len(jobs), B, H), jobs[0]._dev)
+        nv.check(L.tp_gru_recurrence(arr, len(jobs), B, H, nv.PRECISIONS[self.precision], nv.ptr(ws), ws.numel(),
+                                     nv.stream()), "tp_gru_recurrence")
+
+    @staticmethod
+    def _job(dev, gi, col0, w_hh, b_hh, steps, t_in0, t_in_step, h0=None, y=None, ycol=0, y_lp=None,
+             t_out0=0, t_out_step=1, h_final=None, hcol=0):
+        j = nv.GruJob()
+        j.gi = gi.data_ptr() + 4 * col0
+        j.ldg = gi.shape[-1]
+        j.w_hh = w_hh.data_ptr()
+        j.b_hh = b_hh.data_ptr()
+        j.h0 = 0 if h0 is None else h0.data_ptr()
+        j.y = 0 if y is None else y.data_ptr() + 4 * ycol
+        j.ldy = 0 if y is None else y.shape[-1]
+        j.y_lp = 0 if y_lp is None else y_lp.data_ptr() + 2 * ycol
+        j.ldy_lp = 0 if y_lp is None else y_lp.shape[-1]
+        j.h_final = 0 if h_final is None else h_final.data_ptr() + 4 * hcol
+        j.ld_hf = 0 if h_final is None else h_final.shape[-1]
+        j.steps, j.t_in0, j.t_in_step, j.t_out0, j.t_out_step = steps, t_in0, t_in_step, t_out0, t_out_step
+        j._dev = dev
+        return j
+
+    def encode_states(self, x: torch.Tensor, h0=None):
+        """Runs K1 + K2.  Returns (h_fwd [B,H], h_rec [B,2H]) = (y[-1], y_rec[0]) of
+        lib/models/tepose.py:73-80.  h0 = (hF0, hB0) carries state (live-stream mode, L=1)."""
+        nv.require_cuda(x, "input")
+        if x.dim() != 3 or x.shape[2] != INPUT_SIZE:
+            raise ValueError(f"expected input [B,T,{INPUT_SIZE}], got {tuple(x.shape)}")
+        pk = self.packed()
+        L = nv.lib()
+        dev, H, Ln = x.device, self.hidden_size, self.n_layers
+        B, T = x.shape[0], x.shape[1]
+        lp = self.precision == "bf16"
+        adt = torch.bfloat16 if lp else torch.float32
+        prec = nv.PRECISIONS[self.precision]
+        x = x.detach().float()
+        if x.stride(2) != 1:
+            x = x.contiguous()
+        if h0 is not None and Ln != 1:
+            raise ValueError("carried state is only defined for n_layers == 1 (SURVEY.md H5)")
+        h_fwd = torch.empty(B, H, device=dev, dtype=torch.float32)
+        h_rec = torch.empty(B, 2 * H, device=dev, dtype=torch.float32)
+        y_f = y_r = y_f_lp = y_r_lp = None
+        for l in range(Ln):
+            d = pk["layers"][l]
+            last = l == Ln - 1
+            if l == 0:
+                kp = d["kpf"]
+                xp = torch.empty(T * B, kp, device=dev, dtype=adt)
+                nv.check(L.tp_pack_rows(nv.vp(x.data_ptr()), x.stride(0), x.stride(1), B, T, INPUT_SIZE, nv.ptr(xp), kp,
+                                        prec, 0, nv.stream()), "tp_pack_rows")
+                if last:
+                    gi = torch.empty(T * B, 6 * H, device=dev, dtype=torch.float32)      # [fwd | rec-backward]
+                    gs = torch.empty(B, 3 * H, device=dev, dtype=torch.float32)          # rec-forward, newest frame only
+                    self._input_proj(xp, T * B, d["w_ih"], kp, d["b_ih"],
+                                     [(0, T * B, 0, 6 * H), ((T - 1) * B, B, 6 * H, 3 * H)], [gi, gs])
+                    gi_f, c_f, gi_b, c_b, gi_s, c_s = gi, 0, gi, 3 * H, gs, 0
+                    s_t0 = 0     # gs holds a single time block
+                else:
+                    gi = torch.empty(T * B, 9 * H, device=dev, dtype=torch.float32)
+                    self._input_proj(xp, T * B, d["w_ih"], kp, d["b_ih"], [(0, T * B, 0, 9 * H)], [gi])
+                    gi_f, c_f, gi_b, c_b, gi_s, c_s = gi, 0, gi, 3 * H, gi, 6 * H
+                    s_t0 = T - 1
+                # layer-0 rows are in ORIGINAL time order; x_rec index tau = T-1-t
+                f_in, b_in, s_in = (0, 1), (0, 1), (s_t0, -1)
+            else:
+                gi_f = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
+                self._input_proj(y_f_lp if lp else y_f, T * B, d["w_ih_f"], d["kpf"], d["b_ih_f"],
+                                 [(0, T * B, 0, 3 * H)], [gi_f])
+                src = y_r_lp if lp else y_r
+                if last:
+                    gi_b = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
+                    gi_s = torch.empty(B, 3 * H, device=dev, dtype=torch.float32)
+                    self._input_proj(src, T * B, d["w_ih_r"], d["kpr"], d["b_ih_r"],
+                                     [(0, T * B, 0, 3 * H), (0, B, 3 * H, 3 * H)], [gi_b, gi_s])
+                    c_b, c_s = 0, 0
+                else:
+                    gi_r = torch.empty(T * B, 6 * H, device=dev, dtype=torch.float32)
+                    self._input_proj(src, T * B, d["w_ih_r"], d["kpr"], d["b_ih_r"], [(0, T * B, 0, 6 * H)], [gi_r])
+                    gi_b, c_b, gi_s, c_s = gi_r, 0, gi_r, 3 * H
+                c_f = 0
+                # deeper layers of gru_rec are indexed by x_rec time tau: backward dir walks tau = T-1..0
+                f_in, b_in, s_in = (0, 1), (T - 1, -1), (0, 1)
+            if not last:
+                kpn_f, kpn_r = pk["layers"][l + 1]["kpf"], pk["layers"][l + 1]["kpr"]
+                ny_f = torch.zeros(T * B, kpn_f, device=dev, dtype=torch.float32)
+                ny_r = torch.zeros(T * B, kpn_r, device=dev, dtype=torch.float32)
+                ny_f_lp = torch.zeros(T * B, kpn_f, device=dev, dtype=torch.bfloat16) if lp else None
+                ny_r_lp = torch.zeros(T * B, kpn_r, device=dev, dtype=torch.bfloat16) if lp else None
+            hF0, hB0 = (None, None) if h0 is None else h0
+            w, b = d["w_hh"], d["b_hh"]
+            if last:
+                jobs = [
+                    self._job(dev, gi_f, c_f, w[0], b[0], T, f_in[0], f_in[1], h0=hF0, h_final=h_fwd, hcol=0),
+                    self._job(dev, gi_b, c_b, w[1], b[1], T, b_in[0], b_in[1], h0=hB0, h_final=h_rec, hcol=H),
+                    self._job(dev, gi_s, c_s, w[2], b[2], 1, s_in[0] if gi_s.shape[0] != B else 0, s_in[1],
+                              h_final=h_rec, hcol=0),
+                ]
+            else:
+                # outputs of gru_rec are stored by x_rec index tau: forward dir writes tau = s,
+                # backward dir writes tau = T-1-s
+                jobs = [
+                    self._job(dev, gi_f, c_f, w[0], b[0], T, f_in[0], f_in[1], y=ny_f, y_lp=ny_f_lp),
+                    self._job(dev, gi_b, c_b, w[1], b[1], T, b_in[0], b_in[1], y=ny_r, ycol=H, y_lp=ny_r_lp,
+                              t_out0=T - 1, t_out_step=-1),
+                    self._job(dev, gi_s, c_s, w[2], b[2], T, s_in[0], s_in[1], y=ny_r, ycol=0, y_lp=ny_r_lp),
+                ]
+            self._recurrence(jobs, B)
+            if not last:
+                y_f, y_r, y_f_lp, y_r_lp = ny_f, ny_r, ny_f_lp, ny_r_lp
+        return h_fwd, h_rec
+
+    def heads(self, h_fwd, h_rec, is_train=False):
+        """K3 (first half): lib/models/tepose.py:79-85."""
+        pk = self.packed()
+        B, H = h_fwd.shape[0], self.hidden_size
+        feat = torch.empty((B, 2, 2048) if is_train else (B, 2048), device=h_fwd.device, dtype=torch.float32)
+        nv.check(nv.lib().tp_encoder_heads(nv.ptr(pk["w_fwd"]), nv.ptr(pk["b_fwd"]), nv.ptr(pk["w_rec"]), nv.ptr(pk["b_rec"]),
+                                           nv.ptr(h_fwd), h_fwd.shape[1], nv.ptr(h_rec), h_rec.shape[1], B, H,
+                                           1 if is_train else 0, nv.ptr(feat), nv.stream()), "tp_encoder_heads")
+        return feat
+
+    def forward(self, x, is_train=False):
+        h_fwd, h_rec = self.encode_states(x)
+        return self.heads(h_fwd, h_rec, is_train=is_train)
+
+
+class TePose(nn.Module):
+    def __init__(self, seqlen, batch_size=64, n_layers=1, hidden_size=2048,
+                 pretrained=osp.join(BASE_DATA_DIR, 'spin_model_checkpoint.pth.tar'), precision="fp32"):
+        super().__init__()
+        if precision not in nv.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(nv.PRECISIONS)}")
+        self.seqlen = seqlen
+        self.batch_size = batch_size
+        self.encoder = TemporalEncoder(seq_len=seqlen, n_layers=n_layers, hidden_size=hidden_size, precision=precision)
+        self.regressor = Regressor()
+        if pretrained and os.path.isfile(pretrained):       # lib/models/tepose.py:115-119
+            pretrained_dict = torch.load(pretrained)['model']
+            self.regressor.load_state_dict(pretrained_dict, strict=False)
+            print(f'=> loaded pretrained model from \'{pretrained}\'')
+
+    @property
+    def precision(self):
+        return self.encoder.precision
+
+    @precision.setter
+    def precision(self, value):
+        if value not in nv.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(nv.PRECISIONS)}")
+        self.encoder.precision = value
+
+    def forward(self, input, is_train=False, J_regressor=None):
+        if self.training:
+            raise NotImplementedError("tepose_b200.TePose implements the inference path; call .eval() first "
+                                      "(train-mode dropout / backward are not implemented yet)")
+        batch_size = input.shape[0]
+        feature = self.encoder(input, is_train=is_train)
+        feature = feature.reshape(-1, feature.size(-1))
+        smpl_output = self.regressor(feature, is_train=is_train, J_regressor=J_regressor)
+        lead = (batch_size, 2) if is_train else (batch_size,)
+        for s in smpl_output:                                  # lib/models/tepose.py:130-145
+            s['theta'] = s['theta'].reshape(*lead, -1)
+            s['verts'] = s['verts'].reshape(*lead, -1, 3)
+            s['kp_2d'] = s['kp_2d'].reshape(*lead, -1, 2)
+            s['kp_3d'] = s['kp_3d'].reshape(*lead, -1, 3)
+            s['rotmat'] = s['rotmat'].reshape(*lead, -1, 3, 3)
+        return smpl_output
