@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Headline benchmark: output frames/s of the TePose per-sequence inference hot path at
+B=32, T=16 (BASELINE.json configs[1]: encoder + IEF Regressor + SMPL LBS, L=1, H=2048).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|fp32] [--impl reference]
+
+One "step" = one forward of one batch of B sequences = B output frames.
+  value  : whole-job frames/s with inputs resident in HBM, CUDA-event timed per step, L2 flushed
+           between steps (outside the event pairs), max over ranks.
+  e2e    : the same metric through the public API with HOST buffers: pinned H2D of x, forward,
+           D2H of all five outputs inside the timed region.
+  roofline / cpu_baseline : see DESIGN.md "Measurement".
+Under torchrun every rank runs the same per-GPU batch (weak scaling, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B, T, L, H = 32, 16, 1, 2048
+SEED = 0
+METRIC = "output frames/s at B=32,T=16 (TePose encoder + IEF Regressor + SMPL)"
+WORKLOAD = "BASELINE.json configs[1]: 3DPW-eval-shaped batched inference B=32,T=16, L=1,H=2048, 2133-d inputs"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_step_fn(threads):
+    """The CPU restatement of the reference path (oracle/torch_ref.py, kind 'port'): same
+    torch.nn.GRU / Linear / smplx-style LBS ops the reference executes on CPU."""
+    from oracle import synth, torch_ref
+    torch.set_num_threads(threads)
+    sd = synth.make_state_dict(SEED, L, H)
+    m = torch_ref.SmplModel.synthetic(SEED)
+    grus = (torch_ref.build_gru(sd, "gru_fwd", L, H, False), torch_ref.build_gru(sd, "gru_rec", L, H, True))
+    sd_t = {k: torch.as_tensor(v) for k, v in sd.items()}
+    xs = [torch.from_numpy(synth.make_input(SEED + i, B, T)) for i in range(2)]
+
+    def step(i):
+        return torch_ref.tepose_forward(sd_t, m, xs[i % 2], L, H, grus=grus)
+    return step
+
+
+def time_cpu(step, budget_s, min_iters=2, warm=1):
+    for i in range(warm):
+        step(i)
+    times, t_end = [], time.perf_counter() + budget_s
+    while len(times) < min_iters or time.perf_counter() < t_end:
+        t0 = time.perf_counter()
+        step(len(times))
+        times.append(time.perf_counter() - t0)
+        if len(times) >= 200:
+            break
+    return times
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port) with all
+    host threads, on the same config / metric.  Rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    step = oracle_step_fn(cores)
+    for i in range(max(2, args.warmup)):   # oneDNN primitive creation makes the first calls 5x slower
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    fps = B * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch": B, "seqlen": T, "n_layers": L, "hidden": H},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} forwards of the full B=32,T=16 batch (oracle/torch_ref.py, torch {torch.__version__} CPU)"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from oracle import synth
+    from tests.helpers import build_product_model
+    import tepose_b200._native as nv
+    from tepose_b200.graph import GraphedTePose, OUTPUT_KEYS
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path for the product)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    model, _ = build_product_model(SEED, T, L, H, args.precision, dev)
+    n_inputs = 4
+    xs_host = [torch.from_numpy(synth.make_input(SEED + 100 * rank + i, B, T)).pin_memory() for i in range(n_inputs)]
+    xs_dev = [x.to(dev) for x in xs_host]
+    graphed = GraphedTePose(model, B, T)
+    run = (lambda: model(graphed.static_input)[-1]) if args.no_graph else graphed.replay
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    lib = nv.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------------------------------------------------------- device-resident throughput
+    for i in range(args.warmup):
+        graphed.static_input.copy_(xs_dev[i % n_inputs]); run()
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    launches0 = lib.tp_launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    with torch.no_grad():
+        for i in range(args.steps):
+            graphed.static_input.copy_(xs_dev[i % n_inputs])
+            flush.zero_()                                   # evict weights / inputs from L2 (not timed)
+            evs[i][0].record()
+            run()
+            evs[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = np.array([a.elapsed_time(b) for a, b in evs])
+    dev_ms_total = float(step_ms.sum())
+    eager_launches = int(lib.tp_launch_count() - launches0)
+    launches = eager_launches if args.no_graph else graphed.launches_per_replay * args.steps
+
+    # ---------------------------------------------------------------- end to end (host buffers)
+    out_host = {k: torch.empty_like(graphed.static_output[k], device="cpu").pin_memory() for k in OUTPUT_KEYS}
+    h2d_bytes = xs_host[0].numel() * 4
+    d2h_bytes = sum(v.numel() * 4 for v in out_host.values())
+
+    def e2e_step(i):
+        graphed.static_input.copy_(xs_host[i % n_inputs], non_blocking=True)
+        out = run()
+        for k in OUTPUT_KEYS:
+            out_host[k].copy_(out[k], non_blocking=True)
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            e2e_step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        e1.record()
+        barrier()
+    e2e_ms_total = e0.elapsed_time(e1)
+    clocks = sampler.finish()
+
+    # ---------------------------------------------------------------- per-kernel timing (roofline)
+    stage_ms = {}
+    with torch.no_grad():
+        for i in range(min(args.steps, 20)):
+            flush.zero_()
+            torch.cuda._sleep(4_000_000)          # let the CPU run ahead so events bracket GPU work only
+            nv.start_marks()
+            model(xs_dev[i % n_inputs])
+            marks = nv.stop_marks()
+            torch.cuda.synchronize(dev)
+            for (n0, a), (n1, b_) in zip(marks[:-1], marks[1:]):
+                stage_ms.setdefault(n1, []).append(a.elapsed_time(b_))
+    stage_avg = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+    hbm_peak, tf_peak, peak_src = peaks()
+    wbytes = 2 if args.precision == "bf16" else 4
+    k2_ms = stage_avg.get("k2_recurrence_l0", float("nan"))
+    k2_bytes = 2 * 3 * H * H * wbytes                       # W_hh of the two full directions, read once
+    k1_ms = stage_avg.get("k1_input_proj_l0", float("nan"))
+    k1_flops = 2.0 * (2 * B * T + B) * 2133 * 3 * H
+    roofline = {
+        "kernel": "k_gru_bf16 (K2 recurrence)" if args.precision == "bf16" else "k_gru_f32 (K2 recurrence)",
+        "bound": "hbm", "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes": k2_bytes, "avg_ms": k2_ms,
+        "secondary": {"kernel": "k_gemm_bf16_tc (K1 input projection)" if args.precision == "bf16" else "k_gemm_f32 (K1)",
+                      "bound": "tensor", "achieved": k1_flops / (k1_ms * 1e-3) / 1e12, "peak": tf_peak,
+                      "unit": "TFLOP/s", "frac": k1_flops / (k1_ms * 1e-3) / 1e12 / tf_peak, "avg_ms": k1_ms},
+    }
+
+    # ---------------------------------------------------------------- aggregate over ranks
+    t = torch.tensor([dev_ms_total, e2e_ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    frames = B * args.steps * world
+    value = frames / (dev_ms_max * 1e-3)
+    e2e_value = frames / (e2e_ms_max * 1e-3)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        cores = os.cpu_count() or 1
+        times = time_cpu(oracle_step_fn(cores), args.cpu_budget)
+        cpu_fps = B / float(np.median(times))
+        cpu_baseline = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                        "sample": f"{len(times)} forwards of the full B=32,T=16 batch, median "
+                                  f"{1e3 * float(np.median(times)):.1f} ms (oracle/torch_ref.py on torch {torch.__version__} CPU)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "seqlen": T, "n_layers": L, "hidden": H,
+                       "precision": args.precision, "cuda_graph": not args.no_graph,
+                       "l2": "256 MiB memset between steps, outside the per-step event pairs",
+                       "parallelism": f"batch-sharded x{world}, no collective"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": e2e_ms_max / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "stages_ms": stage_avg,
+            "step_ms": {"min": float(step_ms.min()), "median": float(np.median(step_ms)), "max": float(step_ms.max())},
+            "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,8 @@ extern "C" {
 
 TP_API int tp_version(void);
 TP_API const char* tp_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+TP_API unsigned long long tp_launch_count(void);
 /* host out-params; any may be NULL */
 TP_API int tp_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_per_block_optin);
 
@@ -85,6 +87,17 @@ TP_API int tp_pack_rows(const float* src, int64_t stride_b, int64_t stride_t, in
 TP_API int tp_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                 const float* Cin, int64_t ldcin, float* C, int64_t ldc,
                 int M, int N, int K, float alpha, float beta, int relu_a, void* stream);
+
+/* Same GEMM with the K loop split over `splits` CTAs per output tile (skinny M: lets every SM
+ * stream a slice of W).  Partials are reduced in split order by the last CTA to arrive, so the
+ * result is deterministic.  workspace: tp_gemm_f32_splitk_workspace_bytes(M,N,splits) bytes,
+ * 16-byte aligned, whose first 4096 bytes must be ZERO before the first use (the kernel leaves
+ * them zero again).                                                                       */
+TP_API size_t tp_gemm_f32_splitk_workspace_bytes(int M, int N, int splits);
+TP_API int tp_gemm_f32_splitk(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                       const float* Cin, int64_t ldcin, float* C, int64_t ldc,
+                       int M, int N, int K, float alpha, float beta, int relu_a, int splits,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* One segment of a tensor-core GEMM launch: rows [m_start, m_start+m_rows) of A against rows
  * [n_start, n_start+n_cols) of W;  out[(m-m_start)*ldc + (n-n_start)] = dot + bias[n-n_start]. */
@@ -137,9 +150,10 @@ TP_API int tp_gru_recurrence(const tp_gru_job* jobs, int njobs, int B, int H, in
  *   is_train = 1: feat [B,2,2048] = stack(linear_fwd(..), linear_rec(..))
  * h_fwd [B, ld_hf] is y[-1] of gru_fwd (H wide), h_rec [B, ld_hr] is y_rec[0] (2H wide).
  * w_fwd [2048,H], w_rec [2048,2H] row-major fp32 (nn.Linear layout).                     */
+TP_API size_t tp_encoder_heads_workspace_bytes(int B);
 TP_API int tp_encoder_heads(const float* w_fwd, const float* b_fwd, const float* w_rec, const float* b_rec,
                      const float* h_fwd, int64_t ld_hf, const float* h_rec, int64_t ld_hr,
-                     int B, int H, int is_train, float* feat, void* stream);
+                     int B, int H, int is_train, float* feat, void* workspace, size_t workspace_bytes, void* stream);
 
 /* 3-iteration IEF loop (lib/models/spin.py:250-261).  fc1 is split into its feature columns
  * (w1x, iteration-invariant) and its [pose|shape|cam] columns (w1p, zero-padded 157 -> 160);

@@ -21,11 +21,11 @@ PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16}
 
 # every symbol include/tepose_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "tp_version", "tp_last_error", "tp_device_info",
+    "tp_version", "tp_last_error", "tp_launch_count", "tp_device_info",
     "tp_rot6d_to_rotmat", "tp_rotmat_to_angle_axis", "tp_batch_rodrigues", "tp_projection",
-    "tp_pack_rows", "tp_gemm_f32", "tp_gemm_bf16_tc",
+    "tp_pack_rows", "tp_gemm_f32", "tp_gemm_f32_splitk_workspace_bytes", "tp_gemm_f32_splitk", "tp_gemm_bf16_tc",
     "tp_gru_workspace_bytes", "tp_gru_recurrence",
-    "tp_encoder_heads", "tp_ief_workspace_bytes", "tp_ief_forward",
+    "tp_encoder_heads_workspace_bytes", "tp_encoder_heads", "tp_ief_workspace_bytes", "tp_ief_forward",
     "tp_smpl_workspace_bytes", "tp_smpl_forward",
 ]
 
@@ -56,6 +56,7 @@ class SmplModel(C.Structure):
 _SIGNATURES = {
     "tp_version": (C.c_int, []),
     "tp_last_error": (C.c_char_p, []),
+    "tp_launch_count": (C.c_ulonglong, []),
     "tp_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(sz)]),
     "tp_rot6d_to_rotmat": (C.c_int, [vp, vp, i64, vp]),
     "tp_rotmat_to_angle_axis": (C.c_int, [vp, vp, i64, vp]),
@@ -63,10 +64,14 @@ _SIGNATURES = {
     "tp_projection": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp]),
     "tp_pack_rows": (C.c_int, [vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
     "tp_gemm_f32": (C.c_int, [vp, i64, vp, i64, vp, vp, i64, vp, i64, C.c_int, C.c_int, C.c_int, f32, f32, C.c_int, vp]),
+    "tp_gemm_f32_splitk_workspace_bytes": (sz, [C.c_int, C.c_int, C.c_int]),
+    "tp_gemm_f32_splitk": (C.c_int, [vp, i64, vp, i64, vp, vp, i64, vp, i64, C.c_int, C.c_int, C.c_int, f32, f32, C.c_int,
+                                     C.c_int, vp, sz, vp]),
     "tp_gemm_bf16_tc": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.POINTER(GemmSeg), C.c_int, vp]),
     "tp_gru_workspace_bytes": (sz, [C.c_int, C.c_int, C.c_int]),
     "tp_gru_recurrence": (C.c_int, [C.POINTER(GruJob), C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, vp]),
-    "tp_encoder_heads": (C.c_int, [vp, vp, vp, vp, vp, i64, vp, i64, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "tp_encoder_heads_workspace_bytes": (sz, [C.c_int]),
+    "tp_encoder_heads": (C.c_int, [vp, vp, vp, vp, vp, i64, vp, i64, C.c_int, C.c_int, C.c_int, vp, vp, sz, vp]),
     "tp_ief_workspace_bytes": (sz, [C.c_int]),
     "tp_ief_forward": (C.c_int, [C.POINTER(IefWeights), vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, sz, vp]),
     "tp_smpl_workspace_bytes": (sz, [C.POINTER(SmplModel), C.c_int, C.c_int]),
@@ -124,3 +129,25 @@ def stream() -> vp:
 def workspace(nbytes: int, device) -> torch.Tensor:
     """256-byte aligned scratch (torch's caching allocator aligns to 512 B)."""
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ---- optional stage markers (bench.py's per-kernel timing): CUDA events on the current stream
+_marks = None
+
+
+def start_marks():
+    global _marks
+    _marks = []
+
+
+def stop_marks():
+    global _marks
+    out, _marks = _marks, None
+    return out
+
+
+def mark(name: str) -> None:
+    if _marks is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        _marks.append((name, ev))

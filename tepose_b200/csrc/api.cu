@@ -1,6 +1,7 @@
 // Library-level entry points: version, error text, device query.
 #include "common.cuh"
 #include <string.h>
+#include <atomic>
 
 namespace tp {
 static thread_local char g_err[512] = "";
@@ -20,6 +21,10 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -34,6 +39,9 @@ int sm_count() {
 }  // namespace tp
 
 extern "C" int tp_version(void) { return 100; }
+
+namespace tp { unsigned long long launches(); }
+extern "C" unsigned long long tp_launch_count(void) { return tp::launches(); }
 
 extern "C" const char* tp_last_error(void) { return tp::g_err; }
 

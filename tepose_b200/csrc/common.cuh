@@ -29,6 +29,7 @@ int fail(int code, const char* fmt, ...);
 
 #define TP_LAUNCH_CHECK()                                                                   \
   do {                                                                                      \
+    ::tp::count_launch();                                                                   \
     cudaError_t _e = cudaPeekAtLastError();                                                 \
     if (_e != cudaSuccess)                                                                  \
       return ::tp::fail(TP_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
@@ -39,5 +40,6 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int sm_count();  // of the current device (cached)
+void count_launch();  // bumps the counter behind tp_launch_count()
 
 }  // namespace tp

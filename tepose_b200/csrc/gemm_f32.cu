@@ -20,7 +20,7 @@ template <int BM, int BN, int TM, int TN, bool RELU_A>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 k_gemm_f32(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, int64_t ldw,
            const float* __restrict__ bias, const float* Cin, int64_t ldcin, float* C, int64_t ldc,
-           int M, int N, int K, float alpha, float beta) {
+           int M, int N, int K, float alpha, float beta, float* part, unsigned int* tickets) {
   constexpr int BK = 32, LD = BK + 4, STAGES = 3;
   constexpr int RY = BM / TM, RX = BN / TN, NT = RY * RX;
   extern __shared__ __align__(16) float smem[];
@@ -28,10 +28,14 @@ k_gemm_f32(const float* __restrict__ A, int64_t lda, const float* __restrict__ W
   float* Ws = smem + STAGES * BM * LD;      // [STAGES][BN][LD]
   const int tid = threadIdx.x, tx = tid % RX, ty = tid / RX;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int nkt = (K + BK - 1) / BK;
+  // split-K: blockIdx.z owns k-tiles [kt0, kt0 + nkt)
+  const int nkt_all = (K + BK - 1) / BK;
+  const int per = (nkt_all + gridDim.z - 1) / gridDim.z;
+  const int kt0 = blockIdx.z * per;
+  const int nkt = max(0, min(per, nkt_all - kt0));
 
   auto load_stage = [&](int stage, int kt) {
-    const int k0 = kt * BK;
+    const int k0 = (kt0 + kt) * BK;
     for (int c = tid; c < (BM + BN) * (BK / 4); c += NT) {
       int r = c / (BK / 4), q = c % (BK / 4);
       int k = k0 + q * 4;
@@ -91,6 +95,36 @@ k_gemm_f32(const float* __restrict__ A, int64_t lda, const float* __restrict__ W
   }
   cp_async_wait<0>();
 
+  if (gridDim.z > 1) {
+    // publish this split's partial tile; the last CTA to arrive reduces all splits in split order
+    // (deterministic) and applies the epilogue.  Tickets reset themselves for the next launch.
+    __shared__ int s_last;
+    const size_t tile = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    float* mine = part + ((size_t)blockIdx.z * gridDim.x * gridDim.y + tile) * (BM * BN);
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) __stcg(&mine[(ty + i * RY) * BN + tx + j * RX], acc[i][j]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&tickets[tile], 1u) == gridDim.z - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+    for (unsigned z = 0; z < gridDim.z; ++z) {
+      const float* src = part + ((size_t)z * gridDim.x * gridDim.y + tile) * (BM * BN);
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] += __ldcg(&src[(ty + i * RY) * BN + tx + j * RX]);
+    }
+    if (tid == 0) tickets[tile] = 0;
+  }
+
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     int m = m0 + ty + i * RY;
@@ -108,22 +142,39 @@ k_gemm_f32(const float* __restrict__ A, int64_t lda, const float* __restrict__ W
   }
 }
 
+constexpr size_t kSplitTicketBytes = 4096;   // zero-initialised ticket counters at the head of the scratch
+
 template <int BM, int BN, int TM, int TN>
 static int launch(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, const float* Cin,
                   int64_t ldcin, float* C, int64_t ldc, int M, int N, int K, float alpha, float beta, int relu_a,
-                  cudaStream_t st) {
+                  cudaStream_t st, int splits, void* ws, size_t ws_bytes) {
   constexpr int LD = 36, STAGES = 3;
   constexpr size_t smem = (size_t)STAGES * (BM + BN) * LD * sizeof(float);
   dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM));
   dim3 block((BM / TM) * (BN / TN));
+  float* part = nullptr;
+  unsigned int* tickets = nullptr;
+  const int nkt_all = (K + 31) / 32;
+  if (splits > nkt_all) splits = nkt_all;
+  if (splits > 1) {
+    const size_t tiles = (size_t)grid.x * grid.y;
+    const size_t need = kSplitTicketBytes + (size_t)splits * tiles * BM * BN * sizeof(float);
+    if (!ws || ws_bytes < need || tiles * sizeof(unsigned) > kSplitTicketBytes || (reinterpret_cast<uintptr_t>(ws) & 15))
+      splits = 1;   // not enough scratch: fall back to the single-pass kernel (same result)
+    else {
+      tickets = reinterpret_cast<unsigned int*>(ws);
+      part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + kSplitTicketBytes);
+      grid.z = (unsigned)splits;
+    }
+  }
   if (relu_a) {
     auto kfn = k_gemm_f32<BM, BN, TM, TN, true>;
     TP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kfn<<<grid, block, smem, st>>>(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, alpha, beta);
+    kfn<<<grid, block, smem, st>>>(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, alpha, beta, part, tickets);
   } else {
     auto kfn = k_gemm_f32<BM, BN, TM, TN, false>;
     TP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kfn<<<grid, block, smem, st>>>(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, alpha, beta);
+    kfn<<<grid, block, smem, st>>>(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, alpha, beta, part, tickets);
   }
   TP_LAUNCH_CHECK();
   return TP_OK;
@@ -131,18 +182,40 @@ static int launch(const float* A, int64_t lda, const float* W, int64_t ldw, cons
 
 }  // namespace tp
 
+static int gemm_f32_dispatch(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                             const float* Cin, int64_t ldcin, float* C, int64_t ldc, int M, int N, int K,
+                             float alpha, float beta, int relu_a, void* stream, int splits, void* ws, size_t ws_bytes,
+                             const char* who) {
+  using namespace tp;
+  TP_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "%s: negative size", who);
+  if (M == 0 || N == 0) return TP_OK;
+  TP_CHECK_ARG(A && W && C, "%s: null pointer", who);
+  TP_CHECK_ARG(K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0, "%s: K=%d lda=%lld ldw=%lld must be multiples of 4", who,
+               K, (long long)lda, (long long)ldw);
+  TP_CHECK_ARG(aligned16(A) && aligned16(W), "%s: A/W must be 16-byte aligned", who);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M <= 32) return launch<32, 32, 2, 4>(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, alpha, beta, relu_a, st, splits, ws, ws_bytes);
+  if (M <= 64) return launch<64, 32, 4, 4>(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, alpha, beta, relu_a, st, splits, ws, ws_bytes);
+  return launch<128, 64, 8, 4>(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, alpha, beta, relu_a, st, splits, ws, ws_bytes);
+}
+
 extern "C" int tp_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                            const float* Cin, int64_t ldcin, float* C, int64_t ldc, int M, int N, int K,
                            float alpha, float beta, int relu_a, void* stream) {
-  using namespace tp;
-  TP_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "tp_gemm_f32: negative size");
-  if (M == 0 || N == 0) return TP_OK;
-  TP_CHECK_ARG(A && W && C, "tp_gemm_f32: null pointer");
-  TP_CHECK_ARG(K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0, "tp_gemm_f32: K=%d lda=%lld ldw=%lld must be multiples of 4",
-               K, (long long)lda, (long long)ldw);
-  TP_CHECK_ARG(aligned16(A) && aligned16(W), "tp_gemm_f32: A/W must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (M <= 32) return launch<32, 32, 2, 4>(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, alpha, beta, relu_a, st);
-  if (M <= 64) return launch<64, 32, 4, 4>(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, alpha, beta, relu_a, st);
-  return launch<128, 64, 8, 4>(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, alpha, beta, relu_a, st);
+  return gemm_f32_dispatch(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, alpha, beta, relu_a, stream, 1, nullptr, 0,
+                           "tp_gemm_f32");
+}
+
+extern "C" size_t tp_gemm_f32_splitk_workspace_bytes(int M, int N, int splits) {
+  const size_t bm = M <= 32 ? 32 : (M <= 64 ? 64 : 128), bn = M <= 64 ? 32 : 64;
+  const size_t tiles = ((size_t)N + bn - 1) / bn * (((size_t)M + bm - 1) / bm);
+  return tp::kSplitTicketBytes + (size_t)(splits > 1 ? splits : 1) * tiles * bm * bn * sizeof(float);
+}
+
+extern "C" int tp_gemm_f32_splitk(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                                  const float* Cin, int64_t ldcin, float* C, int64_t ldc, int M, int N, int K,
+                                  float alpha, float beta, int relu_a, int splits, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  return gemm_f32_dispatch(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, alpha, beta, relu_a, stream, splits,
+                           workspace, workspace_bytes, "tp_gemm_f32_splitk");
 }

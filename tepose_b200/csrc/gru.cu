@@ -14,9 +14,6 @@
 //          shared memory, 8 warps split K (x M) and reduce through shared memory.
 //          State, gates and accumulation stay fp32.
 #include "common.cuh"
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
 
 namespace tp {
 
@@ -29,7 +26,23 @@ struct GruParams {
   int njobs, B, H, U, max_steps, total_items, any_h0;
   float* hbuf;              // [njobs][2][B][H]  fp32 state ping-pong
   __nv_bfloat16* hbuf_lp;   // [njobs][2][B][H]  bf16 copy (MMA operand of the next step)
+  unsigned int* barrier;    // monotonic grid-barrier counter (zeroed by the host before launch)
 };
+
+// Grid barrier for a co-resident (cooperatively launched) grid: one arrival per CTA on a
+// monotonic counter, release/acquire at gpu scope.  State that crosses the barrier is read with
+// L2-coherent loads (cp.async.cg / ld.global.cg), so no L1 invalidation is needed.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int seen;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -56,21 +69,34 @@ __device__ __forceinline__ void mma_bf16(float* c, uint32_t a0, uint32_t a1, uin
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// Gate math of torch.nn.GRU for one (batch b, hidden unit u): acc_* are W_h* . h_prev.
-__device__ __forceinline__ void gru_finalize(const GruParams& p, int j, int s, int b, int u,
-                                             float acc_r, float acc_z, float acc_n) {
+// Operands of the gate math that do not depend on this step's matmul; fetched early so their
+// latency hides behind the W_hh stream.
+struct GateIn { float gr, gz, gn, br, bz, bn, hp; };
+
+__device__ __forceinline__ GateIn gate_fetch(const GruParams& p, int j, int s, int b, int u) {
   const tp_gru_job& jb = p.jobs[j];
   const int H = p.H, B = p.B;
   const int t_in = jb.t_in0 + s * jb.t_in_step;
   const float* gi = jb.gi + ((int64_t)t_in * B + b) * jb.ldg;
-  float hp = 0.0f;
+  GateIn g;
+  g.gr = __ldg(gi + u); g.gz = __ldg(gi + H + u); g.gn = __ldg(gi + 2 * H + u);
+  g.br = __ldg(jb.b_hh + u); g.bz = __ldg(jb.b_hh + H + u); g.bn = __ldg(jb.b_hh + 2 * H + u);
+  g.hp = 0.0f;
   const bool have_prev = (s > 0) || (jb.h0 != nullptr);
   const float* hprev = p.hbuf + ((int64_t)(j * 2 + ((s + 1) & 1)) * B) * H;
-  if (have_prev) hp = __ldcg(hprev + (int64_t)b * H + u);
-  float r = sigmoidf_(gi[u] + (acc_r + jb.b_hh[u]));
-  float z = sigmoidf_(gi[H + u] + (acc_z + jb.b_hh[H + u]));
-  float n = tanhf(gi[2 * H + u] + r * (acc_n + jb.b_hh[2 * H + u]));
-  float h = (1.0f - z) * n + z * hp;
+  if (have_prev) g.hp = __ldcg(hprev + (int64_t)b * H + u);
+  return g;
+}
+
+// Gate math of torch.nn.GRU for one (batch b, hidden unit u): acc_* are W_h* . h_prev.
+__device__ __forceinline__ void gru_finalize(const GruParams& p, int j, int s, int b, int u, const GateIn& g,
+                                             float acc_r, float acc_z, float acc_n) {
+  const tp_gru_job& jb = p.jobs[j];
+  const int H = p.H, B = p.B;
+  float r = sigmoidf_(g.gr + (acc_r + g.br));
+  float z = sigmoidf_(g.gz + (acc_z + g.bz));
+  float n = tanhf(g.gn + r * (acc_n + g.bn));
+  float h = (1.0f - z) * n + z * g.hp;
   const int64_t slot = ((int64_t)(j * 2 + (s & 1)) * B + b) * H + u;
   p.hbuf[slot] = h;
   p.hbuf_lp[slot] = __float2bfloat16_rn(h);
@@ -111,11 +137,11 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_f32(const GruParams p) {
   extern __shared__ __align__(16) float smem_f[];
   float* Ws = smem_f;                          // [STAGES][3U][LD]
   float* Hs = smem_f + STAGES * 3 * U * LD;    // [STAGES][BT][LD]
-  cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x, u = tid >> 3, bq = tid & 7;
   const int H = p.H, B = p.B;
+  unsigned int epoch = 0;
 
-  if (p.any_h0) { seed_h0(p); grid.sync(); }
+  if (p.any_h0) { seed_h0(p); __threadfence(); grid_barrier(p.barrier, ++epoch * gridDim.x); }
 
   for (int s = 0; s < p.max_steps; ++s) {
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -187,11 +213,11 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_f32(const GruParams p) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           int b = b0 + bq + 8 * i;
-          if (b < B) gru_finalize(p, j, s, b, u0 + u, acc[0][i], acc[1][i], acc[2][i]);
+          if (b < B) gru_finalize(p, j, s, b, u0 + u, gate_fetch(p, j, s, b, u0 + u), acc[0][i], acc[1][i], acc[2][i]);
         }
       }
     }
-    if (s + 1 < p.max_steps) grid.sync();
+    if (s + 1 < p.max_steps) { __threadfence(); grid_barrier(p.barrier, ++epoch * gridDim.x); }
   }
 }
 
@@ -201,17 +227,43 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_f32(const GruParams p) {
 template <int NT, int MG>
 __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) {
   constexpr int KG = 8 / MG, U = 16 * MG, NB = NT * 8, RP = U + 4;
+  constexpr int PF = 4;                                       // W_hh blocks (32 columns) in flight per warp
+  constexpr int GE = (NB * U + kGruThreads - 1) / kGruThreads; // gate elements per thread
   extern __shared__ __align__(16) unsigned char smem_b[];
   const int H = p.H, B = p.B;
   const int HP = H + 32;                                     // bf16 row pitch of the staged h
   __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(smem_b);          // [NB][HP]
   float* red = reinterpret_cast<float*>(smem_b + (size_t)NB * HP * 2);   // [KG][3][NB][RP]
-  cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int kg = warp / MG, mg = warp % MG;
+  const int nblk = H / 32;
+  const int blk_lo = (kg * nblk) / KG, blk_hi = ((kg + 1) * nblk) / KG;
+  unsigned int epoch = 0;
 
-  if (p.any_h0) { seed_h0(p); grid.sync(); }
+  if (p.any_h0) { seed_h0(p); __threadfence(); grid_barrier(p.barrier, ++epoch * gridDim.x); }
+
+  // W_hh ring: buf[q][i] holds rows (g, g+8) of gate i for block (blk_lo + q mod PF)
+  uint4 w_lo[PF][3], w_hi[PF][3];
+  auto w_rows = [&](int j, int u0, const __nv_bfloat16* (&wrow)[3]) {
+    const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(p.jobs[j].w_hh);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) wrow[i] = W + ((int64_t)i * H + u0 + mg * 16 + g) * H + 8 * t;
+  };
+  auto w_prologue = [&](const __nv_bfloat16* (&wrow)[3]) {
+#pragma unroll
+    for (int q = 0; q < PF; ++q)
+      if (blk_lo + q < blk_hi) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          w_lo[q][i] = ldg_stream(wrow[i] + (blk_lo + q) * 32);
+          w_hi[q][i] = ldg_stream(wrow[i] + (int64_t)8 * H + (blk_lo + q) * 32);
+        }
+      }
+  };
+  // single-item CTAs (the common case) start streaming the next step's W_hh before the barrier
+  const bool single_item = p.total_items <= (int)gridDim.x;
+  bool ring_primed = false;
 
   for (int s = 0; s < p.max_steps; ++s) {
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -220,8 +272,9 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
       const tp_gru_job& jb = p.jobs[j];
       if (s >= jb.steps) continue;
       const bool have_prev = (s > 0) || (jb.h0 != nullptr);
-      const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(jb.w_hh);
       const __nv_bfloat16* hprev = p.hbuf_lp + ((int64_t)(j * 2 + ((s + 1) & 1)) * B) * H;
+      const __nv_bfloat16* wrow[3];
+      w_rows(j, u0, wrow);
       for (int b0 = 0; b0 < B; b0 += NB) {
         if (have_prev) {
           // stage h_prev[b0 : b0+NB, :] (bf16) into shared memory
@@ -232,6 +285,18 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
             cp_async16_z(hs + (size_t)bb * HP + q * 8, ok ? (hprev + (int64_t)(b0 + bb) * H + q * 8) : hprev, ok);
           }
           cp_commit();
+          if (!ring_primed) w_prologue(wrow);
+          ring_primed = false;
+        }
+        // gate operands of this thread's (batch, unit) elements: independent of the matmul
+        GateIn gin[GE];
+#pragma unroll
+        for (int e = 0; e < GE; ++e) {
+          const int idx = tid + e * kGruThreads;
+          const int bb = idx / U, uu = idx - bb * U;
+          if (idx < NB * U && b0 + bb < B) gin[e] = gate_fetch(p, j, s, b0 + bb, u0 + uu);
+        }
+        if (have_prev) {
           float acc[3][NT][4];
 #pragma unroll
           for (int i = 0; i < 3; ++i)
@@ -239,42 +304,30 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
             for (int n = 0; n < NT; ++n)
 #pragma unroll
               for (int e = 0; e < 4; ++e) acc[i][n][e] = 0.0f;
-          const int nblk = H / 32;
-          const int blk_lo = (kg * nblk) / KG, blk_hi = ((kg + 1) * nblk) / KG;
-          const __nv_bfloat16* wrow[3];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) wrow[i] = W + ((int64_t)i * H + u0 + mg * 16 + g) * H + 8 * t;
-          uint4 a_lo[3], a_hi[3];
-          if (blk_lo < blk_hi) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              a_lo[i] = ldg_stream(wrow[i] + blk_lo * 32);
-              a_hi[i] = ldg_stream(wrow[i] + (int64_t)8 * H + blk_lo * 32);
-            }
-          }
           cp_wait<0>();
           __syncthreads();
-          for (int blk = blk_lo; blk < blk_hi; ++blk) {
-            uint4 n_lo[3], n_hi[3];
-            if (blk + 1 < blk_hi) {
+          for (int blk = blk_lo; blk < blk_hi; blk += PF) {
 #pragma unroll
-              for (int i = 0; i < 3; ++i) {
-                n_lo[i] = ldg_stream(wrow[i] + (blk + 1) * 32);
-                n_hi[i] = ldg_stream(wrow[i] + (int64_t)8 * H + (blk + 1) * 32);
+            for (int q = 0; q < PF; ++q) {
+              const int cur = blk + q;
+              if (cur < blk_hi) {
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                  const uint4 bv = *reinterpret_cast<const uint4*>(hs + (size_t)(n * 8 + g) * HP + cur * 32 + 8 * t);
+#pragma unroll
+                  for (int i = 0; i < 3; ++i) {
+                    mma_bf16(acc[i][n], w_lo[q][i].x, w_hi[q][i].x, w_lo[q][i].y, w_hi[q][i].y, bv.x, bv.y);
+                    mma_bf16(acc[i][n], w_lo[q][i].z, w_hi[q][i].z, w_lo[q][i].w, w_hi[q][i].w, bv.z, bv.w);
+                  }
+                }
+                if (cur + PF < blk_hi) {
+#pragma unroll
+                  for (int i = 0; i < 3; ++i) {
+                    w_lo[q][i] = ldg_stream(wrow[i] + (cur + PF) * 32);
+                    w_hi[q][i] = ldg_stream(wrow[i] + (int64_t)8 * H + (cur + PF) * 32);
+                  }
+                }
               }
-            }
-#pragma unroll
-            for (int n = 0; n < NT; ++n) {
-              uint4 bv = *reinterpret_cast<const uint4*>(hs + (size_t)(n * 8 + g) * HP + blk * 32 + 8 * t);
-#pragma unroll
-              for (int i = 0; i < 3; ++i) {
-                mma_bf16(acc[i][n], a_lo[i].x, a_hi[i].x, a_lo[i].y, a_hi[i].y, bv.x, bv.y);
-                mma_bf16(acc[i][n], a_lo[i].z, a_hi[i].z, a_lo[i].w, a_hi[i].w, bv.z, bv.w);
-              }
-            }
-            if (blk + 1 < blk_hi) {
-#pragma unroll
-              for (int i = 0; i < 3; ++i) { a_lo[i] = n_lo[i]; a_hi[i] = n_hi[i]; }
             }
           }
           // partial sums -> red[kg][gate][n][unit]
@@ -290,9 +343,11 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
             }
           __syncthreads();
         }
-        for (int idx = tid; idx < NB * U; idx += kGruThreads) {
-          int bb = idx / U, uu = idx - bb * U;
-          if (b0 + bb >= B) continue;
+#pragma unroll
+        for (int e = 0; e < GE; ++e) {
+          const int idx = tid + e * kGruThreads;
+          const int bb = idx / U, uu = idx - bb * U;
+          if (idx >= NB * U || b0 + bb >= B) continue;
           float ar = 0.f, az = 0.f, an = 0.f;
           if (have_prev) {
 #pragma unroll
@@ -302,12 +357,25 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
               an += red[((size_t)(k * 3 + 2) * NB + bb) * RP + uu];
             }
           }
-          gru_finalize(p, j, s, b0 + bb, u0 + uu, ar, az, an);
+          gru_finalize(p, j, s, b0 + bb, u0 + uu, gin[e], ar, az, an);
         }
         __syncthreads();  // hs / red are reused by the next batch tile / item
       }
     }
-    if (s + 1 < p.max_steps) grid.sync();
+    if (s + 1 < p.max_steps) {
+      if (single_item && (int)blockIdx.x < p.total_items && B <= NB) {
+        int j, u0;
+        locate_item(p, blockIdx.x, j, u0);
+        if (s + 1 < p.jobs[j].steps) {      // W_hh does not depend on h: fetch across the barrier
+          const __nv_bfloat16* wrow[3];
+          w_rows(j, u0, wrow);
+          w_prologue(wrow);
+          ring_primed = true;
+        }
+      }
+      __threadfence();
+      grid_barrier(p.barrier, ++epoch * gridDim.x);
+    }
   }
 }
 
@@ -319,7 +387,7 @@ using namespace tp;
 
 extern "C" size_t tp_gru_workspace_bytes(int njobs, int B, int H) {
   size_t per = (size_t)njobs * 2 * B * H;
-  return align_up(per * sizeof(float), 256) + align_up(per * sizeof(__nv_bfloat16), 256);
+  return 256 + align_up(per * sizeof(float), 256) + align_up(per * sizeof(__nv_bfloat16), 256);
 }
 
 template <typename KernelT>
@@ -331,6 +399,7 @@ static int launch_coop(KernelT kfn, const GruParams& p, size_t smem, cudaStream_
   int grid = p.total_items < sm_count() ? p.total_items : sm_count();
   void* args[] = {(void*)&p};
   TP_CUDA(cudaLaunchCooperativeKernel((const void*)kfn, dim3(grid), dim3(kGruThreads), args, smem, st));
+  count_launch();
   return TP_OK;
 }
 
@@ -362,9 +431,11 @@ extern "C" int tp_gru_recurrence(const tp_gru_job* jobs, int njobs, int B, int H
   for (int j = njobs; j <= kMaxJobs; ++j) p.item_begin[j] = items;
   p.total_items = items;
   size_t per = (size_t)njobs * 2 * B * H;
-  p.hbuf = reinterpret_cast<float*>(workspace);
-  p.hbuf_lp = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(workspace) + align_up(per * sizeof(float), 256));
+  p.barrier = reinterpret_cast<unsigned int*>(workspace);
+  p.hbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 256);
+  p.hbuf_lp = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(workspace) + 256 + align_up(per * sizeof(float), 256));
   cudaStream_t st = (cudaStream_t)stream;
+  TP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
 
   if (precision == TP_PRECISION_FP32) {
     size_t smem = (size_t)3 * (3 * 32 + 32) * 36 * sizeof(float);

@@ -19,25 +19,53 @@ using namespace tp;
 
 #define TP_TRY(x) do { int _rc = (x); if (_rc != TP_OK) return _rc; } while (0)
 
+// split-K factor for a skinny layer: enough CTAs to cover the machine ~3x, K slices >= 128
+static int pick_splits(int M, int N, int K) {
+  const int bn = 32, tiles = ((N + bn - 1) / bn) * ((M + (M <= 32 ? 31 : 63)) / (M <= 32 ? 32 : 64));
+  int want = (3 * tp::sm_count() + tiles - 1) / tiles;
+  int maxs = K / 128;
+  if (want > maxs) want = maxs;
+  if (want > 16) want = 16;
+  return want < 1 ? 1 : want;
+}
+static const size_t kSplitScratch = 4096 + (size_t)16 * 64 * 2048 * sizeof(float);   // tickets + 16 splits of a [64,2048] layer
+
+static int skinny(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, const float* Cin,
+                  int64_t ldcin, float* C, int64_t ldc, int M, int N, int K, float alpha, float beta, int relu_a,
+                  void* scratch, void* stream) {
+  return tp_gemm_f32_splitk(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, alpha, beta, relu_a,
+                            pick_splits(M, N, K), scratch, kSplitScratch, stream);
+}
+
+extern "C" size_t tp_encoder_heads_workspace_bytes(int B) { (void)B; return kSplitScratch; }
+
 extern "C" int tp_encoder_heads(const float* w_fwd, const float* b_fwd, const float* w_rec, const float* b_rec,
                                 const float* h_fwd, int64_t ld_hf, const float* h_rec, int64_t ld_hr,
-                                int B, int H, int is_train, float* feat, void* stream) {
+                                int B, int H, int is_train, float* feat, void* workspace, size_t workspace_bytes,
+                                void* stream) {
   TP_CHECK_ARG(w_fwd && b_fwd && w_rec && b_rec && h_fwd && h_rec && feat, "tp_encoder_heads: null pointer");
   TP_CHECK_ARG(B >= 1 && H >= 4 && H % 4 == 0, "tp_encoder_heads: bad sizes B=%d H=%d", B, H);
+  TP_CHECK_ARG(workspace && workspace_bytes >= kSplitScratch && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+               "tp_encoder_heads: workspace too small / misaligned");
+  TP_CUDA(cudaMemsetAsync(workspace, 0, 4096, (cudaStream_t)stream));
+  void* sc = workspace;
+  if (B > 64) {   // the split-K scratch is sized for <= 64 rows
+    sc = nullptr;
+  }
   if (!is_train) {
     // (linear_fwd(relu(hF)) + linear_rec(relu(hR))) / 2  -- halving each term first is exact in fp32
-    TP_TRY(tp_gemm_f32(h_fwd, ld_hf, w_fwd, H, b_fwd, nullptr, 0, feat, 2048, B, 2048, H, 0.5f, 0.f, 1, stream));
-    TP_TRY(tp_gemm_f32(h_rec, ld_hr, w_rec, 2 * H, b_rec, feat, 2048, feat, 2048, B, 2048, 2 * H, 0.5f, 1.f, 1, stream));
+    TP_TRY(skinny(h_fwd, ld_hf, w_fwd, H, b_fwd, nullptr, 0, feat, 2048, B, 2048, H, 0.5f, 0.f, 1, sc, stream));
+    TP_TRY(skinny(h_rec, ld_hr, w_rec, 2 * H, b_rec, feat, 2048, feat, 2048, B, 2048, 2 * H, 0.5f, 1.f, 1, sc, stream));
   } else {
     // stacked [B,2,2048]: row b holds the fwd features then the rec features
-    TP_TRY(tp_gemm_f32(h_fwd, ld_hf, w_fwd, H, b_fwd, nullptr, 0, feat, 4096, B, 2048, H, 1.f, 0.f, 1, stream));
-    TP_TRY(tp_gemm_f32(h_rec, ld_hr, w_rec, 2 * H, b_rec, nullptr, 0, feat + 2048, 4096, B, 2048, 2 * H, 1.f, 0.f, 1, stream));
+    TP_TRY(skinny(h_fwd, ld_hf, w_fwd, H, b_fwd, nullptr, 0, feat, 4096, B, 2048, H, 1.f, 0.f, 1, sc, stream));
+    TP_TRY(skinny(h_rec, ld_hr, w_rec, 2 * H, b_rec, nullptr, 0, feat + 2048, 4096, B, 2048, 2 * H, 1.f, 0.f, 1, sc, stream));
   }
   return TP_OK;
 }
 
 extern "C" size_t tp_ief_workspace_bytes(int n_rows) {
-  return 3 * al256((size_t)(n_rows > 0 ? n_rows : 0) * 1024 * sizeof(float));
+  return 3 * al256((size_t)(n_rows > 0 ? n_rows : 0) * 1024 * sizeof(float)) + kSplitScratch;
 }
 
 extern "C" int tp_ief_forward(const tp_ief_weights* w, const float* feat, int n_rows, const float* init, int init_rows,
@@ -53,13 +81,16 @@ extern "C" int tp_ief_forward(const tp_ief_weights* w, const float* feat, int n_
   float* base = reinterpret_cast<float*>(workspace);
   float* u1 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + slab);
   float* u2 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 2 * slab);
-  TP_TRY(tp_gemm_f32(feat, 2048, w->w1x, 2048, w->b1, nullptr, 0, base, 1024, N, 1024, 2048, 1.f, 0.f, 0, stream));
+  void* sc = reinterpret_cast<unsigned char*>(workspace) + 3 * slab;
+  TP_CUDA(cudaMemsetAsync(sc, 0, 4096, (cudaStream_t)stream));
+  if (N > 64) sc = nullptr;
+  TP_TRY(skinny(feat, 2048, w->w1x, 2048, w->b1, nullptr, 0, base, 1024, N, 1024, 2048, 1.f, 0.f, 0, sc, stream));
   k_broadcast_rows<<<(unsigned)ceil_div((int64_t)N * 160, 256), 256, 0, (cudaStream_t)stream>>>(init, psc, N, 160, init_rows);
   TP_LAUNCH_CHECK();
   for (int it = 0; it < n_iter; ++it) {
-    TP_TRY(tp_gemm_f32(psc, 160, w->w1p, 160, nullptr, base, 1024, u1, 1024, N, 1024, 160, 1.f, 1.f, 0, stream));
-    TP_TRY(tp_gemm_f32(u1, 1024, w->w2, 1024, w->b2, nullptr, 0, u2, 1024, N, 1024, 1024, 1.f, 0.f, 0, stream));
-    TP_TRY(tp_gemm_f32(u2, 1024, w->wdec, 1024, w->bdec, psc, 160, psc, 160, N, 160, 1024, 1.f, 1.f, 0, stream));
+    TP_TRY(skinny(psc, 160, w->w1p, 160, nullptr, base, 1024, u1, 1024, N, 1024, 160, 1.f, 1.f, 0, sc, stream));
+    TP_TRY(skinny(u1, 1024, w->w2, 1024, w->b2, nullptr, 0, u2, 1024, N, 1024, 1024, 1.f, 0.f, 0, sc, stream));
+    TP_TRY(skinny(u2, 1024, w->wdec, 1024, w->bdec, psc, 160, psc, 160, N, 160, 1024, 1.f, 1.f, 0, sc, stream));
   }
   return TP_OK;
 }

@@ -10,19 +10,21 @@ namespace tp {
 // a1 = (x0,x2,x4), a2 = (x1,x3,x5).  F.normalize(v, eps=1e-6) = v / max(||v||, 1e-6).
 // R (row-major 3x3) has COLUMNS b1, b2, b3.
 __device__ __forceinline__ void rot6d_to_rotmat(const float* __restrict__ x, float* R) {
+  // Explicit round-to-nearest mul/add (no FMA contraction): torch evaluates these as separate
+  // elementwise ops, and for near-parallel a1/a2 the result is decided by the last bit.
   float a1x = x[0], a1y = x[2], a1z = x[4];
   float a2x = x[1], a2y = x[3], a2z = x[5];
-  float n1 = sqrtf(a1x * a1x + a1y * a1y + a1z * a1z);
+  float n1 = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a1x, a1x), __fmul_rn(a1y, a1y)), __fmul_rn(a1z, a1z)));
   float i1 = fmaxf(n1, 1e-6f);
   float b1x = a1x / i1, b1y = a1y / i1, b1z = a1z / i1;
-  float d = b1x * a2x + b1y * a2y + b1z * a2z;
-  float ux = a2x - d * b1x, uy = a2y - d * b1y, uz = a2z - d * b1z;
-  float n2 = sqrtf(ux * ux + uy * uy + uz * uz);
+  float d = __fadd_rn(__fadd_rn(__fmul_rn(b1x, a2x), __fmul_rn(b1y, a2y)), __fmul_rn(b1z, a2z));
+  float ux = __fsub_rn(a2x, __fmul_rn(d, b1x)), uy = __fsub_rn(a2y, __fmul_rn(d, b1y)), uz = __fsub_rn(a2z, __fmul_rn(d, b1z));
+  float n2 = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), __fmul_rn(uz, uz)));
   float i2 = fmaxf(n2, 1e-6f);
   float b2x = ux / i2, b2y = uy / i2, b2z = uz / i2;
-  float b3x = b1y * b2z - b1z * b2y;
-  float b3y = b1z * b2x - b1x * b2z;
-  float b3z = b1x * b2y - b1y * b2x;
+  float b3x = __fsub_rn(__fmul_rn(b1y, b2z), __fmul_rn(b1z, b2y));
+  float b3y = __fsub_rn(__fmul_rn(b1z, b2x), __fmul_rn(b1x, b2z));
+  float b3z = __fsub_rn(__fmul_rn(b1x, b2y), __fmul_rn(b1y, b2x));
   R[0] = b1x; R[1] = b2x; R[2] = b3x;
   R[3] = b1y; R[4] = b2y; R[5] = b3y;
   R[6] = b1z; R[7] = b2z; R[8] = b3z;

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kVT) k_smpl_verts(const tp_smpl_model m, int n
 #pragma unroll
     for (int b = 0; b < kNB; ++b) acc[b][0] = acc[b][1] = acc[b][2] = 0.0f;
     const float* bl = m.blend + v;
-#pragma unroll 2
+#pragma unroll 8   // 24 independent loads in flight per thread: this loop is latency-bound otherwise
     for (int k = 0; k < kCoef; ++k) {
       float d0 = __ldg(bl + (int64_t)(k * 3 + 0) * vp);
       float d1 = __ldg(bl + (int64_t)(k * 3 + 1) * vp);

@@ -107,6 +107,7 @@ class Regressor(nn.Module):
         ws = nv.workspace(L.tp_ief_workspace_bytes(N), dev)
         nv.check(L.tp_ief_forward(pk["c"], nv.ptr(feat), N, nv.ptr(init), init_rows, n_iter, nv.ptr(psc),
                                   nv.ptr(ws), ws.numel(), nv.stream()), "tp_ief_forward")
+        nv.mark("k3_ief")
         return self.decode(psc, is_train=is_train, J_regressor=J_regressor)
 
     def decode(self, psc: torch.Tensor, is_train=False, J_regressor=None):
@@ -124,4 +125,5 @@ class Regressor(nn.Module):
         cam = psc[:, 154:]              # columns 154..156
         verts, joints, kp2d, rotmat, theta = smpl_forward_native(
             p, pose, PSC, nv.POSE_ROT6D, betas, PSC, cam, PSC, N, jreg, src, want_theta=True)
+        nv.mark("k45_smpl")
         return [{'theta': theta, 'verts': verts, 'kp_2d': kp2d, 'kp_3d': joints, 'rotmat': rotmat}]

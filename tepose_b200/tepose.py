@@ -175,6 +175,7 @@ class TemporalEncoder(nn.Module):
                 xp = torch.empty(T * B, kp, device=dev, dtype=adt)
                 nv.check(L.tp_pack_rows(nv.vp(x.data_ptr()), x.stride(0), x.stride(1), B, T, INPUT_SIZE, nv.ptr(xp), kp,
                                         prec, 0, nv.stream()), "tp_pack_rows")
+                nv.mark("pack")
                 if last:
                     gi = torch.empty(T * B, 6 * H, device=dev, dtype=torch.float32)      # [fwd | rec-backward]
                     gs = torch.empty(B, 3 * H, device=dev, dtype=torch.float32)          # rec-forward, newest frame only
@@ -213,6 +214,7 @@ class TemporalEncoder(nn.Module):
                 ny_r = torch.zeros(T * B, kpn_r, device=dev, dtype=torch.float32)
                 ny_f_lp = torch.zeros(T * B, kpn_f, device=dev, dtype=torch.bfloat16) if lp else None
                 ny_r_lp = torch.zeros(T * B, kpn_r, device=dev, dtype=torch.bfloat16) if lp else None
+            nv.mark(f"k1_input_proj_l{l}")
             hF0, hB0 = (None, None) if h0 is None else h0
             w, b = d["w_hh"], d["b_hh"]
             if last:
@@ -232,6 +234,7 @@ class TemporalEncoder(nn.Module):
                     self._job(dev, gi_s, c_s, w[2], b[2], T, s_in[0], s_in[1], y=ny_r, ycol=0, y_lp=ny_r_lp),
                 ]
             self._recurrence(jobs, B)
+            nv.mark(f"k2_recurrence_l{l}")
             if not last:
                 y_f, y_r, y_f_lp, y_r_lp = ny_f, ny_r, ny_f_lp, ny_r_lp
         return h_fwd, h_rec
@@ -241,9 +244,13 @@ class TemporalEncoder(nn.Module):
         pk = self.packed()
         B, H = h_fwd.shape[0], self.hidden_size
         feat = torch.empty((B, 2, 2048) if is_train else (B, 2048), device=h_fwd.device, dtype=torch.float32)
-        nv.check(nv.lib().tp_encoder_heads(nv.ptr(pk["w_fwd"]), nv.ptr(pk["b_fwd"]), nv.ptr(pk["w_rec"]), nv.ptr(pk["b_rec"]),
-                                           nv.ptr(h_fwd), h_fwd.shape[1], nv.ptr(h_rec), h_rec.shape[1], B, H,
-                                           1 if is_train else 0, nv.ptr(feat), nv.stream()), "tp_encoder_heads")
+        L = nv.lib()
+        ws = nv.workspace(L.tp_encoder_heads_workspace_bytes(B), h_fwd.device)
+        nv.check(L.tp_encoder_heads(nv.ptr(pk["w_fwd"]), nv.ptr(pk["b_fwd"]), nv.ptr(pk["w_rec"]), nv.ptr(pk["b_rec"]),
+                                    nv.ptr(h_fwd), h_fwd.shape[1], nv.ptr(h_rec), h_rec.shape[1], B, H,
+                                    1 if is_train else 0, nv.ptr(feat), nv.ptr(ws), ws.numel(), nv.stream()),
+                 "tp_encoder_heads")
+        nv.mark("k3_heads")
         return feat
 
     def forward(self, x, is_train=False):
@@ -281,6 +288,7 @@ class TePose(nn.Module):
             raise NotImplementedError("tepose_b200.TePose implements the inference path; call .eval() first "
                                       "(train-mode dropout / backward are not implemented yet)")
         batch_size = input.shape[0]
+        nv.mark("start")
         feature = self.encoder(input, is_train=is_train)
         feature = feature.reshape(-1, feature.size(-1))
         smpl_output = self.regressor(feature, is_train=is_train, J_regressor=J_regressor)

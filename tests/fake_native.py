@@ -136,7 +136,10 @@ class FakeLib:
         return 0
 
     # ---- regressor
-    def tp_encoder_heads(self, w_fwd, b_fwd, w_rec, b_rec, h_fwd, ld_hf, h_rec, ld_hr, B, H, is_train, feat, stream):
+    def tp_encoder_heads_workspace_bytes(self, B):
+        return 256
+
+    def tp_encoder_heads(self, w_fwd, b_fwd, w_rec, b_rec, h_fwd, ld_hf, h_rec, ld_hr, B, H, is_train, feat, ws, ws_bytes, stream):
         a = _mat(h_fwd, B, H, ld_hf).clamp_min(0) @ _mat(w_fwd, 2048, H, H).t() + _view(b_fwd, 2048, torch.float32)
         b = _mat(h_rec, B, 2 * H, ld_hr).clamp_min(0) @ _mat(w_rec, 2048, 2 * H, 2 * H).t() + _view(b_rec, 2048, torch.float32)
         if is_train:

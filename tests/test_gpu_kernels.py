@@ -1,0 +1,256 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) against the CPU oracle.
+Tolerances are written next to each check."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import tepose_b200
+import tepose_b200._native as nv
+from oracle import synth, torch_ref
+from tests.helpers import base_data_cwd
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+
+def cu(a, dtype=torch.float32):
+    return torch.as_tensor(np.asarray(a)).to(DEV, dtype).contiguous()
+
+
+# ------------------------------------------------------------------ geometry
+def test_geometry_against_reference_golden():
+    z = np.load(os.path.join(GOLD, "geometry.npz"))
+    R = tepose_b200.rot6d_to_rotmat(cu(z["x6"])).cpu().numpy()
+    # row 3 has a2 parallel to a1: b2 is normalised rounding noise in the reference itself, so only
+    # its first column is comparable; every other row (incl. the two below-eps rows) must agree.
+    keep = np.array([i for i in range(len(R)) if i != 3])
+    np.testing.assert_allclose(R[keep], z["rot6d"][keep], atol=2e-6)
+    np.testing.assert_allclose(R[3][:, 0], z["rot6d"][3][:, 0], atol=2e-6)
+    aa = tepose_b200.rotation_matrix_to_angle_axis(cu(z["R"])).cpu()
+    ref = torch.from_numpy(z["r2aa"])
+    # compare as rotations (axis-angle is ill-conditioned near pi), and directly away from pi
+    Ra = torch_ref.batch_rodrigues_smplx(aa)
+    Rb = torch_ref.batch_rodrigues_smplx(ref)
+    assert float((Ra - Rb).abs().max()) < 5e-5
+    small = ref.norm(dim=1) < 3.0
+    assert float((aa[small] - ref[small]).abs().max()) < 2e-5
+    q = tepose_b200.batch_rodrigues(cu(z["aa"])).cpu().numpy().reshape(-1, 3, 3)
+    np.testing.assert_allclose(q, z["rod_q"], atol=2e-6)
+    s = tepose_b200.batch_rodrigues(cu(z["aa"]), form="smplx").cpu()
+    assert float((s - torch_ref.batch_rodrigues_smplx(torch.from_numpy(z["aa"]))).abs().max()) < 2e-6
+    kp = tepose_b200.projection(cu(z["joints"]), cu(z["cam"])).cpu().numpy()
+    np.testing.assert_allclose(kp, z["proj"], rtol=2e-6, atol=2e-4)
+
+
+def test_geometry_empty_input():
+    out = tepose_b200.rot6d_to_rotmat(torch.empty(0, 6, device=DEV))
+    assert out.shape == (0, 3, 3)
+
+
+# ------------------------------------------------------------------ GEMMs
+@pytest.mark.parametrize("M,N,K", [(1, 64, 64), (32, 2048, 2048), (32, 160, 1024), (64, 1024, 160),
+                                   (70, 100, 36), (512, 384, 2176), (130, 72, 8)])
+def test_gemm_f32(M, N, K):
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    Cin = torch.randn(M, N, generator=g)
+    ref = 0.5 * (A.clamp_min(0).double() @ W.double().t() + b.double()) + 2.0 * Cin.double()
+    a, w, bb, cin = cu(A), cu(W), cu(b), cu(Cin)
+    out = torch.empty(M, N, device=DEV)
+    nv.check(nv.lib().tp_gemm_f32(nv.ptr(a), K, nv.ptr(w), K, nv.ptr(bb), nv.ptr(cin), N, nv.ptr(out), N,
+                                  M, N, K, 0.5, 2.0, 1, nv.stream()))
+    err = float((out.cpu().double() - ref).abs().max())
+    assert err < 2e-5, err                       # fp32 accumulate over K <= 2176 terms of O(1/sqrt(K))
+    # in-place accumulate (Cin aliases C), no bias, no relu
+    out2 = cin.clone()
+    nv.check(nv.lib().tp_gemm_f32(nv.ptr(a), K, nv.ptr(w), K, nv.vp(0), nv.ptr(out2), N, nv.ptr(out2), N,
+                                  M, N, K, 1.0, 1.0, 0, nv.stream()))
+    ref2 = A.double() @ W.double().t() + Cin.double()
+    assert float((out2.cpu().double() - ref2).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(32, 2048, 4096, 8), (64, 1024, 1024, 4), (32, 160, 1024, 16), (5, 96, 160, 3)])
+def test_gemm_f32_splitk(M, N, K, splits):
+    g = torch.Generator().manual_seed(M + N + K)
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    b, Cin = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    a, w, bb, c = cu(A), cu(W), cu(b), cu(Cin)
+    L = nv.lib()
+    ws = torch.zeros(L.tp_gemm_f32_splitk_workspace_bytes(M, N, splits), dtype=torch.uint8, device=DEV)
+    ref = 0.5 * (A.clamp_min(0).double() @ W.double().t() + b.double()) + Cin.double()
+    outs = []
+    for _ in range(3):   # tickets must reset themselves; result must be bitwise reproducible
+        out = c.clone()
+        nv.check(L.tp_gemm_f32_splitk(nv.ptr(a), K, nv.ptr(w), K, nv.ptr(bb), nv.ptr(out), N, nv.ptr(out), N, M, N, K,
+                                      0.5, 1.0, 1, splits, nv.ptr(ws), ws.numel(), nv.stream()))
+        outs.append(out.cpu())
+    assert float((outs[0].double() - ref).abs().max()) < 2e-5
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    assert int(ws[:4096].view(torch.int32).abs().sum()) == 0
+
+
+def test_pack_rows():
+    x = torch.randn(3, 5, 2133)
+    xs = cu(x)
+    for prec, dt in ((nv.PRECISION_FP32, torch.float32), (nv.PRECISION_BF16, torch.bfloat16)):
+        dst = torch.full((15, 2176), 7.0, device=DEV, dtype=dt)
+        nv.check(nv.lib().tp_pack_rows(nv.ptr(xs), xs.stride(0), xs.stride(1), 3, 5, 2133, nv.ptr(dst), 2176, prec, 0,
+                                       nv.stream()))
+        ref = torch.zeros(15, 2176)
+        ref[:, :2133] = x.permute(1, 0, 2).reshape(15, 2133)
+        assert torch.equal(dst.cpu(), ref.to(dt))          # bit-exact: a copy + RN conversion
+
+
+@pytest.mark.parametrize("rows,wrows,kp", [(8, 192, 128), (512, 768, 2176), (130, 384, 64), (32, 96, 192)])
+def test_gemm_bf16_tcgen05(rows, wrows, kp):
+    g = torch.Generator().manual_seed(rows + wrows)
+    A = torch.randn(rows, kp, generator=g).to(torch.bfloat16)
+    W = (torch.randn(wrows, kp, generator=g) / kp ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(wrows, generator=g)
+    a, w, b = A.to(DEV), W.to(DEV), cu(bias)
+    third = wrows // 3
+    m_tail = max(1, rows // 4)
+    segs = [(0, rows, 0, 2 * third), (rows - m_tail, m_tail, 2 * third, third)]
+    outs = [torch.full((mr, nc), float("nan"), device=DEV) for (_, mr, _, nc) in segs]
+    arr = (nv.GemmSeg * 2)()
+    for i, ((m0, mr, n0, nc), o) in enumerate(zip(segs, outs)):
+        arr[i] = nv.GemmSeg(m0, mr, n0, nc, nv.ptr(o), nc, nv.vp(b.data_ptr() + 4 * n0))
+    nv.check(nv.lib().tp_gemm_bf16_tc(nv.ptr(a), rows, nv.ptr(w), wrows, kp, arr, 2, nv.stream()))
+    torch.cuda.synchronize()
+    full = A.double() @ W.double().t() + bias.double()
+    for (m0, mr, n0, nc), o in zip(segs, outs):
+        ref = full[m0:m0 + mr, n0:n0 + nc]
+        err = float((o.cpu().double() - ref).abs().max())
+        assert err < 1e-4, (err, (m0, mr, n0, nc))       # exact bf16 products, fp32 accumulation order only
+
+
+# ------------------------------------------------------------------ GRU recurrence
+def _gru_case(B, T, H, precision, seed, with_h0=False, reverse=False):
+    g = torch.Generator().manual_seed(seed)
+    k = 1.0 / H ** 0.5
+    u = lambda *s: (torch.rand(*s, generator=g) * 2 - 1) * k
+    w_hh, b_hh = u(3 * H, H), u(3 * H)
+    gi = torch.randn(T, B, 3 * H, generator=g) * 0.5
+    h0 = torch.randn(B, H, generator=g) * 0.3 if with_h0 else None
+    wdt = torch.bfloat16 if precision == "bf16" else torch.float32
+    # oracle: the GRU cell in float64 (torch.nn.GRU semantics)
+    Wd = w_hh.to(wdt).double()
+    h = torch.zeros(B, H, dtype=torch.float64) if h0 is None else h0.double()
+    ys = torch.zeros(T, B, H, dtype=torch.float64)
+    for s in range(T):
+        t = T - 1 - s if reverse else s
+        hm = h.float().to(wdt).double() if precision == "bf16" else h
+        gh = hm @ Wd.t() + b_hh.double()
+        gx = gi[t].double()
+        r = torch.sigmoid(gx[:, :H] + gh[:, :H])
+        z = torch.sigmoid(gx[:, H:2 * H] + gh[:, H:2 * H])
+        n = torch.tanh(gx[:, 2 * H:] + r * gh[:, 2 * H:])
+        h = (1 - z) * n + z * h
+        ys[t] = h
+    return gi, w_hh.to(wdt), b_hh, h0, ys, h
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,T,H", [(2, 4, 64), (32, 16, 256), (5, 3, 96), (1, 6, 1024), (40, 2, 128)])
+def test_gru_recurrence(B, T, H, precision):
+    L = nv.lib()
+    cases = [_gru_case(B, T, H, precision, 1, False, False), _gru_case(B, T, H, precision, 2, True, True),
+             _gru_case(B, 1, H, precision, 3, False, False)]
+    keep, jobs, outs = [], [], []
+    for i, (gi, w, b, h0, ys, hT) in enumerate(cases):
+        Tj = gi.shape[0]
+        rev = i == 1
+        d = dict(gi=gi.to(DEV), w=w.to(DEV).contiguous(), b=cu(b), h0=None if h0 is None else cu(h0),
+                 y=torch.zeros(Tj, B, H + 8, device=DEV), ylp=torch.zeros(Tj, B, H, device=DEV, dtype=torch.bfloat16),
+                 hf=torch.zeros(B, 2 * H, device=DEV))
+        keep.append(d)
+        j = nv.GruJob()
+        j.gi, j.ldg, j.w_hh, j.b_hh = d["gi"].data_ptr(), 3 * H, d["w"].data_ptr(), d["b"].data_ptr()
+        j.h0 = 0 if d["h0"] is None else d["h0"].data_ptr()
+        j.y, j.ldy, j.y_lp, j.ldy_lp = d["y"].data_ptr(), H + 8, d["ylp"].data_ptr(), H
+        j.h_final, j.ld_hf = d["hf"].data_ptr() + 4 * H, 2 * H
+        j.steps = Tj
+        j.t_in0, j.t_in_step = (Tj - 1, -1) if rev else (0, 1)
+        j.t_out0, j.t_out_step = (Tj - 1, -1) if rev else (0, 1)
+        jobs.append(j)
+        outs.append((ys, hT))
+    arr = (nv.GruJob * 3)(*jobs)
+    ws = nv.workspace(L.tp_gru_workspace_bytes(3, B, H), DEV)
+    nv.check(L.tp_gru_recurrence(arr, 3, B, H, nv.PRECISIONS[precision], nv.ptr(ws), ws.numel(), nv.stream()))
+    torch.cuda.synchronize()
+    tol = 2e-5 if precision == "fp32" else 2e-4   # bf16: h is re-quantised each step in both; fp32 accumulation order differs
+    for d, (ys, hT) in zip(keep, outs):
+        y = d["y"][:, :, :H].cpu().double()
+        assert float((y - ys).abs().max()) < tol
+        assert float((d["hf"][:, H:].cpu().double() - hT).abs().max()) < tol
+        assert float(d["hf"][:, :H].abs().max()) == 0.0          # neighbouring columns untouched
+        assert float((d["ylp"].float().cpu().double() - ys).abs().max()) < 1e-2
+
+
+def test_gru_recurrence_full_size_fp32_vs_torch_gru():
+    """B=32, T=16, H=2048 (BASELINE config 2 shape) against torch.nn.GRU on CPU."""
+    B, T, H, F = 32, 16, 2048, 64
+    torch.manual_seed(0)
+    gru = torch.nn.GRU(F, H)
+    x = torch.randn(T, B, F)
+    with torch.no_grad():
+        y_ref, _ = gru(x)
+        gi = x @ gru.weight_ih_l0.t() + gru.bias_ih_l0
+    L = nv.lib()
+    for precision, tol in (("fp32", 3e-5), ("bf16", 3e-3)):
+        wdt = torch.bfloat16 if precision == "bf16" else torch.float32
+        d = dict(gi=gi.to(DEV).contiguous(), w=gru.weight_hh_l0.detach().to(DEV, wdt).contiguous(),
+                 b=gru.bias_hh_l0.detach().to(DEV), y=torch.zeros(T, B, H, device=DEV))
+        j = nv.GruJob()
+        j.gi, j.ldg, j.w_hh, j.b_hh = d["gi"].data_ptr(), 3 * H, d["w"].data_ptr(), d["b"].data_ptr()
+        j.y, j.ldy, j.steps, j.t_in0, j.t_in_step, j.t_out0, j.t_out_step = d["y"].data_ptr(), H, T, 0, 1, 0, 1
+        arr = (nv.GruJob * 1)(j)
+        ws = nv.workspace(L.tp_gru_workspace_bytes(1, B, H), DEV)
+        nv.check(L.tp_gru_recurrence(arr, 1, B, H, nv.PRECISIONS[precision], nv.ptr(ws), ws.numel(), nv.stream()))
+        torch.cuda.synchronize()
+        err = float((d["y"].cpu() - y_ref).abs().max())
+        assert err < tol, (precision, err)
+
+
+# ------------------------------------------------------------------ SMPL
+@pytest.mark.parametrize("n", [1, 5, 32, 100])
+def test_smpl_forward_all_pose_kinds(n):
+    with base_data_cwd(7):
+        smpl = tepose_b200.SMPL(tepose_b200.SMPL_MODEL_DIR, batch_size=1, create_transl=False).to(DEV)
+    m = torch_ref.SmplModel.synthetic(7)
+    bodies = synth.make_bodies(7, n)
+    aa, betas = torch.from_numpy(bodies["pose_aa"]), torch.from_numpy(bodies["betas"])
+    v_ref, j_ref, R = torch_ref.smpl_forward(m, betas, pose_aa=aa)
+    out = smpl(betas=cu(betas), body_pose=cu(aa[:, 3:]), global_orient=cu(aa[:, :3]), pose2rot=True)
+    # north_star: max vertex / joint abs error <= 1e-4 m in fp32 (we hold 2e-5)
+    assert float((out.vertices.cpu() - v_ref).abs().max()) < 2e-5
+    assert float((out.joints.cpu() - j_ref).abs().max()) < 2e-5
+    out = smpl(betas=cu(betas), body_pose=cu(R[:, 1:]), global_orient=cu(R[:, :1]), pose2rot=False)
+    assert float((out.vertices.cpu() - v_ref).abs().max()) < 2e-5
+    assert float((out.joints.cpu() - j_ref).abs().max()) < 2e-5
+
+
+def test_smpl_size_independent_properties_large_batch():
+    """4096 bodies (oracle too slow): identity pose => verts == v_shaped; a global rotation is
+    rigid about the root joint."""
+    n = 4096
+    with base_data_cwd(8):
+        smpl = tepose_b200.SMPL(tepose_b200.SMPL_MODEL_DIR, batch_size=1, create_transl=False).to(DEV)
+    m = torch_ref.SmplModel.synthetic(8)
+    betas = cu(synth.make_bodies(8, n)["betas"])
+    zero = torch.zeros(n, 72, device=DEV)
+    out0 = smpl(betas=betas, body_pose=zero[:, 3:], global_orient=zero[:, :3], pose2rot=True)
+    v_shaped = m.v_template.to(DEV)[None] + torch.einsum("bl,mkl->bmk", betas, m.shapedirs.to(DEV))
+    assert float((out0.vertices - v_shaped).abs().max()) < 1e-5
+    rot = zero.clone()
+    rot[:, :3] = torch.tensor([0.3, -0.5, 0.2], device=DEV)
+    out1 = smpl(betas=betas, body_pose=rot[:, 3:], global_orient=rot[:, :3], pose2rot=True)
+    Rg = torch_ref.batch_rodrigues_smplx(torch.tensor([[0.3, -0.5, 0.2]]))[0].to(DEV)
+    root = torch.einsum("bik,i->bk", v_shaped, m.J_regressor[0].to(DEV))[:, None]
+    assert float((out1.vertices - ((out0.vertices - root) @ Rg.t() + root)).abs().max()) < 1e-5
