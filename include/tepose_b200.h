@@ -99,6 +99,19 @@ TP_API int tp_gemm_f32_splitk(const float* A, int64_t lda, const float* W, int64
                        int M, int N, int K, float alpha, float beta, int relu_a, int splits,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- skinny (M <= 64) tensor-core GEMM with fragment-packed bf16 weights (nn.Linear at batch 32/64)
+ * tp_pack_mma_a_bf16: W [rows, cols] fp32 (row stride ld) -> tp_pack_mma_a_bytes(rows, cols) bytes at
+ * dst in mma.sync A-fragment order (done once per weight update).
+ * tp_skinny_bf16: C[M,N] = alpha*(act(A)[M,K] . W^T + bias) + beta*Cin, A fp32 (rounded to bf16 on
+ * the fly), fp32 accumulate.  splits > 1 splits K over CTAs; workspace as for tp_gemm_f32_splitk
+ * (tp_skinny_bf16_workspace_bytes, first 4096 bytes zero).  K % 4 == 0, lda % 4 == 0.            */
+TP_API size_t tp_pack_mma_a_bytes(int rows, int cols);
+TP_API int tp_pack_mma_a_bf16(const float* w, int64_t ld, int rows, int cols, void* dst, void* stream);
+TP_API size_t tp_skinny_bf16_workspace_bytes(int M, int N, int splits);
+TP_API int tp_skinny_bf16(const float* A, int64_t lda, int M, int K, const void* Wp, int N, const float* bias,
+                   const float* Cin, int64_t ldcin, float* C, int64_t ldc, float alpha, float beta,
+                   int relu_a, int splits, void* workspace, size_t workspace_bytes, void* stream);
+
 /* One segment of a tensor-core GEMM launch: rows [m_start, m_start+m_rows) of A against rows
  * [n_start, n_start+n_cols) of W;  out[(m-m_start)*ldc + (n-n_start)] = dot + bias[n-n_start]. */
 typedef struct tp_gemm_seg {
@@ -122,7 +135,7 @@ TP_API int tp_gemm_bf16_tc(const void* A, int a_rows, const void* W, int w_rows,
 typedef struct tp_gru_job {
   const float* gi;   /* [T, B, ldg] fp32, columns ordered r|z|n (3H wide)                  */
   int64_t ldg;
-  const void* w_hh;  /* fp32: [3H,H] row-major.  bf16: [3H,H] row-major bf16               */
+  const void* w_hh;  /* fp32: [3H,H] row-major.  bf16: fragment-packed by tp_pack_whh_bf16      */
   const float* b_hh; /* [3H]                                                                */
   const float* h0;   /* [B,H] (ld = H) initial state, or NULL for zeros                     */
   float* y;          /* optional [T,B,ldy] fp32 sequence output, or NULL                    */
@@ -136,6 +149,12 @@ typedef struct tp_gru_job {
   int32_t t_out0, t_out_step;
 } tp_gru_job;
 
+/* Packs weight_hh [3H,H] fp32 into the bf16 tensor-core fragment order the bf16 recurrence
+ * streams (3*H*H bf16 = 6*H*H bytes at dst, 16-byte aligned).  Done once per weight update.  */
+TP_API int tp_pack_whh_bf16(const float* w_hh, void* dst, int H, void* stream);
+/* debug hook: when non-NULL, the bf16 recurrence kernel writes SM-clock stamps
+ * [grid][max_steps][8] (int64) into this device buffer; NULL (default) disables it. */
+TP_API void tp_gru_set_trace(void* device_buffer);
 /* bytes of scratch tp_gru_recurrence needs for (njobs, B, H) */
 TP_API size_t tp_gru_workspace_bytes(int njobs, int B, int H);
 /* Runs up to 4 independent jobs (directions) concurrently in ONE persistent cooperative
@@ -149,22 +168,23 @@ TP_API int tp_gru_recurrence(const tp_gru_job* jobs, int njobs, int B, int H, in
  *   is_train = 0: feat [B,2048]   = (linear_fwd(relu(h_fwd)) + linear_rec(relu(h_rec))) / 2
  *   is_train = 1: feat [B,2,2048] = stack(linear_fwd(..), linear_rec(..))
  * h_fwd [B, ld_hf] is y[-1] of gru_fwd (H wide), h_rec [B, ld_hr] is y_rec[0] (2H wide).
- * w_fwd [2048,H], w_rec [2048,2H] row-major fp32 (nn.Linear layout).                     */
+ * precision fp32: w_fwd [2048,H], w_rec [2048,2H] row-major fp32 (nn.Linear layout);
+ * precision bf16: the tp_pack_mma_a_bf16 copies of the same matrices.                     */
 TP_API size_t tp_encoder_heads_workspace_bytes(int B);
-TP_API int tp_encoder_heads(const float* w_fwd, const float* b_fwd, const float* w_rec, const float* b_rec,
+TP_API int tp_encoder_heads(int precision, const void* w_fwd, const float* b_fwd, const void* w_rec, const float* b_rec,
                      const float* h_fwd, int64_t ld_hf, const float* h_rec, int64_t ld_hr,
                      int B, int H, int is_train, float* feat, void* workspace, size_t workspace_bytes, void* stream);
 
 /* 3-iteration IEF loop (lib/models/spin.py:250-261).  fc1 is split into its feature columns
  * (w1x, iteration-invariant) and its [pose|shape|cam] columns (w1p, zero-padded 157 -> 160);
  * decpose/decshape/deccam are stacked into one [160,1024] matrix.                         */
-typedef struct tp_ief_weights {
-  const float* w1x;  /* [1024, 2048] fc1.weight[:, :2048] */
+typedef struct tp_ief_weights { /* matrices: fp32 row-major, or tp_pack_mma_a_bf16 copies (bf16) */
+  const void* w1x;   /* [1024, 2048] fc1.weight[:, :2048] */
   const float* b1;   /* [1024] */
-  const float* w1p;  /* [1024, 160]  fc1.weight[:, 2048:2205] zero-padded */
-  const float* w2;   /* [1024, 1024] */
+  const void* w1p;   /* [1024, 160]  fc1.weight[:, 2048:2205] zero-padded */
+  const void* w2;    /* [1024, 1024] */
   const float* b2;   /* [1024] */
-  const float* wdec; /* [160, 1024]  rows: decpose(144) | decshape(10) | deccam(3) | 0(3) */
+  const void* wdec;  /* [160, 1024]  rows: decpose(144) | decshape(10) | deccam(3) | 0(3) */
   const float* bdec; /* [160] */
 } tp_ief_weights;
 
@@ -172,8 +192,8 @@ TP_API size_t tp_ief_workspace_bytes(int n_rows);
 /* feat [n_rows,2048]; init [init_rows,160] = pose6d(144)|shape(10)|cam(3)|0(3) with
  * init_rows == 1 (broadcast, the init_* buffers) or n_rows; psc [n_rows,160] receives the
  * refined pose6d | shape | cam | pad.                                                      */
-TP_API int tp_ief_forward(const tp_ief_weights* w, const float* feat, int n_rows, const float* init, int init_rows,
-                   int n_iter, float* psc, void* workspace, size_t workspace_bytes, void* stream);
+TP_API int tp_ief_forward(int precision, const tp_ief_weights* w, const float* feat, int n_rows, const float* init,
+                   int init_rows, int n_iter, float* psc, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ SMPL forward (K4 + K5)
  * Packed, device-resident body-model constants (built once by the host, see

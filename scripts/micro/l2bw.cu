@@ -1,0 +1,77 @@
+// Microbenchmark: L2 -> SM streaming bandwidth for a 50 MB L2-resident buffer, (a) LDG.128 with
+// N loads in flight per thread, (b) cp.async.bulk (TMA 1D) chunks through a shared-memory ring.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <vector>
+#define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("err %s line %d\n",cudaGetErrorString(e),__LINE__); return 1;} }while(0)
+
+template<int INFLIGHT>
+__global__ void __launch_bounds__(256) k_ldg(const uint4* __restrict__ src, size_t n16_per_cta, unsigned* sink) {
+  const uint4* p = src + (size_t)blockIdx.x * n16_per_cta;
+  unsigned acc = 0;
+  for (size_t i = threadIdx.x; i < n16_per_cta; i += 256 * INFLIGHT) {
+    uint4 v[INFLIGHT];
+#pragma unroll
+    for (int q = 0; q < INFLIGHT; ++q) {
+      size_t idx = i + (size_t)q * 256;
+      if (idx < n16_per_cta) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[q].x),"=r"(v[q].y),"=r"(v[q].z),"=r"(v[q].w) : "l"(p+idx));
+      else v[q] = make_uint4(0,0,0,0);
+    }
+#pragma unroll
+    for (int q = 0; q < INFLIGHT; ++q) acc ^= v[q].x ^ v[q].y ^ v[q].z ^ v[q].w;
+  }
+  if (acc == 0x12345678u) sink[0] = acc;
+}
+
+__device__ __forceinline__ uint32_t s32(const void* p){ return (uint32_t)__cvta_generic_to_shared(p); }
+template<int CHUNK, int STAGES>
+__global__ void __launch_bounds__(256) k_bulk(const unsigned char* __restrict__ src, size_t bytes_per_cta, unsigned* sink) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  __shared__ uint64_t full[STAGES];
+  const unsigned char* p = src + (size_t)blockIdx.x * bytes_per_cta;
+  const int nchunks = (int)(bytes_per_cta / CHUNK);
+  if (threadIdx.x == 0) { for (int s=0;s<STAGES;++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;"::"r"(s32(&full[s]))); asm volatile("fence.mbarrier_init.release.cluster;"); }
+  __syncthreads();
+  unsigned acc = 0;
+  if (threadIdx.x == 0) for (int c = 0; c < STAGES && c < nchunks; ++c) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"::"r"(s32(&full[c])),"r"(CHUNK):"memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"::"r"(s32(sm + (size_t)c*CHUNK)),"l"(p + (size_t)c*CHUNK),"r"(CHUNK),"r"(s32(&full[c])):"memory");
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    int st = c % STAGES; unsigned ph = (c / STAGES) & 1, done = 0;
+    do { asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0,1,0,p; }":"=r"(done):"r"(s32(&full[st])),"r"(ph):"memory"); } while(!done);
+    // consume: each thread reads one uint4 per 4 KB (token work, like fragment reads)
+    const uint4* q = reinterpret_cast<const uint4*>(sm + (size_t)st*CHUNK);
+    for (int i = threadIdx.x; i < CHUNK/16; i += 256) { uint4 v = q[i]; acc ^= v.x ^ v.w; }
+    __syncthreads();
+    if (threadIdx.x == 0 && c + STAGES < nchunks) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"::"r"(s32(&full[st])),"r"(CHUNK):"memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"::"r"(s32(sm + (size_t)st*CHUNK)),"l"(p + (size_t)(c+STAGES)*CHUNK),"r"(CHUNK),"r"(s32(&full[st])):"memory");
+    }
+  }
+  if (acc == 0x12345678u) sink[0] = acc;
+}
+
+int main() {
+  const int ctas = 128;
+  const size_t per = 384 * 1024;                 // 384 KB per CTA  (~ the W_hh slice)
+  const size_t total = per * ctas;               // 48 MB
+  unsigned char* buf; unsigned* sink;
+  CK(cudaMalloc(&buf, total)); CK(cudaMalloc(&sink, 4)); CK(cudaMemset(buf, 1, total));
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  auto report = [&](const char* name, float ms, int iters) { printf("%-28s %8.2f us/pass  %7.1f GB/s\n", name, 1e3*ms/iters, total/(ms/iters*1e-3)/1e9); };
+  const int iters = 30;
+#define RUN_LDG(N) { for(int w=0;w<3;++w) k_ldg<N><<<ctas,256>>>((const uint4*)buf, per/16, sink); cudaEventRecord(e0); for(int i=0;i<iters;++i) k_ldg<N><<<ctas,256>>>((const uint4*)buf, per/16, sink); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); float ms; cudaEventElapsedTime(&ms,e0,e1); report("ldg.128 inflight=" #N, ms, iters);}  
+  RUN_LDG(4) RUN_LDG(8) RUN_LDG(16) RUN_LDG(24) RUN_LDG(32)
+#define RUN_BULK(C,S) { size_t smem=(size_t)C*S; CK(cudaFuncSetAttribute(k_bulk<C,S>, cudaFuncAttributeMaxDynamicSharedMemorySize,(int)smem)); for(int w=0;w<3;++w) k_bulk<C,S><<<ctas,256,smem>>>(buf, per, sink); cudaEventRecord(e0); for(int i=0;i<iters;++i) k_bulk<C,S><<<ctas,256,smem>>>(buf, per, sink); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); float ms; cudaEventElapsedTime(&ms,e0,e1); report("bulk chunk=" #C " stages=" #S, ms, iters);} 
+  RUN_BULK(8192,4) RUN_BULK(16384,4) RUN_BULK(16384,8) RUN_BULK(32768,4) RUN_BULK(32768,6)
+  // all CTAs read the SAME 128 KB (the h broadcast pattern)
+  { const size_t hb = 128*1024; for(int w=0;w<3;++w) k_ldg<16><<<ctas,256>>>((const uint4*)buf, 0, sink);
+    auto k = k_bulk<16384,8>; size_t smem=16384*8; 
+    // same-source variant: bytes_per_cta=hb but stride 0 -> emulate by launching with src offset trick: use a tiny wrapper
+  }
+  CK(cudaDeviceSynchronize());
+  printf("done\n");
+  return 0;
+}

@@ -23,8 +23,9 @@ PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16}
 EXPORTS = [
     "tp_version", "tp_last_error", "tp_launch_count", "tp_device_info",
     "tp_rot6d_to_rotmat", "tp_rotmat_to_angle_axis", "tp_batch_rodrigues", "tp_projection",
-    "tp_pack_rows", "tp_gemm_f32", "tp_gemm_f32_splitk_workspace_bytes", "tp_gemm_f32_splitk", "tp_gemm_bf16_tc",
-    "tp_gru_workspace_bytes", "tp_gru_recurrence",
+    "tp_pack_rows", "tp_gemm_f32", "tp_gemm_f32_splitk_workspace_bytes", "tp_gemm_f32_splitk",
+    "tp_pack_mma_a_bytes", "tp_pack_mma_a_bf16", "tp_skinny_bf16_workspace_bytes", "tp_skinny_bf16", "tp_gemm_bf16_tc",
+    "tp_pack_whh_bf16", "tp_gru_set_trace", "tp_gru_workspace_bytes", "tp_gru_recurrence",
     "tp_encoder_heads_workspace_bytes", "tp_encoder_heads", "tp_ief_workspace_bytes", "tp_ief_forward",
     "tp_smpl_workspace_bytes", "tp_smpl_forward",
 ]
@@ -67,13 +68,20 @@ _SIGNATURES = {
     "tp_gemm_f32_splitk_workspace_bytes": (sz, [C.c_int, C.c_int, C.c_int]),
     "tp_gemm_f32_splitk": (C.c_int, [vp, i64, vp, i64, vp, vp, i64, vp, i64, C.c_int, C.c_int, C.c_int, f32, f32, C.c_int,
                                      C.c_int, vp, sz, vp]),
+    "tp_pack_mma_a_bytes": (sz, [C.c_int, C.c_int]),
+    "tp_pack_mma_a_bf16": (C.c_int, [vp, i64, C.c_int, C.c_int, vp, vp]),
+    "tp_skinny_bf16_workspace_bytes": (sz, [C.c_int, C.c_int, C.c_int]),
+    "tp_skinny_bf16": (C.c_int, [vp, i64, C.c_int, C.c_int, vp, C.c_int, vp, vp, i64, vp, i64, f32, f32, C.c_int, C.c_int,
+                                 vp, sz, vp]),
     "tp_gemm_bf16_tc": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.POINTER(GemmSeg), C.c_int, vp]),
+    "tp_pack_whh_bf16": (C.c_int, [vp, vp, C.c_int, vp]),
+    "tp_gru_set_trace": (None, [vp]),
     "tp_gru_workspace_bytes": (sz, [C.c_int, C.c_int, C.c_int]),
     "tp_gru_recurrence": (C.c_int, [C.POINTER(GruJob), C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, vp]),
     "tp_encoder_heads_workspace_bytes": (sz, [C.c_int]),
-    "tp_encoder_heads": (C.c_int, [vp, vp, vp, vp, vp, i64, vp, i64, C.c_int, C.c_int, C.c_int, vp, vp, sz, vp]),
+    "tp_encoder_heads": (C.c_int, [C.c_int, vp, vp, vp, vp, vp, i64, vp, i64, C.c_int, C.c_int, C.c_int, vp, vp, sz, vp]),
     "tp_ief_workspace_bytes": (sz, [C.c_int]),
-    "tp_ief_forward": (C.c_int, [C.POINTER(IefWeights), vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, sz, vp]),
+    "tp_ief_forward": (C.c_int, [C.c_int, C.POINTER(IefWeights), vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, sz, vp]),
     "tp_smpl_workspace_bytes": (sz, [C.POINTER(SmplModel), C.c_int, C.c_int]),
     "tp_smpl_forward": (C.c_int, [C.POINTER(SmplModel), C.c_int, vp, i64, C.c_int, vp, i64, vp, i64,
                                   vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, sz, vp]),
@@ -151,3 +159,15 @@ def mark(name: str) -> None:
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()
         _marks.append((name, ev))
+
+
+def pack_linear(w: torch.Tensor, precision: str) -> torch.Tensor:
+    """nn.Linear weight [N,K] -> the operand layout the K3 kernels stream for `precision`:
+    fp32: contiguous fp32 as is; bf16: tensor-core fragment order (tp_pack_mma_a_bf16)."""
+    w = w.detach().float().contiguous()
+    if precision != "bf16":
+        return w
+    n, k = w.shape
+    out = torch.empty(lib().tp_pack_mma_a_bytes(n, k), dtype=torch.uint8, device=w.device)
+    check(lib().tp_pack_mma_a_bf16(ptr(w), k, n, k, ptr(out), stream()), "tp_pack_mma_a_bf16")
+    return out

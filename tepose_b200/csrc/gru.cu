@@ -27,7 +27,13 @@ struct GruParams {
   float* hbuf;              // [njobs][2][B][H]  fp32 state ping-pong
   __nv_bfloat16* hbuf_lp;   // [njobs][2][B][H]  bf16 copy (MMA operand of the next step)
   unsigned int* barrier;    // monotonic grid-barrier counter (zeroed by the host before launch)
+  long long* trace;         // debug: [gridDim][max_steps][8] SM-clock stamps (tp_gru_set_trace), or null
 };
+
+#define TP_TRACE(slot)                                                                       \
+  do {                                                                                       \
+    if (p.trace && threadIdx.x == 0) p.trace[((size_t)blockIdx.x * p.max_steps + s) * 8 + (slot)] = clock64(); \
+  } while (0)
 
 // Grid barrier for a co-resident (cooperatively launched) grid: one arrival per CTA on a
 // monotonic counter, release/acquire at gpu scope.  State that crosses the barrier is read with
@@ -36,6 +42,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned int seen;
+    __threadfence();   // cumulative: orders the whole CTA's prior writes (observed via bar.sync) before the arrival
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(counter) : "memory");
@@ -141,7 +148,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_f32(const GruParams p) {
   const int H = p.H, B = p.B;
   unsigned int epoch = 0;
 
-  if (p.any_h0) { seed_h0(p); __threadfence(); grid_barrier(p.barrier, ++epoch * gridDim.x); }
+  if (p.any_h0) { seed_h0(p); grid_barrier(p.barrier, ++epoch * gridDim.x); }
 
   for (int s = 0; s < p.max_steps; ++s) {
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_f32(const GruParams p) {
         }
       }
     }
-    if (s + 1 < p.max_steps) { __threadfence(); grid_barrier(p.barrier, ++epoch * gridDim.x); }
+    if (s + 1 < p.max_steps) grid_barrier(p.barrier, ++epoch * gridDim.x);
   }
 }
 
@@ -241,23 +248,25 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
   const int blk_lo = (kg * nblk) / KG, blk_hi = ((kg + 1) * nblk) / KG;
   unsigned int epoch = 0;
 
-  if (p.any_h0) { seed_h0(p); __threadfence(); grid_barrier(p.barrier, ++epoch * gridDim.x); }
+  if (p.any_h0) { seed_h0(p); grid_barrier(p.barrier, ++epoch * gridDim.x); }
 
   // W_hh ring: buf[q][i] holds rows (g, g+8) of gate i for block (blk_lo + q mod PF)
-  uint4 w_lo[PF][3], w_hi[PF][3];
-  auto w_rows = [&](int j, int u0, const __nv_bfloat16* (&wrow)[3]) {
-    const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(p.jobs[j].w_hh);
+  // fragment-packed W_hh (tp_pack_whh_bf16): w_a[q][i] / w_b[q][i] are the two k-subtiles of block q, gate i
+  uint4 w_a[PF][3], w_b[PF][3];
+  auto w_rows = [&](int j, int u0, const uint4* (&wrow)[3]) {
+    const uint4* W = reinterpret_cast<const uint4*>(p.jobs[j].w_hh);
+    const int64_t ut = (u0 >> 4) + mg;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) wrow[i] = W + ((int64_t)i * H + u0 + mg * 16 + g) * H + 8 * t;
+    for (int i = 0; i < 3; ++i) wrow[i] = W + (((int64_t)i * (H / 16) + ut) * nblk) * 64 + lane;
   };
-  auto w_prologue = [&](const __nv_bfloat16* (&wrow)[3]) {
+  auto w_prologue = [&](const uint4* (&wrow)[3]) {
 #pragma unroll
     for (int q = 0; q < PF; ++q)
       if (blk_lo + q < blk_hi) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          w_lo[q][i] = ldg_stream(wrow[i] + (blk_lo + q) * 32);
-          w_hi[q][i] = ldg_stream(wrow[i] + (int64_t)8 * H + (blk_lo + q) * 32);
+          w_a[q][i] = ldg_stream(wrow[i] + (int64_t)(blk_lo + q) * 64);
+          w_b[q][i] = ldg_stream(wrow[i] + (int64_t)(blk_lo + q) * 64 + 32);
         }
       }
   };
@@ -266,6 +275,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
   bool ring_primed = false;
 
   for (int s = 0; s < p.max_steps; ++s) {
+    TP_TRACE(0);
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       int j, u0;
       locate_item(p, item, j, u0);
@@ -273,16 +283,23 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
       if (s >= jb.steps) continue;
       const bool have_prev = (s > 0) || (jb.h0 != nullptr);
       const __nv_bfloat16* hprev = p.hbuf_lp + ((int64_t)(j * 2 + ((s + 1) & 1)) * B) * H;
-      const __nv_bfloat16* wrow[3];
+      const uint4* wrow[3];
       w_rows(j, u0, wrow);
       for (int b0 = 0; b0 < B; b0 += NB) {
         if (have_prev) {
-          // stage h_prev[b0 : b0+NB, :] (bf16) into shared memory
-          const int chunks = H / 8;
-          for (int c = tid; c < NB * chunks; c += kGruThreads) {
-            int bb = c / chunks, q = c - bb * chunks;
-            bool ok = (b0 + bb) < B;
-            cp_async16_z(hs + (size_t)bb * HP + q * 8, ok ? (hprev + (int64_t)(b0 + bb) * H + q * 8) : hprev, ok);
+          // stage h_prev[b0 : b0+NB, K-slice of this warp group] (bf16): each K group copies and
+          // consumes its own columns, so groups never wait for each other
+          {
+            const int c_lo = blk_lo * 4, c_n = (blk_hi - blk_lo) * 4;      // 16-byte chunks per row
+            const int gt = mg * 32 + lane;                                  // thread index inside the K group
+#pragma unroll 4
+            for (int bb = 0; bb < NB; ++bb) {
+              const bool ok = (b0 + bb) < B;
+              for (int c = gt; c < c_n; c += MG * 32) {
+                const int q = c_lo + c;
+                cp_async16_z(hs + (size_t)bb * HP + q * 8, ok ? (hprev + (int64_t)(b0 + bb) * H + q * 8) : hprev, ok);
+              }
+            }
           }
           cp_commit();
           if (!ring_primed) w_prologue(wrow);
@@ -305,7 +322,9 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
 #pragma unroll
               for (int e = 0; e < 4; ++e) acc[i][n][e] = 0.0f;
           cp_wait<0>();
-          __syncthreads();
+          if (MG == 1) __syncwarp();
+          else asm volatile("bar.sync %0, %1;\n" ::"r"(1 + kg), "r"(MG * 32) : "memory");
+          TP_TRACE(1);
           for (int blk = blk_lo; blk < blk_hi; blk += PF) {
 #pragma unroll
             for (int q = 0; q < PF; ++q) {
@@ -316,20 +335,21 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
                   const uint4 bv = *reinterpret_cast<const uint4*>(hs + (size_t)(n * 8 + g) * HP + cur * 32 + 8 * t);
 #pragma unroll
                   for (int i = 0; i < 3; ++i) {
-                    mma_bf16(acc[i][n], w_lo[q][i].x, w_hi[q][i].x, w_lo[q][i].y, w_hi[q][i].y, bv.x, bv.y);
-                    mma_bf16(acc[i][n], w_lo[q][i].z, w_hi[q][i].z, w_lo[q][i].w, w_hi[q][i].w, bv.z, bv.w);
+                    mma_bf16(acc[i][n], w_a[q][i].x, w_a[q][i].y, w_a[q][i].z, w_a[q][i].w, bv.x, bv.y);
+                    mma_bf16(acc[i][n], w_b[q][i].x, w_b[q][i].y, w_b[q][i].z, w_b[q][i].w, bv.z, bv.w);
                   }
                 }
                 if (cur + PF < blk_hi) {
 #pragma unroll
                   for (int i = 0; i < 3; ++i) {
-                    w_lo[q][i] = ldg_stream(wrow[i] + (cur + PF) * 32);
-                    w_hi[q][i] = ldg_stream(wrow[i] + (int64_t)8 * H + (cur + PF) * 32);
+                    w_a[q][i] = ldg_stream(wrow[i] + (int64_t)(cur + PF) * 64);
+                    w_b[q][i] = ldg_stream(wrow[i] + (int64_t)(cur + PF) * 64 + 32);
                   }
                 }
               }
             }
           }
+          TP_TRACE(2);
           // partial sums -> red[kg][gate][n][unit]
 #pragma unroll
           for (int i = 0; i < 3; ++i)
@@ -342,6 +362,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
               r0[RP + 8] = acc[i][n][3];
             }
           __syncthreads();
+          TP_TRACE(3);
         }
 #pragma unroll
         for (int e = 0; e < GE; ++e) {
@@ -367,14 +388,15 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
         int j, u0;
         locate_item(p, blockIdx.x, j, u0);
         if (s + 1 < p.jobs[j].steps) {      // W_hh does not depend on h: fetch across the barrier
-          const __nv_bfloat16* wrow[3];
+          const uint4* wrow[3];
           w_rows(j, u0, wrow);
           w_prologue(wrow);
           ring_primed = true;
         }
       }
-      __threadfence();
+      TP_TRACE(4);
       grid_barrier(p.barrier, ++epoch * gridDim.x);
+      TP_TRACE(5);
     }
   }
 }
@@ -384,6 +406,16 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 }  // namespace tp
 
 using namespace tp;
+
+extern "C" int tp_pack_whh_bf16(const float* w_hh, void* dst, int H, void* stream) {
+  TP_CHECK_ARG(w_hh && dst && H >= 32 && H % 32 == 0, "tp_pack_whh_bf16: need non-null pointers and H %% 32 == 0 (H=%d)", H);
+  // [3H,H] row-major: the generic fragment packing with 16-row tiles ordered gate-major is exactly
+  // the [gate][unit_tile][k block][q][lane][word] order k_gru_bf16 streams.
+  return tp_pack_mma_a_bf16(w_hh, H, 3 * H, H, dst, stream);
+}
+
+static long long* g_gru_trace = nullptr;
+extern "C" void tp_gru_set_trace(void* device_buffer) { g_gru_trace = reinterpret_cast<long long*>(device_buffer); }
 
 extern "C" size_t tp_gru_workspace_bytes(int njobs, int B, int H) {
   size_t per = (size_t)njobs * 2 * B * H;
@@ -431,6 +463,7 @@ extern "C" int tp_gru_recurrence(const tp_gru_job* jobs, int njobs, int B, int H
   for (int j = njobs; j <= kMaxJobs; ++j) p.item_begin[j] = items;
   p.total_items = items;
   size_t per = (size_t)njobs * 2 * B * H;
+  p.trace = g_gru_trace;
   p.barrier = reinterpret_cast<unsigned int*>(workspace);
   p.hbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 256);
   p.hbuf_lp = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(workspace) + 256 + align_up(per * sizeof(float), 256));

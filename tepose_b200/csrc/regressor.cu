@@ -19,30 +19,42 @@ using namespace tp;
 
 #define TP_TRY(x) do { int _rc = (x); if (_rc != TP_OK) return _rc; } while (0)
 
-// split-K factor for a skinny layer: enough CTAs to cover the machine ~3x, K slices >= 128
-static int pick_splits(int M, int N, int K) {
-  const int bn = 32, tiles = ((N + bn - 1) / bn) * ((M + (M <= 32 ? 31 : 63)) / (M <= 32 ? 32 : 64));
-  int want = (3 * tp::sm_count() + tiles - 1) / tiles;
-  int maxs = K / 128;
-  if (want > maxs) want = maxs;
-  if (want > 16) want = 16;
-  return want < 1 ? 1 : want;
-}
-static const size_t kSplitScratch = 4096 + (size_t)16 * 64 * 2048 * sizeof(float);   // tickets + 16 splits of a [64,2048] layer
+// One nn.Linear at skinny M.  fp32: W is [N,K] row-major fp32 (FFMA, split-K).  bf16: W is the
+// fragment-packed bf16 copy (tp_pack_mma_a_bf16) streamed by the tensor-core skinny kernel.
+static const size_t kSplitScratch = 4096 + ((size_t)8 << 20);
 
-static int skinny(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, const float* Cin,
+static int linear(int precision, const float* A, int64_t lda, const void* W, const float* bias, const float* Cin,
                   int64_t ldcin, float* C, int64_t ldc, int M, int N, int K, float alpha, float beta, int relu_a,
                   void* scratch, void* stream) {
-  return tp_gemm_f32_splitk(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, alpha, beta, relu_a,
-                            pick_splits(M, N, K), scratch, kSplitScratch, stream);
+  const int sms = tp::sm_count();
+  if (precision == TP_PRECISION_BF16 && M <= 64) {
+    const int groups = (N + 127) / 128, kb = (K + 31) / 32;
+    int splits = (sms + groups - 1) / groups;
+    if (splits > kb / 4) splits = kb / 4;
+    if (splits < 1 || !scratch) splits = 1;
+    while (splits > 1 && tp_skinny_bf16_workspace_bytes(M, N, splits) > kSplitScratch) --splits;
+    return tp_skinny_bf16(A, lda, M, K, W, N, bias, Cin, ldcin, C, ldc, alpha, beta, relu_a, splits, scratch,
+                          kSplitScratch, stream);
+  }
+  const int bm = M <= 32 ? 32 : 64;
+  const int tiles = ((N + 31) / 32) * ((M + bm - 1) / bm);
+  int splits = (3 * sms + tiles - 1) / tiles;
+  if (splits > K / 128) splits = K / 128;
+  if (splits > 16) splits = 16;
+  if (splits < 1 || !scratch) splits = 1;
+  while (splits > 1 && tp_gemm_f32_splitk_workspace_bytes(M, N, splits) > kSplitScratch) --splits;
+  return tp_gemm_f32_splitk(A, lda, reinterpret_cast<const float*>(W), K, bias, Cin, ldcin, C, ldc, M, N, K, alpha, beta,
+                            relu_a, splits, scratch, kSplitScratch, stream);
 }
 
 extern "C" size_t tp_encoder_heads_workspace_bytes(int B) { (void)B; return kSplitScratch; }
 
-extern "C" int tp_encoder_heads(const float* w_fwd, const float* b_fwd, const float* w_rec, const float* b_rec,
-                                const float* h_fwd, int64_t ld_hf, const float* h_rec, int64_t ld_hr,
+extern "C" int tp_encoder_heads(int precision, const void* w_fwd, const float* b_fwd, const void* w_rec,
+                                const float* b_rec, const float* h_fwd, int64_t ld_hf, const float* h_rec, int64_t ld_hr,
                                 int B, int H, int is_train, float* feat, void* workspace, size_t workspace_bytes,
                                 void* stream) {
+  TP_CHECK_ARG(precision == TP_PRECISION_FP32 || precision == TP_PRECISION_BF16, "tp_encoder_heads: bad precision");
+  const int P = precision;
   TP_CHECK_ARG(w_fwd && b_fwd && w_rec && b_rec && h_fwd && h_rec && feat, "tp_encoder_heads: null pointer");
   TP_CHECK_ARG(B >= 1 && H >= 4 && H % 4 == 0, "tp_encoder_heads: bad sizes B=%d H=%d", B, H);
   TP_CHECK_ARG(workspace && workspace_bytes >= kSplitScratch && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
@@ -54,12 +66,12 @@ extern "C" int tp_encoder_heads(const float* w_fwd, const float* b_fwd, const fl
   }
   if (!is_train) {
     // (linear_fwd(relu(hF)) + linear_rec(relu(hR))) / 2  -- halving each term first is exact in fp32
-    TP_TRY(skinny(h_fwd, ld_hf, w_fwd, H, b_fwd, nullptr, 0, feat, 2048, B, 2048, H, 0.5f, 0.f, 1, sc, stream));
-    TP_TRY(skinny(h_rec, ld_hr, w_rec, 2 * H, b_rec, feat, 2048, feat, 2048, B, 2048, 2 * H, 0.5f, 1.f, 1, sc, stream));
+    TP_TRY(linear(P, h_fwd, ld_hf, w_fwd, b_fwd, nullptr, 0, feat, 2048, B, 2048, H, 0.5f, 0.f, 1, sc, stream));
+    TP_TRY(linear(P, h_rec, ld_hr, w_rec, b_rec, feat, 2048, feat, 2048, B, 2048, 2 * H, 0.5f, 1.f, 1, sc, stream));
   } else {
     // stacked [B,2,2048]: row b holds the fwd features then the rec features
-    TP_TRY(skinny(h_fwd, ld_hf, w_fwd, H, b_fwd, nullptr, 0, feat, 4096, B, 2048, H, 1.f, 0.f, 1, sc, stream));
-    TP_TRY(skinny(h_rec, ld_hr, w_rec, 2 * H, b_rec, nullptr, 0, feat + 2048, 4096, B, 2048, 2 * H, 1.f, 0.f, 1, sc, stream));
+    TP_TRY(linear(P, h_fwd, ld_hf, w_fwd, b_fwd, nullptr, 0, feat, 4096, B, 2048, H, 1.f, 0.f, 1, sc, stream));
+    TP_TRY(linear(P, h_rec, ld_hr, w_rec, b_rec, nullptr, 0, feat + 2048, 4096, B, 2048, 2 * H, 1.f, 0.f, 1, sc, stream));
   }
   return TP_OK;
 }
@@ -68,8 +80,10 @@ extern "C" size_t tp_ief_workspace_bytes(int n_rows) {
   return 3 * al256((size_t)(n_rows > 0 ? n_rows : 0) * 1024 * sizeof(float)) + kSplitScratch;
 }
 
-extern "C" int tp_ief_forward(const tp_ief_weights* w, const float* feat, int n_rows, const float* init, int init_rows,
-                              int n_iter, float* psc, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int tp_ief_forward(int precision, const tp_ief_weights* w, const float* feat, int n_rows, const float* init,
+                              int init_rows, int n_iter, float* psc, void* workspace, size_t workspace_bytes, void* stream) {
+  TP_CHECK_ARG(precision == TP_PRECISION_FP32 || precision == TP_PRECISION_BF16, "tp_ief_forward: bad precision");
+  const int P = precision;
   TP_CHECK_ARG(w && feat && init && psc, "tp_ief_forward: null pointer");
   TP_CHECK_ARG(n_rows >= 1 && n_iter >= 0, "tp_ief_forward: bad sizes n_rows=%d n_iter=%d", n_rows, n_iter);
   TP_CHECK_ARG(init_rows == 1 || init_rows == n_rows, "tp_ief_forward: init_rows must be 1 or n_rows");
@@ -84,13 +98,13 @@ extern "C" int tp_ief_forward(const tp_ief_weights* w, const float* feat, int n_
   void* sc = reinterpret_cast<unsigned char*>(workspace) + 3 * slab;
   TP_CUDA(cudaMemsetAsync(sc, 0, 4096, (cudaStream_t)stream));
   if (N > 64) sc = nullptr;
-  TP_TRY(skinny(feat, 2048, w->w1x, 2048, w->b1, nullptr, 0, base, 1024, N, 1024, 2048, 1.f, 0.f, 0, sc, stream));
+  TP_TRY(linear(P, feat, 2048, w->w1x, w->b1, nullptr, 0, base, 1024, N, 1024, 2048, 1.f, 0.f, 0, sc, stream));
   k_broadcast_rows<<<(unsigned)ceil_div((int64_t)N * 160, 256), 256, 0, (cudaStream_t)stream>>>(init, psc, N, 160, init_rows);
   TP_LAUNCH_CHECK();
   for (int it = 0; it < n_iter; ++it) {
-    TP_TRY(skinny(psc, 160, w->w1p, 160, nullptr, base, 1024, u1, 1024, N, 1024, 160, 1.f, 1.f, 0, sc, stream));
-    TP_TRY(skinny(u1, 1024, w->w2, 1024, w->b2, nullptr, 0, u2, 1024, N, 1024, 1024, 1.f, 0.f, 0, sc, stream));
-    TP_TRY(skinny(u2, 1024, w->wdec, 1024, w->bdec, psc, 160, psc, 160, N, 160, 1024, 1.f, 1.f, 0, sc, stream));
+    TP_TRY(linear(P, psc, 160, w->w1p, nullptr, base, 1024, u1, 1024, N, 1024, 160, 1.f, 1.f, 0, sc, stream));
+    TP_TRY(linear(P, u1, 1024, w->w2, w->b2, nullptr, 0, u2, 1024, N, 1024, 1024, 1.f, 0.f, 0, sc, stream));
+    TP_TRY(linear(P, u2, 1024, w->wdec, w->bdec, psc, 160, psc, 160, N, 160, 1024, 1.f, 1.f, 0, sc, stream));
   }
   return TP_OK;
 }

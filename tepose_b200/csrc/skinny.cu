@@ -1,0 +1,273 @@
+// Weight-streaming "skinny" GEMM for M <= 64 activation rows (nn.Linear at batch 32/64, the
+// live-stream input projection at batch 1):
+//     C[M,N] = alpha * ( act(A)[M,K] . W[N,K]^T + bias ) + beta * Cin
+// At these sizes the op is bound by streaming W once from HBM, not by math, so:
+//   * W is pre-packed (tp_pack_mma_a_bf16) in mma.sync m16n8k16 A-fragment order: every lane
+//     fetches its 4 fragment registers with ONE 16-byte load, a warp reads 512 contiguous bytes;
+//   * a CTA owns 128 weight rows (8 warps x one 16-row tile) and one K slice (split-K over
+//     blockIdx.y keeps all SMs streaming); each lane keeps up to 16 fragment loads in flight;
+//   * the activation slice is converted to bf16 once per CTA into shared memory (relu fused);
+//   * split-K partials are reduced in split order by the last CTA to arrive (deterministic).
+// Tensor throughput is irrelevant here (M <= 64), which is why this path uses mma.sync rather
+// than tcgen05: no TMEM round trip, accumulators stay in registers for the fused epilogue.
+#include "common.cuh"
+
+namespace tp {
+
+constexpr int kSkThreads = 256;
+constexpr int kSkRows = 128;          // weight rows per CTA
+constexpr int kSkPF = 8;              // 32-column blocks in flight per warp
+constexpr size_t kSkTicketBytes = 4096;
+
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void mma16816(float* c, const uint4& a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+// W [rows, cols] fp32 (row stride ld) -> bf16 fragments  dst[ut = ceil(rows/16)][kb = ceil(cols/32)][q=2][lane=32][word=4].
+// Lane (g = lane/4, t = lane%4), word w = 2*e2 + hi holds
+//   W[ut*16 + hi*8 + g][kb*32 + 8t + 4q + 2*e2 + {0,1}]   (zero beyond rows / cols).
+// The K order inside a 32-column block is permuted so that the matching B fragments of both
+// k-subtiles are one plain 16-byte read of row-major activations at column kb*32 + 8t.
+__global__ void k_pack_mma_a(const float* __restrict__ w, int64_t ld, int rows, int cols, uint32_t* __restrict__ dst) {
+  const int KB = (cols + 31) / 32, UT = (rows + 15) / 16;
+  const int64_t words = (int64_t)UT * KB * 256;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x) {
+    const int wd = (int)(i & 3), lane = (int)((i >> 2) & 31), q = (int)((i >> 7) & 1);
+    const int64_t rest = i >> 8;
+    const int kb = (int)(rest % KB), ut = (int)(rest / KB);
+    const int e2 = wd >> 1, hi = wd & 1, g = lane >> 2, t = lane & 3;
+    const int row = ut * 16 + hi * 8 + g;
+    const int col = kb * 32 + 8 * t + 4 * q + 2 * e2;
+    float v0 = 0.f, v1 = 0.f;
+    if (row < rows) {
+      if (col < cols) v0 = w[(int64_t)row * ld + col];
+      if (col + 1 < cols) v1 = w[(int64_t)row * ld + col + 1];
+    }
+    __nv_bfloat162 v = __floats2bfloat162_rn(v0, v1);
+    dst[i] = *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+
+struct SkArgs {
+  const float* A; int64_t lda; int M, K, N;
+  const uint4* Wp; int ut_total, kb_total, kb_per_split;
+  const float* bias; const float* Cin; int64_t ldcin; float* C; int64_t ldc;
+  float alpha, beta; int relu_a;
+  float* part; unsigned int* tickets;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(kSkThreads, 1) k_skinny_bf16(const SkArgs a) {
+  constexpr int NB = NT * 8;
+  extern __shared__ __align__(16) unsigned char sk_smem[];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int kb_lo = blockIdx.y * a.kb_per_split;
+  const int kb_hi = min(a.kb_total, kb_lo + a.kb_per_split);
+  const int nkb = max(0, kb_hi - kb_lo);
+  const int pitch = ((nkb * 32 + 63) / 64) * 64 + 32;          // bf16 elements per staged row
+  __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(sk_smem);
+  const int ut = blockIdx.x * (kSkRows / 16) + warp;
+  const bool live = ut < a.ut_total;
+
+  // W fragments: issue the first ring of loads before touching the activations
+  uint4 wa[kSkPF], wb[kSkPF];
+  const uint4* wp = a.Wp + ((int64_t)ut * a.kb_total + kb_lo) * 64 + lane;
+  if (live) {
+#pragma unroll
+    for (int q = 0; q < kSkPF; ++q)
+      if (q < nkb) { wa[q] = ldg_stream16(wp + (int64_t)q * 64); wb[q] = ldg_stream16(wp + (int64_t)q * 64 + 32); }
+  }
+  // stage act(A)[0:NB, K slice] as bf16
+  {
+    const int c4n = nkb * 8;                                   // float4 groups per row
+#pragma unroll 4
+    for (int r = warp; r < NB; r += kSkThreads / 32) {
+#pragma unroll 2
+      for (int c4 = lane; c4 < c4n; c4 += 32) {
+        const int col = kb_lo * 32 + c4 * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < a.M && col < a.K) v = *reinterpret_cast<const float4*>(a.A + (int64_t)r * a.lda + col);  // K % 4 == 0
+        if (a.relu_a) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        *reinterpret_cast<uint2*>(As + (size_t)r * pitch + c4 * 4) = pk;
+      }
+    }
+  }
+  __syncthreads();
+
+  float acc[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.0f;
+  if (live) {
+    for (int blk = 0; blk < nkb; blk += kSkPF) {
+#pragma unroll
+      for (int q = 0; q < kSkPF; ++q) {
+        const int cur = blk + q;
+        if (cur < nkb) {
+#pragma unroll
+          for (int n = 0; n < NT; ++n) {
+            const uint4 bv = *reinterpret_cast<const uint4*>(As + (size_t)(n * 8 + g) * pitch + cur * 32 + 8 * t);
+            mma16816(acc[n], wa[q], bv.x, bv.y);
+            mma16816(acc[n], wb[q], bv.z, bv.w);
+          }
+          if (cur + kSkPF < nkb) {
+            wa[q] = ldg_stream16(wp + (int64_t)(cur + kSkPF) * 64);
+            wb[q] = ldg_stream16(wp + (int64_t)(cur + kSkPF) * 64 + 32);
+          }
+        }
+      }
+    }
+  }
+
+  // accumulator fragment: c0 (row g, col 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1);
+  // "row" is the weight row (output column nn), "col" the activation row m.
+  if (gridDim.y == 1) {
+    if (live) {
+      float cin[NT][4], bia[2] = {0.f, 0.f};
+      const int nn0 = ut * 16 + g;
+      if (a.bias) {
+        if (nn0 < a.N) bia[0] = __ldg(a.bias + nn0);
+        if (nn0 + 8 < a.N) bia[1] = __ldg(a.bias + nn0 + 8);
+      }
+      // all addend loads first (C may alias Cin, so the compiler cannot hoist them itself)
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int m = n * 8 + 2 * t + (e & 1), nn = nn0 + (e >> 1) * 8;
+          cin[n][e] = (a.Cin && m < a.M && nn < a.N) ? __ldcg(a.Cin + (int64_t)m * a.ldcin + nn) : 0.0f;
+        }
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int m = n * 8 + 2 * t + (e & 1), nn = nn0 + (e >> 1) * 8;
+          if (m < a.M && nn < a.N) a.C[(int64_t)m * a.ldc + nn] = (acc[n][e] + bia[e >> 1]) * a.alpha + a.beta * cin[n][e];
+        }
+    }
+    return;
+  }
+  // split-K: partial tile [NB][128] per (split, n-group), reduced by the last CTA of the group
+  float* mine = a.part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (NB * kSkRows);
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const int m = n * 8 + 2 * t, nl = warp * 16 + g;
+    __stcg(&mine[(m) * kSkRows + nl], acc[n][0]);
+    __stcg(&mine[(m + 1) * kSkRows + nl], acc[n][1]);
+    __stcg(&mine[(m) * kSkRows + nl + 8], acc[n][2]);
+    __stcg(&mine[(m + 1) * kSkRows + nl + 8], acc[n][3]);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&a.tickets[blockIdx.x], 1u) == gridDim.y - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // element e = tid + 256*i: all EPT loads of one split are in flight together (the naive
+  // element-outer loop costs EPT * splits serialized L2 round trips)
+  constexpr int EPT = NB * kSkRows / kSkThreads;
+  float sum[EPT], cin[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) sum[i] = 0.0f;
+  const size_t zstride = (size_t)gridDim.x * (NB * kSkRows);
+  const float* p0 = a.part + (size_t)blockIdx.x * (NB * kSkRows) + tid;
+  for (unsigned z = 0; z < gridDim.y; ++z) {
+    float v[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) v[i] = __ldcg(p0 + z * zstride + i * kSkThreads);
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) sum[i] += v[i];
+  }
+  const int nl = tid % kSkRows, nn = blockIdx.x * kSkRows + nl;
+  const float bia = (a.bias && nn < a.N) ? __ldg(a.bias + nn) : 0.0f;
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int m = (tid + i * kSkThreads) / kSkRows;
+    cin[i] = (a.Cin && m < a.M && nn < a.N) ? __ldcg(a.Cin + (int64_t)m * a.ldcin + nn) : 0.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int m = (tid + i * kSkThreads) / kSkRows;
+    if (m < a.M && nn < a.N) a.C[(int64_t)m * a.ldc + nn] = (sum[i] + bia) * a.alpha + a.beta * cin[i];
+  }
+  if (tid == 0) a.tickets[blockIdx.x] = 0;
+}
+
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" size_t tp_pack_mma_a_bytes(int rows, int cols) {
+  return (size_t)((rows + 15) / 16) * ((cols + 31) / 32) * 1024;
+}
+
+extern "C" int tp_pack_mma_a_bf16(const float* w, int64_t ld, int rows, int cols, void* dst, void* stream) {
+  TP_CHECK_ARG(w && dst && rows > 0 && cols > 0 && ld >= cols, "tp_pack_mma_a_bf16: bad arguments");
+  TP_CHECK_ARG(aligned16(dst), "tp_pack_mma_a_bf16: dst must be 16-byte aligned");
+  k_pack_mma_a<<<1024, 256, 0, (cudaStream_t)stream>>>(w, ld, rows, cols, reinterpret_cast<uint32_t*>(dst));
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}
+
+extern "C" size_t tp_skinny_bf16_workspace_bytes(int M, int N, int splits) {
+  const size_t nb = M <= 8 ? 8 : (M <= 32 ? 32 : 64);
+  const size_t groups = ((size_t)N + kSkRows - 1) / kSkRows;
+  return kSkTicketBytes + (size_t)(splits > 1 ? splits : 0) * groups * nb * kSkRows * sizeof(float);
+}
+
+extern "C" int tp_skinny_bf16(const float* A, int64_t lda, int M, int K, const void* Wp, int N, const float* bias,
+                              const float* Cin, int64_t ldcin, float* C, int64_t ldc, float alpha, float beta,
+                              int relu_a, int splits, void* workspace, size_t workspace_bytes, void* stream) {
+  TP_CHECK_ARG(A && Wp && C, "tp_skinny_bf16: null pointer");
+  TP_CHECK_ARG(M >= 1 && M <= 64, "tp_skinny_bf16: M=%d must be in [1,64]", M);
+  TP_CHECK_ARG(N >= 1 && K >= 4 && K % 4 == 0 && lda % 4 == 0, "tp_skinny_bf16: need K %% 4 == 0 and lda %% 4 == 0 (K=%d lda=%lld)", K, (long long)lda);
+  TP_CHECK_ARG(aligned16(A) && aligned16(Wp), "tp_skinny_bf16: A / Wp must be 16-byte aligned");
+  SkArgs a;
+  a.A = A; a.lda = lda; a.M = M; a.K = K; a.N = N;
+  a.Wp = reinterpret_cast<const uint4*>(Wp);
+  a.ut_total = (N + 15) / 16; a.kb_total = (K + 31) / 32;
+  a.bias = bias; a.Cin = Cin; a.ldcin = ldcin; a.C = C; a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.relu_a = relu_a;
+  const int groups = (N + kSkRows - 1) / kSkRows;
+  if (splits < 1) splits = 1;
+  if (splits > a.kb_total) splits = a.kb_total;
+  a.kb_per_split = (a.kb_total + splits - 1) / splits;
+  splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
+  a.part = nullptr; a.tickets = nullptr;
+  const int nb = M <= 8 ? 8 : (M <= 32 ? 32 : 64);
+  if (splits > 1) {
+    const size_t need = kSkTicketBytes + (size_t)splits * groups * nb * kSkRows * sizeof(float);
+    TP_CHECK_ARG(workspace && workspace_bytes >= need && (size_t)groups * 4 <= kSkTicketBytes && aligned16(workspace),
+                 "tp_skinny_bf16: split-K workspace too small (%zu < %zu)", workspace_bytes, need);
+    a.tickets = reinterpret_cast<unsigned int*>(workspace);
+    a.part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + kSkTicketBytes);
+  }
+  const int pitch = ((a.kb_per_split * 32 + 63) / 64) * 64 + 32;
+  const size_t smem = (size_t)nb * pitch * 2;
+  if (smem > 200 * 1024) return fail(TP_ERR_UNSUPPORTED, "tp_skinny_bf16: K slice of %d columns does not fit in shared memory; raise splits", a.kb_per_split * 32);
+  dim3 grid((unsigned)groups, (unsigned)splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nb == 8) {
+    TP_CUDA(cudaFuncSetAttribute(k_skinny_bf16<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_skinny_bf16<1><<<grid, kSkThreads, smem, st>>>(a);
+  } else if (nb == 32) {
+    TP_CUDA(cudaFuncSetAttribute(k_skinny_bf16<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_skinny_bf16<4><<<grid, kSkThreads, smem, st>>>(a);
+  } else {
+    TP_CUDA(cudaFuncSetAttribute(k_skinny_bf16<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_skinny_bf16<8><<<grid, kSkThreads, smem, st>>>(a);
+  }
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}

@@ -18,8 +18,9 @@ PSC = 160  # pose6d(144) | shape(10) | cam(3) | pad(3)
 
 
 class Regressor(nn.Module):
-    def __init__(self, smpl_mean_params=SMPL_MEAN_PARAMS):
+    def __init__(self, smpl_mean_params=SMPL_MEAN_PARAMS, precision="fp32"):
         super().__init__()
+        self.precision = precision
         # parameter containers: same names / shapes / default init as lib/models/spin.py:215-224
         self.fc1 = nn.Linear(512 * 4 + NPOSE + 13, 1024)
         self.drop1 = nn.Dropout()
@@ -44,7 +45,7 @@ class Regressor(nn.Module):
         ts = [self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, self.decpose.weight, self.decpose.bias,
               self.decshape.weight, self.decshape.bias, self.deccam.weight, self.deccam.bias,
               self.init_pose, self.init_shape, self.init_cam]
-        return tuple((t.device, t.data_ptr(), t._version) for t in ts)
+        return (self.precision,) + tuple((t.device, t.data_ptr(), t._version) for t in ts)
 
     def packed(self):
         key = self._key()
@@ -76,6 +77,8 @@ class Regressor(nn.Module):
             init[0, 144:154] = f(self.init_shape)[0]
             init[0, 154:157] = f(self.init_cam)[0]
             pk["init"] = init
+            for name in ("w1x", "w1p", "w2", "wdec"):
+                pk[name] = nv.pack_linear(pk[name], self.precision)
             pk["c"] = nv.IefWeights(*[nv.ptr(pk[n]) for n in ("w1x", "b1", "w1p", "w2", "b2", "wdec", "bdec")])
             self._pack, self._pack_key = pk, key
         return self._pack
@@ -105,7 +108,7 @@ class Regressor(nn.Module):
         L = nv.lib()
         psc = torch.empty(N, PSC, device=dev, dtype=torch.float32)
         ws = nv.workspace(L.tp_ief_workspace_bytes(N), dev)
-        nv.check(L.tp_ief_forward(pk["c"], nv.ptr(feat), N, nv.ptr(init), init_rows, n_iter, nv.ptr(psc),
+        nv.check(L.tp_ief_forward(nv.PRECISIONS[self.precision], pk["c"], nv.ptr(feat), N, nv.ptr(init), init_rows, n_iter, nv.ptr(psc),
                                   nv.ptr(ws), ws.numel(), nv.stream()), "tp_ief_forward")
         nv.mark("k3_ief")
         return self.decode(psc, is_train=is_train, J_regressor=J_regressor)

@@ -90,18 +90,28 @@ class TemporalEncoder(nn.Module):
                 d["b_ih_f"] = g(self.gru_fwd, f"bias_ih_l{l}").contiguous()
                 d["w_ih_r"] = torch.cat([pad_k(wb, kpr), pad_k(wr, kpr)], dim=0).contiguous()   # [backward | forward]
                 d["b_ih_r"] = torch.cat([g(self.gru_rec, f"bias_ih_l{l}_reverse"), g(self.gru_rec, f"bias_ih_l{l}")]).contiguous()
-            d["w_hh"] = [g(self.gru_fwd, f"weight_hh_l{l}").to(wdt).contiguous(),
-                         g(self.gru_rec, f"weight_hh_l{l}_reverse").to(wdt).contiguous(),
-                         g(self.gru_rec, f"weight_hh_l{l}").to(wdt).contiguous()]
+            d["w_hh"] = [self._pack_whh(g(self.gru_fwd, f"weight_hh_l{l}"), lp),
+                         self._pack_whh(g(self.gru_rec, f"weight_hh_l{l}_reverse"), lp),
+                         self._pack_whh(g(self.gru_rec, f"weight_hh_l{l}"), lp)]
             d["b_hh"] = [g(self.gru_fwd, f"bias_hh_l{l}").contiguous(),
                          g(self.gru_rec, f"bias_hh_l{l}_reverse").contiguous(),
                          g(self.gru_rec, f"bias_hh_l{l}").contiguous()]
             layers.append(d)
         pk = {"layers": layers,
-              "w_fwd": g(self.linear_fwd, "weight").contiguous(), "b_fwd": g(self.linear_fwd, "bias").contiguous(),
-              "w_rec": g(self.linear_rec, "weight").contiguous(), "b_rec": g(self.linear_rec, "bias").contiguous()}
+              "w_fwd": nv.pack_linear(g(self.linear_fwd, "weight"), self.precision), "b_fwd": g(self.linear_fwd, "bias").contiguous(),
+              "w_rec": nv.pack_linear(g(self.linear_rec, "weight"), self.precision), "b_rec": g(self.linear_rec, "bias").contiguous()}
         self._pack, self._pack_key = pk, key
         return pk
+
+    @staticmethod
+    def _pack_whh(w: torch.Tensor, lp: bool) -> torch.Tensor:
+        """fp32 mode: [3H,H] fp32 as is.  bf16 mode: tensor-core fragment order (tp_pack_whh_bf16)."""
+        w = w.contiguous()
+        if not lp:
+            return w
+        out = torch.empty(w.shape[0], w.shape[1], device=w.device, dtype=torch.bfloat16)
+        nv.check(nv.lib().tp_pack_whh_bf16(nv.ptr(w), nv.ptr(out), w.shape[1], nv.stream()), "tp_pack_whh_bf16")
+        return out
 
     # ------------------------------------------------------------------ kernels
     def _input_proj(self, A, a_rows, W, kp, bias, segs, outs):
@@ -246,7 +256,7 @@ class TemporalEncoder(nn.Module):
         feat = torch.empty((B, 2, 2048) if is_train else (B, 2048), device=h_fwd.device, dtype=torch.float32)
         L = nv.lib()
         ws = nv.workspace(L.tp_encoder_heads_workspace_bytes(B), h_fwd.device)
-        nv.check(L.tp_encoder_heads(nv.ptr(pk["w_fwd"]), nv.ptr(pk["b_fwd"]), nv.ptr(pk["w_rec"]), nv.ptr(pk["b_rec"]),
+        nv.check(L.tp_encoder_heads(nv.PRECISIONS[self.precision], nv.ptr(pk["w_fwd"]), nv.ptr(pk["b_fwd"]), nv.ptr(pk["w_rec"]), nv.ptr(pk["b_rec"]),
                                     nv.ptr(h_fwd), h_fwd.shape[1], nv.ptr(h_rec), h_rec.shape[1], B, H,
                                     1 if is_train else 0, nv.ptr(feat), nv.ptr(ws), ws.numel(), nv.stream()),
                  "tp_encoder_heads")
@@ -267,7 +277,7 @@ class TePose(nn.Module):
         self.seqlen = seqlen
         self.batch_size = batch_size
         self.encoder = TemporalEncoder(seq_len=seqlen, n_layers=n_layers, hidden_size=hidden_size, precision=precision)
-        self.regressor = Regressor()
+        self.regressor = Regressor(precision=precision)
         if pretrained and os.path.isfile(pretrained):       # lib/models/tepose.py:115-119
             pretrained_dict = torch.load(pretrained)['model']
             self.regressor.load_state_dict(pretrained_dict, strict=False)
@@ -282,6 +292,7 @@ class TePose(nn.Module):
         if value not in nv.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(nv.PRECISIONS)}")
         self.encoder.precision = value
+        self.regressor.precision = value
 
     def forward(self, input, is_train=False, J_regressor=None):
         if self.training:

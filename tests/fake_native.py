@@ -106,6 +106,17 @@ class FakeLib:
         return 0
 
     # ---- recurrence
+    def tp_skinny_bf16_workspace_bytes(self, M, N, splits):
+        return 4096
+
+    def tp_pack_whh_bf16(self, w_hh, dst, H, stream):
+        # the emulation keeps W_hh row-major bf16 (the fragment order only matters to the CUDA kernel)
+        _mat(dst, 3 * H, H, H, torch.bfloat16).copy_(_mat(w_hh, 3 * H, H, H).to(torch.bfloat16))
+        return 0
+
+    def tp_gru_set_trace(self, buf):
+        return None
+
     def tp_gru_workspace_bytes(self, njobs, B, H):
         return 256
 
@@ -139,9 +150,26 @@ class FakeLib:
     def tp_encoder_heads_workspace_bytes(self, B):
         return 256
 
-    def tp_encoder_heads(self, w_fwd, b_fwd, w_rec, b_rec, h_fwd, ld_hf, h_rec, ld_hr, B, H, is_train, feat, ws, ws_bytes, stream):
-        a = _mat(h_fwd, B, H, ld_hf).clamp_min(0) @ _mat(w_fwd, 2048, H, H).t() + _view(b_fwd, 2048, torch.float32)
-        b = _mat(h_rec, B, 2 * H, ld_hr).clamp_min(0) @ _mat(w_rec, 2048, 2 * H, 2 * H).t() + _view(b_rec, 2048, torch.float32)
+    def tp_pack_mma_a_bytes(self, rows, cols):
+        return ((rows + 15) // 16) * ((cols + 31) // 32) * 1024
+
+    def tp_pack_mma_a_bf16(self, w, ld, rows, cols, dst, stream):
+        # the emulation keeps the matrix row-major bf16 at the head of the (larger) packed buffer
+        _mat(dst, rows, cols, cols, torch.bfloat16).copy_(_mat(w, rows, cols, ld).to(torch.bfloat16))
+        return 0
+
+    @staticmethod
+    def _lin(precision, w, n, k):
+        return _mat(w, n, k, k, torch.bfloat16).float() if precision == nv.PRECISION_BF16 else _mat(w, n, k, k)
+
+    @staticmethod
+    def _act(precision, a):
+        return a.to(torch.bfloat16).float() if precision == nv.PRECISION_BF16 else a
+
+    def tp_encoder_heads(self, precision, w_fwd, b_fwd, w_rec, b_rec, h_fwd, ld_hf, h_rec, ld_hr, B, H, is_train, feat, ws, ws_bytes, stream):
+        q = lambda t: self._act(precision, t)
+        a = q(_mat(h_fwd, B, H, ld_hf).clamp_min(0)) @ self._lin(precision, w_fwd, 2048, H).t() + _view(b_fwd, 2048, torch.float32)
+        b = q(_mat(h_rec, B, 2 * H, ld_hr).clamp_min(0)) @ self._lin(precision, w_rec, 2048, 2 * H).t() + _view(b_rec, 2048, torch.float32)
         if is_train:
             _view(feat, B * 4096, torch.float32).copy_(torch.stack([a, b], 1).reshape(-1))
         else:
@@ -151,15 +179,17 @@ class FakeLib:
     def tp_ief_workspace_bytes(self, n):
         return 256
 
-    def tp_ief_forward(self, w, feat, n_rows, init, init_rows, n_iter, psc, ws, ws_bytes, stream):
+    def tp_ief_forward(self, precision, w, feat, n_rows, init, init_rows, n_iter, psc, ws, ws_bytes, stream):
         w = w.contents if hasattr(w, "contents") else w
+        q = lambda t: self._act(precision, t)
+        lin = lambda ptr_, n, k: self._lin(precision, ptr_, n, k)
         x = _mat(feat, n_rows, 2048, 2048)
         p = _mat(init, init_rows, 160, 160).clone().expand(n_rows, -1).clone()
-        base = x @ _mat(w.w1x, 1024, 2048, 2048).t() + _view(w.b1, 1024, torch.float32)
+        base = q(x) @ lin(w.w1x, 1024, 2048).t() + _view(w.b1, 1024, torch.float32)
         for _ in range(n_iter):
-            u1 = p @ _mat(w.w1p, 1024, 160, 160).t() + base
-            u2 = u1 @ _mat(w.w2, 1024, 1024, 1024).t() + _view(w.b2, 1024, torch.float32)
-            p = p + u2 @ _mat(w.wdec, 160, 1024, 1024).t() + _view(w.bdec, 160, torch.float32)
+            u1 = q(p) @ lin(w.w1p, 1024, 160).t() + base
+            u2 = q(u1) @ lin(w.w2, 1024, 1024).t() + _view(w.b2, 1024, torch.float32)
+            p = p + q(u2) @ lin(w.wdec, 160, 1024).t() + _view(w.bdec, 160, torch.float32)
         _mat(psc, n_rows, 160, 160).copy_(p)
         return 0
 

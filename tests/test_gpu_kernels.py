@@ -95,6 +95,31 @@ def test_gemm_f32_splitk(M, N, K, splits):
     assert int(ws[:4096].view(torch.int32).abs().sum()) == 0
 
 
+@pytest.mark.parametrize("M,N,K,splits", [(32, 2048, 4096, 9), (32, 2048, 2048, 1), (64, 1024, 1024, 8), (32, 160, 1024, 8),
+                                          (1, 18432, 2176, 1), (7, 1024, 160, 1), (32, 1000, 100, 2)])
+def test_skinny_bf16(M, N, K, splits):
+    g = torch.Generator().manual_seed(M + N + K)
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    b, Cin = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    a, bb, c = cu(A), cu(b), cu(Cin)
+    L = nv.lib()
+    wp = nv.pack_linear(cu(W), "bf16")
+    assert wp.numel() == L.tp_pack_mma_a_bytes(N, K)
+    ws = torch.zeros(L.tp_skinny_bf16_workspace_bytes(M, N, splits), dtype=torch.uint8, device=DEV)
+    Ab = A.clamp_min(0).to(torch.bfloat16).double()
+    ref = 0.5 * (Ab @ W.to(torch.bfloat16).double().t() + b.double()) + Cin.double()
+    outs = []
+    for _ in range(2):
+        out = c.clone()
+        nv.check(L.tp_skinny_bf16(nv.ptr(a), K, M, K, nv.ptr(wp), N, nv.ptr(bb), nv.ptr(out), N, nv.ptr(out), N, 0.5, 1.0, 1,
+                                  splits, nv.ptr(ws), ws.numel(), nv.stream()))
+        outs.append(out.cpu())
+    err = float((outs[0].double() - ref).abs().max())
+    assert err < 1e-4, err                        # exact bf16 products; fp32 accumulation order only
+    assert torch.equal(outs[0], outs[1])
+    assert int(ws[:4096].view(torch.int32).abs().sum()) == 0
+
+
 def test_pack_rows():
     x = torch.randn(3, 5, 2133)
     xs = cu(x)
@@ -156,6 +181,16 @@ def _gru_case(B, T, H, precision, seed, with_h0=False, reverse=False):
     return gi, w_hh.to(wdt), b_hh, h0, ys, h
 
 
+def _dev_whh(w, precision):
+    """W_hh on the device in the layout tp_gru_recurrence expects for `precision`."""
+    wf = w.float().to(DEV).contiguous()
+    if precision == "fp32":
+        return wf
+    out = torch.empty(wf.shape, device=DEV, dtype=torch.bfloat16)
+    nv.check(nv.lib().tp_pack_whh_bf16(nv.ptr(wf), nv.ptr(out), wf.shape[1], nv.stream()))
+    return out
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("B,T,H", [(2, 4, 64), (32, 16, 256), (5, 3, 96), (1, 6, 1024), (40, 2, 128)])
 def test_gru_recurrence(B, T, H, precision):
@@ -166,7 +201,7 @@ def test_gru_recurrence(B, T, H, precision):
     for i, (gi, w, b, h0, ys, hT) in enumerate(cases):
         Tj = gi.shape[0]
         rev = i == 1
-        d = dict(gi=gi.to(DEV), w=w.to(DEV).contiguous(), b=cu(b), h0=None if h0 is None else cu(h0),
+        d = dict(gi=gi.to(DEV), w=_dev_whh(w, precision), b=cu(b), h0=None if h0 is None else cu(h0),
                  y=torch.zeros(Tj, B, H + 8, device=DEV), ylp=torch.zeros(Tj, B, H, device=DEV, dtype=torch.bfloat16),
                  hf=torch.zeros(B, 2 * H, device=DEV))
         keep.append(d)
@@ -205,7 +240,7 @@ def test_gru_recurrence_full_size_fp32_vs_torch_gru():
     L = nv.lib()
     for precision, tol in (("fp32", 3e-5), ("bf16", 3e-3)):
         wdt = torch.bfloat16 if precision == "bf16" else torch.float32
-        d = dict(gi=gi.to(DEV).contiguous(), w=gru.weight_hh_l0.detach().to(DEV, wdt).contiguous(),
+        d = dict(gi=gi.to(DEV).contiguous(), w=_dev_whh(gru.weight_hh_l0.detach(), precision),
                  b=gru.bias_hh_l0.detach().to(DEV), y=torch.zeros(T, B, H, device=DEV))
         j = nv.GruJob()
         j.gi, j.ldg, j.w_hh, j.b_hh = d["gi"].data_ptr(), 3 * H, d["w"].data_ptr(), d["b"].data_ptr()
