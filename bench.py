@@ -231,7 +231,7 @@ def main():
     with torch.no_grad():
         for i in range(min(args.steps, 20)):
             flush.zero_()
-            torch.cuda._sleep(4_000_000)          # let the CPU run ahead so events bracket GPU work only
+            torch.cuda._sleep(20_000_000)         # ~10 ms: let the CPU run ahead so events bracket GPU work only
             nv.start_marks()
             model(xs_dev[i % n_inputs])
             marks = nv.stop_marks()

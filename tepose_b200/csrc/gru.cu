@@ -14,6 +14,7 @@
 //          shared memory, 8 warps split K (x M) and reduce through shared memory.
 //          State, gates and accumulation stay fp32.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace tp {
 
@@ -24,6 +25,7 @@ struct GruParams {
   tp_gru_job jobs[kMaxJobs];
   int item_begin[kMaxJobs + 1];
   int njobs, B, H, U, max_steps, total_items, any_h0;
+  int n_item_jobs;          // jobs [0, n_item_jobs) are cut into items; the rest are step-0-only elementwise jobs
   float* hbuf;              // [njobs][2][B][H]  fp32 state ping-pong
   __nv_bfloat16* hbuf_lp;   // [njobs][2][B][H]  bf16 copy (MMA operand of the next step)
   unsigned int* barrier;    // monotonic grid-barrier counter (zeroed by the host before launch)
@@ -401,6 +403,8 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
   }
 }
 
+#include "gru_tma.inl"
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace tp
@@ -435,40 +439,85 @@ static int launch_coop(KernelT kfn, const GruParams& p, size_t smem, cudaStream_
   return TP_OK;
 }
 
-extern "C" int tp_gru_recurrence(const tp_gru_job* jobs, int njobs, int B, int H, int precision,
+template <typename KernelT>
+static int launch_coop_n(KernelT kfn, const GruParams& p, int stages, int threads, int grid, size_t smem, cudaStream_t st) {
+  TP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  TP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem));
+  if (per_sm < 1) return fail(TP_ERR_UNSUPPORTED, "tp_gru_recurrence: kernel does not fit on an SM (smem=%zu)", smem);
+  void* args[] = {(void*)&p, (void*)&stages};
+  TP_CUDA(cudaLaunchCooperativeKernel((const void*)kfn, dim3(grid), dim3(threads), args, smem, st));
+  count_launch();
+  return TP_OK;
+}
+
+extern "C" int tp_gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, int H, int precision,
                                  void* workspace, size_t workspace_bytes, void* stream) {
-  TP_CHECK_ARG(jobs && njobs >= 1 && njobs <= kMaxJobs, "tp_gru_recurrence: njobs=%d out of range [1,%d]", njobs, kMaxJobs);
+  TP_CHECK_ARG(jobs_in && njobs >= 1 && njobs <= kMaxJobs, "tp_gru_recurrence: njobs=%d out of range [1,%d]", njobs, kMaxJobs);
   TP_CHECK_ARG(B >= 1 && H >= 32 && H % 32 == 0, "tp_gru_recurrence: need B>=1 and H a multiple of 32 (B=%d H=%d)", B, H);
   TP_CHECK_ARG(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "tp_gru_recurrence: workspace must be 256-byte aligned");
   TP_CHECK_ARG(workspace_bytes >= tp_gru_workspace_bytes(njobs, B, H), "tp_gru_recurrence: workspace too small");
   TP_CHECK_ARG(precision == TP_PRECISION_FP32 || precision == TP_PRECISION_BF16, "tp_gru_recurrence: bad precision");
+  // jobs with a recurrent matmul first; single-step jobs from a zero state are pure gate math
+  tp_gru_job jobs[kMaxJobs];
+  int n_mat = 0;
+  for (int j = 0; j < njobs; ++j)
+    if (!(jobs_in[j].steps == 1 && jobs_in[j].h0 == nullptr)) jobs[n_mat++] = jobs_in[j];
+  int n_all = n_mat;
+  for (int j = 0; j < njobs; ++j)
+    if (jobs_in[j].steps == 1 && jobs_in[j].h0 == nullptr) jobs[n_all++] = jobs_in[j];
   GruParams p;
   memset(&p, 0, sizeof(p));
-  p.njobs = njobs; p.B = B; p.H = H;
-  int units_total = njobs * H;
-  int U = 32;
-  if (precision == TP_PRECISION_BF16 && units_total / 16 <= sm_count()) U = 16;
-  p.U = U;
-  int items = 0;
+  p.njobs = njobs; p.B = B; p.H = H; p.trace = g_gru_trace;
   for (int j = 0; j < njobs; ++j) {
     const tp_gru_job& jb = jobs[j];
-    TP_CHECK_ARG(jb.gi && jb.w_hh && jb.b_hh && jb.steps >= 1, "tp_gru_recurrence: job %d has null gi/w_hh/b_hh or steps<1", j);
-    TP_CHECK_ARG(aligned16(jb.w_hh), "tp_gru_recurrence: job %d w_hh must be 16-byte aligned", j);
+    TP_CHECK_ARG(jb.gi && jb.w_hh && jb.b_hh && jb.steps >= 1, "tp_gru_recurrence: a job has null gi/w_hh/b_hh or steps<1");
+    TP_CHECK_ARG(aligned16(jb.w_hh), "tp_gru_recurrence: w_hh must be 16-byte aligned");
     p.jobs[j] = jb;
-    p.item_begin[j] = items;
-    items += H / U;
     if (jb.steps > p.max_steps) p.max_steps = jb.steps;
     if (jb.h0) p.any_h0 = 1;
   }
-  for (int j = njobs; j <= kMaxJobs; ++j) p.item_begin[j] = items;
-  p.total_items = items;
   size_t per = (size_t)njobs * 2 * B * H;
-  p.trace = g_gru_trace;
   p.barrier = reinterpret_cast<unsigned int*>(workspace);
   p.hbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 256);
   p.hbuf_lp = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(workspace) + 256 + align_up(per * sizeof(float), 256));
   cudaStream_t st = (cudaStream_t)stream;
   TP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+  const int sms = sm_count();
+
+  // ---- bf16 fast path: TMA-fed ring, one item per CTA
+  static const bool no_tma = getenv("TP_GRU_NO_TMA") != nullptr;
+  if (precision == TP_PRECISION_BF16 && !no_tma && n_mat >= 1 && H % 128 == 0 && B <= 32 && n_mat * (H / 32) <= sms) {
+    const int NB = B <= 8 ? 8 : 32;
+    size_t region = (size_t)NB * (H + 32) * 2;
+    const size_t redb = (size_t)4 * 3 * NB * 36 * 4;
+    if (region < redb) region = redb;
+    region = (region + 1023) & ~(size_t)1023;
+    const size_t budget = 225 * 1024;
+    int stages = region + 256 < budget ? (int)((budget - region - 256) / kChunkBytes) : 0;
+    if (stages > 8) stages = 8;
+    if (stages > H / 128) stages = H / 128;
+    if (stages >= 2 || (stages == 1 && H == 128)) {
+      p.U = 32; p.n_item_jobs = n_mat;
+      int items = 0;
+      for (int j = 0; j < n_mat; ++j) { p.item_begin[j] = items; items += H / 32; }
+      for (int j = n_mat; j <= kMaxJobs; ++j) p.item_begin[j] = items;
+      p.total_items = items;
+      const size_t smem = region + (size_t)stages * kChunkBytes + 256;
+      if (NB == 8) return launch_coop_n(k_gru_bf16_tma<1>, p, stages, kTmaThreads, items, smem, st);
+      return launch_coop_n(k_gru_bf16_tma<4>, p, stages, kTmaThreads, items, smem, st);
+    }
+  }
+
+  // ---- generic paths: every job is cut into items
+  int units_total = njobs * H;
+  int U = 32;
+  if (precision == TP_PRECISION_BF16 && units_total / 16 <= sms) U = 16;
+  p.U = U; p.n_item_jobs = njobs;
+  int items = 0;
+  for (int j = 0; j < njobs; ++j) { p.item_begin[j] = items; items += H / U; }
+  for (int j = njobs; j <= kMaxJobs; ++j) p.item_begin[j] = items;
+  p.total_items = items;
 
   if (precision == TP_PRECISION_FP32) {
     size_t smem = (size_t)3 * (3 * 32 + 32) * 36 * sizeof(float);

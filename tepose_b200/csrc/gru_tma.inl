@@ -1,0 +1,205 @@
+// Included by gru.cu (inside namespace tp, after GruParams / gate_fetch / gru_finalize / grid_barrier).
+//
+// bf16 recurrence, TMA ring variant.  Same decomposition as k_gru_bf16<NT, 2> (U = 32 units per
+// CTA = 6 m-tiles, 4 K groups x 2 unit tiles), but the operands arrive through the async proxy:
+// a ninth warp issues cp.async.bulk copies that
+//   * stage h_{t-1} (bf16) once per step, and
+//   * stream the CTA's fragment-packed W_hh slice through a ring of 24 KB chunks
+//     (6 m-tiles x 4 column blocks), guarded by full / empty mbarriers.
+// W_hh does not depend on h, so the producer runs ahead: while the consumers do the gate math and
+// wait at the grid barrier, the ring is already refilled with the next step's first chunks -- the
+// L2 -> SM stream overlaps the phases that used to leave the L2 idle (measured: the recurrence is
+// bound by L2 bandwidth, ~7 TB/s for 128 streaming CTAs, see scripts/micro/l2bw.cu).
+constexpr int kTmaThreads = 288;
+constexpr int kChunkBlocks = 4;
+constexpr int kChunkBytes = 6 * kChunkBlocks * 1024;
+
+__device__ __forceinline__ uint32_t sm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* b, uint32_t n) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(sm_u32(b)), "r"(n));
+}
+__device__ __forceinline__ void mb_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(sm_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(sm_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* b, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = sm_u32(b);
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+                   "r"(sm_u32(dst)), "l"(src), "r"(bytes), "r"(sm_u32(bar)) : "memory");
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams p, const int stages) {
+  constexpr int NB = NT * 8, U = 32, KG = 4, RP = U + 4;
+  constexpr int GE = (NB * U + 255) / 256;
+  extern __shared__ __align__(1024) unsigned char smem_t[];
+  const int H = p.H, B = p.B, HP = H + 32;
+  const int nblk = H / 32, nchunks = nblk / kChunkBlocks;
+  size_t region = (size_t)NB * HP * 2;
+  if (region < (size_t)KG * 3 * NB * RP * 4) region = (size_t)KG * 3 * NB * RP * 4;
+  region = (region + 1023) & ~(size_t)1023;
+  __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(smem_t);      // [NB][HP]; aliased by red after the MMA loop
+  float* red = reinterpret_cast<float*>(smem_t);                      // [KG][3][NB][RP]
+  unsigned char* ring = smem_t + region;                              // [stages][24 KB]
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(ring + (size_t)stages * kChunkBytes);
+  uint64_t* w_empty = w_full + 8;
+  uint64_t* h_full = w_empty + 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3, kg = (warp >> 1) & 3, mg = warp & 1;
+  const bool producer = warp == 8;
+
+  if (tid == 0) {
+    for (int i = 0; i < stages; ++i) { mb_init(&w_full[i], 1); mb_init(&w_empty[i], 8); }
+    mb_init(h_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  // step-0-only jobs without an initial state have no matmul at all: plain gate math, grid-strided
+  for (int je = p.n_item_jobs; je < p.njobs; ++je)
+    for (int64_t i = blockIdx.x * (int64_t)kTmaThreads + tid; i < (int64_t)B * H; i += (int64_t)gridDim.x * kTmaThreads) {
+      const int b = (int)(i / H), u = (int)(i - (int64_t)b * H);
+      gru_finalize(p, je, 0, b, u, gate_fetch(p, je, 0, b, u), 0.f, 0.f, 0.f);
+    }
+
+  unsigned int epoch = 0;
+  if (p.any_h0) { seed_h0(p); grid_barrier(p.barrier, ++epoch * gridDim.x); }
+
+  int j, u0;
+  locate_item(p, blockIdx.x, j, u0);          // exactly one item per CTA on this path
+  const tp_gru_job& jb = p.jobs[j];
+  const unsigned char* wbase = reinterpret_cast<const unsigned char*>(jb.w_hh);
+  uint32_t cons = 0, prod = 0, msteps = 0;    // chunk counters (ring position / phase), matmul steps seen
+  int prefetched = 0;
+
+  auto issue_chunk = [&](int c) {             // producer lane only
+    const int st = prod % stages;
+    mb_wait(&w_empty[st], ((prod / stages) & 1) ^ 1);
+    mb_expect_tx(&w_full[st], kChunkBytes);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const size_t src = ((((size_t)i * (H / 16) + (u0 >> 4) + m) * nblk) + (size_t)c * kChunkBlocks) * 1024;
+        bulk_g2s(ring + (size_t)st * kChunkBytes + (size_t)((i * 2 + m) * kChunkBlocks) * 1024, wbase + src,
+                 kChunkBlocks * 1024, &w_full[st]);
+      }
+    ++prod;
+  };
+
+  for (int s = 0; s < p.max_steps; ++s) {
+    TP_TRACE(0);
+    const bool active = s < jb.steps;
+    const bool have_prev = active && ((s > 0) || (jb.h0 != nullptr));
+    if (producer) {
+      if (lane == 0 && have_prev) {
+        asm volatile("fence.proxy.async;\n" ::: "memory");
+        const __nv_bfloat16* hprev = p.hbuf_lp + ((int64_t)(j * 2 + ((s + 1) & 1)) * B) * H;
+        mb_expect_tx(h_full, (uint32_t)B * H * 2);
+        for (int b = 0; b < B; ++b) bulk_g2s(hs + (size_t)b * HP, hprev + (int64_t)b * H, (uint32_t)H * 2, h_full);
+        for (int c = prefetched; c < nchunks; ++c) issue_chunk(c);
+        prefetched = 0;
+        if (s + 1 < jb.steps) {               // W_hh is step-invariant: refill the ring for the next step now
+          const int n = stages < nchunks ? stages : nchunks;
+          for (int c = 0; c < n; ++c) issue_chunk(c);
+          prefetched = n;
+        }
+      }
+      __syncwarp();
+    } else {
+      GateIn gin[GE];
+      if (active) {
+#pragma unroll
+        for (int e = 0; e < GE; ++e) {
+          const int idx = tid + e * 256;
+          const int bb = idx / U, uu = idx - bb * U;
+          if (idx < NB * U && bb < B) gin[e] = gate_fetch(p, j, s, bb, u0 + uu);
+        }
+      }
+      if (have_prev) {
+        float acc[3][NT][4];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][n][e] = 0.0f;
+        mb_wait(h_full, msteps & 1);
+        TP_TRACE(1);
+        for (int c = 0; c < nchunks; ++c) {
+          const int st = cons % stages;
+          mb_wait(&w_full[st], (cons / stages) & 1);
+          const unsigned char* cb = ring + (size_t)st * kChunkBytes + (size_t)kg * 1024 + (size_t)lane * 16;
+          uint4 wa[3], wb[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            wa[i] = *reinterpret_cast<const uint4*>(cb + (size_t)((i * 2 + mg) * kChunkBlocks) * 1024);
+            wb[i] = *reinterpret_cast<const uint4*>(cb + (size_t)((i * 2 + mg) * kChunkBlocks) * 1024 + 512);
+          }
+#pragma unroll
+          for (int n = 0; n < NT; ++n) {
+            const uint4 bv = *reinterpret_cast<const uint4*>(hs + (size_t)(n * 8 + g) * HP + (c * kChunkBlocks + kg) * 32 + 8 * t);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              mma_bf16(acc[i][n], wa[i].x, wa[i].y, wa[i].z, wa[i].w, bv.x, bv.y);
+              mma_bf16(acc[i][n], wb[i].x, wb[i].y, wb[i].z, wb[i].w, bv.z, bv.w);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mb_arrive(&w_empty[st]);
+          ++cons;
+        }
+        ++msteps;
+        TP_TRACE(2);
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");     // every consumer is done reading hs (red aliases it)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int n = 0; n < NT; ++n) {
+            float* r0 = red + ((size_t)(kg * 3 + i) * NB + n * 8 + 2 * t) * RP + mg * 16 + g;
+            r0[0] = acc[i][n][0];
+            r0[RP] = acc[i][n][1];
+            r0[8] = acc[i][n][2];
+            r0[RP + 8] = acc[i][n][3];
+          }
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        TP_TRACE(3);
+      }
+      if (active) {
+#pragma unroll
+        for (int e = 0; e < GE; ++e) {
+          const int idx = tid + e * 256;
+          const int bb = idx / U, uu = idx - bb * U;
+          if (idx >= NB * U || bb >= B) continue;
+          float ar = 0.f, az = 0.f, an = 0.f;
+          if (have_prev) {
+#pragma unroll
+            for (int k = 0; k < KG; ++k) {
+              ar += red[((size_t)(k * 3 + 0) * NB + bb) * RP + uu];
+              az += red[((size_t)(k * 3 + 1) * NB + bb) * RP + uu];
+              an += red[((size_t)(k * 3 + 2) * NB + bb) * RP + uu];
+            }
+          }
+          gru_finalize(p, j, s, bb, u0 + uu, gin[e], ar, az, an);
+        }
+      }
+      // generic-proxy writes (red in shared memory, h_t in global memory) must be ordered before the
+      // async-proxy (TMA) refill of hs / reads of h_t after the barrier
+      asm volatile("fence.proxy.async;\n" ::: "memory");
+    }
+    if (s + 1 < p.max_steps) {
+      TP_TRACE(4);
+      grid_barrier(p.barrier, ++epoch * gridDim.x);
+      TP_TRACE(5);
+    }
+  }
+}
