@@ -143,6 +143,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-live", action="store_true", help="skip the live-stream latency measurement")
+    ap.add_argument("--no-smpl", action="store_true", help="skip the SMPL-standalone (65,536 bodies) measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
 
@@ -255,11 +257,54 @@ def main():
                       "unit": "TFLOP/s", "frac": k1_flops / (k1_ms * 1e-3) / 1e12 / tf_peak, "avg_ms": k1_ms},
     }
 
+    # ---------------------------------------------------------------- live-stream latency (config 3, rank 0)
+    live = None
+    if rank == 0 and not args.no_live:
+        from tepose_b200.live import LiveTePose
+        stream = LiveTePose(model, batch=1)
+        feats = torch.from_numpy(synth.make_input(SEED + 7, 1, 64)[0, :, :2048]).to(dev)
+        n_live = 400
+        lev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_live)]
+        for i in range(50):
+            stream.step(feats[i % 64][None])
+        torch.cuda.synchronize(dev)
+        for i in range(n_live):
+            lev[i][0].record()
+            stream.step(feats[i % 64][None])          # device-resident feature row in, theta fed back on device
+            lev[i][1].record()
+        torch.cuda.synchronize(dev)
+        lat = np.array([a.elapsed_time(b_) for a, b_ in lev])
+        live = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)), "frames": n_live,
+                "mode": "carried-state causal step, B=1, theta feedback on device, CUDA graph per frame"}
+
+    # ---------------------------------------------------------------- SMPL standalone (config 4 shape, this rank's shard)
+    smpl_sa = None
+    if not args.no_smpl:
+        from tepose_b200 import shard as _shard
+        n_total = 65536
+        lo, hi = _shard.partition(n_total, world, rank)
+        bodies = synth.make_bodies(SEED + rank, hi - lo)
+        smpl = model.regressor.smpl
+        aa = torch.from_numpy(bodies["pose_aa"]).to(dev)
+        betas = torch.from_numpy(bodies["betas"]).to(dev)
+        with torch.no_grad():
+            smpl(betas=betas, body_pose=aa[:, 3:], global_orient=aa[:, :3])
+            torch.cuda.synchronize(dev)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(3):
+                smpl(betas=betas, body_pose=aa[:, 3:], global_orient=aa[:, :3])
+            s1.record()
+            torch.cuda.synchronize(dev)
+        sm_ms = s0.elapsed_time(s1) / 3
+        bps, sm_ms_max = _shard.aggregate_throughput(hi - lo, sm_ms, dev)
+        smpl_sa = {"bodies": n_total, "bodies_per_s": bps, "ms": sm_ms_max, "algorithmic_GBps_per_gpu":
+                   (hi - lo) * 85780 / (sm_ms * 1e-3) / 1e9, "hbm_frac": (hi - lo) * 85780 / (sm_ms * 1e-3) / 1e9 / hbm_peak}
+        del aa, betas
+
     # ---------------------------------------------------------------- aggregate over ranks
-    t = torch.tensor([dev_ms_total, e2e_ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    from tepose_b200 import shard as _sh
+    dev_ms_max, e2e_ms_max = _sh.max_over_ranks([dev_ms_total, e2e_ms_total], dev)
     frames = B * args.steps * world
     value = frames / (dev_ms_max * 1e-3)
     e2e_value = frames / (e2e_ms_max * 1e-3)
@@ -290,6 +335,8 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "stages_ms": stage_avg,
+            "live": live,
+            "smpl_standalone": smpl_sa,
             "step_ms": {"min": float(step_ms.min()), "median": float(np.median(step_ms)), "max": float(step_ms.max())},
             "wall_s_timed_region": t_wall,
         }

@@ -156,9 +156,11 @@ class TemporalEncoder(nn.Module):
         j._dev = dev
         return j
 
-    def encode_states(self, x: torch.Tensor, h0=None):
+    def encode_states(self, x: torch.Tensor, h0=None, return_states=False):
         """Runs K1 + K2.  Returns (h_fwd [B,H], h_rec [B,2H]) = (y[-1], y_rec[0]) of
-        lib/models/tepose.py:73-80.  h0 = (hF0, hB0) carries state (live-stream mode, L=1)."""
+        lib/models/tepose.py:73-80.  h0 = (hF0, hB0) carries state (live-stream mode, L=1);
+        with return_states the per-step states (yF [T,B,H], yB [T,B,H]) of the two causal
+        directions are returned as well."""
         nv.require_cuda(x, "input")
         if x.dim() != 3 or x.shape[2] != INPUT_SIZE:
             raise ValueError(f"expected input [B,T,{INPUT_SIZE}], got {tuple(x.shape)}")
@@ -172,8 +174,10 @@ class TemporalEncoder(nn.Module):
         x = x.detach().float()
         if x.stride(2) != 1:
             x = x.contiguous()
-        if h0 is not None and Ln != 1:
+        if (h0 is not None or return_states) and Ln != 1:
             raise ValueError("carried state is only defined for n_layers == 1 (SURVEY.md H5)")
+        seq_f = torch.empty(T, B, H, device=dev, dtype=torch.float32) if return_states else None
+        seq_b = torch.empty(T, B, H, device=dev, dtype=torch.float32) if return_states else None
         h_fwd = torch.empty(B, H, device=dev, dtype=torch.float32)
         h_rec = torch.empty(B, 2 * H, device=dev, dtype=torch.float32)
         y_f = y_r = y_f_lp = y_r_lp = None
@@ -229,8 +233,8 @@ class TemporalEncoder(nn.Module):
             w, b = d["w_hh"], d["b_hh"]
             if last:
                 jobs = [
-                    self._job(dev, gi_f, c_f, w[0], b[0], T, f_in[0], f_in[1], h0=hF0, h_final=h_fwd, hcol=0),
-                    self._job(dev, gi_b, c_b, w[1], b[1], T, b_in[0], b_in[1], h0=hB0, h_final=h_rec, hcol=H),
+                    self._job(dev, gi_f, c_f, w[0], b[0], T, f_in[0], f_in[1], h0=hF0, h_final=h_fwd, hcol=0, y=seq_f),
+                    self._job(dev, gi_b, c_b, w[1], b[1], T, b_in[0], b_in[1], h0=hB0, h_final=h_rec, hcol=H, y=seq_b),
                     self._job(dev, gi_s, c_s, w[2], b[2], 1, s_in[0] if gi_s.shape[0] != B else 0, s_in[1],
                               h_final=h_rec, hcol=0),
                 ]
@@ -247,6 +251,8 @@ class TemporalEncoder(nn.Module):
             nv.mark(f"k2_recurrence_l{l}")
             if not last:
                 y_f, y_r, y_f_lp, y_r_lp = ny_f, ny_r, ny_f_lp, ny_r_lp
+        if return_states:
+            return h_fwd, h_rec, seq_f, seq_b
         return h_fwd, h_rec
 
     def heads(self, h_fwd, h_rec, is_train=False):

@@ -48,3 +48,41 @@ def test_forward_full_size_against_oracle(L, H, T, B, precision):
         mpjpe = float((out["kp_3d"].cpu() - ref["kp_3d"]).norm(dim=-1).mean())
         assert mpjpe < 1e-3, mpjpe        # <= 1 mm MPJPE delta
     print(L, H, T, B, precision, errs)
+
+
+@pytest.mark.parametrize("precision,H,graph", [("fp32", 256, False), ("bf16", 2048, True)])
+def test_live_stream_carried_state(precision, H, graph):
+    """Config 3: causal carried-state stepping (B=1) against torch.nn.GRU stepped with explicit h0."""
+    from tepose_b200.live import LiveTePose
+    seed, B, N = 51, 1, 6
+    model, sd = build_product_model(seed, 16, 1, H, precision, DEV)
+    m = torch_ref.SmplModel.synthetic(seed)
+    feats = torch.from_numpy(synth.make_input(seed, B, N))[:, :, :2048]
+    live = LiveTePose(model, batch=B, use_graph=graph)
+    outs = [{k: v.clone().cpu() for k, v in live.step(feats[:, t].to(DEV)).items()} for t in range(N)]
+    hF = hB = prev = None
+    tol = {} if precision == "fp32" else dict(vert_tol=1e-3, rot_tol=2e-3, kp2d_tol=5e-2)
+    for t in range(N):
+        newest = torch.cat([feats[:, t], torch.zeros(B, 85)], dim=1)[:, None]
+        if prev is None:
+            hFt, hBt, hS = torch_ref.encoder_causal_states(sd, newest, H)
+        else:
+            hF, hB, _ = torch_ref.encoder_causal_states(sd, prev, H, h0=None if hF is None else (hF, hB))
+            hFt, hBt, hS = torch_ref.encoder_causal_states(sd, newest, H, h0=(hF, hB))
+        ref = torch_ref.regressor_forward(sd, m, torch_ref.encoder_from_states(sd, hFt, hBt, hS))
+        compare_outputs(outs[t], ref, label=f"live {precision} frame {t}", **tol)
+        # feed the oracle its own theta (the product feeds back its own): both chains stay within tolerance
+        prev = torch.cat([feats[:, t], ref["theta"]], dim=1)[:, None]
+
+
+def test_graphed_forward_equals_eager():
+    from tepose_b200.graph import GraphedTePose
+    model, sd = build_product_model(61, 16, 1, 256, "bf16", DEV)
+    x = torch.from_numpy(synth.make_input(61, 4, 16)).to(DEV)
+    eager = {k: v.clone() for k, v in model(x)[-1].items()}
+    g = GraphedTePose(model, 4, 16)
+    out = g(x)
+    torch.cuda.synchronize()
+    for k in eager:
+        assert torch.equal(out[k], eager[k]), k          # same kernels, same order: bitwise
+    assert g.launches_per_replay >= 15

@@ -111,3 +111,30 @@ def test_cpu_tensor_is_rejected_without_fallback():
     model, _ = build_product_model(34, 3, 1, 32)
     with pytest.raises(RuntimeError, match="no CPU path|CUDA"):
         model(torch.from_numpy(synth.make_input(34, 1, 3)))
+
+
+def test_live_stream_matches_causal_oracle():
+    """Carried-state live mode against torch.nn.GRU stepped with explicit h0."""
+    from tepose_b200.live import LiveTePose
+    seed, H, B, N = 41, 64, 2, 5
+    model, sd = build_product_model(seed, 16, 1, H)
+    m = torch_ref.SmplModel.synthetic(seed)
+    feats = torch.from_numpy(synth.make_input(seed, B, N))[:, :, :2048]
+    with fake_native.install():
+        live = LiveTePose(model, batch=B, use_graph=False)
+        outs = [{k: v.clone() for k, v in live.step(feats[:, t]).items()} for t in range(N)]
+    # oracle: feed frames in order, each committed with its own predicted theta
+    hF = hB = None
+    prev = None
+    for t in range(N):
+        newest = torch.cat([feats[:, t], torch.zeros(B, 85)], dim=1)[:, None]
+        if prev is None:
+            hFt, hBt, hS = torch_ref.encoder_causal_states(sd, newest, H)
+        else:
+            hFc, hBc, _ = torch_ref.encoder_causal_states(sd, prev, H, h0=None if hF is None else (hF, hB))
+            hF, hB = hFc, hBc
+            hFt, hBt, hS = torch_ref.encoder_causal_states(sd, newest, H, h0=(hF, hB))
+        feat = torch_ref.encoder_from_states(sd, hFt, hBt, hS)
+        ref = torch_ref.regressor_forward(sd, m, feat)
+        compare_outputs(outs[t], ref, label=f"live frame {t}")
+        prev = torch.cat([feats[:, t], ref["theta"]], dim=1)[:, None]
