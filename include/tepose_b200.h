@@ -112,6 +112,15 @@ TP_API int tp_skinny_bf16(const float* A, int64_t lda, int M, int K, const void*
                    const float* Cin, int64_t ldcin, float* C, int64_t ldc, float alpha, float beta,
                    int relu_a, int splits, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Extended form: A may also be given as a bf16 copy (A_bf16 [M, lda_bf16], read instead of A when
+ * non-NULL; K % 8 == 0), and the output can additionally be written as bf16 (C_bf16) for the next
+ * layer.  mode 0 = auto, 1 = split-K kernel (128 rows per CTA), 2 = single-phase kernel (one 16-row
+ * tile per CTA, K split over the warps; no workspace needed).                                    */
+TP_API int tp_skinny_bf16_ex(const float* A, int64_t lda, const void* A_bf16, int64_t lda_bf16, int M, int K,
+                      const void* Wp, int N, const float* bias, const float* Cin, int64_t ldcin, float* C,
+                      int64_t ldc, void* C_bf16, int64_t ldc_bf16, float alpha, float beta, int relu_a,
+                      int splits, int mode, void* workspace, size_t workspace_bytes, void* stream);
+
 /* One segment of a tensor-core GEMM launch: rows [m_start, m_start+m_rows) of A against rows
  * [n_start, n_start+n_cols) of W;  out[(m-m_start)*ldc + (n-n_start)] = dot + bias[n-n_start]. */
 typedef struct tp_gemm_seg {
@@ -173,7 +182,8 @@ TP_API int tp_gru_recurrence(const tp_gru_job* jobs, int njobs, int B, int H, in
 TP_API size_t tp_encoder_heads_workspace_bytes(int B);
 TP_API int tp_encoder_heads(int precision, const void* w_fwd, const float* b_fwd, const void* w_rec, const float* b_rec,
                      const float* h_fwd, int64_t ld_hf, const float* h_rec, int64_t ld_hr,
-                     int B, int H, int is_train, float* feat, void* workspace, size_t workspace_bytes, void* stream);
+                     int B, int H, int is_train, float* feat, void* feat_bf16 /* optional bf16 copy, same shape */,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* 3-iteration IEF loop (lib/models/spin.py:250-261).  fc1 is split into its feature columns
  * (w1x, iteration-invariant) and its [pose|shape|cam] columns (w1p, zero-padded 157 -> 160);
@@ -192,7 +202,8 @@ TP_API size_t tp_ief_workspace_bytes(int n_rows);
 /* feat [n_rows,2048]; init [init_rows,160] = pose6d(144)|shape(10)|cam(3)|0(3) with
  * init_rows == 1 (broadcast, the init_* buffers) or n_rows; psc [n_rows,160] receives the
  * refined pose6d | shape | cam | pad.                                                      */
-TP_API int tp_ief_forward(int precision, const tp_ief_weights* w, const float* feat, int n_rows, const float* init,
+TP_API int tp_ief_forward(int precision, const tp_ief_weights* w, const float* feat,
+                   const void* feat_bf16 /* optional bf16 copy of feat (bf16 precision) */, int n_rows, const float* init,
                    int init_rows, int n_iter, float* psc, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ SMPL forward (K4 + K5)

@@ -24,7 +24,7 @@ EXPORTS = [
     "tp_version", "tp_last_error", "tp_launch_count", "tp_device_info",
     "tp_rot6d_to_rotmat", "tp_rotmat_to_angle_axis", "tp_batch_rodrigues", "tp_projection",
     "tp_pack_rows", "tp_gemm_f32", "tp_gemm_f32_splitk_workspace_bytes", "tp_gemm_f32_splitk",
-    "tp_pack_mma_a_bytes", "tp_pack_mma_a_bf16", "tp_skinny_bf16_workspace_bytes", "tp_skinny_bf16", "tp_gemm_bf16_tc",
+    "tp_pack_mma_a_bytes", "tp_pack_mma_a_bf16", "tp_skinny_bf16_workspace_bytes", "tp_skinny_bf16", "tp_skinny_bf16_ex", "tp_gemm_bf16_tc",
     "tp_pack_whh_bf16", "tp_gru_set_trace", "tp_gru_workspace_bytes", "tp_gru_recurrence",
     "tp_encoder_heads_workspace_bytes", "tp_encoder_heads", "tp_ief_workspace_bytes", "tp_ief_forward",
     "tp_smpl_workspace_bytes", "tp_smpl_forward",
@@ -73,15 +73,17 @@ _SIGNATURES = {
     "tp_skinny_bf16_workspace_bytes": (sz, [C.c_int, C.c_int, C.c_int]),
     "tp_skinny_bf16": (C.c_int, [vp, i64, C.c_int, C.c_int, vp, C.c_int, vp, vp, i64, vp, i64, f32, f32, C.c_int, C.c_int,
                                  vp, sz, vp]),
+    "tp_skinny_bf16_ex": (C.c_int, [vp, i64, vp, i64, C.c_int, C.c_int, vp, C.c_int, vp, vp, i64, vp, i64, vp, i64, f32, f32,
+                                    C.c_int, C.c_int, C.c_int, vp, sz, vp]),
     "tp_gemm_bf16_tc": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.POINTER(GemmSeg), C.c_int, vp]),
     "tp_pack_whh_bf16": (C.c_int, [vp, vp, C.c_int, vp]),
     "tp_gru_set_trace": (None, [vp]),
     "tp_gru_workspace_bytes": (sz, [C.c_int, C.c_int, C.c_int]),
     "tp_gru_recurrence": (C.c_int, [C.POINTER(GruJob), C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, vp]),
     "tp_encoder_heads_workspace_bytes": (sz, [C.c_int]),
-    "tp_encoder_heads": (C.c_int, [C.c_int, vp, vp, vp, vp, vp, i64, vp, i64, C.c_int, C.c_int, C.c_int, vp, vp, sz, vp]),
+    "tp_encoder_heads": (C.c_int, [C.c_int, vp, vp, vp, vp, vp, i64, vp, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp, sz, vp]),
     "tp_ief_workspace_bytes": (sz, [C.c_int]),
-    "tp_ief_forward": (C.c_int, [C.c_int, C.POINTER(IefWeights), vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, sz, vp]),
+    "tp_ief_forward": (C.c_int, [C.c_int, C.POINTER(IefWeights), vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, sz, vp]),
     "tp_smpl_workspace_bytes": (sz, [C.POINTER(SmplModel), C.c_int, C.c_int]),
     "tp_smpl_forward": (C.c_int, [C.POINTER(SmplModel), C.c_int, vp, i64, C.c_int, vp, i64, vp, i64,
                                   vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, sz, vp]),

@@ -133,6 +133,9 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
   }
+  // bias of this tile's 128 columns -> shared memory now, so the epilogue does not wait on global loads
+  __shared__ float s_bias[TC_BN];
+  s_bias[threadIdx.x] = (sg.bias && n0 + (int)threadIdx.x < sg.n_cols) ? sg.bias[n0 + threadIdx.x] : 0.0f;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TC_BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
@@ -198,16 +201,14 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float4 o;
         o.x = __uint_as_float(v[q * 4 + 0]); o.y = __uint_as_float(v[q * 4 + 1]);
         o.z = __uint_as_float(v[q * 4 + 2]); o.w = __uint_as_float(v[q * 4 + 3]);
+        const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + q * 4]);
+        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
         if (n + 3 < sg.n_cols && vec_ok) {
-          if (sg.bias) {
-            const float4 bb = *reinterpret_cast<const float4*>(sg.bias + n);
-            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-          }
           *reinterpret_cast<float4*>(out_row + n) = o;
         } else {
           const float e[4] = {o.x, o.y, o.z, o.w};
           for (int i = 0; i < 4; ++i)
-            if (n + i < sg.n_cols) out_row[n + i] = e[i] + (sg.bias ? sg.bias[n + i] : 0.0f);
+            if (n + i < sg.n_cols) out_row[n + i] = e[i];
         }
       }
     }

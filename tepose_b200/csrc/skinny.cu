@@ -62,7 +62,50 @@ struct SkArgs {
   const float* bias; const float* Cin; int64_t ldcin; float* C; int64_t ldc;
   float alpha, beta; int relu_a;
   float* part; unsigned int* tickets;
+  const __nv_bfloat16* Alp; int64_t ldalp;   // optional bf16 copy of A (read instead of A when non-null)
+  __nv_bfloat16* Clp; int64_t ldclp;         // optional bf16 copy of the output (next layer's Alp)
 };
+
+// act(A)[0:NB, 32*kb_lo : 32*(kb_lo+nkb)] -> bf16 rows of `pitch` elements in shared memory.
+// Reads the bf16 copy when the producer left one (no conversion, half the bytes), else converts fp32.
+template <int NB>
+__device__ __forceinline__ void stage_activations(const SkArgs& a, __nv_bfloat16* As, int pitch, int kb_lo, int nkb,
+                                                  int warp, int lane) {
+  if (a.Alp) {
+    const int c8n = nkb * 4;                                   // 16-byte (8 x bf16) groups per row
+#pragma unroll 4
+    for (int r = warp; r < NB; r += kSkThreads / 32) {
+#pragma unroll 2
+      for (int c8 = lane; c8 < c8n; c8 += 32) {
+        const int col = kb_lo * 32 + c8 * 8;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < a.M && col < a.K) v = __ldcg(reinterpret_cast<const uint4*>(a.Alp + (int64_t)r * a.ldalp + col));  // K % 8 == 0
+        if (a.relu_a) {
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+          const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) h[i] = __hmax2(h[i], z);
+        }
+        *reinterpret_cast<uint4*>(As + (size_t)r * pitch + c8 * 8) = v;
+      }
+    }
+    return;
+  }
+  const int c4n = nkb * 8;                                     // float4 groups per row
+#pragma unroll 4
+  for (int r = warp; r < NB; r += kSkThreads / 32) {
+#pragma unroll 2
+    for (int c4 = lane; c4 < c4n; c4 += 32) {
+      const int col = kb_lo * 32 + c4 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < a.M && col < a.K) v = __ldcg(reinterpret_cast<const float4*>(a.A + (int64_t)r * a.lda + col));  // K % 4 == 0
+      if (a.relu_a) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      *reinterpret_cast<uint2*>(As + (size_t)r * pitch + c4 * 4) = pk;
+    }
+  }
+}
 
 template <int NT>
 __global__ void __launch_bounds__(kSkThreads, 1) k_skinny_bf16(const SkArgs a) {
@@ -86,23 +129,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_skinny_bf16(const SkArgs a) {
     for (int q = 0; q < kSkPF; ++q)
       if (q < nkb) { wa[q] = ldg_stream16(wp + (int64_t)q * 64); wb[q] = ldg_stream16(wp + (int64_t)q * 64 + 32); }
   }
-  // stage act(A)[0:NB, K slice] as bf16
-  {
-    const int c4n = nkb * 8;                                   // float4 groups per row
-#pragma unroll 4
-    for (int r = warp; r < NB; r += kSkThreads / 32) {
-#pragma unroll 2
-      for (int c4 = lane; c4 < c4n; c4 += 32) {
-        const int col = kb_lo * 32 + c4 * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < a.M && col < a.K) v = *reinterpret_cast<const float4*>(a.A + (int64_t)r * a.lda + col);  // K % 4 == 0
-        if (a.relu_a) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-        uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-        *reinterpret_cast<uint2*>(As + (size_t)r * pitch + c4 * 4) = pk;
-      }
-    }
-  }
+  stage_activations<NB>(a, As, pitch, kb_lo, nkb, warp, lane);
   __syncthreads();
 
   float acc[NT][4];
@@ -152,7 +179,11 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_skinny_bf16(const SkArgs a) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int m = n * 8 + 2 * t + (e & 1), nn = nn0 + (e >> 1) * 8;
-          if (m < a.M && nn < a.N) a.C[(int64_t)m * a.ldc + nn] = (acc[n][e] + bia[e >> 1]) * a.alpha + a.beta * cin[n][e];
+          if (m < a.M && nn < a.N) {
+            const float v = (acc[n][e] + bia[e >> 1]) * a.alpha + a.beta * cin[n][e];
+            a.C[(int64_t)m * a.ldc + nn] = v;
+            if (a.Clp) a.Clp[(int64_t)m * a.ldclp + nn] = __float2bfloat16_rn(v);
+          }
         }
     }
     return;
@@ -200,9 +231,86 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_skinny_bf16(const SkArgs a) {
 #pragma unroll
   for (int i = 0; i < EPT; ++i) {
     const int m = (tid + i * kSkThreads) / kSkRows;
-    if (m < a.M && nn < a.N) a.C[(int64_t)m * a.ldc + nn] = (sum[i] + bia) * a.alpha + a.beta * cin[i];
+    if (m < a.M && nn < a.N) {
+      const float v = (sum[i] + bia) * a.alpha + a.beta * cin[i];
+      a.C[(int64_t)m * a.ldc + nn] = v;
+      if (a.Clp) a.Clp[(int64_t)m * a.ldclp + nn] = __float2bfloat16_rn(v);
+    }
   }
   if (tid == 0) a.tickets[blockIdx.x] = 0;
+}
+
+// Single-phase variant for small layers (N <= ~1024): one 16-row weight tile per CTA, the 8 warps
+// split K, partial sums meet in shared memory, no cross-CTA reduction and no second dependent pass.
+template <int NT>
+__global__ void __launch_bounds__(kSkThreads, 1) k_skinny_mt(const SkArgs a) {
+  constexpr int NB = NT * 8, RPW = 17;
+  extern __shared__ __align__(16) unsigned char sk_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int nkb = a.kb_total;
+  const int pitch = ((nkb * 32 + 63) / 64) * 64 + 32;
+  __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(sk_smem);
+  float* red = reinterpret_cast<float*>(sk_smem + (size_t)NB * pitch * 2);      // [8][NB][17]
+  const int ut = blockIdx.x;
+  const int b_lo = (warp * nkb) / 8, b_hi = ((warp + 1) * nkb) / 8, nb = b_hi - b_lo;
+
+  uint4 wa[kSkPF], wb[kSkPF];
+  const uint4* wp = a.Wp + ((int64_t)ut * a.kb_total + b_lo) * 64 + lane;
+#pragma unroll
+  for (int q = 0; q < kSkPF; ++q)
+    if (q < nb) { wa[q] = ldg_stream16(wp + (int64_t)q * 64); wb[q] = ldg_stream16(wp + (int64_t)q * 64 + 32); }
+  stage_activations<NB>(a, As, pitch, 0, nkb, warp, lane);
+  __syncthreads();
+
+  float acc[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.0f;
+  for (int blk = 0; blk < nb; blk += kSkPF) {
+#pragma unroll
+    for (int q = 0; q < kSkPF; ++q) {
+      const int cur = blk + q;
+      if (cur < nb) {
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          const uint4 bv = *reinterpret_cast<const uint4*>(As + (size_t)(n * 8 + g) * pitch + (b_lo + cur) * 32 + 8 * t);
+          mma16816(acc[n], wa[q], bv.x, bv.y);
+          mma16816(acc[n], wb[q], bv.z, bv.w);
+        }
+        if (cur + kSkPF < nb) {
+          wa[q] = ldg_stream16(wp + (int64_t)(cur + kSkPF) * 64);
+          wb[q] = ldg_stream16(wp + (int64_t)(cur + kSkPF) * 64 + 32);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    float* r0 = red + ((size_t)warp * NB + n * 8 + 2 * t) * RPW + g;
+    r0[0] = acc[n][0]; r0[RPW] = acc[n][1]; r0[8] = acc[n][2]; r0[RPW + 8] = acc[n][3];
+  }
+  __syncthreads();
+  constexpr int EPT = NB * 16 / kSkThreads;                     // 2 (NB = 32) or 4 (NB = 64); NB = 8 -> 1 with a guard
+  float sum[EPT > 0 ? EPT : 1], cin[EPT > 0 ? EPT : 1];
+  constexpr int E = EPT > 0 ? EPT : 1;
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    const int idx = tid + i * kSkThreads, m = idx >> 4, r = idx & 15, nn = ut * 16 + r;
+    sum[i] = 0.0f; cin[i] = 0.0f;
+    if (idx < NB * 16) {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum[i] += red[((size_t)w * NB + m) * RPW + r];
+      if (a.Cin && m < a.M && nn < a.N) cin[i] = __ldcg(a.Cin + (int64_t)m * a.ldcin + nn);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    const int idx = tid + i * kSkThreads, m = idx >> 4, r = idx & 15, nn = ut * 16 + r;
+    if (idx < NB * 16 && m < a.M && nn < a.N) {
+      const float v = (sum[i] + (a.bias ? __ldg(a.bias + nn) : 0.0f)) * a.alpha + a.beta * cin[i];
+      a.C[(int64_t)m * a.ldc + nn] = v;
+      if (a.Clp) a.Clp[(int64_t)m * a.ldclp + nn] = __float2bfloat16_rn(v);
+    }
+  }
 }
 
 }  // namespace tp
@@ -227,25 +335,54 @@ extern "C" size_t tp_skinny_bf16_workspace_bytes(int M, int N, int splits) {
   return kSkTicketBytes + (size_t)(splits > 1 ? splits : 0) * groups * nb * kSkRows * sizeof(float);
 }
 
-extern "C" int tp_skinny_bf16(const float* A, int64_t lda, int M, int K, const void* Wp, int N, const float* bias,
-                              const float* Cin, int64_t ldcin, float* C, int64_t ldc, float alpha, float beta,
-                              int relu_a, int splits, void* workspace, size_t workspace_bytes, void* stream) {
-  TP_CHECK_ARG(A && Wp && C, "tp_skinny_bf16: null pointer");
+// mode: 0 = auto, 1 = force split kernel, 2 = force single-phase kernel
+static int skinny_dispatch(const float* A, int64_t lda, const void* Alp, int64_t ldalp, int M, int K, const void* Wp, int N,
+                           const float* bias, const float* Cin, int64_t ldcin, float* C, int64_t ldc, void* Clp,
+                           int64_t ldclp, float alpha, float beta, int relu_a, int splits, int mode, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  TP_CHECK_ARG((A || Alp) && Wp && C, "tp_skinny_bf16: null pointer");
   TP_CHECK_ARG(M >= 1 && M <= 64, "tp_skinny_bf16: M=%d must be in [1,64]", M);
-  TP_CHECK_ARG(N >= 1 && K >= 4 && K % 4 == 0 && lda % 4 == 0, "tp_skinny_bf16: need K %% 4 == 0 and lda %% 4 == 0 (K=%d lda=%lld)", K, (long long)lda);
-  TP_CHECK_ARG(aligned16(A) && aligned16(Wp), "tp_skinny_bf16: A / Wp must be 16-byte aligned");
+  TP_CHECK_ARG(N >= 1 && K >= 4 && K % 4 == 0, "tp_skinny_bf16: need K %% 4 == 0 (K=%d)", K);
+  TP_CHECK_ARG(!A || (lda % 4 == 0 && aligned16(A)), "tp_skinny_bf16: A must be 16-byte aligned with lda %% 4 == 0");
+  TP_CHECK_ARG(!Alp || (K % 8 == 0 && ldalp % 8 == 0 && aligned16(Alp)), "tp_skinny_bf16: bf16 A needs K, ld %% 8 == 0 and 16-byte alignment");
+  TP_CHECK_ARG(aligned16(Wp), "tp_skinny_bf16: Wp must be 16-byte aligned");
   SkArgs a;
   a.A = A; a.lda = lda; a.M = M; a.K = K; a.N = N;
+  a.Alp = reinterpret_cast<const __nv_bfloat16*>(Alp); a.ldalp = ldalp;
+  a.Clp = reinterpret_cast<__nv_bfloat16*>(Clp); a.ldclp = ldclp;
   a.Wp = reinterpret_cast<const uint4*>(Wp);
   a.ut_total = (N + 15) / 16; a.kb_total = (K + 31) / 32;
   a.bias = bias; a.Cin = Cin; a.ldcin = ldcin; a.C = C; a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.relu_a = relu_a;
+  a.part = nullptr; a.tickets = nullptr; a.kb_per_split = a.kb_total;
+  const int nb = M <= 8 ? 8 : (M <= 32 ? 32 : 64);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  // single-phase kernel: whole K staged per CTA
+  const int pitch_all = ((a.kb_total * 32 + 63) / 64) * 64 + 32;
+  const size_t smem_mt = (size_t)nb * pitch_all * 2 + (size_t)8 * nb * 17 * 4;
+  const bool mt_ok = smem_mt <= 200 * 1024;
+  if (mode == 2 || (mode == 0 && mt_ok && N <= 1024)) {
+    if (!mt_ok) return fail(TP_ERR_UNSUPPORTED, "tp_skinny_bf16: K=%d too large for the single-phase kernel", K);
+    dim3 grid((unsigned)a.ut_total);
+    if (nb == 8) {
+      TP_CUDA(cudaFuncSetAttribute(k_skinny_mt<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mt));
+      k_skinny_mt<1><<<grid, kSkThreads, smem_mt, st>>>(a);
+    } else if (nb == 32) {
+      TP_CUDA(cudaFuncSetAttribute(k_skinny_mt<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mt));
+      k_skinny_mt<4><<<grid, kSkThreads, smem_mt, st>>>(a);
+    } else {
+      TP_CUDA(cudaFuncSetAttribute(k_skinny_mt<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mt));
+      k_skinny_mt<8><<<grid, kSkThreads, smem_mt, st>>>(a);
+    }
+    TP_LAUNCH_CHECK();
+    return TP_OK;
+  }
+
   const int groups = (N + kSkRows - 1) / kSkRows;
   if (splits < 1) splits = 1;
   if (splits > a.kb_total) splits = a.kb_total;
   a.kb_per_split = (a.kb_total + splits - 1) / splits;
   splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
-  a.part = nullptr; a.tickets = nullptr;
-  const int nb = M <= 8 ? 8 : (M <= 32 ? 32 : 64);
   if (splits > 1) {
     const size_t need = kSkTicketBytes + (size_t)splits * groups * nb * kSkRows * sizeof(float);
     TP_CHECK_ARG(workspace && workspace_bytes >= need && (size_t)groups * 4 <= kSkTicketBytes && aligned16(workspace),
@@ -257,7 +394,6 @@ extern "C" int tp_skinny_bf16(const float* A, int64_t lda, int M, int K, const v
   const size_t smem = (size_t)nb * pitch * 2;
   if (smem > 200 * 1024) return fail(TP_ERR_UNSUPPORTED, "tp_skinny_bf16: K slice of %d columns does not fit in shared memory; raise splits", a.kb_per_split * 32);
   dim3 grid((unsigned)groups, (unsigned)splits);
-  cudaStream_t st = (cudaStream_t)stream;
   if (nb == 8) {
     TP_CUDA(cudaFuncSetAttribute(k_skinny_bf16<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_skinny_bf16<1><<<grid, kSkThreads, smem, st>>>(a);
@@ -270,4 +406,20 @@ extern "C" int tp_skinny_bf16(const float* A, int64_t lda, int M, int K, const v
   }
   TP_LAUNCH_CHECK();
   return TP_OK;
+}
+
+extern "C" int tp_skinny_bf16(const float* A, int64_t lda, int M, int K, const void* Wp, int N, const float* bias,
+                              const float* Cin, int64_t ldcin, float* C, int64_t ldc, float alpha, float beta,
+                              int relu_a, int splits, void* workspace, size_t workspace_bytes, void* stream) {
+  TP_CHECK_ARG(A != nullptr, "tp_skinny_bf16: null A");
+  return skinny_dispatch(A, lda, nullptr, 0, M, K, Wp, N, bias, Cin, ldcin, C, ldc, nullptr, 0, alpha, beta, relu_a,
+                         splits, splits > 1 ? 1 : 0, workspace, workspace_bytes, stream);
+}
+
+extern "C" int tp_skinny_bf16_ex(const float* A, int64_t lda, const void* A_bf16, int64_t lda_bf16, int M, int K,
+                                 const void* Wp, int N, const float* bias, const float* Cin, int64_t ldcin, float* C,
+                                 int64_t ldc, void* C_bf16, int64_t ldc_bf16, float alpha, float beta, int relu_a,
+                                 int splits, int mode, void* workspace, size_t workspace_bytes, void* stream) {
+  return skinny_dispatch(A, lda, A_bf16, lda_bf16, M, K, Wp, N, bias, Cin, ldcin, C, ldc, C_bf16, ldc_bf16, alpha, beta,
+                         relu_a, splits, mode, workspace, workspace_bytes, stream);
 }

@@ -94,6 +94,9 @@ class Regressor(nn.Module):
         dev = x.device
         N = x.shape[0]
         feat = x.detach().contiguous().float()
+        feat_lp = getattr(x, "_tp_bf16", None) if self.precision == "bf16" else None
+        if feat_lp is not None and (feat_lp.shape != feat.shape or not feat_lp.is_contiguous()):
+            feat_lp = None
         if init_pose is None and init_shape is None and init_cam is None:
             init, init_rows = pk["init"], 1
         else:
@@ -108,7 +111,7 @@ class Regressor(nn.Module):
         L = nv.lib()
         psc = torch.empty(N, PSC, device=dev, dtype=torch.float32)
         ws = nv.workspace(L.tp_ief_workspace_bytes(N), dev)
-        nv.check(L.tp_ief_forward(nv.PRECISIONS[self.precision], pk["c"], nv.ptr(feat), N, nv.ptr(init), init_rows, n_iter, nv.ptr(psc),
+        nv.check(L.tp_ief_forward(nv.PRECISIONS[self.precision], pk["c"], nv.ptr(feat), nv.ptr(feat_lp), N, nv.ptr(init), init_rows, n_iter, nv.ptr(psc),
                                   nv.ptr(ws), ws.numel(), nv.stream()), "tp_ief_forward")
         nv.mark("k3_ief")
         return self.decode(psc, is_train=is_train, J_regressor=J_regressor)

@@ -261,11 +261,13 @@ class TemporalEncoder(nn.Module):
         B, H = h_fwd.shape[0], self.hidden_size
         feat = torch.empty((B, 2, 2048) if is_train else (B, 2048), device=h_fwd.device, dtype=torch.float32)
         L = nv.lib()
+        feat_lp = torch.empty_like(feat, dtype=torch.bfloat16) if self.precision == "bf16" else None
         ws = nv.workspace(L.tp_encoder_heads_workspace_bytes(B), h_fwd.device)
         nv.check(L.tp_encoder_heads(nv.PRECISIONS[self.precision], nv.ptr(pk["w_fwd"]), nv.ptr(pk["b_fwd"]), nv.ptr(pk["w_rec"]), nv.ptr(pk["b_rec"]),
                                     nv.ptr(h_fwd), h_fwd.shape[1], nv.ptr(h_rec), h_rec.shape[1], B, H,
-                                    1 if is_train else 0, nv.ptr(feat), nv.ptr(ws), ws.numel(), nv.stream()),
+                                    1 if is_train else 0, nv.ptr(feat), nv.ptr(feat_lp), nv.ptr(ws), ws.numel(), nv.stream()),
                  "tp_encoder_heads")
+        feat._tp_bf16 = feat_lp          # bf16 copy rides along for the IEF (same storage order)
         nv.mark("k3_heads")
         return feat
 
@@ -307,7 +309,10 @@ class TePose(nn.Module):
         batch_size = input.shape[0]
         nv.mark("start")
         feature = self.encoder(input, is_train=is_train)
+        lp = getattr(feature, "_tp_bf16", None)
         feature = feature.reshape(-1, feature.size(-1))
+        if lp is not None:
+            feature._tp_bf16 = lp.reshape(-1, lp.size(-1))
         smpl_output = self.regressor(feature, is_train=is_train, J_regressor=J_regressor)
         lead = (batch_size, 2) if is_train else (batch_size,)
         for s in smpl_output:                                  # lib/models/tepose.py:130-145

@@ -166,7 +166,7 @@ class FakeLib:
     def _act(precision, a):
         return a.to(torch.bfloat16).float() if precision == nv.PRECISION_BF16 else a
 
-    def tp_encoder_heads(self, precision, w_fwd, b_fwd, w_rec, b_rec, h_fwd, ld_hf, h_rec, ld_hr, B, H, is_train, feat, ws, ws_bytes, stream):
+    def tp_encoder_heads(self, precision, w_fwd, b_fwd, w_rec, b_rec, h_fwd, ld_hf, h_rec, ld_hr, B, H, is_train, feat, feat_lp, ws, ws_bytes, stream):
         q = lambda t: self._act(precision, t)
         a = q(_mat(h_fwd, B, H, ld_hf).clamp_min(0)) @ self._lin(precision, w_fwd, 2048, H).t() + _view(b_fwd, 2048, torch.float32)
         b = q(_mat(h_rec, B, 2 * H, ld_hr).clamp_min(0)) @ self._lin(precision, w_rec, 2048, 2 * H).t() + _view(b_rec, 2048, torch.float32)
@@ -179,7 +179,7 @@ class FakeLib:
     def tp_ief_workspace_bytes(self, n):
         return 256
 
-    def tp_ief_forward(self, precision, w, feat, n_rows, init, init_rows, n_iter, psc, ws, ws_bytes, stream):
+    def tp_ief_forward(self, precision, w, feat, feat_lp, n_rows, init, init_rows, n_iter, psc, ws, ws_bytes, stream):
         w = w.contents if hasattr(w, "contents") else w
         q = lambda t: self._act(precision, t)
         lin = lambda ptr_, n, k: self._lin(precision, ptr_, n, k)

@@ -120,6 +120,27 @@ def test_skinny_bf16(M, N, K, splits):
     assert int(ws[:4096].view(torch.int32).abs().sum()) == 0
 
 
+@pytest.mark.parametrize("M,N,K", [(32, 1024, 1024), (32, 160, 1024), (32, 1024, 160), (64, 1024, 2048), (3, 96, 64)])
+def test_skinny_bf16_single_phase_and_bf16_io(M, N, K):
+    g = torch.Generator().manual_seed(3 * M + N + K)
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    b, Cin = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    a, bb, c = cu(A), cu(b), cu(Cin)
+    a_lp = A.to(torch.bfloat16).to(DEV)
+    L = nv.lib()
+    wp = nv.pack_linear(cu(W), "bf16")
+    ref = (A.to(torch.bfloat16).double() @ W.to(torch.bfloat16).double().t() + b.double()) + Cin.double()
+    for use_lp in (False, True):
+        out = c.clone()
+        out_lp = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+        nv.check(L.tp_skinny_bf16_ex(nv.vp(0) if use_lp else nv.ptr(a), K, nv.ptr(a_lp) if use_lp else nv.vp(0), K, M, K,
+                                     nv.ptr(wp), N, nv.ptr(bb), nv.ptr(out), N, nv.ptr(out), N, nv.ptr(out_lp), N,
+                                     1.0, 1.0, 0, 1, 2, nv.vp(0), 0, nv.stream()))
+        err = float((out.cpu().double() - ref).abs().max())
+        assert err < 1e-4, (use_lp, err)
+        assert torch.equal(out_lp.cpu(), out.cpu().to(torch.bfloat16))
+
+
 def test_pack_rows():
     x = torch.randn(3, 5, 2133)
     xs = cu(x)
