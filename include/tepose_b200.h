@@ -185,6 +185,13 @@ TP_API int tp_encoder_heads(int precision, const void* w_fwd, const float* b_fwd
                      int B, int H, int is_train, float* feat, void* feat_bf16 /* optional bf16 copy, same shape */,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Eval-mode heads as one GEMM over the concatenated state h_cat [B,3H] = [y[-1] | y_rec[0]] with
+ * w_cat = [0.5 W_fwd | 0.5 W_rec] ([2048,3H]; fp32 row-major or tp_pack_mma_a_bf16) and
+ * b_cat = 0.5 (b_fwd + b_rec): identical to (linear_fwd(relu) + linear_rec(relu)) / 2.            */
+TP_API int tp_encoder_heads_cat(int precision, const void* w_cat, const float* b_cat, const float* h_cat, int64_t ld_h,
+                         int B, int H, float* feat, void* feat_bf16, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* 3-iteration IEF loop (lib/models/spin.py:250-261).  fc1 is split into its feature columns
  * (w1x, iteration-invariant) and its [pose|shape|cam] columns (w1p, zero-padded 157 -> 160);
  * decpose/decshape/deccam are stacked into one [160,1024] matrix.                         */
@@ -220,9 +227,16 @@ typedef struct tp_smpl_model {
   int32_t ks;              /* retained weights per vertex (4 for SMPL; up to 24)                */
   int32_t n_verts;         /* 6890 */
   int32_t vp;              /* n_verts rounded up to a multiple of 128 */
+  /* optional tables of the tensor-core blend path (blend_mode 1); NULL disables it:
+   * blend_tc    : tp_pack_mma_a_bf16 of the [3*vp, 256] matrix whose row ((v/16)*3 + c)*16 + v%16 holds, for
+   *               vertex v / coordinate c: 207 pose-blend columns | S_hi (10) | S_hi (10) | S_lo (10) | 0,
+   *               with S_hi = bf16(shapedirs), S_lo = shapedirs - S_hi
+   * template_pad: [vp,3] fp32 v_template (zero rows beyond n_verts)                                      */
+  const void* blend_tc;
+  const float* template_pad;
 } tp_smpl_model;
 
-TP_API size_t tp_smpl_workspace_bytes(const tp_smpl_model* m, int n, int nreg);
+TP_API size_t tp_smpl_workspace_bytes(const tp_smpl_model* m, int n, int nreg, int blend_mode);
 /* smplx.SMPL.forward + lbs (restated third-party code), the wrapper
  * lib/models/smpl.py:72-84, the optional H36M regression lib/models/spin.py:275-278, the
  * projection spin.py:280 and the theta assembly spin.py:282-285 in three launches:
@@ -237,6 +251,7 @@ TP_API int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose, int
                     const float* betas, int64_t ld_betas, const float* cam, int64_t ld_cam,
                     const float* jreg, int nreg, const int32_t* joint_src, int nj,
                     float* verts, float* joints, float* kp2d, float* rotmat, float* theta,
+                    int blend_mode /* 0: fp32 FFMA blend (strict); 1: bf16 tensor-core blend (needs blend_tc) */,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

@@ -8,7 +8,7 @@ run() { # name, timeout, pytest args...
   timeout "$t" python -m pytest "$@" -q --no-header -p no:cacheprovider > "gpurun_out/$name.log" 2>&1
   echo "== $name exit=$? $(tail -1 gpurun_out/$name.log)"
 }
-run safe 600 tests/test_gpu_kernels.py -m gpu -k "geometry or gemm_f32 or pack_rows or smpl"
+run safe 600 tests/test_gpu_kernels.py -m gpu -k "geometry or gemm_f32 or pack_rows or smpl or skinny"
 run gru 600 tests/test_gpu_kernels.py -m gpu -k "gru"
 run tc 300 tests/test_gpu_kernels.py -m gpu -k "tcgen05"
 run e2e 900 tests/test_gpu_e2e.py -m gpu -s

@@ -1,6 +1,8 @@
 #!/bin/bash
-# full GPU parity suites + bench (bf16) in one call
+# full GPU parity suites + traces + bench (bf16) in one call
 bash scripts/gpu_check.sh
+timeout 300 python scripts/ief_trace.py 2>&1 | grep -E "cta 0|layer [0-3]:|span|regressor" | head -8
+timeout 300 python scripts/gru_trace.py 2>&1 | grep -E "cta   0|cta 100"
 timeout 900 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err; echo "bench bf16 exit=$?"
 python - <<'PY'
 import json

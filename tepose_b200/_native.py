@@ -26,7 +26,7 @@ EXPORTS = [
     "tp_pack_rows", "tp_gemm_f32", "tp_gemm_f32_splitk_workspace_bytes", "tp_gemm_f32_splitk",
     "tp_pack_mma_a_bytes", "tp_pack_mma_a_bf16", "tp_skinny_bf16_workspace_bytes", "tp_skinny_bf16", "tp_skinny_bf16_ex", "tp_gemm_bf16_tc",
     "tp_pack_whh_bf16", "tp_gru_set_trace", "tp_gru_workspace_bytes", "tp_gru_recurrence",
-    "tp_encoder_heads_workspace_bytes", "tp_encoder_heads", "tp_ief_workspace_bytes", "tp_ief_forward",
+    "tp_encoder_heads_workspace_bytes", "tp_encoder_heads", "tp_encoder_heads_cat", "tp_ief_workspace_bytes", "tp_ief_forward",
     "tp_smpl_workspace_bytes", "tp_smpl_forward",
 ]
 
@@ -51,7 +51,8 @@ class IefWeights(C.Structure):
 
 class SmplModel(C.Structure):
     _fields_ = [("blend", vp), ("j_template", vp), ("j_shapedirs", vp), ("parents", vp),
-                ("skin_idx", vp), ("skin_w", vp), ("ks", i32), ("n_verts", i32), ("vp", i32)]
+                ("skin_idx", vp), ("skin_w", vp), ("ks", i32), ("n_verts", i32), ("vp", i32),
+                ("blend_tc", vp), ("template_pad", vp)]
 
 
 _SIGNATURES = {
@@ -82,11 +83,12 @@ _SIGNATURES = {
     "tp_gru_recurrence": (C.c_int, [C.POINTER(GruJob), C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, vp]),
     "tp_encoder_heads_workspace_bytes": (sz, [C.c_int]),
     "tp_encoder_heads": (C.c_int, [C.c_int, vp, vp, vp, vp, vp, i64, vp, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp, sz, vp]),
+    "tp_encoder_heads_cat": (C.c_int, [C.c_int, vp, vp, vp, i64, C.c_int, C.c_int, vp, vp, vp, sz, vp]),
     "tp_ief_workspace_bytes": (sz, [C.c_int]),
     "tp_ief_forward": (C.c_int, [C.c_int, C.POINTER(IefWeights), vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, sz, vp]),
-    "tp_smpl_workspace_bytes": (sz, [C.POINTER(SmplModel), C.c_int, C.c_int]),
+    "tp_smpl_workspace_bytes": (sz, [C.POINTER(SmplModel), C.c_int, C.c_int, C.c_int]),
     "tp_smpl_forward": (C.c_int, [C.POINTER(SmplModel), C.c_int, vp, i64, C.c_int, vp, i64, vp, i64,
-                                  vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, sz, vp]),
+                                  vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, sz, vp]),
 }
 
 _lib = None

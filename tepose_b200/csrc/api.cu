@@ -25,6 +25,10 @@ static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
+static long long* g_trace = nullptr;
+long long* trace_ptr() { return g_trace; }
+void set_trace_ptr(long long* p) { g_trace = p; }
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;

@@ -40,6 +40,31 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int sm_count();  // of the current device (cached)
-void count_launch();  // bumps the counter behind tp_launch_count()
+void count_launch();
+long long* trace_ptr();          // debug stamp buffer (tp_gru_set_trace), or null
+void set_trace_ptr(long long* p);  // bumps the counter behind tp_launch_count()
+
+
+#ifdef __CUDACC__
+// Grid barrier for a co-resident (cooperatively launched) grid: one arrival per CTA on a
+// monotonic counter, release/acquire at gpu scope (the release is cumulative over the CTA's
+// writes that thread 0 observed through bar.sync).  State that crosses the barrier is read with
+// L2-coherent loads (cp.async.cg / ld.global.cg), so no L1 invalidation is needed.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int seen;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
+    // relaxed polls (ld.acquire in the loop would invalidate the whole L1 -- CCTL.IVALL -- on every
+    // iteration), then ONE acquire fence once the last arrival has been observed
+    do {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+    asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+  }
+  __syncthreads();
+}
+
+#endif
 
 }  // namespace tp

@@ -19,6 +19,7 @@
 namespace tp {
 
 constexpr int kMaxJobs = 4;
+constexpr int kHRep = 4;          // replicas of the bf16 state (readers spread over them: L2 hot-spot relief)
 constexpr int kGruThreads = 256;
 
 struct GruParams {
@@ -27,7 +28,8 @@ struct GruParams {
   int njobs, B, H, U, max_steps, total_items, any_h0;
   int n_item_jobs;          // jobs [0, n_item_jobs) are cut into items; the rest are step-0-only elementwise jobs
   float* hbuf;              // [njobs][2][B][H]  fp32 state ping-pong
-  __nv_bfloat16* hbuf_lp;   // [njobs][2][B][H]  bf16 copy (MMA operand of the next step)
+  __nv_bfloat16* hbuf_lp;   // [kHRep][njobs][2][B][H]  bf16 copies (MMA operand of the next step)
+  size_t lp_rep_stride;     // elements between replicas
   unsigned int* barrier;    // monotonic grid-barrier counter (zeroed by the host before launch)
   long long* trace;         // debug: [gridDim][max_steps][8] SM-clock stamps (tp_gru_set_trace), or null
 };
@@ -37,23 +39,11 @@ struct GruParams {
     if (p.trace && threadIdx.x == 0) p.trace[((size_t)blockIdx.x * p.max_steps + s) * 8 + (slot)] = clock64(); \
   } while (0)
 
-// Grid barrier for a co-resident (cooperatively launched) grid: one arrival per CTA on a
-// monotonic counter, release/acquire at gpu scope.  State that crosses the barrier is read with
-// L2-coherent loads (cp.async.cg / ld.global.cg), so no L1 invalidation is needed.
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int seen;
-    __threadfence();   // cumulative: orders the whole CTA's prior writes (observed via bar.sync) before the arrival
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(counter) : "memory");
-    } while (seen < target);
-  }
-  __syncthreads();
-}
-
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// bf16 mode: the state is re-quantised to bf16 every step (2^-9 relative), so SFU-based
+// exp / divide (~1e-6 absolute) are far below the mode's own rounding.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 2.0f * sigmoid_fast(2.0f * x) - 1.0f; }
 
 __device__ __forceinline__ void cp_async16_z(void* smem, const void* gmem, bool valid) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -98,17 +88,29 @@ __device__ __forceinline__ GateIn gate_fetch(const GruParams& p, int j, int s, i
 }
 
 // Gate math of torch.nn.GRU for one (batch b, hidden unit u): acc_* are W_h* . h_prev.
+template <bool FAST = false>
 __device__ __forceinline__ void gru_finalize(const GruParams& p, int j, int s, int b, int u, const GateIn& g,
                                              float acc_r, float acc_z, float acc_n) {
   const tp_gru_job& jb = p.jobs[j];
   const int H = p.H, B = p.B;
-  float r = sigmoidf_(g.gr + (acc_r + g.br));
-  float z = sigmoidf_(g.gz + (acc_z + g.bz));
-  float n = tanhf(g.gn + r * (acc_n + g.bn));
+  float r, z, n;
+  if (FAST) {
+    r = sigmoid_fast(g.gr + (acc_r + g.br));
+    z = sigmoid_fast(g.gz + (acc_z + g.bz));
+    n = tanh_fast(g.gn + r * (acc_n + g.bn));
+  } else {
+    r = sigmoidf_(g.gr + (acc_r + g.br));
+    z = sigmoidf_(g.gz + (acc_z + g.bz));
+    n = tanhf(g.gn + r * (acc_n + g.bn));
+  }
   float h = (1.0f - z) * n + z * g.hp;
   const int64_t slot = ((int64_t)(j * 2 + (s & 1)) * B + b) * H + u;
   p.hbuf[slot] = h;
-  p.hbuf_lp[slot] = __float2bfloat16_rn(h);
+  {
+    const __nv_bfloat16 hb = __float2bfloat16_rn(h);
+#pragma unroll
+    for (int r = 0; r < kHRep; ++r) p.hbuf_lp[(size_t)r * p.lp_rep_stride + slot] = hb;
+  }
   const int t_out = jb.t_out0 + s * jb.t_out_step;
   if (jb.y) jb.y[((int64_t)t_out * B + b) * jb.ldy + u] = h;
   if (jb.y_lp) reinterpret_cast<__nv_bfloat16*>(jb.y_lp)[((int64_t)t_out * B + b) * jb.ldy_lp + u] = __float2bfloat16_rn(h);
@@ -132,7 +134,8 @@ __device__ void seed_h0(const GruParams& p) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
       float v = h0[i];
       p.hbuf[(int64_t)(j * 2 + 1) * per + i] = v;
-      p.hbuf_lp[(int64_t)(j * 2 + 1) * per + i] = __float2bfloat16_rn(v);
+#pragma unroll
+      for (int r = 0; r < kHRep; ++r) p.hbuf_lp[(size_t)r * p.lp_rep_stride + (int64_t)(j * 2 + 1) * per + i] = __float2bfloat16_rn(v);
     }
   }
 }
@@ -418,12 +421,11 @@ extern "C" int tp_pack_whh_bf16(const float* w_hh, void* dst, int H, void* strea
   return tp_pack_mma_a_bf16(w_hh, H, 3 * H, H, dst, stream);
 }
 
-static long long* g_gru_trace = nullptr;
-extern "C" void tp_gru_set_trace(void* device_buffer) { g_gru_trace = reinterpret_cast<long long*>(device_buffer); }
+extern "C" void tp_gru_set_trace(void* device_buffer) { tp::set_trace_ptr(reinterpret_cast<long long*>(device_buffer)); }
 
 extern "C" size_t tp_gru_workspace_bytes(int njobs, int B, int H) {
   size_t per = (size_t)njobs * 2 * B * H;
-  return 256 + align_up(per * sizeof(float), 256) + align_up(per * sizeof(__nv_bfloat16), 256);
+  return 256 + align_up(per * sizeof(float), 256) + kHRep * align_up(per * sizeof(__nv_bfloat16), 256);
 }
 
 template <typename KernelT>
@@ -468,7 +470,7 @@ extern "C" int tp_gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, in
     if (jobs_in[j].steps == 1 && jobs_in[j].h0 == nullptr) jobs[n_all++] = jobs_in[j];
   GruParams p;
   memset(&p, 0, sizeof(p));
-  p.njobs = njobs; p.B = B; p.H = H; p.trace = g_gru_trace;
+  p.njobs = njobs; p.B = B; p.H = H; p.trace = trace_ptr();
   for (int j = 0; j < njobs; ++j) {
     const tp_gru_job& jb = jobs[j];
     TP_CHECK_ARG(jb.gi && jb.w_hh && jb.b_hh && jb.steps >= 1, "tp_gru_recurrence: a job has null gi/w_hh/b_hh or steps<1");
@@ -481,6 +483,7 @@ extern "C" int tp_gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, in
   p.barrier = reinterpret_cast<unsigned int*>(workspace);
   p.hbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 256);
   p.hbuf_lp = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(workspace) + 256 + align_up(per * sizeof(float), 256));
+  p.lp_rep_stride = align_up(per * sizeof(__nv_bfloat16), 256) / sizeof(__nv_bfloat16);
   cudaStream_t st = (cudaStream_t)stream;
   TP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
   const int sms = sm_count();

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
   for (int je = p.n_item_jobs; je < p.njobs; ++je)
     for (int64_t i = blockIdx.x * (int64_t)kTmaThreads + tid; i < (int64_t)B * H; i += (int64_t)gridDim.x * kTmaThreads) {
       const int b = (int)(i / H), u = (int)(i - (int64_t)b * H);
-      gru_finalize(p, je, 0, b, u, gate_fetch(p, je, 0, b, u), 0.f, 0.f, 0.f);
+      gru_finalize<true>(p, je, 0, b, u, gate_fetch(p, je, 0, b, u), 0.f, 0.f, 0.f);
     }
 
   unsigned int epoch = 0;
@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
     if (producer) {
       if (lane == 0 && have_prev) {
         asm volatile("fence.proxy.async;\n" ::: "memory");
-        const __nv_bfloat16* hprev = p.hbuf_lp + ((int64_t)(j * 2 + ((s + 1) & 1)) * B) * H;
+        const __nv_bfloat16* hprev = p.hbuf_lp + (size_t)(blockIdx.x % kHRep) * p.lp_rep_stride +
+                                     ((int64_t)(j * 2 + ((s + 1) & 1)) * B) * H;
         mb_expect_tx(h_full, (uint32_t)B * H * 2);
         for (int b = 0; b < B; ++b) bulk_g2s(hs + (size_t)b * HP, hprev + (int64_t)b * H, (uint32_t)H * 2, h_full);
         for (int c = prefetched; c < nchunks; ++c) issue_chunk(c);
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
               an += red[((size_t)(k * 3 + 2) * NB + bb) * RP + uu];
             }
           }
-          gru_finalize(p, j, s, bb, u0 + uu, gin[e], ar, az, an);
+          gru_finalize<true>(p, j, s, bb, u0 + uu, gin[e], ar, az, an);
         }
       }
       // generic-proxy writes (red in shared memory, h_t in global memory) must be ordered before the

@@ -2,7 +2,8 @@
 // lib/models/spin.py:250-261).  v1: a fixed sequence of fp32 FFMA GEMM launches on one
 // stream (graph-capturable); fc1 is evaluated as  x.W1x^T (once)  +  [pose|shape|cam].W1p^T
 // (per iteration) -- algebraically identical to fc1(cat[x, pose, shape, cam]).
-#include "common.cuh"
+#include "skinny.cuh"
+#include <stdlib.h>
 
 namespace tp {
 
@@ -50,6 +51,23 @@ static int linear(int precision, const float* A, int64_t lda, const void* W, con
 
 extern "C" size_t tp_encoder_heads_workspace_bytes(int B) { (void)B; return kSplitScratch; }
 
+// Eval-mode heads as ONE skinny GEMM: feat = relu([h_fwd | h_rec]) . [0.5 W_fwd | 0.5 W_rec]^T + 0.5 (b_fwd + b_rec)
+// (halving is exact in fp32/bf16, so this is the same arithmetic as (lin_fwd + lin_rec) / 2 up to summation order).
+// h_cat [B, 3H] holds y[-1] of gru_fwd in columns [0,H) and y_rec[0] in [H,3H); w_cat is the packed [2048, 3H] matrix.
+extern "C" int tp_encoder_heads_cat(int precision, const void* w_cat, const float* b_cat, const float* h_cat, int64_t ld_h,
+                                    int B, int H, float* feat, void* feat_bf16, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  TP_CHECK_ARG(precision == TP_PRECISION_FP32 || precision == TP_PRECISION_BF16, "tp_encoder_heads_cat: bad precision");
+  TP_CHECK_ARG(w_cat && b_cat && h_cat && feat, "tp_encoder_heads_cat: null pointer");
+  TP_CHECK_ARG(B >= 1 && H >= 4 && H % 4 == 0, "tp_encoder_heads_cat: bad sizes B=%d H=%d", B, H);
+  TP_CHECK_ARG(workspace && workspace_bytes >= kSplitScratch && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+               "tp_encoder_heads_cat: workspace too small / misaligned");
+  TP_CUDA(cudaMemsetAsync(workspace, 0, 4096, (cudaStream_t)stream));
+  void* sc = B > 64 ? nullptr : workspace;
+  return linear(precision, h_cat, ld_h, w_cat, b_cat, nullptr, 0, feat, 2048, B, 2048, 3 * H, 1.f, 0.f, 1, sc, stream,
+                nullptr, 0, precision == TP_PRECISION_BF16 ? feat_bf16 : nullptr, 2048);
+}
+
 extern "C" int tp_encoder_heads(int precision, const void* w_fwd, const float* b_fwd, const void* w_rec,
                                 const float* b_rec, const float* h_fwd, int64_t ld_hf, const float* h_rec, int64_t ld_hr,
                                 int B, int H, int is_train, float* feat, void* feat_bf16, void* workspace,
@@ -80,6 +98,217 @@ extern "C" int tp_encoder_heads(int precision, const void* w_fwd, const float* b
   return TP_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused IEF (bf16 mode, <= 32 rows): the whole chain  base = fc1_x(feat);  3 x { fc1_p, fc2, dec }
+// as ONE persistent cooperative kernel.  64 CTAs, CTA c owns the 16-row weight tile c of every layer
+// (8 warps split K, partials meet in shared memory); activations travel between layers as bf16 rows
+// in global memory (L2), layers are separated by a release/acquire grid barrier and the next layer's
+// weight fragments are already in flight when a CTA arrives at the barrier.  Every CTA needs the WHOLE
+// activation block of a layer; 64 CTAs fetching the same 64 KB at once serialise on the L2 slices that
+// own those lines (measured 5.7K cycles per layer), so producers write kIefRep replicas and CTA c reads
+// replica c % kIefRep.
+namespace tp {
+
+constexpr int kIefMaxLayers = 12;
+constexpr int kIefRep = 8;        // replicas of every inter-layer activation block (see k_ief_fused)
+struct IefLayer {
+  const __nv_bfloat16* A; int lda; int K; int rep_in;     // rep_in: element stride between input replicas (0 = single copy)
+  const uint4* Wp; int N;
+  const float* bias; const float* Cin; int ldcin;
+  float* C; int ldc; __nv_bfloat16* Clp; int ldclp; int rep_out;   // Clp is written kIefRep times, rep_out elements apart
+};
+struct IefFusedParams {
+  IefLayer layer[kIefMaxLayers];
+  int nlayers, M;
+  unsigned int* barrier;
+  const float* feat; const __nv_bfloat16* feat_lp; __nv_bfloat16* feat_cvt;   // feat_cvt: kIefRep bf16 replicas of feat
+  const float* init; int init_rows; float* psc; __nv_bfloat16* psc_lp;
+  long long* trace;   // debug: [grid][layers][4] clock stamps
+};
+#define IEF_TRACE(slot) do { if (p.trace && threadIdx.x == 0) p.trace[((size_t)blockIdx.x * kIefMaxLayers + l) * 4 + (slot)] = clock64(); } while (0)
+
+template <int NT>
+__global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParams p) {
+  constexpr int NB = NT * 8, RPW = 17;
+  extern __shared__ __align__(16) unsigned char ief_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int ut = blockIdx.x;
+  unsigned int epoch = 0;
+
+  // prologue: IEF state <- init (fp32 + bf16 copy), optional feat conversion
+  for (int i = blockIdx.x * kSkThreads + tid; i < p.M * 160; i += gridDim.x * kSkThreads) {
+    const float v = p.init_rows == 1 ? p.init[i % 160] : p.init[i];
+    p.psc[i] = v;
+#pragma unroll
+    for (int r = 0; r < kIefRep; ++r) p.psc_lp[(size_t)r * p.M * 160 + i] = __float2bfloat16_rn(v);
+  }
+  // feat (bf16 from the heads, or fp32) -> kIefRep bf16 replicas
+  for (int i = blockIdx.x * kSkThreads + tid; i < p.M * 2048; i += gridDim.x * kSkThreads) {
+    const __nv_bfloat16 v = p.feat_lp ? p.feat_lp[i] : __float2bfloat16_rn(p.feat[i]);
+#pragma unroll
+    for (int r = 0; r < kIefRep; ++r) p.feat_cvt[(size_t)r * p.M * 2048 + i] = v;
+  }
+  grid_barrier(p.barrier, ++epoch * gridDim.x);
+
+  uint4 wa[kSkPF], wb[kSkPF];
+  auto prefetch = [&](const IefLayer& L) {
+    const int nkb = (L.K + 31) / 32;
+    const int b_lo = (warp * nkb) / 8, nb = ((warp + 1) * nkb) / 8 - b_lo;
+    const uint4* wp = L.Wp + ((int64_t)ut * nkb + b_lo) * 64 + lane;
+#pragma unroll
+    for (int q = 0; q < kSkPF; ++q)
+      if (q < nb) { wa[q] = ldg_stream16(wp + (int64_t)q * 64); wb[q] = ldg_stream16(wp + (int64_t)q * 64 + 32); }
+  };
+  if (ut < (p.layer[0].N + 15) / 16) prefetch(p.layer[0]);
+
+  for (int l = 0; l < p.nlayers; ++l) {
+    const IefLayer& L = p.layer[l];
+    IEF_TRACE(0);
+    if (ut < (L.N + 15) / 16) {
+      const int nkb = (L.K + 31) / 32;
+      const int pitch = ((nkb * 32 + 63) / 64) * 64 + 32;
+      __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(ief_smem);
+      float* red = reinterpret_cast<float*>(ief_smem + (size_t)NB * pitch * 2);
+      const int b_lo = (warp * nkb) / 8, nb = ((warp + 1) * nkb) / 8 - b_lo;
+      // epilogue operands do not depend on this layer's matmul: fetch them first
+      constexpr int E = (NB * 16 + kSkThreads - 1) / kSkThreads;
+      float cin[E], bia[E];
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const int idx = tid + i * kSkThreads, m = idx >> 4, r = idx & 15, nn = ut * 16 + r;
+        const bool ok = idx < NB * 16 && m < p.M && nn < L.N;
+        cin[i] = (ok && L.Cin) ? L.Cin[(int64_t)m * L.ldcin + nn] : 0.0f;
+        bia[i] = (ok && L.bias) ? __ldg(L.bias + nn) : 0.0f;
+      }
+      // activations of this layer (bf16 rows written by the previous layer / the prologue): own replica
+      const __nv_bfloat16* Ain = L.A + (size_t)(blockIdx.x % kIefRep) * L.rep_in;
+      // every thread keeps ALL its 16-byte loads of a half block in flight before the first store:
+      // this phase is a pure L2 round trip, so bytes in flight decide its duration
+      const int c8n = nkb * 4;                                  // 16-byte groups per row
+      const int per_row = (c8n + 31) / 32;                      // groups per lane per row (<= 8 for K <= 2048)
+      for (int r0 = warp; r0 < NB; r0 += 2 * (kSkThreads / 32)) {
+        uint4 v[2][8];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int r = r0 + rr * (kSkThreads / 32);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int col = (lane + 32 * k) * 8;
+            v[rr][k] = make_uint4(0u, 0u, 0u, 0u);
+            if (k < per_row && r < NB && r < p.M && col < L.K) v[rr][k] = *reinterpret_cast<const uint4*>(Ain + (int64_t)r * L.lda + col);   // weak load: the barrier's acquire invalidated L1
+          }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int r = r0 + rr * (kSkThreads / 32);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int col = (lane + 32 * k) * 8;
+            if (k < per_row && r < NB && col < nkb * 32) *reinterpret_cast<uint4*>(As + (size_t)r * pitch + col) = v[rr][k];
+          }
+        }
+      }
+      __syncthreads();
+      IEF_TRACE(1);
+      float acc[NT][4];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.0f;
+#pragma unroll
+      for (int q = 0; q < kSkPF; ++q) {
+        if (q < nb) {
+#pragma unroll
+          for (int n = 0; n < NT; ++n) {
+            const uint4 bv = *reinterpret_cast<const uint4*>(As + (size_t)(n * 8 + g) * pitch + (b_lo + q) * 32 + 8 * t);
+            mma16816(acc[n], wa[q], bv.x, bv.y);
+            mma16816(acc[n], wb[q], bv.z, bv.w);
+          }
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        float* r0 = red + ((size_t)warp * NB + n * 8 + 2 * t) * RPW + g;
+        r0[0] = acc[n][0]; r0[RPW] = acc[n][1]; r0[8] = acc[n][2]; r0[RPW + 8] = acc[n][3];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const int idx = tid + i * kSkThreads, m = idx >> 4, r = idx & 15, nn = ut * 16 + r;
+        if (idx < NB * 16 && m < p.M && nn < L.N) {
+          float sum = 0.0f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) sum += red[((size_t)w * NB + m) * RPW + r];
+          const float v = sum + bia[i] + cin[i];
+          if (L.C) L.C[(int64_t)m * L.ldc + nn] = v;
+          if (L.Clp) {
+            const __nv_bfloat16 vb = __float2bfloat16_rn(v);
+#pragma unroll
+            for (int rr = 0; rr < kIefRep; ++rr) L.Clp[(size_t)rr * L.rep_out + (int64_t)m * L.ldclp + nn] = vb;
+          }
+        }
+      }
+      __syncthreads();     // As / red are reused by the next layer
+    }
+    IEF_TRACE(2);
+    if (l + 1 < p.nlayers) {
+      if (ut < (p.layer[l + 1].N + 15) / 16) prefetch(p.layer[l + 1]);   // weights do not depend on the barrier
+      grid_barrier(p.barrier, ++epoch * gridDim.x);
+    }
+    IEF_TRACE(3);
+  }
+}
+
+}  // namespace tp
+
+static int ief_fused(const tp_ief_weights* w, const float* feat, const void* feat_bf16, int N, const float* init,
+                     int init_rows, int n_iter, float* psc, unsigned char* ws, cudaStream_t st) {
+  // workspace (see tp_ief_workspace_bytes): [base fp32 | ...per-layer buffers of the unfused path... | scratch];
+  // the fused kernel keeps its barrier counter and all replica buffers in the 8 MB scratch region
+  const size_t slab = al256((size_t)N * 1024 * sizeof(float));
+  const size_t slab_lp = al256((size_t)N * 1024 * 2), slab_p = al256((size_t)N * 160 * 2);
+  float* base = reinterpret_cast<float*>(ws);
+  unsigned char* sc = ws + 3 * slab + 2 * slab_lp + slab_p;
+  const size_t n1024 = (size_t)N * 1024, n160 = (size_t)N * 160, n2048 = (size_t)N * 2048;
+  __nv_bfloat16* rep = reinterpret_cast<__nv_bfloat16*>(sc + 4096);
+  __nv_bfloat16* u1_lp = rep;                                   // [8][N,1024]
+  __nv_bfloat16* u2_lp = u1_lp + kIefRep * n1024;               // [8][N,1024]
+  __nv_bfloat16* psc_lp = u2_lp + kIefRep * n1024;              // [8][N,160]
+  __nv_bfloat16* feat_rep = psc_lp + kIefRep * n160;            // [8][N,2048]   (total <= 2.2 MB for N = 32)
+  IefFusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = N; p.barrier = reinterpret_cast<unsigned int*>(sc);
+  p.feat = feat; p.feat_lp = reinterpret_cast<const __nv_bfloat16*>(feat_bf16); p.feat_cvt = feat_rep;
+  p.init = init; p.init_rows = init_rows; p.psc = psc; p.psc_lp = psc_lp;
+  p.trace = tp::trace_ptr();
+  int n = 0;
+  auto add = [&](const __nv_bfloat16* A, int lda, int K, size_t rep_in, const void* Wp, int Nn, const float* bias,
+                 const float* Cin, int ldcin, float* C, int ldc, __nv_bfloat16* Clp, int ldclp, size_t rep_out) {
+    IefLayer& L = p.layer[n++];
+    L.A = A; L.lda = lda; L.K = K; L.rep_in = (int)rep_in; L.Wp = reinterpret_cast<const uint4*>(Wp); L.N = Nn;
+    L.bias = bias; L.Cin = Cin; L.ldcin = ldcin; L.C = C; L.ldc = ldc; L.Clp = Clp; L.ldclp = ldclp; L.rep_out = (int)rep_out;
+  };
+  add(feat_rep, 2048, 2048, n2048, w->w1x, 1024, w->b1, nullptr, 0, base, 1024, nullptr, 0, 0);
+  for (int it = 0; it < n_iter; ++it) {
+    add(psc_lp, 160, 160, n160, w->w1p, 1024, nullptr, base, 1024, nullptr, 0, u1_lp, 1024, n1024);
+    add(u1_lp, 1024, 1024, n1024, w->w2, 1024, w->b2, nullptr, 0, nullptr, 0, u2_lp, 1024, n1024);
+    add(u2_lp, 1024, 1024, n1024, w->wdec, 160, w->bdec, psc, 160, psc, 160, psc_lp, 160, n160);
+  }
+  p.nlayers = n;
+  TP_CUDA(cudaMemsetAsync(sc, 0, 256, st));
+  const int nb = N <= 8 ? 8 : 32;
+  const size_t smem = (size_t)nb * (2048 + 32) * 2 + (size_t)8 * nb * 17 * 4;
+  void* args[] = {(void*)&p};
+  if (nb == 8) {
+    TP_CUDA(cudaFuncSetAttribute(tp::k_ief_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TP_CUDA(cudaLaunchCooperativeKernel((const void*)tp::k_ief_fused<1>, dim3(64), dim3(tp::kSkThreads), args, smem, st));
+  } else {
+    TP_CUDA(cudaFuncSetAttribute(tp::k_ief_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TP_CUDA(cudaLaunchCooperativeKernel((const void*)tp::k_ief_fused<4>, dim3(64), dim3(tp::kSkThreads), args, smem, st));
+  }
+  tp::count_launch();
+  return TP_OK;
+}
+
 extern "C" size_t tp_ief_workspace_bytes(int n_rows) {
   const size_t n = (size_t)(n_rows > 0 ? n_rows : 0);
   return 3 * al256(n * 1024 * sizeof(float)) + 2 * al256(n * 1024 * 2) + al256(n * 160 * 2) + kSplitScratch;
@@ -96,6 +325,10 @@ extern "C" int tp_ief_forward(int precision, const tp_ief_weights* w, const floa
   TP_CHECK_ARG(workspace && workspace_bytes >= tp_ief_workspace_bytes(n_rows), "tp_ief_forward: workspace too small");
   TP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "tp_ief_forward: workspace must be 256-byte aligned");
   const int N = n_rows;
+  static const bool unfused = getenv("TP_IEF_UNFUSED") != nullptr;
+  if (P == TP_PRECISION_BF16 && N <= 32 && n_iter >= 0 && 1 + 3 * n_iter <= kIefMaxLayers && !unfused && sm_count() >= 64)
+    return ief_fused(w, feat, feat_bf16, N, init, init_rows, n_iter, psc, reinterpret_cast<unsigned char*>(workspace),
+                     (cudaStream_t)stream);
   const size_t slab = al256((size_t)N * 1024 * sizeof(float));
   float* base = reinterpret_cast<float*>(workspace);
   float* u1 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + slab);

@@ -10,26 +10,11 @@
 //   * split-K partials are reduced in split order by the last CTA to arrive (deterministic).
 // Tensor throughput is irrelevant here (M <= 64), which is why this path uses mma.sync rather
 // than tcgen05: no TMEM round trip, accumulators stay in registers for the fused epilogue.
-#include "common.cuh"
+#include "skinny.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace tp {
-
-constexpr int kSkThreads = 256;
-constexpr int kSkRows = 128;          // weight rows per CTA
-constexpr int kSkPF = 8;              // 32-column blocks in flight per warp
-constexpr size_t kSkTicketBytes = 4096;
-
-__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void mma16816(float* c, const uint4& a, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
-}
 
 // W [rows, cols] fp32 (row stride ld) -> bf16 fragments  dst[ut = ceil(rows/16)][kb = ceil(cols/32)][q=2][lane=32][word=4].
 // Lane (g = lane/4, t = lane%4), word w = 2*e2 + hi holds
@@ -56,57 +41,6 @@ __global__ void k_pack_mma_a(const float* __restrict__ w, int64_t ld, int rows, 
   }
 }
 
-struct SkArgs {
-  const float* A; int64_t lda; int M, K, N;
-  const uint4* Wp; int ut_total, kb_total, kb_per_split;
-  const float* bias; const float* Cin; int64_t ldcin; float* C; int64_t ldc;
-  float alpha, beta; int relu_a;
-  float* part; unsigned int* tickets;
-  const __nv_bfloat16* Alp; int64_t ldalp;   // optional bf16 copy of A (read instead of A when non-null)
-  __nv_bfloat16* Clp; int64_t ldclp;         // optional bf16 copy of the output (next layer's Alp)
-};
-
-// act(A)[0:NB, 32*kb_lo : 32*(kb_lo+nkb)] -> bf16 rows of `pitch` elements in shared memory.
-// Reads the bf16 copy when the producer left one (no conversion, half the bytes), else converts fp32.
-template <int NB>
-__device__ __forceinline__ void stage_activations(const SkArgs& a, __nv_bfloat16* As, int pitch, int kb_lo, int nkb,
-                                                  int warp, int lane) {
-  if (a.Alp) {
-    const int c8n = nkb * 4;                                   // 16-byte (8 x bf16) groups per row
-#pragma unroll 4
-    for (int r = warp; r < NB; r += kSkThreads / 32) {
-#pragma unroll 2
-      for (int c8 = lane; c8 < c8n; c8 += 32) {
-        const int col = kb_lo * 32 + c8 * 8;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (r < a.M && col < a.K) v = __ldcg(reinterpret_cast<const uint4*>(a.Alp + (int64_t)r * a.ldalp + col));  // K % 8 == 0
-        if (a.relu_a) {
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
-          const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) h[i] = __hmax2(h[i], z);
-        }
-        *reinterpret_cast<uint4*>(As + (size_t)r * pitch + c8 * 8) = v;
-      }
-    }
-    return;
-  }
-  const int c4n = nkb * 8;                                     // float4 groups per row
-#pragma unroll 4
-  for (int r = warp; r < NB; r += kSkThreads / 32) {
-#pragma unroll 2
-    for (int c4 = lane; c4 < c4n; c4 += 32) {
-      const int col = kb_lo * 32 + c4 * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < a.M && col < a.K) v = __ldcg(reinterpret_cast<const float4*>(a.A + (int64_t)r * a.lda + col));  // K % 4 == 0
-      if (a.relu_a) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-      uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-      *reinterpret_cast<uint2*>(As + (size_t)r * pitch + c4 * 4) = pk;
-    }
-  }
-}
-
 template <int NT>
 __global__ void __launch_bounds__(kSkThreads, 1) k_skinny_bf16(const SkArgs a) {
   constexpr int NB = NT * 8;
@@ -129,6 +63,10 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_skinny_bf16(const SkArgs a) {
     for (int q = 0; q < kSkPF; ++q)
       if (q < nkb) { wa[q] = ldg_stream16(wp + (int64_t)q * 64); wb[q] = ldg_stream16(wp + (int64_t)q * 64 + 32); }
   }
+  // programmatic dependent launch: everything above only touched constant weights; the activations
+  // (and Cin / tickets) come from the preceding kernel in the stream
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   stage_activations<NB>(a, As, pitch, kb_lo, nkb, warp, lane);
   __syncthreads();
 
@@ -259,6 +197,8 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_skinny_mt(const SkArgs a) {
 #pragma unroll
   for (int q = 0; q < kSkPF; ++q)
     if (q < nb) { wa[q] = ldg_stream16(wp + (int64_t)q * 64); wb[q] = ldg_stream16(wp + (int64_t)q * 64 + 32); }
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   stage_activations<NB>(a, As, pitch, 0, nkb, warp, lane);
   __syncthreads();
 
@@ -335,6 +275,22 @@ extern "C" size_t tp_skinny_bf16_workspace_bytes(int M, int N, int splits) {
   return kSkTicketBytes + (size_t)(splits > 1 ? splits : 0) * groups * nb * kSkRows * sizeof(float);
 }
 
+template <typename KernelT>
+static int launch_pdl(KernelT kfn, dim3 grid, size_t smem, cudaStream_t st, const SkArgs& a) {
+  static const bool no_pdl = getenv("TP_NO_PDL") != nullptr;
+  TP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(kSkThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+  TP_CUDA(cudaLaunchKernelEx(&cfg, kfn, a));
+  count_launch();
+  return TP_OK;
+}
+
 // mode: 0 = auto, 1 = force split kernel, 2 = force single-phase kernel
 static int skinny_dispatch(const float* A, int64_t lda, const void* Alp, int64_t ldalp, int M, int K, const void* Wp, int N,
                            const float* bias, const float* Cin, int64_t ldcin, float* C, int64_t ldc, void* Clp,
@@ -364,18 +320,9 @@ static int skinny_dispatch(const float* A, int64_t lda, const void* Alp, int64_t
   if (mode == 2 || (mode == 0 && mt_ok && N <= 1024)) {
     if (!mt_ok) return fail(TP_ERR_UNSUPPORTED, "tp_skinny_bf16: K=%d too large for the single-phase kernel", K);
     dim3 grid((unsigned)a.ut_total);
-    if (nb == 8) {
-      TP_CUDA(cudaFuncSetAttribute(k_skinny_mt<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mt));
-      k_skinny_mt<1><<<grid, kSkThreads, smem_mt, st>>>(a);
-    } else if (nb == 32) {
-      TP_CUDA(cudaFuncSetAttribute(k_skinny_mt<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mt));
-      k_skinny_mt<4><<<grid, kSkThreads, smem_mt, st>>>(a);
-    } else {
-      TP_CUDA(cudaFuncSetAttribute(k_skinny_mt<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mt));
-      k_skinny_mt<8><<<grid, kSkThreads, smem_mt, st>>>(a);
-    }
-    TP_LAUNCH_CHECK();
-    return TP_OK;
+    if (nb == 8) return launch_pdl(k_skinny_mt<1>, grid, smem_mt, st, a);
+    if (nb == 32) return launch_pdl(k_skinny_mt<4>, grid, smem_mt, st, a);
+    return launch_pdl(k_skinny_mt<8>, grid, smem_mt, st, a);
   }
 
   const int groups = (N + kSkRows - 1) / kSkRows;
@@ -394,18 +341,9 @@ static int skinny_dispatch(const float* A, int64_t lda, const void* Alp, int64_t
   const size_t smem = (size_t)nb * pitch * 2;
   if (smem > 200 * 1024) return fail(TP_ERR_UNSUPPORTED, "tp_skinny_bf16: K slice of %d columns does not fit in shared memory; raise splits", a.kb_per_split * 32);
   dim3 grid((unsigned)groups, (unsigned)splits);
-  if (nb == 8) {
-    TP_CUDA(cudaFuncSetAttribute(k_skinny_bf16<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_skinny_bf16<1><<<grid, kSkThreads, smem, st>>>(a);
-  } else if (nb == 32) {
-    TP_CUDA(cudaFuncSetAttribute(k_skinny_bf16<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_skinny_bf16<4><<<grid, kSkThreads, smem, st>>>(a);
-  } else {
-    TP_CUDA(cudaFuncSetAttribute(k_skinny_bf16<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_skinny_bf16<8><<<grid, kSkThreads, smem, st>>>(a);
-  }
-  TP_LAUNCH_CHECK();
-  return TP_OK;
+  if (nb == 8) return launch_pdl(k_skinny_bf16<1>, grid, smem, st, a);
+  if (nb == 32) return launch_pdl(k_skinny_bf16<4>, grid, smem, st, a);
+  return launch_pdl(k_skinny_bf16<8>, grid, smem, st, a);
 }
 
 extern "C" int tp_skinny_bf16(const float* A, int64_t lda, int M, int K, const void* Wp, int N, const float* bias,

@@ -14,6 +14,7 @@
 //                  on chip -- vertices never round-trip HBM.
 //  k_smpl_finalize per body: reduce regressor partials, compose the output joint set, project.
 #include "rotations.cuh"
+#include "skinny.cuh"
 
 namespace tp {
 
@@ -42,6 +43,7 @@ struct PrepArgs {
   float* coef;     // [n][kCoefLd]
   float* rotmat;   // [n][24][9] or null
   float* theta;    // [n][85] or null
+  __nv_bfloat16* coef_tc;  // [n][256] bf16: pf(207) | beta_hi(10) | beta_lo(10) | beta_hi(10) | 0   (tensor-core path) or null
 };
 
 __global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int n, const PrepArgs a) {
@@ -133,6 +135,21 @@ __global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int
     for (int l = 0; l < 10; ++l) cf[207 + l] = beta[l];
     cf[217] = 1.0f;
     for (int k = kCoef; k < kCoefLd; ++k) cf[k] = 0.0f;
+  }
+  if (a.coef_tc) {
+    __nv_bfloat16* ct = a.coef_tc + (int64_t)b * 256;
+    if (j >= 1) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) ct[(j - 1) * 9 + k] = __float2bfloat16_rn(R[k] - ((k == 0 || k == 4 || k == 8) ? 1.0f : 0.0f));
+    } else {
+#pragma unroll
+      for (int l = 0; l < 10; ++l) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(beta[l]);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(beta[l] - __bfloat162float(hi));
+        ct[207 + l] = hi; ct[217 + l] = lo; ct[227 + l] = hi;
+      }
+      for (int k = 237; k < 256; ++k) ct[k] = __float2bfloat16_rn(0.0f);
+    }
   }
   if (a.rotmat) {
 #pragma unroll
@@ -295,6 +312,170 @@ __global__ void __launch_bounds__(kVT) k_smpl_verts(const tp_smpl_model m, int n
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core variant of the vertex kernel (bf16 mode; K4 of the north star): the 256-term
+// contraction  [64 vertices x 3 coords] x [K = 256] x [32 bodies]  runs on mma.sync m16n8k16 with the
+// vertex tile's blend fragments RESIDENT in shared memory (96 KB, loaded once per CTA and reused
+// for every 32-body group the CTA walks through).  K layout: 207 pose-blend rows | 10 shape rows
+// (beta_hi x S_hi) | 10 (beta_lo x S_hi) | 10 (beta_hi x S_lo) -- the shape blend keeps ~16 mantissa
+// bits; the template is added in fp32.  Warp w: 16-vertex sub-tile w&3, body half w>>2; a thread ends up
+// with x,y,z of 2 vertices x 4 bodies and skins them from registers.
+constexpr int kTcVT = 64;                    // vertices per CTA
+constexpr int kTcNB = 32;                    // bodies per group
+constexpr int kTcK = 256;
+constexpr int kTcCsPitch = kTcK + 32;        // bf16 elements per coefficient row (conflict-free 16-byte reads)
+constexpr int kTcAStride = kJ * 12 + 4;      // floats per body in A_s
+constexpr int kTcJtPitch = kTcVT + 1;
+constexpr size_t kTcSmW = 12 * 8 * 1024;
+constexpr size_t kTcSmC = (size_t)kTcNB * kTcCsPitch * 2;
+constexpr size_t kTcSmA = (size_t)kTcNB * kTcAStride * 4;
+constexpr size_t kTcSmV = (size_t)kTcNB * kTcVT * 3 * 4;
+constexpr size_t kTcSmJ = (size_t)kMaxReg * kTcJtPitch * 4;
+constexpr size_t kTcSmem = kTcSmW + kTcSmC + kTcSmA + kTcSmV + kTcSmJ;
+
+__global__ void __launch_bounds__(256, 1)
+k_smpl_verts_tc(const tp_smpl_model m, int n, const __nv_bfloat16* __restrict__ coef_tc, const float* __restrict__ A,
+                const float* __restrict__ jreg, int nreg, float* __restrict__ verts, float* __restrict__ jpart,
+                int ntiles, int groups_per_cta) {
+  extern __shared__ __align__(16) unsigned char tsm[];
+  unsigned char* Wt = tsm;
+  __nv_bfloat16* Cs = reinterpret_cast<__nv_bfloat16*>(tsm + kTcSmW);
+  float* A_s = reinterpret_cast<float*>(tsm + kTcSmW + kTcSmC);
+  float* vout = reinterpret_cast<float*>(tsm + kTcSmW + kTcSmC + kTcSmA);
+  float* Jt = reinterpret_cast<float*>(tsm + kTcSmW + kTcSmC + kTcSmA + kTcSmV);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int st = warp & 3, nh = warp >> 2;
+  const int tile = blockIdx.x;
+  const int v0 = tile * kTcVT;
+
+  // resident operands of this vertex tile: blend fragments (12 m-tiles x 8 blocks), regressor columns
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(m.blend_tc) + (size_t)tile * (kTcSmW / 16);
+    uint4* dst = reinterpret_cast<uint4*>(Wt);
+    for (int i = tid; i < (int)(kTcSmW / 16); i += 256) dst[i] = ldg_stream16(src + i);
+    for (int i = tid; i < nreg * kTcVT; i += 256) {
+      const int r = i / kTcVT, v = i - r * kTcVT;
+      Jt[r * kTcJtPitch + v] = jreg[(int64_t)r * m.vp + v0 + v];
+    }
+  }
+  // per-thread vertex constants: template, retained skinning weights (ks <= 4 on this path)
+  const int vA = v0 + st * 16 + g, vB = vA + 8;
+  float tmpl[2][3];
+  int sj[2][4]; float sw[2][4];
+#pragma unroll
+  for (int x = 0; x < 2; ++x) {
+    const int v = x ? vB : vA;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tmpl[x][c] = m.template_pad[(int64_t)v * 3 + c];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      sj[x][k] = k < m.ks ? m.skin_idx[(int64_t)v * m.ks + k] : 0;
+      sw[x][k] = k < m.ks ? m.skin_w[(int64_t)v * m.ks + k] : 0.0f;
+    }
+  }
+
+  const int ngroups = (n + kTcNB - 1) / kTcNB;
+  const int g_lo = blockIdx.y * groups_per_cta, g_hi = min(ngroups, g_lo + groups_per_cta);
+  for (int grp = g_lo; grp < g_hi; ++grp) {
+    const int body0 = grp * kTcNB;
+    // (1) coefficients (bf16 rows) and skinning transforms of this body group
+    for (int i = tid; i < kTcNB * (kTcK / 8); i += 256) {
+      const int b = i / (kTcK / 8), c8 = i - b * (kTcK / 8);
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (body0 + b < n) v = __ldg(reinterpret_cast<const uint4*>(coef_tc + (int64_t)(body0 + b) * kTcK) + c8);
+      *reinterpret_cast<uint4*>(Cs + (size_t)b * kTcCsPitch + c8 * 8) = v;
+    }
+    for (int i = tid; i < kTcNB * (kJ * 3); i += 256) {
+      const int b = i / (kJ * 3), q = i - b * (kJ * 3);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (body0 + b < n) v = __ldg(reinterpret_cast<const float4*>(A + (int64_t)(body0 + b) * kJ * 12) + q);
+      *reinterpret_cast<float4*>(A_s + (size_t)b * kTcAStride + q * 4) = v;
+    }
+    __syncthreads();
+    // (2) blend contraction on tensor cores
+    float acc[3][2][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) acc[c][nn][0] = acc[c][nn][1] = acc[c][nn][2] = acc[c][nn][3] = 0.0f;
+#pragma unroll
+    for (int kb = 0; kb < kTcK / 32; ++kb) {
+      uint4 bv[2];
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn)
+        bv[nn] = *reinterpret_cast<const uint4*>(Cs + (size_t)((nh * 2 + nn) * 8 + g) * kTcCsPitch + kb * 32 + 8 * t);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const unsigned char* wp = Wt + (size_t)((st * 3 + c) * 8 + kb) * 1024 + lane * 16;
+        const uint4 wa = *reinterpret_cast<const uint4*>(wp), wb = *reinterpret_cast<const uint4*>(wp + 512);
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn) {
+          mma16816(acc[c][nn], wa, bv[nn].x, bv[nn].y);
+          mma16816(acc[c][nn], wb, bv[nn].z, bv[nn].w);
+        }
+      }
+    }
+    // skinning from registers: element e of acc[c][nn] is (vertex x = e>>1, body (nh*2+nn)*8 + 2t + (e&1))
+#pragma unroll
+    for (int nn = 0; nn < 2; ++nn)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int x = e >> 1, bl = (nh * 2 + nn) * 8 + 2 * t + (e & 1);
+        const float px = acc[0][nn][e] + tmpl[x][0], py = acc[1][nn][e] + tmpl[x][1], pz = acc[2][nn][e] + tmpl[x][2];
+        float T[12];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) T[q] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4* Aj = reinterpret_cast<const float4*>(A_s + (size_t)bl * kTcAStride + sj[x][k] * 12);
+          const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+          const float w = sw[x][k];
+          T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
+          T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
+          T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
+        }
+        const int vloc = st * 16 + g + 8 * x;
+        const bool vvalid = (v0 + vloc) < m.n_verts;
+        float* o = vout + ((size_t)bl * kTcVT + vloc) * 3;
+        o[0] = vvalid ? (T[0] * px + T[1] * py + T[2] * pz + T[3]) : 0.0f;
+        o[1] = vvalid ? (T[4] * px + T[5] * py + T[6] * pz + T[7]) : 0.0f;
+        o[2] = vvalid ? (T[8] * px + T[9] * py + T[10] * pz + T[11]) : 0.0f;
+      }
+    __syncthreads();
+    // (3) coalesced vertex store (768 contiguous bytes per body) + joint regressors on the on-chip tile
+    if (verts) {
+      const int64_t nv3 = (int64_t)m.n_verts * 3;
+      const int64_t base = (int64_t)v0 * 3;
+      for (int i = tid; i < kTcNB * (kTcVT * 3 / 2); i += 256) {
+        const int b = i / (kTcVT * 3 / 2), q = i - b * (kTcVT * 3 / 2);
+        if (body0 + b >= n) continue;
+        const float2 v = *reinterpret_cast<const float2*>(vout + (size_t)b * kTcVT * 3 + q * 2);
+        float* dst = verts + (int64_t)(body0 + b) * nv3 + base + q * 2;
+        if (base + q * 2 + 1 < nv3) *reinterpret_cast<float2*>(dst) = v;
+        else if (base + q * 2 < nv3) dst[0] = v.x;
+      }
+    }
+    if (lane < nreg) {
+#pragma unroll
+      for (int bi = 0; bi < kTcNB / 8; ++bi) {
+        const int b = warp * (kTcNB / 8) + bi;
+        if (body0 + b >= n) continue;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        const float* vb = vout + (size_t)b * kTcVT * 3;
+        const float* jr = Jt + lane * kTcJtPitch;
+#pragma unroll 8
+        for (int v = 0; v < kTcVT; ++v) {
+          const float w = jr[v];
+          s0 = fmaf(w, vb[3 * v], s0); s1 = fmaf(w, vb[3 * v + 1], s1); s2 = fmaf(w, vb[3 * v + 2], s2);
+        }
+        float* dst = jpart + (((int64_t)(body0 + b) * ntiles + tile) * nreg + lane) * 3;
+        dst[0] = s0; dst[1] = s1; dst[2] = s2;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(128) k_smpl_finalize(int n, int n_verts, const float* __restrict__ posedJ,
                                                        const float* __restrict__ jpart, int nsplit, int nreg,
                                                        const float* __restrict__ verts, const int32_t* __restrict__ joint_src,
@@ -335,10 +516,21 @@ __global__ void __launch_bounds__(128) k_smpl_finalize(int n, int n_verts, const
 
 static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
-struct SmplPlan { int ntiles, nsplit, tiles_per_split, ngroups; size_t off_A, off_J, off_coef, off_part, total; };
+struct SmplPlan { int ntiles, nsplit, tiles_per_split, ngroups; size_t off_A, off_J, off_coef, off_part, off_ctc, total;
+                  int tc, tc_tiles, tc_gsplit, tc_gpc; };
 
-static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg) {
+static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg, int blend_mode) {
   SmplPlan p;
+  p.tc = (blend_mode == 1 && m->blend_tc && m->template_pad && m->ks <= 4 && m->vp % kTcVT == 0) ? 1 : 0;
+  p.tc_tiles = m->vp / kTcVT;
+  {
+    const int groups = (n + kTcNB - 1) / kTcNB;
+    int want = (2 * sm_count() + p.tc_tiles - 1) / p.tc_tiles;      // body splits so the grid covers the machine ~2x
+    if (want > groups) want = groups;
+    if (want < 1) want = 1;
+    p.tc_gpc = (groups + want - 1) / want;
+    p.tc_gsplit = (groups + p.tc_gpc - 1) / p.tc_gpc;
+  }
   p.ntiles = m->vp / kVT;
   p.ngroups = (n + kNB - 1) / kNB;
   int want = (2 * sm_count() + p.ngroups - 1) / p.ngroups;   // aim for >= 2 CTAs per SM
@@ -350,7 +542,9 @@ static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg) {
   p.off_A = o; o += al256((size_t)n * kJ * 12 * 4);
   p.off_J = o; o += al256((size_t)n * kJ * 3 * 4);
   p.off_coef = o; o += al256((size_t)n * kCoefLd * 4);
-  p.off_part = o; o += al256((size_t)n * p.nsplit * (nreg > 0 ? nreg : 1) * 3 * 4);
+  const int part_tiles = p.tc ? p.tc_tiles : p.nsplit;
+  p.off_part = o; o += al256((size_t)n * part_tiles * (nreg > 0 ? nreg : 1) * 3 * 4);
+  p.off_ctc = o; o += p.tc ? al256((size_t)n * kTcK * 2) : 0;
   p.total = o;
   return p;
 }
@@ -359,15 +553,15 @@ static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg) {
 
 using namespace tp;
 
-extern "C" size_t tp_smpl_workspace_bytes(const tp_smpl_model* m, int n, int nreg) {
+extern "C" size_t tp_smpl_workspace_bytes(const tp_smpl_model* m, int n, int nreg, int blend_mode) {
   if (!m || n <= 0 || m->vp <= 0) return 0;
-  return make_plan(m, n, nreg).total;
+  return make_plan(m, n, nreg, blend_mode).total;
 }
 
 extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose, int64_t ld_pose, int pose_kind,
                                const float* betas, int64_t ld_betas, const float* cam, int64_t ld_cam,
                                const float* jreg, int nreg, const int32_t* joint_src, int nj,
-                               float* verts, float* joints, float* kp2d, float* rotmat, float* theta,
+                               float* verts, float* joints, float* kp2d, float* rotmat, float* theta, int blend_mode,
                                void* workspace, size_t workspace_bytes, void* stream) {
   TP_CHECK_ARG(m != nullptr, "tp_smpl_forward: null model");
   TP_CHECK_ARG(n >= 0, "tp_smpl_forward: n=%d", n);
@@ -381,7 +575,8 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
   TP_CHECK_ARG(nreg >= 0 && nreg <= kMaxReg && (nreg == 0 || jreg), "tp_smpl_forward: nreg=%d (max %d) / null jreg", nreg, kMaxReg);
   TP_CHECK_ARG(nj >= 0 && (nj == 0 || joint_src), "tp_smpl_forward: null joint_src");
   TP_CHECK_ARG(aligned16(m->blend), "tp_smpl_forward: blend table must be 16-byte aligned");
-  SmplPlan pl = make_plan(m, n, nreg);
+  TP_CHECK_ARG(blend_mode == 0 || blend_mode == 1, "tp_smpl_forward: bad blend_mode %d", blend_mode);
+  SmplPlan pl = make_plan(m, n, nreg, blend_mode);
   TP_CHECK_ARG(workspace && workspace_bytes >= pl.total, "tp_smpl_forward: workspace too small (%zu < %zu)", workspace_bytes, pl.total);
   TP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "tp_smpl_forward: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -393,12 +588,18 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
   pa.posedJ = reinterpret_cast<float*>(ws + pl.off_J);
   pa.coef = reinterpret_cast<float*>(ws + pl.off_coef);
   pa.rotmat = rotmat; pa.theta = theta;
+  pa.coef_tc = pl.tc ? reinterpret_cast<__nv_bfloat16*>(ws + pl.off_ctc) : nullptr;
   float* jpart = reinterpret_cast<float*>(ws + pl.off_part);
 
   k_smpl_prepare<<<(unsigned)ceil_div(n, 4), 128, 0, st>>>(*m, n, pa);
   TP_LAUNCH_CHECK();
   const bool need_verts_pass = verts != nullptr || nreg > 0;
-  if (need_verts_pass) {
+  if (need_verts_pass && pl.tc) {
+    TP_CUDA(cudaFuncSetAttribute(k_smpl_verts_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+    dim3 grid((unsigned)pl.tc_tiles, (unsigned)pl.tc_gsplit);
+    k_smpl_verts_tc<<<grid, 256, kTcSmem, st>>>(*m, n, pa.coef_tc, pa.A, jreg, nreg, verts, jpart, pl.tc_tiles, pl.tc_gpc);
+    TP_LAUNCH_CHECK();
+  } else if (need_verts_pass) {
     constexpr size_t smem = (size_t)kSmVertsFloats * sizeof(float);
     TP_CUDA(cudaFuncSetAttribute(k_smpl_verts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)pl.ngroups, (unsigned)pl.nsplit);
@@ -408,7 +609,7 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
   }
   if (nj > 0 && (joints || kp2d)) {
     TP_CHECK_ARG(verts != nullptr, "tp_smpl_forward: verts is required when joints are requested (vertex picks read it)");
-    k_smpl_finalize<<<(unsigned)n, 128, 0, st>>>(n, m->n_verts, pa.posedJ, jpart, pl.nsplit, nreg, verts, joint_src,
+    k_smpl_finalize<<<(unsigned)n, 128, 0, st>>>(n, m->n_verts, pa.posedJ, jpart, pl.tc ? pl.tc_tiles : pl.nsplit, nreg, verts, joint_src,
                                                 nj, cam, ld_cam, joints, kp2d);
     TP_LAUNCH_CHECK();
   }

@@ -145,14 +145,31 @@ class PackedSmpl:
         self.skin_idx[:V] = idx.to(torch.int32)
         self.skin_w[:V] = wsel
         self.device = device
+        # tensor-core blend tables (bf16 mode): [3*vp, 256] rows ((v//16)*3 + c)*16 + v%16
+        self.blend_tc = self.template_pad = None
+        if ks <= 4:
+            S = shapedirs.detach().to(device).float()[:, :, :10]                       # [V,3,10]
+            S_hi = S.to(torch.bfloat16).float()
+            cols = torch.zeros(vp, 3, 256, device=device, dtype=torch.float32)
+            cols[:V, :, :207] = posedirs.detach().to(device).float().reshape(207, V, 3).permute(1, 2, 0)
+            cols[:V, :, 207:217] = S_hi
+            cols[:V, :, 217:227] = S_hi
+            cols[:V, :, 227:237] = S - S_hi
+            rows = cols.reshape(vp // 16, 16, 3, 256).permute(0, 2, 1, 3).reshape(vp * 3, 256).contiguous()
+            self.blend_tc = torch.empty(nv.lib().tp_pack_mma_a_bytes(vp * 3, 256), dtype=torch.uint8, device=device)
+            nv.check(nv.lib().tp_pack_mma_a_bf16(nv.ptr(rows), 256, vp * 3, 256, nv.ptr(self.blend_tc), nv.stream()),
+                     "tp_pack_mma_a_bf16")
+            self.template_pad = torch.zeros(vp, 3, device=device, dtype=torch.float32)
+            self.template_pad[:V] = v_template.detach().to(device).float()
         self.c_model = nv.SmplModel(nv.ptr(self.blend), nv.ptr(self.j_template), nv.ptr(self.j_shapedirs),
                                     nv.ptr(self.parents), nv.ptr(self.skin_idx), nv.ptr(self.skin_w),
-                                    ks, V, vp)
+                                    ks, V, vp, nv.ptr(self.blend_tc), nv.ptr(self.template_pad))
 
 
 def smpl_forward_native(packed: PackedSmpl, pose: torch.Tensor, ld_pose: int, pose_kind: int,
                         betas: torch.Tensor, ld_betas: int, cam, ld_cam: int, n: int,
-                        jreg, joint_src: torch.Tensor, want_theta: bool, want_rotmat: bool = True):
+                        jreg, joint_src: torch.Tensor, want_theta: bool, want_rotmat: bool = True,
+                        blend_mode: int = 0):
     """One tp_smpl_forward call.  `pose`/`betas`/`cam` may be column views into a wider row
     (e.g. the IEF state [N,160]); pointers + row strides are passed as they are."""
     dev = packed.device
@@ -164,12 +181,14 @@ def smpl_forward_native(packed: PackedSmpl, pose: torch.Tensor, ld_pose: int, po
     rotmat = torch.empty(n, 24, 3, 3, device=dev, dtype=torch.float32) if want_rotmat else None
     theta = torch.empty(n, 85, device=dev, dtype=torch.float32) if want_theta else None
     L = nv.lib()
-    nbytes = L.tp_smpl_workspace_bytes(packed.c_model, n, nreg)
+    if packed.blend_tc is None:
+        blend_mode = 0
+    nbytes = L.tp_smpl_workspace_bytes(packed.c_model, n, nreg, blend_mode)
     ws = nv.workspace(nbytes, dev)
     P = lambda t: nv.vp(0) if t is None else nv.vp(t.data_ptr())
     nv.check(L.tp_smpl_forward(packed.c_model, n, P(pose), ld_pose, pose_kind, P(betas), ld_betas, P(cam), ld_cam,
                                P(jreg), nreg, P(joint_src), nj, P(verts), P(joints), P(kp2d), P(rotmat), P(theta),
-                               P(ws), ws.numel(), nv.stream()), "tp_smpl_forward")
+                               blend_mode, P(ws), ws.numel(), nv.stream()), "tp_smpl_forward")
     return verts, joints, kp2d, rotmat, theta
 
 
@@ -221,6 +240,8 @@ class SMPL(nn.Module):
         self._packed = None
         self._pack_key = None
         self._jreg_cache = {}
+        # "fp32": strict FFMA blend (default, reference numerics); "bf16": tensor-core blend (<= 1 mm)
+        self.blend_precision = "fp32"
 
     # ------------------------------------------------------------------ packing
     def _key(self):
@@ -271,7 +292,8 @@ class SMPL(nn.Module):
             kind, width = nv.POSE_ROTMAT, 216
         flat = full.detach().to(dev, torch.float32).reshape(-1, width).expand(n, -1).contiguous()
         verts, joints, _, _, _ = smpl_forward_native(p, flat, width, kind, betas_c, 10, None, 0, n,
-                                                     self._jreg_extra, self._src49, want_theta=False, want_rotmat=False)
+                                                     self._jreg_extra, self._src49, want_theta=False, want_rotmat=False,
+                                                     blend_mode=1 if self.blend_precision == "bf16" else 0)
         if transl is not None:
             tr = transl.detach().to(dev, torch.float32)
             verts = verts + tr[:, None]

@@ -130,6 +130,7 @@ class Regressor(nn.Module):
         betas = psc[:, 144:]            # columns 144..153
         cam = psc[:, 154:]              # columns 154..156
         verts, joints, kp2d, rotmat, theta = smpl_forward_native(
-            p, pose, PSC, nv.POSE_ROT6D, betas, PSC, cam, PSC, N, jreg, src, want_theta=True)
+            p, pose, PSC, nv.POSE_ROT6D, betas, PSC, cam, PSC, N, jreg, src, want_theta=True,
+            blend_mode=1 if self.precision == "bf16" else 0)
         nv.mark("k45_smpl")
         return [{'theta': theta, 'verts': verts, 'kp_2d': kp2d, 'kp_3d': joints, 'rotmat': rotmat}]

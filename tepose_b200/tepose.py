@@ -99,7 +99,10 @@ class TemporalEncoder(nn.Module):
             layers.append(d)
         pk = {"layers": layers,
               "w_fwd": nv.pack_linear(g(self.linear_fwd, "weight"), self.precision), "b_fwd": g(self.linear_fwd, "bias").contiguous(),
-              "w_rec": nv.pack_linear(g(self.linear_rec, "weight"), self.precision), "b_rec": g(self.linear_rec, "bias").contiguous()}
+              "w_rec": nv.pack_linear(g(self.linear_rec, "weight"), self.precision), "b_rec": g(self.linear_rec, "bias").contiguous(),
+              "w_cat": nv.pack_linear(torch.cat([0.5 * g(self.linear_fwd, "weight"), 0.5 * g(self.linear_rec, "weight")], dim=1),
+                                      self.precision),
+              "b_cat": (0.5 * (g(self.linear_fwd, "bias") + g(self.linear_rec, "bias"))).contiguous()}
         self._pack, self._pack_key = pk, key
         return pk
 
@@ -151,7 +154,7 @@ class TemporalEncoder(nn.Module):
         j.y_lp = 0 if y_lp is None else y_lp.data_ptr() + 2 * ycol
         j.ldy_lp = 0 if y_lp is None else y_lp.shape[-1]
         j.h_final = 0 if h_final is None else h_final.data_ptr() + 4 * hcol
-        j.ld_hf = 0 if h_final is None else h_final.shape[-1]
+        j.ld_hf = 0 if h_final is None else h_final.stride(0)
         j.steps, j.t_in0, j.t_in_step, j.t_out0, j.t_out_step = steps, t_in0, t_in_step, t_out0, t_out_step
         j._dev = dev
         return j
@@ -178,8 +181,8 @@ class TemporalEncoder(nn.Module):
             raise ValueError("carried state is only defined for n_layers == 1 (SURVEY.md H5)")
         seq_f = torch.empty(T, B, H, device=dev, dtype=torch.float32) if return_states else None
         seq_b = torch.empty(T, B, H, device=dev, dtype=torch.float32) if return_states else None
-        h_fwd = torch.empty(B, H, device=dev, dtype=torch.float32)
-        h_rec = torch.empty(B, 2 * H, device=dev, dtype=torch.float32)
+        h_cat = torch.empty(B, 3 * H, device=dev, dtype=torch.float32)     # [y[-1] | y_rec[0]]
+        h_fwd, h_rec = h_cat[:, :H], h_cat[:, H:]
         y_f = y_r = y_f_lp = y_r_lp = None
         for l in range(Ln):
             d = pk["layers"][l]
@@ -263,10 +266,17 @@ class TemporalEncoder(nn.Module):
         L = nv.lib()
         feat_lp = torch.empty_like(feat, dtype=torch.bfloat16) if self.precision == "bf16" else None
         ws = nv.workspace(L.tp_encoder_heads_workspace_bytes(B), h_fwd.device)
-        nv.check(L.tp_encoder_heads(nv.PRECISIONS[self.precision], nv.ptr(pk["w_fwd"]), nv.ptr(pk["b_fwd"]), nv.ptr(pk["w_rec"]), nv.ptr(pk["b_rec"]),
-                                    nv.ptr(h_fwd), h_fwd.shape[1], nv.ptr(h_rec), h_rec.shape[1], B, H,
-                                    1 if is_train else 0, nv.ptr(feat), nv.ptr(feat_lp), nv.ptr(ws), ws.numel(), nv.stream()),
-                 "tp_encoder_heads")
+        P = lambda t: nv.vp(0) if t is None else nv.vp(t.data_ptr())
+        adjacent = (h_fwd.stride(0) == 3 * H and h_rec.stride(0) == 3 * H
+                    and h_rec.data_ptr() == h_fwd.data_ptr() + 4 * H)
+        if not is_train and adjacent:      # one GEMM over the concatenated state
+            nv.check(L.tp_encoder_heads_cat(nv.PRECISIONS[self.precision], P(pk["w_cat"]), P(pk["b_cat"]), P(h_fwd), 3 * H,
+                                            B, H, P(feat), P(feat_lp), P(ws), ws.numel(), nv.stream()), "tp_encoder_heads_cat")
+        else:
+            nv.check(L.tp_encoder_heads(nv.PRECISIONS[self.precision], P(pk["w_fwd"]), P(pk["b_fwd"]), P(pk["w_rec"]), P(pk["b_rec"]),
+                                        P(h_fwd), h_fwd.stride(0), P(h_rec), h_rec.stride(0), B, H,
+                                        1 if is_train else 0, P(feat), P(feat_lp), P(ws), ws.numel(), nv.stream()),
+                     "tp_encoder_heads")
         feat._tp_bf16 = feat_lp          # bf16 copy rides along for the IEF (same storage order)
         nv.mark("k3_heads")
         return feat

@@ -176,6 +176,13 @@ class FakeLib:
             _view(feat, B * 2048, torch.float32).copy_(((a + b) / 2).reshape(-1))
         return 0
 
+    def tp_encoder_heads_cat(self, precision, w_cat, b_cat, h_cat, ld_h, B, H, feat, feat_lp, ws, ws_bytes, stream):
+        a = self._act(precision, _mat(h_cat, B, 3 * H, ld_h).clamp_min(0))
+        v = a @ self._lin(precision, w_cat, 2048, 3 * H).t() + _view(b_cat, 2048, torch.float32)
+        _view(feat, B * 2048, torch.float32).copy_(v.reshape(-1))
+        self.calls.append(("heads_cat", B, H))
+        return 0
+
     def tp_ief_workspace_bytes(self, n):
         return 256
 
@@ -194,11 +201,11 @@ class FakeLib:
         return 0
 
     # ---- SMPL
-    def tp_smpl_workspace_bytes(self, m, n, nreg):
+    def tp_smpl_workspace_bytes(self, m, n, nreg, blend_mode=0):
         return 256
 
     def tp_smpl_forward(self, m, n, pose, ld_pose, pose_kind, betas, ld_betas, cam, ld_cam, jreg, nreg, joint_src, nj,
-                        verts, joints, kp2d, rotmat, theta, ws, ws_bytes, stream):
+                        verts, joints, kp2d, rotmat, theta, blend_mode, ws, ws_bytes, stream):
         m = m.contents if hasattr(m, "contents") else m
         V, vp = m.n_verts, m.vp
         blend = _view(m.blend, 218 * 3 * vp, torch.float32).reshape(218, 3, vp)[:, :, :V]

@@ -120,7 +120,7 @@ def test_skinny_bf16(M, N, K, splits):
     assert int(ws[:4096].view(torch.int32).abs().sum()) == 0
 
 
-@pytest.mark.parametrize("M,N,K", [(32, 1024, 1024), (32, 160, 1024), (32, 1024, 160), (64, 1024, 2048), (3, 96, 64)])
+@pytest.mark.parametrize("M,N,K", [(32, 1024, 1024), (32, 160, 1024), (32, 1024, 160), (64, 1024, 1024), (32, 1024, 2048), (3, 96, 64)])
 def test_skinny_bf16_single_phase_and_bf16_io(M, N, K):
     g = torch.Generator().manual_seed(3 * M + N + K)
     A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
@@ -290,6 +290,22 @@ def test_smpl_forward_all_pose_kinds(n):
     out = smpl(betas=cu(betas), body_pose=cu(R[:, 1:]), global_orient=cu(R[:, :1]), pose2rot=False)
     assert float((out.vertices.cpu() - v_ref).abs().max()) < 2e-5
     assert float((out.joints.cpu() - j_ref).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("n", [1, 33, 100])
+def test_smpl_forward_tensor_core_blend(n):
+    """bf16 tensor-core blend (K4): <= 1 mm by the north star; we hold 1e-4 m on SMPL-shaped data."""
+    with base_data_cwd(9):
+        smpl = tepose_b200.SMPL(tepose_b200.SMPL_MODEL_DIR, batch_size=1, create_transl=False).to(DEV)
+    smpl.blend_precision = "bf16"
+    m = torch_ref.SmplModel.synthetic(9)
+    bodies = synth.make_bodies(9, n)
+    aa, betas = torch.from_numpy(bodies["pose_aa"]), torch.from_numpy(bodies["betas"])
+    v_ref, j_ref, R = torch_ref.smpl_forward(m, betas, pose_aa=aa)
+    out = smpl(betas=cu(betas), body_pose=cu(aa[:, 3:]), global_orient=cu(aa[:, :3]), pose2rot=True)
+    ev = float((out.vertices.cpu() - v_ref).abs().max())
+    ej = float((out.joints.cpu() - j_ref).abs().max())
+    assert ev < 1e-4 and ej < 1e-4, (ev, ej)
 
 
 def test_smpl_size_independent_properties_large_batch():
