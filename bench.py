@@ -285,6 +285,7 @@ def main():
         lo, hi = _shard.partition(n_total, world, rank)
         bodies = synth.make_bodies(SEED + rank, hi - lo)
         smpl = model.regressor.smpl
+        smpl.blend_precision = "bf16" if args.precision == "bf16" else "fp32"     # K4 on tensor cores in bf16 mode
         aa = torch.from_numpy(bodies["pose_aa"]).to(dev)
         betas = torch.from_numpy(bodies["betas"]).to(dev)
         with torch.no_grad():
@@ -298,7 +299,8 @@ def main():
             torch.cuda.synchronize(dev)
         sm_ms = s0.elapsed_time(s1) / 3
         bps, sm_ms_max = _shard.aggregate_throughput(hi - lo, sm_ms, dev)
-        smpl_sa = {"bodies": n_total, "bodies_per_s": bps, "ms": sm_ms_max, "algorithmic_GBps_per_gpu":
+        smpl.blend_precision = "fp32"
+        smpl_sa = {"bodies": n_total, "blend": args.precision, "bodies_per_s": bps, "ms": sm_ms_max, "algorithmic_GBps_per_gpu":
                    (hi - lo) * 85780 / (sm_ms * 1e-3) / 1e9, "hbm_frac": (hi - lo) * 85780 / (sm_ms * 1e-3) / 1e9 / hbm_peak}
         del aa, betas
 

@@ -48,7 +48,8 @@ void set_trace_ptr(long long* p);  // bumps the counter behind tp_launch_count()
 #ifdef __CUDACC__
 // Grid barrier for a co-resident (cooperatively launched) grid: one arrival per CTA on a
 // monotonic counter, release/acquire at gpu scope (the release is cumulative over the CTA's
-// writes that thread 0 observed through bar.sync).  State that crosses the barrier is read with
+// writes that thread 0 observed through bar.sync).  CONTRACT: after this barrier, data written by
+// other CTAs must be read with L2-coherent loads (__ldcg / cp.async.bulk), never through L1.  State that crosses the barrier is read with
 // L2-coherent loads (cp.async.cg / ld.global.cg), so no L1 invalidation is needed.
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
   __syncthreads();
@@ -60,7 +61,13 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     do {
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(counter) : "memory");
     } while (seen < target);
+#ifdef TP_BARRIER_ACQUIRE_FENCE
+    // Formal acquire.  It compiles to MEMBAR + CCTL.IVALL, and the L1 invalidate stalls every load the
+    // CTA issues next for ~4-5K cycles (measured, profiles/).  It is only needed when data produced by
+    // other CTAs is read through L1; the kernels using this barrier read such data exclusively with
+    // L2-coherent accesses (ld.global.cg -> LDG.STRONG.GPU, cp.async.bulk), so it is off by default.
     asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+#endif
   }
   __syncthreads();
 }

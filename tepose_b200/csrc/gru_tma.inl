@@ -81,18 +81,22 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
   uint32_t cons = 0, prod = 0, msteps = 0;    // chunk counters (ring position / phase), matmul steps seen
   int prefetched = 0;
 
-  auto issue_chunk = [&](int c) {             // producer lane only
+  // Producer warp: lane 0 owns the barrier bookkeeping, lanes 0..5 each issue one of the six bulk
+  // copies of a chunk and lanes 0..B-1 one row of h (cp.async.bulk issue is ~50 cycles a piece, so
+  // a single issuing lane would serialise 32 + 6 * chunks of them on the critical path).
+  auto issue_chunk = [&](int c) {
     const int st = prod % stages;
-    mb_wait(&w_empty[st], ((prod / stages) & 1) ^ 1);
-    mb_expect_tx(&w_full[st], kChunkBytes);
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        const size_t src = ((((size_t)i * (H / 16) + (u0 >> 4) + m) * nblk) + (size_t)c * kChunkBlocks) * 1024;
-        bulk_g2s(ring + (size_t)st * kChunkBytes + (size_t)((i * 2 + m) * kChunkBlocks) * 1024, wbase + src,
-                 kChunkBlocks * 1024, &w_full[st]);
-      }
+    if (lane == 0) {
+      mb_wait(&w_empty[st], ((prod / stages) & 1) ^ 1);
+      mb_expect_tx(&w_full[st], kChunkBytes);
+    }
+    __syncwarp();
+    if (lane < 6) {
+      const int i = lane >> 1, m = lane & 1;
+      const size_t src = ((((size_t)i * (H / 16) + (u0 >> 4) + m) * nblk) + (size_t)c * kChunkBlocks) * 1024;
+      bulk_g2s(ring + (size_t)st * kChunkBytes + (size_t)((i * 2 + m) * kChunkBlocks) * 1024, wbase + src,
+               kChunkBlocks * 1024, &w_full[st]);
+    }
     ++prod;
   };
 
@@ -101,12 +105,13 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
     const bool active = s < jb.steps;
     const bool have_prev = active && ((s > 0) || (jb.h0 != nullptr));
     if (producer) {
-      if (lane == 0 && have_prev) {
+      if (have_prev) {
         asm volatile("fence.proxy.async;\n" ::: "memory");
         const __nv_bfloat16* hprev = p.hbuf_lp + (size_t)(blockIdx.x % kHRep) * p.lp_rep_stride +
                                      ((int64_t)(j * 2 + ((s + 1) & 1)) * B) * H;
-        mb_expect_tx(h_full, (uint32_t)B * H * 2);
-        for (int b = 0; b < B; ++b) bulk_g2s(hs + (size_t)b * HP, hprev + (int64_t)b * H, (uint32_t)H * 2, h_full);
+        if (lane == 0) mb_expect_tx(h_full, (uint32_t)B * H * 2);
+        __syncwarp();
+        for (int b = lane; b < B; b += 32) bulk_g2s(hs + (size_t)b * HP, hprev + (int64_t)b * H, (uint32_t)H * 2, h_full);
         for (int c = prefetched; c < nchunks; ++c) issue_chunk(c);
         prefetched = 0;
         if (s + 1 < jb.steps) {               // W_hh is step-invariant: refill the ring for the next step now

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
       for (int i = 0; i < E; ++i) {
         const int idx = tid + i * kSkThreads, m = idx >> 4, r = idx & 15, nn = ut * 16 + r;
         const bool ok = idx < NB * 16 && m < p.M && nn < L.N;
-        cin[i] = (ok && L.Cin) ? L.Cin[(int64_t)m * L.ldcin + nn] : 0.0f;
+        cin[i] = (ok && L.Cin) ? __ldcg(L.Cin + (int64_t)m * L.ldcin + nn) : 0.0f;
         bia[i] = (ok && L.bias) ? __ldg(L.bias + nn) : 0.0f;
       }
       // activations of this layer (bf16 rows written by the previous layer / the prologue): own replica
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
           for (int k = 0; k < 8; ++k) {
             const int col = (lane + 32 * k) * 8;
             v[rr][k] = make_uint4(0u, 0u, 0u, 0u);
-            if (k < per_row && r < NB && r < p.M && col < L.K) v[rr][k] = *reinterpret_cast<const uint4*>(Ain + (int64_t)r * L.lda + col);   // weak load: the barrier's acquire invalidated L1
+            if (k < per_row && r < NB && r < p.M && col < L.K) v[rr][k] = __ldcg(reinterpret_cast<const uint4*>(Ain + (int64_t)r * L.lda + col));   // L2-coherent (barrier contract)
           }
         }
 #pragma unroll
