@@ -118,8 +118,13 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
   for (int q = 1; q < TC_MAX_SEGS; ++q)
     if (q < p.nseg && (int)blockIdx.x >= p.tile_begin[q]) s = q;
-  const tp_gemm_seg sg = p.seg[s];
-  const int local = blockIdx.x - p.tile_begin[s];
+  // static-index select: a dynamic index into the kernel parameters costs a constant-cache miss per field
+  tp_gemm_seg sg = p.seg[0];
+  int tile0 = p.tile_begin[0];
+#pragma unroll
+  for (int q = 1; q < TC_MAX_SEGS; ++q)
+    if (q == s) { sg = p.seg[q]; tile0 = p.tile_begin[q]; }
+  const int local = blockIdx.x - tile0;
   const int m_tiles = (sg.m_rows + TC_BM - 1) / TC_BM;
   const int n_tile = local / m_tiles, m_tile = local - n_tile * m_tiles;
   const int m0 = m_tile * TC_BM, n0 = n_tile * TC_BN;   // segment-local

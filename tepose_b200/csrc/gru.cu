@@ -72,26 +72,27 @@ __device__ __forceinline__ void mma_bf16(float* c, uint32_t a0, uint32_t a1, uin
 // latency hides behind the W_hh stream.
 struct GateIn { float gr, gz, gn, br, bz, bn, hp; };
 
-__device__ __forceinline__ GateIn gate_fetch(const GruParams& p, int j, int s, int b, int u) {
-  const tp_gru_job& jb = p.jobs[j];
+__device__ __forceinline__ GateIn gate_fetch(const GruParams& p, const tp_gru_job& jb, int j, int s, int b, int u) {
   const int H = p.H, B = p.B;
   const int t_in = jb.t_in0 + s * jb.t_in_step;
   const float* gi = jb.gi + ((int64_t)t_in * B + b) * jb.ldg;
   GateIn g;
-  g.gr = __ldg(gi + u); g.gz = __ldg(gi + H + u); g.gn = __ldg(gi + 2 * H + u);
-  g.br = __ldg(jb.b_hh + u); g.bz = __ldg(jb.b_hh + H + u); g.bn = __ldg(jb.b_hh + 2 * H + u);
+  // volatile asm loads: the compiler must not sink them below the (asm volatile) MMA loop -- the whole
+  // point is that they are in flight while W_hh streams
+  auto ldnc = [](const float* ptr) { float v; asm volatile("ld.global.nc.f32 %0, [%1];\n" : "=f"(v) : "l"(ptr)); return v; };
+  g.gr = ldnc(gi + u); g.gz = ldnc(gi + H + u); g.gn = ldnc(gi + 2 * H + u);
+  g.br = ldnc(jb.b_hh + u); g.bz = ldnc(jb.b_hh + H + u); g.bn = ldnc(jb.b_hh + 2 * H + u);
   g.hp = 0.0f;
   const bool have_prev = (s > 0) || (jb.h0 != nullptr);
   const float* hprev = p.hbuf + ((int64_t)(j * 2 + ((s + 1) & 1)) * B) * H;
-  if (have_prev) g.hp = __ldcg(hprev + (int64_t)b * H + u);
+  if (have_prev) asm volatile("ld.global.cg.f32 %0, [%1];\n" : "=f"(g.hp) : "l"(hprev + (int64_t)b * H + u));
   return g;
 }
 
 // Gate math of torch.nn.GRU for one (batch b, hidden unit u): acc_* are W_h* . h_prev.
 template <bool FAST = false>
-__device__ __forceinline__ void gru_finalize(const GruParams& p, int j, int s, int b, int u, const GateIn& g,
-                                             float acc_r, float acc_z, float acc_n) {
-  const tp_gru_job& jb = p.jobs[j];
+__device__ __forceinline__ void gru_finalize(const GruParams& p, const tp_gru_job& jb, int j, int s, int b, int u,
+                                             const GateIn& g, float acc_r, float acc_z, float acc_n) {
   const int H = p.H, B = p.B;
   float r, z, n;
   if (FAST) {
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_f32(const GruParams p) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           int b = b0 + bq + 8 * i;
-          if (b < B) gru_finalize(p, j, s, b, u0 + u, gate_fetch(p, j, s, b, u0 + u), acc[0][i], acc[1][i], acc[2][i]);
+          if (b < B) gru_finalize(p, jb, j, s, b, u0 + u, gate_fetch(p, jb, j, s, b, u0 + u), acc[0][i], acc[1][i], acc[2][i]);
         }
       }
     }
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
         for (int e = 0; e < GE; ++e) {
           const int idx = tid + e * kGruThreads;
           const int bb = idx / U, uu = idx - bb * U;
-          if (idx < NB * U && b0 + bb < B) gin[e] = gate_fetch(p, j, s, b0 + bb, u0 + uu);
+          if (idx < NB * U && b0 + bb < B) gin[e] = gate_fetch(p, jb, j, s, b0 + bb, u0 + uu);
         }
         if (have_prev) {
           float acc[3][NT][4];
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
               an += red[((size_t)(k * 3 + 2) * NB + bb) * RP + uu];
             }
           }
-          gru_finalize(p, j, s, b0 + bb, u0 + uu, gin[e], ar, az, an);
+          gru_finalize(p, jb, j, s, b0 + bb, u0 + uu, gin[e], ar, az, an);
         }
         __syncthreads();  // hs / red are reused by the next batch tile / item
       }

@@ -64,11 +64,18 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
   }
   __syncthreads();
 
+  // job table -> shared memory (dynamic indexing of the kernel-parameter copy costs a constant-cache
+  // round trip per field access; measured ~2.5K cycles per use site)
+  __shared__ tp_gru_job sjobs[kMaxJobs];
+  for (int i = tid; i < (int)(sizeof(tp_gru_job) * kMaxJobs / 4); i += kTmaThreads)
+    reinterpret_cast<int*>(sjobs)[i] = reinterpret_cast<const int*>(p.jobs)[i];
+  __syncthreads();
+
   // step-0-only jobs without an initial state have no matmul at all: plain gate math, grid-strided
   for (int je = p.n_item_jobs; je < p.njobs; ++je)
     for (int64_t i = blockIdx.x * (int64_t)kTmaThreads + tid; i < (int64_t)B * H; i += (int64_t)gridDim.x * kTmaThreads) {
       const int b = (int)(i / H), u = (int)(i - (int64_t)b * H);
-      gru_finalize<true>(p, je, 0, b, u, gate_fetch(p, je, 0, b, u), 0.f, 0.f, 0.f);
+      gru_finalize<true>(p, sjobs[je], je, 0, b, u, gate_fetch(p, sjobs[je], je, 0, b, u), 0.f, 0.f, 0.f);
     }
 
   unsigned int epoch = 0;
@@ -76,7 +83,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
 
   int j, u0;
   locate_item(p, blockIdx.x, j, u0);          // exactly one item per CTA on this path
-  const tp_gru_job& jb = p.jobs[j];
+  const tp_gru_job& jb = sjobs[j];
   const unsigned char* wbase = reinterpret_cast<const unsigned char*>(jb.w_hh);
   uint32_t cons = 0, prod = 0, msteps = 0;    // chunk counters (ring position / phase), matmul steps seen
   int prefetched = 0;
@@ -128,7 +135,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
         for (int e = 0; e < GE; ++e) {
           const int idx = tid + e * 256;
           const int bb = idx / U, uu = idx - bb * U;
-          if (idx < NB * U && bb < B) gin[e] = gate_fetch(p, j, s, bb, u0 + uu);
+          if (idx < NB * U && bb < B) gin[e] = gate_fetch(p, jb, j, s, bb, u0 + uu);
         }
       }
       if (have_prev) {
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
               an += red[((size_t)(k * 3 + 2) * NB + bb) * RP + uu];
             }
           }
-          gru_finalize<true>(p, j, s, bb, u0 + uu, gin[e], ar, az, an);
+          gru_finalize<true>(p, jb, j, s, bb, u0 + uu, gin[e], ar, az, an);
         }
       }
       // generic-proxy writes (red in shared memory, h_t in global memory) must be ordered before the

@@ -126,7 +126,7 @@ struct IefFusedParams {
   const float* init; int init_rows; float* psc; __nv_bfloat16* psc_lp;
   long long* trace;   // debug: [grid][layers][4] clock stamps
 };
-#define IEF_TRACE(slot) do { if (p.trace && threadIdx.x == 0) p.trace[((size_t)blockIdx.x * kIefMaxLayers + l) * 4 + (slot)] = clock64(); } while (0)
+#define IEF_TRACE(slot) do { if (p.trace && threadIdx.x == 0) p.trace[((size_t)blockIdx.x * kIefMaxLayers + l) * 8 + (slot)] = clock64(); } while (0)
 
 template <int NT>
 __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParams p) {
@@ -135,6 +135,12 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int ut = blockIdx.x;
   unsigned int epoch = 0;
+  // layer table -> shared memory: indexing the kernel-parameter copy with the (dynamic) layer index
+  // costs a constant-cache round trip per field
+  __shared__ IefLayer sL[kIefMaxLayers];
+  for (int i = tid; i < (int)(sizeof(IefLayer) * kIefMaxLayers / 4); i += kSkThreads)
+    reinterpret_cast<int*>(sL)[i] = reinterpret_cast<const int*>(p.layer)[i];
+  __syncthreads();
 
   // prologue: IEF state <- init (fp32 + bf16 copy), optional feat conversion
   for (int i = blockIdx.x * kSkThreads + tid; i < p.M * 160; i += gridDim.x * kSkThreads) {
@@ -160,10 +166,10 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
     for (int q = 0; q < kSkPF; ++q)
       if (q < nb) { wa[q] = ldg_stream16(wp + (int64_t)q * 64); wb[q] = ldg_stream16(wp + (int64_t)q * 64 + 32); }
   };
-  if (ut < (p.layer[0].N + 15) / 16) prefetch(p.layer[0]);
+  if (ut < (sL[0].N + 15) / 16) prefetch(sL[0]);
 
   for (int l = 0; l < p.nlayers; ++l) {
-    const IefLayer& L = p.layer[l];
+    const IefLayer L = sL[l];
     IEF_TRACE(0);
     if (ut < (L.N + 15) / 16) {
       const int nkb = (L.K + 31) / 32;
@@ -199,6 +205,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
             if (k < per_row && r < NB && r < p.M && col < L.K) v[rr][k] = __ldcg(reinterpret_cast<const uint4*>(Ain + (int64_t)r * L.lda + col));   // L2-coherent (barrier contract)
           }
         }
+        if (r0 == warp) IEF_TRACE(4);          // all loads of the first half issued
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
           const int r = r0 + rr * (kSkThreads / 32);
@@ -208,7 +215,9 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
             if (k < per_row && r < NB && col < nkb * 32) *reinterpret_cast<uint4*>(As + (size_t)r * pitch + col) = v[rr][k];
           }
         }
+        if (r0 == warp) IEF_TRACE(5);          // first half landed and stored
       }
+      IEF_TRACE(6);                              // this warp done staging
       __syncthreads();
       IEF_TRACE(1);
       float acc[NT][4];
@@ -251,7 +260,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
     }
     IEF_TRACE(2);
     if (l + 1 < p.nlayers) {
-      if (ut < (p.layer[l + 1].N + 15) / 16) prefetch(p.layer[l + 1]);   // weights do not depend on the barrier
+      if (ut < (sL[l + 1].N + 15) / 16) prefetch(sL[l + 1]);   // weights do not depend on the barrier
       grid_barrier(p.barrier, ++epoch * gridDim.x);
     }
     IEF_TRACE(3);
