@@ -205,27 +205,32 @@ def main():
     launches = eager_launches if args.no_graph else graphed.launches_per_replay * args.steps
 
     # ---------------------------------------------------------------- end to end (host buffers)
-    out_host = {k: torch.empty_like(graphed.static_output[k], device="cpu").pin_memory() for k in OUTPUT_KEYS}
-    h2d_bytes = xs_host[0].numel() * 4
-    d2h_bytes = sum(v.numel() * 4 for v in out_host.values())
-
-    def e2e_step(i):
-        graphed.static_input.copy_(xs_host[i % n_inputs], non_blocking=True)
-        out = run()
-        for k in OUTPUT_KEYS:
-            out_host[k].copy_(out[k], non_blocking=True)
-
+    # public host-buffer API: pinned x -> H2D -> forward -> D2H of all five outputs, every step; copies of
+    # neighbouring steps overlap compute through a 3-slot ring (tepose_b200/pipeline.py)
+    from tepose_b200.pipeline import PipelinedTePose
+    pipe = PipelinedTePose(model, B, T, depth=3)
+    h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes
     with torch.no_grad():
         for i in range(args.warmup):
-            e2e_step(i)
+            pipe.result(pipe.submit(xs_host[i % n_inputs]))
+        pipe.drain()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        checksum = 0.0
         e0.record()
+        t_e2e0 = time.perf_counter()
+        tickets = []
         for i in range(args.steps):
-            e2e_step(i)
+            tickets.append(pipe.submit(xs_host[i % n_inputs]))
+            if len(tickets) >= pipe.depth:                       # consume results as they complete
+                checksum += float(pipe.result(tickets.pop(0))["theta"][0, 0])
+        for tk in tickets:
+            checksum += float(pipe.result(tk)["theta"][0, 0])
+        pipe.drain()
         e1.record()
         barrier()
-    e2e_ms_total = e0.elapsed_time(e1)
+        t_e2e = time.perf_counter() - t_e2e0
+    e2e_ms_total = max(e0.elapsed_time(e1), 1e3 * t_e2e)     # host-visible completion: the slower of the two clocks
     clocks = sampler.finish()
 
     # ---------------------------------------------------------------- per-kernel timing (roofline)
@@ -331,7 +336,7 @@ def main():
                        "l2": "256 MiB memset between steps, outside the per-step event pairs",
                        "parallelism": f"batch-sharded x{world}, no collective"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": e2e_ms_max / args.steps},
+                    "ms_per_step": e2e_ms_max / args.steps, "pipeline_depth": 3},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,

@@ -205,9 +205,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
           gru_finalize<true>(p, jb, j, s, bb, u0 + uu, gin[e], ar, az, an);
         }
       }
-      // generic-proxy writes (red in shared memory, h_t in global memory) must be ordered before the
-      // async-proxy (TMA) refill of hs / reads of h_t after the barrier
-      asm volatile("fence.proxy.async;\n" ::: "memory");
+      // generic-proxy writes to red (shared memory) must be ordered before the async-proxy (TMA) refill of
+      // hs in the next step.  h_t in GLOBAL memory is ordered by the grid barrier's release and by the
+      // producer's own fence.proxy.async before it issues the bulk reads.
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
     if (s + 1 < p.max_steps) {
       TP_TRACE(4);

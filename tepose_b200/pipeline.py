@@ -1,0 +1,66 @@
+"""Host-buffer throughput API: overlaps the H2D copy of step i+1 and the D2H copy of step i-1 with the
+compute of step i.  Each of the `depth` slots owns a static device input, a captured CUDA graph of the
+forward and pinned host output buffers; copies run on their own streams, ordered by events.
+
+    pipe = PipelinedTePose(model, batch=32, seqlen=16, depth=3)
+    t0 = pipe.submit(x_host_0)            # pinned [B,T,2133] float32
+    t1 = pipe.submit(x_host_1)
+    out0 = pipe.result(t0)                # dict of pinned host tensors; valid until slot reuse (depth submits later)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native as nv
+from .graph import GraphedTePose, OUTPUT_KEYS
+
+
+class PipelinedTePose:
+    def __init__(self, model, batch, seqlen, depth=3, J_regressor=None):
+        p = next(model.parameters())
+        nv.require_cuda(p, "model parameters")
+        self.device, self.depth = p.device, depth
+        self.slots = [GraphedTePose(model, batch, seqlen, J_regressor=J_regressor) for _ in range(depth)]
+        self.out_host = [{k: torch.empty_like(s.static_output[k], device="cpu").pin_memory() for k in OUTPUT_KEYS}
+                         for s in self.slots]
+        self.compute = torch.cuda.current_stream(self.device)
+        self.h2d = torch.cuda.Stream(device=self.device)
+        self.d2h = torch.cuda.Stream(device=self.device)
+        ev = lambda: torch.cuda.Event(enable_timing=False)
+        self.h2d_done = [ev() for _ in range(depth)]
+        self.compute_done = [ev() for _ in range(depth)]
+        self.d2h_done = [ev() for _ in range(depth)]
+        self.count = 0
+        self.h2d_bytes = self.slots[0].static_input.numel() * 4
+        self.d2h_bytes = sum(v.numel() * 4 for v in self.out_host[0].values())
+
+    def submit(self, x_host: torch.Tensor) -> int:
+        i, slot = self.count, self.count % self.depth
+        s = self.slots[slot]
+        with torch.cuda.stream(self.h2d):
+            if i >= self.depth:
+                self.h2d.wait_event(self.compute_done[slot])       # previous occupant has been consumed by its graph
+            s.static_input.copy_(x_host, non_blocking=True)
+            self.h2d_done[slot].record(self.h2d)
+        self.compute.wait_event(self.h2d_done[slot])
+        if i >= self.depth:
+            self.compute.wait_event(self.d2h_done[slot])           # previous outputs of this slot have left the device
+        s.replay()
+        self.compute_done[slot].record(self.compute)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(self.compute_done[slot])
+            for k in OUTPUT_KEYS:
+                self.out_host[slot][k].copy_(s.static_output[k], non_blocking=True)
+            self.d2h_done[slot].record(self.d2h)
+        self.count += 1
+        return i
+
+    def result(self, ticket: int):
+        if not (self.count - self.depth <= ticket < self.count):
+            raise ValueError("ticket is no longer (or not yet) resident in the ring")
+        slot = ticket % self.depth
+        self.d2h_done[slot].synchronize()
+        return self.out_host[slot]
+
+    def drain(self):
+        self.h2d.synchronize(); self.d2h.synchronize(); self.compute.synchronize()

@@ -86,3 +86,25 @@ def test_graphed_forward_equals_eager():
     for k in eager:
         assert torch.equal(out[k], eager[k]), k          # same kernels, same order: bitwise
     assert g.launches_per_replay >= 6
+
+
+def test_pipelined_host_buffer_api_matches_direct_forward():
+    """tepose_b200.pipeline: overlapped H2D / compute / D2H must return exactly the direct results."""
+    from tepose_b200.pipeline import PipelinedTePose
+    model, sd = build_product_model(71, 16, 1, 256, "bf16", DEV)
+    xs = [torch.from_numpy(synth.make_input(71 + i, 4, 16)).pin_memory() for i in range(7)]
+    direct = [{k: v.clone().cpu() for k, v in model(x.to(DEV))[-1].items()} for x in xs]
+    pipe = PipelinedTePose(model, 4, 16, depth=3)
+    tickets, got = [], []
+    for x in xs:
+        tickets.append(pipe.submit(x))
+        if len(tickets) >= pipe.depth:
+            got.append({k: v.clone() for k, v in pipe.result(tickets.pop(0)).items()})
+    for tk in tickets:
+        got.append({k: v.clone() for k, v in pipe.result(tk).items()})
+    assert len(got) == len(xs)
+    for a, b in zip(got, direct):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+    with pytest.raises(ValueError):
+        pipe.result(0)          # slot already recycled
