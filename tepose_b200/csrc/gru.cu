@@ -30,6 +30,9 @@ struct GruParams {
   float* hbuf;              // [njobs][2][B][H]  fp32 state ping-pong
   __nv_bfloat16* hbuf_lp;   // [kHRep][njobs][2][B][H]  bf16 copies (MMA operand of the next step)
   size_t lp_rep_stride;     // elements between replicas
+  int64_t lp_slot;          // elements per (job, parity) bf16 state slot
+  int lp_tiled;             // 1: bf16 state is stored [chunk = H/128][32 rows][128] with 16-byte group index XOR ((row & 1) << 2)
+                            //    (one contiguous 8 KB block per ring stage of k_gru_bf16_tma); 0: row-major [B][H]
   unsigned int* barrier;    // monotonic grid-barrier counter (zeroed by the host before launch)
   long long* trace;         // debug: [gridDim][max_steps][8] SM-clock stamps (tp_gru_set_trace), or null
 };
@@ -66,6 +69,13 @@ __device__ __forceinline__ void mma_bf16(float* c, uint32_t a0, uint32_t a1, uin
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// element index of (batch b, unit u) inside one [B,H] bf16 state slot
+__device__ __forceinline__ int64_t lp_index(const GruParams& p, int b, int u) {
+  if (!p.lp_tiled) return (int64_t)b * p.H + u;
+  const int chunk = u >> 7, c = u & 127;
+  return ((int64_t)chunk * 32 + b) * 128 + ((((c >> 3) ^ ((b & 1) << 2)) << 3) | (c & 7));
 }
 
 // Operands of the gate math that do not depend on this step's matmul; fetched early so their
@@ -109,8 +119,9 @@ __device__ __forceinline__ void gru_finalize(const GruParams& p, const tp_gru_jo
   p.hbuf[slot] = h;
   {
     const __nv_bfloat16 hb = __float2bfloat16_rn(h);
+    const int64_t lp = (int64_t)(j * 2 + (s & 1)) * p.lp_slot + lp_index(p, b, u);
 #pragma unroll
-    for (int r = 0; r < kHRep; ++r) p.hbuf_lp[(size_t)r * p.lp_rep_stride + slot] = hb;
+    for (int r = 0; r < kHRep; ++r) p.hbuf_lp[(size_t)r * p.lp_rep_stride + lp] = hb;
   }
   const int t_out = jb.t_out0 + s * jb.t_out_step;
   if (jb.y) jb.y[((int64_t)t_out * B + b) * jb.ldy + u] = h;
@@ -135,8 +146,9 @@ __device__ void seed_h0(const GruParams& p) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
       float v = h0[i];
       p.hbuf[(int64_t)(j * 2 + 1) * per + i] = v;
+      const int64_t lp = (int64_t)(j * 2 + 1) * p.lp_slot + lp_index(p, (int)(i / p.H), (int)(i % p.H));
 #pragma unroll
-      for (int r = 0; r < kHRep; ++r) p.hbuf_lp[(size_t)r * p.lp_rep_stride + (int64_t)(j * 2 + 1) * per + i] = __float2bfloat16_rn(v);
+      for (int r = 0; r < kHRep; ++r) p.hbuf_lp[(size_t)r * p.lp_rep_stride + lp] = __float2bfloat16_rn(v);
     }
   }
 }
@@ -288,7 +300,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
       const tp_gru_job& jb = p.jobs[j];
       if (s >= jb.steps) continue;
       const bool have_prev = (s > 0) || (jb.h0 != nullptr);
-      const __nv_bfloat16* hprev = p.hbuf_lp + ((int64_t)(j * 2 + ((s + 1) & 1)) * B) * H;
+      const __nv_bfloat16* hprev = p.hbuf_lp + (int64_t)(j * 2 + ((s + 1) & 1)) * p.lp_slot;
       const uint4* wrow[3];
       w_rows(j, u0, wrow);
       for (int b0 = 0; b0 < B; b0 += NB) {
@@ -426,7 +438,8 @@ extern "C" void tp_gru_set_trace(void* device_buffer) { tp::set_trace_ptr(reinte
 
 extern "C" size_t tp_gru_workspace_bytes(int njobs, int B, int H) {
   size_t per = (size_t)njobs * 2 * B * H;
-  return 256 + align_up(per * sizeof(float), 256) + kHRep * align_up(per * sizeof(__nv_bfloat16), 256);
+  size_t per_lp = (size_t)njobs * 2 * (B < 32 ? 32 : B) * H;      // the tiled layout pads a slot to 32 rows
+  return 256 + align_up(per * sizeof(float), 256) + kHRep * align_up(per_lp * sizeof(__nv_bfloat16), 256);
 }
 
 template <typename KernelT>
@@ -484,7 +497,9 @@ extern "C" int tp_gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, in
   p.barrier = reinterpret_cast<unsigned int*>(workspace);
   p.hbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 256);
   p.hbuf_lp = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(workspace) + 256 + align_up(per * sizeof(float), 256));
-  p.lp_rep_stride = align_up(per * sizeof(__nv_bfloat16), 256) / sizeof(__nv_bfloat16);
+  const size_t per_lp = (size_t)njobs * 2 * (B < 32 ? 32 : B) * H;
+  p.lp_rep_stride = align_up(per_lp * sizeof(__nv_bfloat16), 256) / sizeof(__nv_bfloat16);
+  p.lp_slot = (int64_t)B * H; p.lp_tiled = 0;
   cudaStream_t st = (cudaStream_t)stream;
   TP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
   const int sms = sm_count();
@@ -493,12 +508,9 @@ extern "C" int tp_gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, in
   static const bool no_tma = getenv("TP_GRU_NO_TMA") != nullptr;
   if (precision == TP_PRECISION_BF16 && !no_tma && n_mat >= 1 && H % 128 == 0 && B <= 32 && n_mat * (H / 32) <= sms) {
     const int NB = B <= 8 ? 8 : 32;
-    size_t region = (size_t)NB * (H + 32) * 2;
-    const size_t redb = (size_t)4 * 3 * NB * 36 * 4;
-    if (region < redb) region = redb;
-    region = (region + 1023) & ~(size_t)1023;
+    const size_t region = ((size_t)4 * 3 * NB * 36 * 4 + 1023) & ~(size_t)1023;     // red only: h rides in the ring
     const size_t budget = 225 * 1024;
-    int stages = region + 256 < budget ? (int)((budget - region - 256) / kChunkBytes) : 0;
+    int stages = (int)((budget - region - 256) / kStageBytes);
     if (stages > 8) stages = 8;
     if (stages > H / 128) stages = H / 128;
     if (stages >= 2 || (stages == 1 && H == 128)) {
@@ -507,7 +519,8 @@ extern "C" int tp_gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, in
       for (int j = 0; j < n_mat; ++j) { p.item_begin[j] = items; items += H / 32; }
       for (int j = n_mat; j <= kMaxJobs; ++j) p.item_begin[j] = items;
       p.total_items = items;
-      const size_t smem = region + (size_t)stages * kChunkBytes + 256;
+      const size_t smem = region + (size_t)stages * kStageBytes + 256;
+      p.lp_tiled = 1; p.lp_slot = (int64_t)32 * H;
       if (NB == 8) return launch_coop_n(k_gru_bf16_tma<1>, p, stages, kTmaThreads, items, smem, st);
       return launch_coop_n(k_gru_bf16_tma<4>, p, stages, kTmaThreads, items, smem, st);
     }

@@ -3,16 +3,20 @@
 // bf16 recurrence, TMA ring variant.  Same decomposition as k_gru_bf16<NT, 2> (U = 32 units per
 // CTA = 6 m-tiles, 4 K groups x 2 unit tiles), but the operands arrive through the async proxy:
 // a ninth warp issues cp.async.bulk copies that
-//   * stage h_{t-1} (bf16) once per step, and
-//   * stream the CTA's fragment-packed W_hh slice through a ring of 24 KB chunks
-//     (6 m-tiles x 4 column blocks), guarded by full / empty mbarriers.
+//   * stream the CTA's fragment-packed W_hh slice through a ring of stages (24 KB = 6 m-tiles x 4 column
+//     blocks) guarded by full / empty mbarriers, and
+//   * attach to every stage the matching 8 KB slice of h_{t-1} (bf16; kept chunk-tiled and XOR-swizzled in
+//     global memory by the gate epilogue, so a slice is ONE contiguous bulk copy and the B-fragment reads
+//     are bank-conflict free without padding) -- there is no separate h buffer and no staging phase.
 // W_hh does not depend on h, so the producer runs ahead: while the consumers do the gate math and
 // wait at the grid barrier, the ring is already refilled with the next step's first chunks -- the
 // L2 -> SM stream overlaps the phases that used to leave the L2 idle (measured: the recurrence is
 // bound by L2 bandwidth, ~7 TB/s for 128 streaming CTAs, see scripts/micro/l2bw.cu).
 constexpr int kTmaThreads = 288;
 constexpr int kChunkBlocks = 4;
-constexpr int kChunkBytes = 6 * kChunkBlocks * 1024;
+constexpr int kChunkBytes = 6 * kChunkBlocks * 1024;      // W_hh part of a ring stage: 24 KB
+constexpr int kHChunkBytes = 32 * 128 * 2;                // h part: 32 rows x 128 columns bf16 = 8 KB (tiled + swizzled in global)
+constexpr int kStageBytes = kChunkBytes + kHChunkBytes;
 
 __device__ __forceinline__ uint32_t sm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mb_init(uint64_t* b, uint32_t n) {
@@ -42,24 +46,19 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
   constexpr int NB = NT * 8, U = 32, KG = 4, RP = U + 4;
   constexpr int GE = (NB * U + 255) / 256;
   extern __shared__ __align__(1024) unsigned char smem_t[];
-  const int H = p.H, B = p.B, HP = H + 32;
+  const int H = p.H, B = p.B;
   const int nblk = H / 32, nchunks = nblk / kChunkBlocks;
-  size_t region = (size_t)NB * HP * 2;
-  if (region < (size_t)KG * 3 * NB * RP * 4) region = (size_t)KG * 3 * NB * RP * 4;
-  region = (region + 1023) & ~(size_t)1023;
-  __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(smem_t);      // [NB][HP]; aliased by red after the MMA loop
+  const size_t region = ((size_t)KG * 3 * NB * RP * 4 + 1023) & ~(size_t)1023;
   float* red = reinterpret_cast<float*>(smem_t);                      // [KG][3][NB][RP]
-  unsigned char* ring = smem_t + region;                              // [stages][24 KB]
-  uint64_t* w_full = reinterpret_cast<uint64_t*>(ring + (size_t)stages * kChunkBytes);
+  unsigned char* ring = smem_t + region;                              // [stages][24 KB W | 8 KB h]
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(ring + (size_t)stages * kStageBytes);
   uint64_t* w_empty = w_full + 8;
-  uint64_t* h_full = w_empty + 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3, kg = (warp >> 1) & 3, mg = warp & 1;
   const bool producer = warp == 8;
 
   if (tid == 0) {
-    for (int i = 0; i < stages; ++i) { mb_init(&w_full[i], 1); mb_init(&w_empty[i], 8); }
-    mb_init(h_full, 1);
+    for (int i = 0; i < stages; ++i) { mb_init(&w_full[i], 2); mb_init(&w_empty[i], 8); }   // full: W arrival + h arrival
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -85,13 +84,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
   locate_item(p, blockIdx.x, j, u0);          // exactly one item per CTA on this path
   const tp_gru_job& jb = sjobs[j];
   const unsigned char* wbase = reinterpret_cast<const unsigned char*>(jb.w_hh);
-  uint32_t cons = 0, prod = 0, msteps = 0;    // chunk counters (ring position / phase), matmul steps seen
+  uint32_t cons = 0, prod = 0, hprod = 0;     // ring positions: consumed stages, W parts issued, h parts issued
   int prefetched = 0;
 
-  // Producer warp: lane 0 owns the barrier bookkeeping, lanes 0..5 each issue one of the six bulk
-  // copies of a chunk and lanes 0..B-1 one row of h (cp.async.bulk issue is ~50 cycles a piece, so
-  // a single issuing lane would serialise 32 + 6 * chunks of them on the critical path).
-  auto issue_chunk = [&](int c) {
+  // Producer warp: lane 0 owns the barrier bookkeeping, lanes 0..5 each issue one of the six W copies of a
+  // stage (cp.async.bulk issue is ~50 cycles a piece), lane 6 the h slice.
+  auto issue_w = [&](int c) {
     const int st = prod % stages;
     if (lane == 0) {
       mb_wait(&w_empty[st], ((prod / stages) & 1) ^ 1);
@@ -101,10 +99,18 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
     if (lane < 6) {
       const int i = lane >> 1, m = lane & 1;
       const size_t src = ((((size_t)i * (H / 16) + (u0 >> 4) + m) * nblk) + (size_t)c * kChunkBlocks) * 1024;
-      bulk_g2s(ring + (size_t)st * kChunkBytes + (size_t)((i * 2 + m) * kChunkBlocks) * 1024, wbase + src,
+      bulk_g2s(ring + (size_t)st * kStageBytes + (size_t)((i * 2 + m) * kChunkBlocks) * 1024, wbase + src,
                kChunkBlocks * 1024, &w_full[st]);
     }
     ++prod;
+  };
+  auto issue_h = [&](int c, const __nv_bfloat16* hprev) {     // stage order == W order: hprod trails prod
+    const int st = hprod % stages;
+    if (lane == 6) {
+      mb_expect_tx(&w_full[st], kHChunkBytes);
+      bulk_g2s(ring + (size_t)st * kStageBytes + kChunkBytes, hprev + (size_t)c * 32 * 128, kHChunkBytes, &w_full[st]);
+    }
+    ++hprod;
   };
 
   for (int s = 0; s < p.max_steps; ++s) {
@@ -115,15 +121,14 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
       if (have_prev) {
         asm volatile("fence.proxy.async;\n" ::: "memory");
         const __nv_bfloat16* hprev = p.hbuf_lp + (size_t)(blockIdx.x % kHRep) * p.lp_rep_stride +
-                                     ((int64_t)(j * 2 + ((s + 1) & 1)) * B) * H;
-        if (lane == 0) mb_expect_tx(h_full, (uint32_t)B * H * 2);
-        __syncwarp();
-        for (int b = lane; b < B; b += 32) bulk_g2s(hs + (size_t)b * HP, hprev + (int64_t)b * H, (uint32_t)H * 2, h_full);
-        for (int c = prefetched; c < nchunks; ++c) issue_chunk(c);
+                                     (int64_t)(j * 2 + ((s + 1) & 1)) * p.lp_slot;
+        // h slices for the stages whose W part was prefetched across the barrier, then the rest in lock-step
+        for (int c = 0; c < prefetched; ++c) issue_h(c, hprev);
+        for (int c = prefetched; c < nchunks; ++c) { issue_w(c); issue_h(c, hprev); }
         prefetched = 0;
         if (s + 1 < jb.steps) {               // W_hh is step-invariant: refill the ring for the next step now
           const int n = stages < nchunks ? stages : nchunks;
-          for (int c = 0; c < n; ++c) issue_chunk(c);
+          for (int c = 0; c < n; ++c) issue_w(c);
           prefetched = n;
         }
       }
@@ -146,12 +151,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
           for (int n = 0; n < NT; ++n)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[i][n][e] = 0.0f;
-        mb_wait(h_full, msteps & 1);
         TP_TRACE(1);
         for (int c = 0; c < nchunks; ++c) {
           const int st = cons % stages;
           mb_wait(&w_full[st], (cons / stages) & 1);
-          const unsigned char* cb = ring + (size_t)st * kChunkBytes + (size_t)kg * 1024 + (size_t)lane * 16;
+          const unsigned char* cb = ring + (size_t)st * kStageBytes + (size_t)kg * 1024 + (size_t)lane * 16;
+          const unsigned char* hb = ring + (size_t)st * kStageBytes + kChunkBytes;      // [32 rows][128] bf16, swizzled
           uint4 wa[3], wb[3];
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
@@ -160,7 +165,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
           }
 #pragma unroll
           for (int n = 0; n < NT; ++n) {
-            const uint4 bv = *reinterpret_cast<const uint4*>(hs + (size_t)(n * 8 + g) * HP + (c * kChunkBlocks + kg) * 32 + 8 * t);
+            const uint4 bv = *reinterpret_cast<const uint4*>(hb + (size_t)(n * 8 + g) * 256 + (size_t)(((kg * 4 + t) ^ ((g & 1) << 2)) << 4));   // rows g, g+1 of a quarter-warp hit different bank halves
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
               mma_bf16(acc[i][n], wa[i].x, wa[i].y, wa[i].z, wa[i].w, bv.x, bv.y);
@@ -171,9 +176,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
           if (lane == 0) mb_arrive(&w_empty[st]);
           ++cons;
         }
-        ++msteps;
         TP_TRACE(2);
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");     // every consumer is done reading hs (red aliases it)
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -205,10 +208,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
           gru_finalize<true>(p, jb, j, s, bb, u0 + uu, gin[e], ar, az, an);
         }
       }
-      // generic-proxy writes to red (shared memory) must be ordered before the async-proxy (TMA) refill of
-      // hs in the next step.  h_t in GLOBAL memory is ordered by the grid barrier's release and by the
-      // producer's own fence.proxy.async before it issues the bulk reads.
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      // h_t in GLOBAL memory is ordered by the grid barrier's release and by the producer's own
+      // fence.proxy.async before it issues the bulk reads; red is never touched by the async proxy.
     }
     if (s + 1 < p.max_steps) {
       TP_TRACE(4);
