@@ -19,7 +19,8 @@
 namespace tp {
 
 constexpr int kMaxJobs = 4;
-constexpr int kHRep = 4;          // replicas of the bf16 state (readers spread over them: L2 hot-spot relief)
+constexpr int kHRep = 1;          // replicas of the bf16 state; >1 spreads readers over copies (measured: no gain, the
+                                  // h broadcast is not L2-hot-spot bound), kept as a knob
 constexpr int kGruThreads = 256;
 
 struct GruParams {

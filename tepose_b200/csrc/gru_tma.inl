@@ -84,8 +84,16 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
   locate_item(p, blockIdx.x, j, u0);          // exactly one item per CTA on this path
   const tp_gru_job& jb = sjobs[j];
   const unsigned char* wbase = reinterpret_cast<const unsigned char*>(jb.w_hh);
-  uint32_t cons = 0, prod = 0, hprod = 0;     // ring positions: consumed stages, W parts issued, h parts issued
+  uint32_t prod = 0, hprod = 0;               // producer ring positions: W parts issued, h parts issued
   int prefetched = 0;
+  int c_stage = 0; uint32_t c_phase = 0;      // consumer ring position (no runtime division in the hot loop)
+  // gate-math operands that never change: this thread always owns unit u0 + (tid & 31) and batches
+  // (tid >> 5) + 8e, so b_hh is loaded once per kernel and gi / h_prev are one base pointer + strides
+  const int uu = tid & 31, bb0 = (tid >> 5) & 7;
+  float bh_r = 0.f, bh_z = 0.f, bh_n = 0.f;
+  if (!producer) { bh_r = __ldg(jb.b_hh + u0 + uu); bh_z = __ldg(jb.b_hh + H + u0 + uu); bh_n = __ldg(jb.b_hh + 2 * H + u0 + uu); }
+  auto ldnc = [](const float* ptr) { float v; asm volatile("ld.global.nc.f32 %0, [%1];\n" : "=f"(v) : "l"(ptr)); return v; };
+  auto ldcg = [](const float* ptr) { float v; asm volatile("ld.global.cg.f32 %0, [%1];\n" : "=f"(v) : "l"(ptr)); return v; };
 
   // Producer warp: lane 0 owns the barrier bookkeeping, lanes 0..5 each issue one of the six W copies of a
   // stage (cp.async.bulk issue is ~50 cycles a piece), lane 6 the h slice.
@@ -136,11 +144,25 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
     } else {
       GateIn gin[GE];
       if (active) {
+        // all address arithmetic first (one base + strides), then the loads back to back: no address
+        // computation may wait on a register that is the destination of a load still in flight
+        const int t_in = jb.t_in0 + s * jb.t_in_step;
+        const float* g0 = jb.gi + ((int64_t)t_in * B + bb0) * jb.ldg + (u0 + uu);
+        const float* h0 = p.hbuf + ((int64_t)(j * 2 + ((s + 1) & 1)) * B + bb0) * H + (u0 + uu);
+        const int64_t gstride = (int64_t)8 * jb.ldg, hstride = (int64_t)8 * H;
 #pragma unroll
         for (int e = 0; e < GE; ++e) {
-          const int idx = tid + e * 256;
-          const int bb = idx / U, uu = idx - bb * U;
-          if (idx < NB * U && bb < B) gin[e] = gate_fetch(p, jb, j, s, bb, u0 + uu);
+          gin[e].br = bh_r; gin[e].bz = bh_z; gin[e].bn = bh_n; gin[e].hp = 0.0f;
+          gin[e].gr = gin[e].gz = gin[e].gn = 0.0f;
+        }
+#pragma unroll
+        for (int e = 0; e < GE; ++e) {
+          if (bb0 + 8 * e < B && (NT > 1 || e == 0)) {
+            gin[e].gr = ldnc(g0 + e * gstride);
+            gin[e].gz = ldnc(g0 + e * gstride + H);
+            gin[e].gn = ldnc(g0 + e * gstride + 2 * H);
+            if (have_prev) gin[e].hp = ldcg(h0 + e * hstride);
+          }
         }
       }
       if (have_prev) {
@@ -153,8 +175,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
             for (int e = 0; e < 4; ++e) acc[i][n][e] = 0.0f;
         TP_TRACE(1);
         for (int c = 0; c < nchunks; ++c) {
-          const int st = cons % stages;
-          mb_wait(&w_full[st], (cons / stages) & 1);
+          const int st = c_stage;
+          mb_wait(&w_full[st], c_phase);
           const unsigned char* cb = ring + (size_t)st * kStageBytes + (size_t)kg * 1024 + (size_t)lane * 16;
           const unsigned char* hb = ring + (size_t)st * kStageBytes + kChunkBytes;      // [32 rows][128] bf16, swizzled
           uint4 wa[3], wb[3];
@@ -174,7 +196,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
           }
           __syncwarp();
           if (lane == 0) mb_arrive(&w_empty[st]);
-          ++cons;
+          if (++c_stage == stages) { c_stage = 0; c_phase ^= 1; }
         }
         TP_TRACE(2);
 #pragma unroll

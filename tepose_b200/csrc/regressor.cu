@@ -105,13 +105,12 @@ extern "C" int tp_encoder_heads(int precision, const void* w_fwd, const float* b
 // (8 warps split K, partials meet in shared memory); activations travel between layers as bf16 rows
 // in global memory (L2), layers are separated by a release/acquire grid barrier and the next layer's
 // weight fragments are already in flight when a CTA arrives at the barrier.  Every CTA needs the WHOLE
-// activation block of a layer; 64 CTAs fetching the same 64 KB at once serialise on the L2 slices that
-// own those lines (measured 5.7K cycles per layer), so producers write kIefRep replicas and CTA c reads
-// replica c % kIefRep.
+// activation block of a layer (kIefRep > 1 would give groups of CTAs their own copy).
 namespace tp {
 
 constexpr int kIefMaxLayers = 12;
-constexpr int kIefRep = 8;        // replicas of every inter-layer activation block (see k_ief_fused)
+constexpr int kIefRep = 1;        // replicas of every inter-layer activation block; >1 spreads the 64 reader CTAs over
+                                  // copies (measured: no gain -- the staging phase was bound by constant-cache misses, not L2)
 struct IefLayer {
   const __nv_bfloat16* A; int lda; int K; int rep_in;     // rep_in: element stride between input replicas (0 = single copy)
   const uint4* Wp; int N;
