@@ -81,8 +81,20 @@ __global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int
     Jx[c] = s;
   }
   const int parent = m.parents[j];
+  // depth in the kinematic tree by walking up through SHUFFLES (the table lives in the lanes already;
+  // chasing m.parents[] through global memory costs one dependent L2 round trip per level)
   int depth = 0;
-  for (int p = parent; p >= 0; p = m.parents[p]) ++depth;
+  {
+    int anc = parent;
+#pragma unroll 1
+    for (int it = 0; it < kJ; ++it) {
+      const bool up = anc >= 0;
+      const int nxt = __shfl_sync(0xffffffffu, parent, up ? anc : 0);
+      depth += up ? 1 : 0;
+      anc = up ? nxt : -1;
+      if (__all_sync(0xffffffffu, anc < 0)) break;
+    }
+  }
   int maxd = depth;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
@@ -483,10 +495,17 @@ __global__ void __launch_bounds__(128) k_smpl_finalize(int n, int n_verts, const
                                                        float* __restrict__ joints, float* __restrict__ kp2d) {
   __shared__ float Jr[kMaxReg * 3];
   const int b = blockIdx.x, tid = threadIdx.x;
-  for (int i = tid; i < nreg * 3; i += blockDim.x) {
-    float s = 0.0f;
-    for (int sp = 0; sp < nsplit; ++sp) s += jpart[((int64_t)b * nsplit + sp) * nreg * 3 + i];
-    Jr[i] = s;
+  // regressor partials: one warp per value, lanes stride over the vertex tiles (independent loads in
+  // flight), fixed-shape shuffle tree -> deterministic
+  {
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int i = warp; i < nreg * 3; i += nwarps) {
+      float s = 0.0f;
+      for (int sp = lane; sp < nsplit; sp += 32) s += __ldcg(&jpart[((int64_t)b * nsplit + sp) * nreg * 3 + i]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) Jr[i] = s;
+    }
   }
   __syncthreads();
   for (int o = tid; o < nj; o += blockDim.x) {
