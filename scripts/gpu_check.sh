@@ -11,5 +11,5 @@ run() { # name, timeout, pytest args...
 run safe 600 tests/test_gpu_kernels.py -m gpu -k "geometry or gemm_f32 or pack_rows or smpl or skinny"
 run gru 600 tests/test_gpu_kernels.py -m gpu -k "gru"
 run tc 300 tests/test_gpu_kernels.py -m gpu -k "tcgen05"
-run e2e 900 tests/test_gpu_e2e.py -m gpu -s
+run e2e 1200 tests/test_gpu_e2e.py -m gpu -s
 grep -h -E "FAILED|ERROR|passed|failed|Error|error:" gpurun_out/*.log | sort | uniq -c | sort -rn | head -40

@@ -108,3 +108,46 @@ def test_pipelined_host_buffer_api_matches_direct_forward():
             assert torch.equal(a[k], b[k]), k
     with pytest.raises(ValueError):
         pipe.result(0)          # slot already recycled
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("L,H,T,B,train,h36m", [
+    (1, 256, 1, 3, False, False),      # single-frame window
+    (1, 256, 16, 33, False, True),     # batch just above one MMA tile -> generic recurrence path, H36M joints
+    (1, 128, 5, 64, False, False),     # 64 sequences
+    (2, 256, 6, 32, True, False),      # released depth, train-shaped output (2 rows per sequence)
+    (3, 96, 4, 2, False, False),       # three layers, H not a multiple of 128
+    (1, 2048, 16, 7, False, False),    # ragged batch at full width
+])
+def test_forward_edge_shapes_against_oracle(L, H, T, B, train, h36m, precision):
+    seed = 80 + L + B
+    model, sd = build_product_model(seed, T, L, H, precision, DEV)
+    x = synth.make_input(seed, B, T)
+    ref, m = oracle_forward(seed, sd, x, L, H, is_train=train, use_h36m=h36m)
+    Jr = m.J_regressor_h36m.to(DEV) if h36m else None
+    out = model(torch.from_numpy(x).to(DEV), is_train=train, J_regressor=Jr)[-1]
+    tol = {} if precision == "fp32" else dict(vert_tol=1e-3, rot_tol=2e-3, kp2d_tol=5e-2)
+    compare_outputs(out, ref, label=f"L{L}H{H}T{T}B{B}", **tol)
+
+
+def test_non_contiguous_and_repeated_calls():
+    """Inputs that are views (strided batch / time) and back-to-back calls must give identical results."""
+    model, sd = build_product_model(90, 8, 1, 256, "fp32", DEV)
+    big = torch.from_numpy(synth.make_input(90, 6, 16)).to(DEV)
+    view = big[::2, 4:12]                       # non-contiguous in batch and time
+    a = model(view)[-1]
+    b = model(view.contiguous())[-1]
+    c = model(view)[-1]
+    for k in a:
+        assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), k
+
+
+def test_errors_are_loud():
+    model, _ = build_product_model(91, 4, 1, 128, "fp32", DEV)
+    with pytest.raises(ValueError):
+        model(torch.zeros(2, 4, 100, device=DEV))              # wrong feature width
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(2, 4, 2133))                          # CPU tensor: no fallback
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model(torch.zeros(2, 4, 2133, device=DEV))
