@@ -26,10 +26,10 @@ __global__ void __launch_bounds__(256) k_ldg(const uint4* __restrict__ src, size
 
 __device__ __forceinline__ uint32_t s32(const void* p){ return (uint32_t)__cvta_generic_to_shared(p); }
 template<int CHUNK, int STAGES>
-__global__ void __launch_bounds__(256) k_bulk(const unsigned char* __restrict__ src, size_t bytes_per_cta, unsigned* sink) {
+__global__ void __launch_bounds__(256) k_bulk(const unsigned char* __restrict__ src, size_t bytes_per_cta, unsigned* sink, size_t cta_stride) {
   extern __shared__ __align__(128) unsigned char sm[];
   __shared__ uint64_t full[STAGES];
-  const unsigned char* p = src + (size_t)blockIdx.x * bytes_per_cta;
+  const unsigned char* p = src + (size_t)blockIdx.x * cta_stride;
   const int nchunks = (int)(bytes_per_cta / CHUNK);
   if (threadIdx.x == 0) { for (int s=0;s<STAGES;++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;"::"r"(s32(&full[s]))); asm volatile("fence.mbarrier_init.release.cluster;"); }
   __syncthreads();
@@ -64,13 +64,13 @@ int main() {
   const int iters = 30;
 #define RUN_LDG(N) { for(int w=0;w<3;++w) k_ldg<N><<<ctas,256>>>((const uint4*)buf, per/16, sink); cudaEventRecord(e0); for(int i=0;i<iters;++i) k_ldg<N><<<ctas,256>>>((const uint4*)buf, per/16, sink); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); float ms; cudaEventElapsedTime(&ms,e0,e1); report("ldg.128 inflight=" #N, ms, iters);}  
   RUN_LDG(4) RUN_LDG(8) RUN_LDG(16) RUN_LDG(24) RUN_LDG(32)
-#define RUN_BULK(C,S) { size_t smem=(size_t)C*S; CK(cudaFuncSetAttribute(k_bulk<C,S>, cudaFuncAttributeMaxDynamicSharedMemorySize,(int)smem)); for(int w=0;w<3;++w) k_bulk<C,S><<<ctas,256,smem>>>(buf, per, sink); cudaEventRecord(e0); for(int i=0;i<iters;++i) k_bulk<C,S><<<ctas,256,smem>>>(buf, per, sink); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); float ms; cudaEventElapsedTime(&ms,e0,e1); report("bulk chunk=" #C " stages=" #S, ms, iters);} 
+#define RUN_BULK(C,S) { size_t smem=(size_t)C*S; CK(cudaFuncSetAttribute(k_bulk<C,S>, cudaFuncAttributeMaxDynamicSharedMemorySize,(int)smem)); for(int w=0;w<3;++w) k_bulk<C,S><<<ctas,256,smem>>>(buf, per, sink, STRIDE); cudaEventRecord(e0); for(int i=0;i<iters;++i) k_bulk<C,S><<<ctas,256,smem>>>(buf, per, sink, STRIDE); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); float ms; cudaEventElapsedTime(&ms,e0,e1); report("bulk chunk=" #C " stages=" #S, ms, iters);} 
+  size_t STRIDE = per;
   RUN_BULK(8192,4) RUN_BULK(16384,4) RUN_BULK(16384,8) RUN_BULK(32768,4) RUN_BULK(32768,6)
+  printf("-- every CTA reads the SAME 384 KB (broadcast pattern)\n"); STRIDE = 0;
+  RUN_BULK(8192,4) RUN_BULK(32768,6)
+  printf("-- groups of 4 neighbouring CTAs share a block\n");
   // all CTAs read the SAME 128 KB (the h broadcast pattern)
-  { const size_t hb = 128*1024; for(int w=0;w<3;++w) k_ldg<16><<<ctas,256>>>((const uint4*)buf, 0, sink);
-    auto k = k_bulk<16384,8>; size_t smem=16384*8; 
-    // same-source variant: bytes_per_cta=hb but stride 0 -> emulate by launching with src offset trick: use a tiny wrapper
-  }
   CK(cudaDeviceSynchronize());
   printf("done\n");
   return 0;
