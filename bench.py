@@ -163,8 +163,9 @@ def main():
         return
 
     import torch.distributed as dist
-    from oracle import synth
-    from tests.helpers import build_product_model
+    # the product arm touches tepose_b200 only (oracle/ is used by the cpu_baseline leg further down)
+    from tepose_b200 import synthetic as synth
+    from tepose_b200.synthetic import build_synthetic_model as build_product_model
     import tepose_b200._native as nv
     from tepose_b200.graph import GraphedTePose, OUTPUT_KEYS
 

@@ -1,186 +1,3 @@
-"""Deterministic synthetic assets for the TePose hot path (TEST INFRASTRUCTURE).
-
-The licensed SMPL model, the SPIN mean parameters and the released checkpoints are
-not redistributable and are absent here, so every test, golden
-fixture and bench run uses the SMPL-*shaped* stand-ins below.  Everything is drawn
-from ``numpy.random.Generator(PCG64(seed))`` -- never from torch's RNG -- so the
-same seed yields the same bytes on any box / torch version and golden fixtures only
-need to store the seed, not 93 M weights.
-
-Shapes follow the reference:
-  * GRU / Linear parameter shapes and names: /root/reference/lib/models/tepose.py:53-68
-    and lib/models/spin.py:215-224 (state_dict keys listed in SURVEY.md App. A.1).
-  * init distributions: torch defaults U(+-1/sqrt(H)) for nn.GRU, U(+-1/sqrt(fan_in)) for
-    nn.Linear, xavier_uniform(gain=0.01) for dec* (lib/models/spin.py:222-224).
-  * SMPL-shaped body model: 6890 vertices, 24 joints, 10 betas, 207 pose-blend rows,
-    exactly 4 non-zero skinning weights per vertex (SURVEY.md section 8d recipe).
-"""
-from __future__ import annotations
-
-import math
-import os
-import pickle
-
-import numpy as np
-
-NUM_VERTS = 6890
-NUM_JOINTS = 24
-NUM_BETAS = 10
-NUM_POSE_BASIS = 207
-INPUT_SIZE = 2133  # 2048 features + 85 theta   (lib/models/tepose.py:54,60)
-FEAT_SIZE = 2048
-NPOSE = 144
-
-# Kinematic tree of the SMPL body (smplx: parents = kintree_table[0], root = -1).
-SMPL_PARENTS = np.array(
-    [-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21],
-    dtype=np.int64,
-)
-
-# smplx.vertex_ids['smplh'] picked vertices appended after the 24 posed joints by
-# smplx.vertex_joint_selector.VertexJointSelector (face 5, feet 6, hand tips 10).
-SMPL_EXTRA_VERTEX_IDS = np.array(
-    [332, 6260, 2800, 4071, 583,
-     3216, 3226, 3387, 6617, 6624, 6787,
-     2746, 2319, 2445, 2556, 2673,
-     6191, 5782, 5905, 6016, 6133],
-    dtype=np.int64,
-)
-
-
-def _rng(seed: int, stream: int) -> np.random.Generator:
-    return np.random.Generator(np.random.PCG64([int(seed), int(stream)]))
-
-
-def make_smpl_model(seed: int = 0) -> dict:
-    """SMPL-shaped random body model (float32 arrays, pkl-style key names)."""
-    g = _rng(seed, 1)
-    V, J = NUM_VERTS, NUM_JOINTS
-    v_template = (0.3 * g.standard_normal((V, 3))).astype(np.float32)
-    shapedirs = (0.01 * g.standard_normal((V, 3, NUM_BETAS))).astype(np.float32)
-    posedirs = (0.001 * g.standard_normal((V, 3, NUM_POSE_BASIS))).astype(np.float32)
-
-    J_regressor = np.zeros((J, V), dtype=np.float32)
-    for j in range(J):
-        idx = g.choice(V, size=16, replace=False)
-        w = g.random(16).astype(np.float32) + 0.05
-        J_regressor[j, idx] = w / w.sum()
-
-    weights = np.zeros((V, J), dtype=np.float32)
-    cols = np.stack([g.permutation(J)[:4] for _ in range(V)])
-    w = g.random((V, 4)).astype(np.float32) + 0.05
-    w = w / w.sum(axis=1, keepdims=True)
-    np.put_along_axis(weights, cols, w, axis=1)
-
-    faces = g.integers(0, V, size=(13776, 3)).astype(np.int64)
-    kintree = np.stack([np.where(SMPL_PARENTS < 0, 2 ** 32 - 1, SMPL_PARENTS),
-                        np.arange(J)]).astype(np.int64)
-    return {
-        "v_template": v_template,
-        "shapedirs": shapedirs,
-        "posedirs": posedirs,
-        "J_regressor": J_regressor,
-        "weights": weights,
-        "kintree_table": kintree,
-        "f": faces,
-    }
-
-
-def make_extra_regressors(seed: int = 0, sparse: bool = False) -> dict:
-    """J_regressor_extra [9,6890] (lib/models/smpl.py:54,67), J_regressor_h36m [17,6890]
-    (evaluate.py:109).  Dense |N(0,1)|/6890 rows per the SURVEY recipe."""
-    g = _rng(seed, 2)
-    extra = (np.abs(g.standard_normal((9, NUM_VERTS))) / NUM_VERTS).astype(np.float32)
-    h36m = (np.abs(g.standard_normal((17, NUM_VERTS))) / NUM_VERTS).astype(np.float32)
-    if sparse:
-        for m in (extra, h36m):
-            keep = g.random(m.shape) < 0.01
-            m *= keep
-            m /= np.maximum(m.sum(axis=1, keepdims=True), 1e-12)
-    return {"J_regressor_extra": extra, "J_regressor_h36m": h36m}
-
-
-def make_mean_params() -> dict:
-    """smpl_mean_params.npz stand-in (keys read at lib/models/spin.py:232-235)."""
-    pose = np.tile(np.array([1, 0, 0, 1, 0, 0], dtype=np.float32), NUM_JOINTS)
-    shape = np.full((NUM_BETAS,), 0.1, dtype=np.float32)
-    cam = np.array([0.9, 0.0, 0.0], dtype=np.float32)
-    return {"pose": pose, "shape": shape, "cam": cam}
-
-
-def write_base_data(dirname: str, seed: int = 0) -> str:
-    """Materialise ``data/base_data`` the way lib/core/config.py:31 expects it."""
-    os.makedirs(dirname, exist_ok=True)
-    with open(os.path.join(dirname, "SMPL_NEUTRAL.pkl"), "wb") as fh:
-        pickle.dump(make_smpl_model(seed), fh)
-    ex = make_extra_regressors(seed)
-    np.save(os.path.join(dirname, "J_regressor_extra.npy"), ex["J_regressor_extra"])
-    np.save(os.path.join(dirname, "J_regressor_h36m.npy"), ex["J_regressor_h36m"])
-    np.savez(os.path.join(dirname, "smpl_mean_params.npz"), **make_mean_params())
-    return dirname
-
-
-def _uniform(g, shape, bound):
-    return ((g.random(shape, dtype=np.float32) * 2.0 - 1.0) * np.float32(bound)).astype(np.float32)
-
-
-def make_state_dict(seed: int = 0, n_layers: int = 1, hidden: int = 2048,
-                    scale_dec: float = 1.0) -> dict:
-    """Encoder + Regressor parameters, keyed exactly like TePose.state_dict()
-     minus the regressor.smpl.* buffers.  numpy float32."""
-    g = _rng(seed, 3)
-    H = hidden
-    sd = {}
-    kH = 1.0 / math.sqrt(H)
-    for name, bidir in (("gru_fwd", False), ("gru_rec", True)):
-        ndir = 2 if bidir else 1
-        for layer in range(n_layers):
-            in_sz = INPUT_SIZE if layer == 0 else H * ndir
-            for sfx in ([""] if not bidir else ["", "_reverse"]):
-                p = f"encoder.{name}."
-                sd[p + f"weight_ih_l{layer}{sfx}"] = _uniform(g, (3 * H, in_sz), kH)
-                sd[p + f"weight_hh_l{layer}{sfx}"] = _uniform(g, (3 * H, H), kH)
-                sd[p + f"bias_ih_l{layer}{sfx}"] = _uniform(g, (3 * H,), kH)
-                sd[p + f"bias_hh_l{layer}{sfx}"] = _uniform(g, (3 * H,), kH)
-
-    def linear(prefix, out_f, in_f, xavier_gain=None):
-        if xavier_gain is None:
-            b = 1.0 / math.sqrt(in_f)
-            sd[prefix + ".weight"] = _uniform(g, (out_f, in_f), b)
-        else:
-            b = xavier_gain * math.sqrt(6.0 / (in_f + out_f))
-            sd[prefix + ".weight"] = _uniform(g, (out_f, in_f), b)
-        sd[prefix + ".bias"] = _uniform(g, (out_f,), 1.0 / math.sqrt(in_f))
-
-    linear("encoder.linear_fwd", FEAT_SIZE, H)
-    linear("encoder.linear_rec", FEAT_SIZE, 2 * H)
-    linear("regressor.fc1", 1024, FEAT_SIZE + NPOSE + 13)
-    linear("regressor.fc2", 1024, 1024)
-    linear("regressor.decpose", NPOSE, 1024, xavier_gain=0.01 * scale_dec)
-    linear("regressor.decshape", 10, 1024, xavier_gain=0.01 * scale_dec)
-    linear("regressor.deccam", 3, 1024, xavier_gain=0.01 * scale_dec)
-    mp = make_mean_params()
-    sd["regressor.init_pose"] = mp["pose"][None]
-    sd["regressor.init_shape"] = mp["shape"][None]
-    sd["regressor.init_cam"] = mp["cam"][None]
-    return sd
-
-
-def make_input(seed: int, batch: int, seqlen: int) -> np.ndarray:
-    """x ~ N(0,1) [B,T,2133] with the newest frame's theta slot zeroed
-    (evaluate.py:248-252 leaves input_feat[0,-1,2048:] at zero)."""
-    g = _rng(seed, 4)
-    x = g.standard_normal((batch, seqlen, INPUT_SIZE), dtype=np.float32)
-    x[:, -1, FEAT_SIZE:] = 0.0
-    return x
-
-
-def make_bodies(seed: int, n: int, pose_scale: float = 0.3) -> dict:
-    """Config-4 inputs: axis-angle poses, betas and cameras for ``n`` bodies."""
-    g = _rng(seed, 5)
-    return {
-        "pose_aa": (pose_scale * g.standard_normal((n, 72), dtype=np.float32)),
-        "pose_6d": g.standard_normal((n, 144), dtype=np.float32),
-        "betas": g.standard_normal((n, 10), dtype=np.float32),
-        "cam": (np.array([0.9, 0, 0], np.float32) + 0.1 * g.standard_normal((n, 3), dtype=np.float32)),
-    }
+"""Synthetic assets live in the product package (tepose_b200/synthetic.py); re-exported for the oracle / tests."""
+from tepose_b200.synthetic import *  # noqa: F401,F403
+from tepose_b200.synthetic import _rng, _uniform  # noqa: F401

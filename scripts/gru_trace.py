@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 import tepose_b200._native as nv
-from oracle import synth
+from tepose_b200 import synthetic as synth
 from tests.helpers import build_product_model
 B, T, H = 32, 16, 2048
 model, _ = build_product_model(0, T, 1, H, "bf16", "cuda:0")

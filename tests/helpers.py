@@ -24,17 +24,8 @@ def base_data_cwd(seed=0):
 
 
 def build_product_model(seed, seqlen, n_layers, hidden, precision="fp32", device="cpu"):
-    import tepose_b200
-    with base_data_cwd(seed):
-        model = tepose_b200.TePose(seqlen=seqlen, n_layers=n_layers, hidden_size=hidden, pretrained="",
-                                   precision=precision)
-    sd = synth.make_state_dict(seed, n_layers, hidden)
-    own = model.state_dict()
-    for k, v in sd.items():
-        assert k in own and tuple(own[k].shape) == tuple(v.shape), k
-        own[k] = torch.as_tensor(v)
-    model.load_state_dict(own, strict=True)
-    return model.to(device).eval(), sd
+    from tepose_b200.synthetic import build_synthetic_model
+    return build_synthetic_model(seed, seqlen, n_layers, hidden, precision, device)
 
 
 def oracle_forward(seed, sd, x, n_layers, hidden, is_train=False, use_h36m=False):
