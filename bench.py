@@ -141,13 +141,46 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_reference_gpu(args, rank):
+    """Informative second baseline: the reference's own op sequence as PyTorch executes it on the
+    B200 (cuDNN GRU, cuBLAS Linear, ~40 ATen launches of LBS), fp32, no CUDA graph.  Not a bench arm."""
+    if rank != 0:
+        return
+    from oracle import synth, torch_ref
+    dev = torch.device("cuda", 0)
+    sd = synth.make_state_dict(SEED, L, H)
+    m = torch_ref.SmplModel.synthetic(SEED)
+    for k, v in vars(m).items():
+        if torch.is_tensor(v):
+            setattr(m, k, v.to(dev))
+    grus = (torch_ref.build_gru(sd, "gru_fwd", L, H, False).to(dev), torch_ref.build_gru(sd, "gru_rec", L, H, True).to(dev))
+    sd_t = {k: torch.as_tensor(v).to(dev) for k, v in sd.items()}
+    x = torch.from_numpy(synth.make_input(SEED, B, T)).to(dev)
+    import oracle.torch_ref as tr
+    for _ in range(max(3, args.warmup)):
+        tr.tepose_forward(sd_t, m, x, L, H, grus=grus)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        tr.tepose_forward(sd_t, m, x, L, H, grus=grus)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({"impl": "reference-gpu", "metric": METRIC, "value": B / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
+                      "steps": args.steps, "dtype": "f32", "note": "torch ops of the reference path on cuda:0 (cuDNN/cuBLAS/ATen), eager"}),
+          flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "reference-gpu"],
+                    help="reference: CPU port of the reference path (the reference arm); reference-gpu: the same torch ops "
+                         "(nn.GRU -> cuDNN, F.linear -> cuBLAS, smplx-style LBS) on cuda:0, informative only")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-live", action="store_true", help="skip the live-stream latency measurement")
@@ -160,6 +193,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.impl == "reference-gpu":
+        run_reference_gpu(args, rank)
         return
 
     import torch.distributed as dist

@@ -116,7 +116,7 @@ def batch_rodrigues_smplx(aa: torch.Tensor) -> torch.Tensor:
     kx, ky, kz = k.unbind(1)
     z = torch.zeros_like(kx)
     K = torch.stack([z, -kz, ky, kz, z, -kx, -ky, kx, z], dim=1).reshape(-1, 3, 3)
-    eye = torch.eye(3, dtype=aa.dtype)[None]
+    eye = torch.eye(3, dtype=aa.dtype, device=aa.device)[None]
     return eye + s * K + (1 - c) * torch.bmm(K, K)
 
 
@@ -153,13 +153,13 @@ def smpl_lbs(m: SmplModel, betas: torch.Tensor, R: torch.Tensor):
     dt = betas.dtype
     v_shaped = m.v_template[None] + torch.einsum("bl,mkl->bmk", betas, m.shapedirs)
     J = torch.einsum("bik,ji->bjk", v_shaped, m.J_regressor)
-    eye = torch.eye(3, dtype=dt)
+    eye = torch.eye(3, dtype=dt, device=betas.device)
     pose_feature = (R[:, 1:] - eye).reshape(N, -1)
     v_posed = v_shaped + torch.matmul(pose_feature, m.posedirs).reshape(N, -1, 3)
     # rigid chain (smplx.lbs.batch_rigid_transform)
     rel = J.clone()
     rel[:, 1:] = rel[:, 1:] - J[:, m.parents[1:]]
-    G = torch.zeros(N, 24, 4, 4, dtype=dt)
+    G = torch.zeros(N, 24, 4, 4, dtype=dt, device=betas.device)
     G[:, :, :3, :3] = R
     G[:, :, :3, 3] = rel
     G[:, :, 3, 3] = 1

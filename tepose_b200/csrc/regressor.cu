@@ -31,7 +31,7 @@ static int linear(int precision, const float* A, int64_t lda, const void* W, con
   const int sms = tp::sm_count();
   if (precision == TP_PRECISION_BF16 && M <= 64) {
     const int groups = (N + 127) / 128, kb = (K + 31) / 32;
-    int splits = (sms + groups - 1) / groups;
+    int splits = sms / groups;                       // one wave: groups * splits <= #SMs (the CTAs hold 1 CTA/SM worth of registers)
     if (splits > kb / 4) splits = kb / 4;
     if (splits < 1 || !scratch) splits = 1;
     while (splits > 1 && tp_skinny_bf16_workspace_bytes(M, N, splits) > kSplitScratch) --splits;

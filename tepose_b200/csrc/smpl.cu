@@ -543,11 +543,19 @@ static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg, int blend_mod
   p.tc = (blend_mode == 1 && m->blend_tc && m->template_pad && m->ks <= 4 && m->vp % kTcVT == 0) ? 1 : 0;
   p.tc_tiles = m->vp / kTcVT;
   {
+    // body splits: as many CTAs as there are SM slots in a whole number of waves (1 CTA per SM);
+    // among split counts up to 64 pick the one with the best last-wave fill
     const int groups = (n + kTcNB - 1) / kTcNB;
-    int want = (2 * sm_count() + p.tc_tiles - 1) / p.tc_tiles;      // body splits so the grid covers the machine ~2x
-    if (want > groups) want = groups;
-    if (want < 1) want = 1;
-    p.tc_gpc = (groups + want - 1) / want;
+    const int sms = sm_count();
+    int best = 1; double best_eff = 0.0;
+    for (int sp = 1; sp <= 64 && sp <= groups; ++sp) {
+      const int gpc = (groups + sp - 1) / sp, real = (groups + gpc - 1) / gpc;
+      const long ctas = (long)p.tc_tiles * real;
+      const long waves = (ctas + sms - 1) / sms;
+      const double eff = (double)ctas / (double)(waves * sms);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = real; }
+    }
+    p.tc_gpc = (groups + best - 1) / best;
     p.tc_gsplit = (groups + p.tc_gpc - 1) / p.tc_gpc;
   }
   p.ntiles = m->vp / kVT;
