@@ -78,6 +78,11 @@ TP_API int tp_projection(const float* joints, const float* cam, float* kp2d, int
  * Replaces x.permute(1,0,2) (lib/models/tepose.py:73,76).  kp >= k, kp % 8 == 0.        */
 TP_API int tp_pack_rows(const float* src, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t, int k,
                  void* dst, int kp, int dst_precision, int relu, void* stream);
+/* The way back, with the residual of lib/models/vibe.py:60-63 folded in (y + x, then TNF -> NTF):
+ * out[b*rows_t + t, c] = y[(t*rows_b + b)*ld_y + c] + x[b*stride_b + t*stride_t + c]   (x may be NULL: no residual).
+ * out is dense [rows_b*rows_t, k] fp32; out_bf16 (optional) receives the same rows in bf16.  k even.              */
+TP_API int tp_unpack_rows_residual(const float* y, int64_t ld_y, const float* x, int64_t stride_b, int64_t stride_t,
+                            int rows_b, int rows_t, int k, float* out, void* out_bf16, void* stream);
 
 /* ------------------------------------------------------------------ GEMMs (torch.nn.Linear / GRU input projection)
  * C[M,N] = alpha * ( act(A)[M,K] . W[N,K]^T + bias[N] ) + beta * Cin[M,N]

@@ -12,6 +12,7 @@ SMPL outputs come from the smplx stand-in (parity unpinned, see oracle/torch_ref
 from __future__ import annotations
 
 import os
+import sys
 
 import numpy as np
 import torch
@@ -27,6 +28,13 @@ FORWARD_CASES = {
     "fwd_L2_H64_B2_T6": dict(seed=13, batch=2, seqlen=6, n_layers=2, hidden=64),
     "fwd_L1_H64_B2_T5_train": dict(seed=14, batch=2, seqlen=5, n_layers=1, hidden=64, is_train=True),
     "fwd_L2_H96_B1_T3_train": dict(seed=15, batch=1, seqlen=3, n_layers=2, hidden=96, is_train=True),
+}
+
+# name -> configuration of a VIBE bootstrap forward (lib/models/vibe.py; evaluate.py:89-99 uses L2, add_linear)
+VIBE_CASES = {
+    "vibe_L2_H64_B2_T3_linear_h36m": dict(seed=21, batch=2, seqlen=3, n_layers=2, hidden=64, add_linear=True, use_h36m=True),
+    "vibe_L1_H32_B1_T4_bidir": dict(seed=22, batch=1, seqlen=4, n_layers=1, hidden=32, bidirectional=True),
+    "vibe_L1_H2048_B1_T2_plain": dict(seed=23, batch=1, seqlen=2, n_layers=1, hidden=2048),
 }
 
 
@@ -54,6 +62,13 @@ def edge_rotations() -> np.ndarray:
 
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for name, cfg in VIBE_CASES.items():
+        out = ref_harness.run_reference_vibe(**cfg)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"),
+                            cfg=np.array(repr(cfg)), **{k: v.astype(np.float32) for k, v in out.items()})
+        print(name, {k: v.shape for k, v in out.items()})
+    if "--vibe-only" in sys.argv:
+        return
     for name, cfg in FORWARD_CASES.items():
         out = ref_harness.run_reference(**cfg)
         np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"),

@@ -186,3 +186,30 @@ def run_reference(seed, batch, seqlen, n_layers, hidden, is_train=False, use_h36
         with torch.no_grad():
             out = model(torch.from_numpy(x), is_train=is_train, J_regressor=Jr)[-1]
     return {k: v.detach().numpy().copy() for k, v in out.items()}
+
+
+def run_reference_vibe(seed, batch, seqlen, n_layers, hidden, add_linear=False, bidirectional=False, use_residual=True,
+                       use_h36m=False, x=None):
+    """The unmodified lib/models/vibe.py VIBE on the synthetic parameters of `seed`."""
+    import importlib
+    sd = synth.make_vibe_state_dict(seed, n_layers, hidden, add_linear, bidirectional)
+    if x is None:
+        x = synth.make_vibe_input(seed, batch, seqlen)
+    with reference_env(seed):
+        vibe = importlib.import_module("lib.models.vibe")
+        model = vibe.VIBE(seqlen=seqlen, n_layers=n_layers, hidden_size=hidden, add_linear=add_linear,
+                          bidirectional=bidirectional, use_residual=use_residual, pretrained="")
+        own = model.state_dict()
+        for k, v in sd.items():
+            assert k in own and tuple(own[k].shape) == tuple(v.shape), k
+            own[k] = torch.as_tensor(v)
+        missing = [k for k in own if k not in sd and not k.startswith("regressor.smpl.")]
+        assert not missing, missing
+        model.load_state_dict(own, strict=True)
+        model.eval()
+        Jr = None
+        if use_h36m:
+            Jr = torch.from_numpy(np.load(os.path.join("data", "base_data", "J_regressor_h36m.npy"))).float()
+        with torch.no_grad():
+            out = model(torch.from_numpy(x), J_regressor=Jr)[-1]
+    return {k: v.detach().numpy().copy() for k, v in out.items()}

@@ -277,6 +277,41 @@ def tepose_forward(sd: dict, m: SmplModel, x: torch.Tensor, n_layers: int, hidde
     }
 
 
+# --------------------------------------------------------------------------- VIBE bootstrap (evaluate.py:89-99,234)
+def vibe_encoder_forward(sd: dict, x: torch.Tensor, n_layers: int, hidden: int, add_linear: bool = False,
+                         bidirectional: bool = False, use_residual: bool = True) -> torch.Tensor:
+    """lib/models/vibe.py:52-65.  x [B,T,2048] -> [B,T,F]."""
+    gru = torch.nn.GRU(input_size=2048, hidden_size=hidden, bidirectional=bidirectional, num_layers=n_layers)
+    pref = "encoder.gru."
+    gru.load_state_dict({k[len(pref):]: _t(sd, k) for k in sd if k.startswith(pref)})
+    gru.eval()
+    n, t, f = x.shape
+    xt = x.permute(1, 0, 2)
+    y, _ = gru(xt)
+    if bidirectional or add_linear:
+        y = F.linear(F.relu(y).reshape(-1, y.size(-1)), _t(sd, "encoder.linear.weight"), _t(sd, "encoder.linear.bias"))
+        y = y.reshape(t, n, f)
+    if use_residual and y.shape[-1] == 2048:
+        y = y + xt
+    return y.permute(1, 0, 2)
+
+
+def vibe_forward(sd: dict, m: SmplModel, x: torch.Tensor, n_layers: int, hidden: int, add_linear: bool = False,
+                 bidirectional: bool = False, use_residual: bool = True, J_regressor=None) -> dict:
+    """lib/models/vibe.py:104-119 (list-of-one-dict flattened)."""
+    B, T = x.shape[:2]
+    with torch.no_grad():
+        feat = vibe_encoder_forward(sd, x, n_layers, hidden, add_linear, bidirectional, use_residual)
+        out = regressor_forward(sd, m, feat.reshape(-1, feat.shape[-1]), J_regressor, False)
+    return {
+        "theta": out["theta"].reshape(B, T, -1),
+        "verts": out["verts"].reshape(B, T, -1, 3),
+        "kp_2d": out["kp_2d"].reshape(B, T, -1, 2),
+        "kp_3d": out["kp_3d"].reshape(B, T, -1, 3),
+        "rotmat": out["rotmat"].reshape(B, T, -1, 3, 3),
+    }
+
+
 # --------------------------------------------------------------------------- carried state
 def encoder_causal_states(sd: dict, x: torch.Tensor, hidden: int, h0=None):
     """Live-stream oracle (SURVEY.md F3/F4, L=1 only): the encoder restated as three

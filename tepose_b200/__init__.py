@@ -1,6 +1,7 @@
 """tepose_b200 -- B200-native (sm_100a) implementation of TePose's per-sequence inference hot
 path behind the reference's lib.models API.  See DESIGN.md / INTEGRATION.md."""
 from .tepose import TePose, TemporalEncoder  # noqa: F401
+from .vibe import VIBE  # noqa: F401
 from .spin import Regressor, projection  # noqa: F401
 from .smpl import (SMPL, SMPLOutput, JOINT_MAP, JOINT_NAMES, JOINT_IDS, H36M_TO_J14, H36M_TO_J17,  # noqa: F401
                    SMPL_MODEL_DIR, SMPL_MEAN_PARAMS, BASE_DATA_DIR, get_smpl_faces)

@@ -26,6 +26,24 @@ __global__ void k_pack_rows(const float* __restrict__ src, int64_t stride_b, int
   }
 }
 
+// Inverse of k_pack_rows with the residual of lib/models/vibe.py:60-62 folded in:
+// out[b*rows_t + t, c] = y[t*rows_b + b, c] (+ x[b, t, c]); an optional bf16 copy rides along.
+__global__ void k_unpack_rows_residual(const float* __restrict__ y, int64_t ld_y, const float* __restrict__ x, int64_t stride_b,
+                                       int64_t stride_t, int rows_b, int rows_t, int k, float* __restrict__ out,
+                                       __nv_bfloat16* __restrict__ out_lp) {
+  int row = blockIdx.x;               // b * rows_t + t
+  int b = row / rows_t, t = row - b * rows_t;
+  const float* s = y + ((int64_t)t * rows_b + b) * ld_y;
+  const float* r = x ? x + (int64_t)b * stride_b + (int64_t)t * stride_t : nullptr;
+  float* d = out + (int64_t)row * k;
+  for (int c = 2 * threadIdx.x; c < k; c += 2 * blockDim.x) {     // k is even
+    float v0 = s[c], v1 = s[c + 1];
+    if (r) { v0 += r[c]; v1 += r[c + 1]; }
+    *reinterpret_cast<float2*>(d + c) = make_float2(v0, v1);
+    if (out_lp) *reinterpret_cast<__nv_bfloat162*>(out_lp + (int64_t)row * k + c) = __floats2bfloat162_rn(v0, v1);
+  }
+}
+
 }  // namespace tp
 
 extern "C" int tp_pack_rows(const float* src, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t,
@@ -42,6 +60,21 @@ extern "C" int tp_pack_rows(const float* src, int64_t stride_b, int64_t stride_t
   else
     k_pack_rows<float><<<grid, 256, 0, (cudaStream_t)stream>>>(src, stride_b, stride_t, rows_b, rows_t, k,
                                                               (float*)dst, kp, relu);
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}
+
+extern "C" int tp_unpack_rows_residual(const float* y, int64_t ld_y, const float* x, int64_t stride_b, int64_t stride_t,
+                                       int rows_b, int rows_t, int k, float* out, void* out_bf16, void* stream) {
+  using namespace tp;
+  TP_CHECK_ARG(rows_b >= 0 && rows_t >= 0 && k >= 0 && k % 2 == 0 && ld_y >= k && ld_y % 2 == 0,
+               "tp_unpack_rows_residual: bad sizes (k=%d must be even, ld_y >= k)", k);
+  if (rows_b == 0 || rows_t == 0 || k == 0) return TP_OK;
+  TP_CHECK_ARG(y && out, "tp_unpack_rows_residual: null pointer");
+  TP_CHECK_ARG(((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 7) == 0 &&
+               (!x || ((reinterpret_cast<uintptr_t>(x) & 3) == 0)), "tp_unpack_rows_residual: misaligned pointer");
+  k_unpack_rows_residual<<<(unsigned)(rows_b * rows_t), 256, 0, (cudaStream_t)stream>>>(
+      y, ld_y, x, stride_b, stride_t, rows_b, rows_t, k, out, reinterpret_cast<__nv_bfloat16*>(out_bf16));
   TP_LAUNCH_CHECK();
   return TP_OK;
 }

@@ -29,14 +29,24 @@ static int linear(int precision, const float* A, int64_t lda, const void* W, con
                   void* scratch, void* stream, const void* Alp = nullptr, int64_t ldalp = 0, void* Clp = nullptr,
                   int64_t ldclp = 0) {
   const int sms = tp::sm_count();
-  if (precision == TP_PRECISION_BF16 && M <= 64) {
+  if (precision == TP_PRECISION_BF16) {
+    // the tensor-core skinny kernel covers <= 64 rows per launch; more rows go in 64-row chunks
+    // (the packed weights stay L2-resident between chunks)
     const int groups = (N + 127) / 128, kb = (K + 31) / 32;
-    int splits = sms / groups;                       // one wave: groups * splits <= #SMs (the CTAs hold 1 CTA/SM worth of registers)
-    if (splits > kb / 4) splits = kb / 4;
-    if (splits < 1 || !scratch) splits = 1;
-    while (splits > 1 && tp_skinny_bf16_workspace_bytes(M, N, splits) > kSplitScratch) --splits;
-    return tp_skinny_bf16_ex(A, lda, Alp, ldalp, M, K, W, N, bias, Cin, ldcin, C, ldc, Clp, ldclp, alpha, beta, relu_a,
-                             splits, 0, scratch, kSplitScratch, stream);
+    const unsigned char* alp = reinterpret_cast<const unsigned char*>(Alp);
+    unsigned char* clp = reinterpret_cast<unsigned char*>(Clp);
+    for (int m0 = 0; m0 < M; m0 += 64) {
+      const int mc = M - m0 < 64 ? M - m0 : 64;
+      int splits = sms / groups;                     // one wave: groups * splits <= #SMs (the CTAs hold 1 CTA/SM worth of registers)
+      if (splits > kb / 4) splits = kb / 4;
+      if (splits < 1 || !scratch) splits = 1;
+      while (splits > 1 && tp_skinny_bf16_workspace_bytes(mc, N, splits) > kSplitScratch) --splits;
+      TP_TRY(tp_skinny_bf16_ex(A + (int64_t)m0 * lda, lda, alp ? alp + (int64_t)m0 * ldalp * 2 : nullptr, ldalp, mc, K, W, N, bias,
+                               Cin ? Cin + (int64_t)m0 * ldcin : nullptr, ldcin, C + (int64_t)m0 * ldc, ldc,
+                               clp ? clp + (int64_t)m0 * ldclp * 2 : nullptr, ldclp, alpha, beta, relu_a, splits, 0, scratch,
+                               kSplitScratch, stream));
+    }
+    return TP_OK;
   }
   const int bm = M <= 32 ? 32 : 64;
   const int tiles = ((N + 31) / 32) * ((M + bm - 1) / bm);
@@ -63,7 +73,7 @@ extern "C" int tp_encoder_heads_cat(int precision, const void* w_cat, const floa
   TP_CHECK_ARG(workspace && workspace_bytes >= kSplitScratch && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
                "tp_encoder_heads_cat: workspace too small / misaligned");
   TP_CUDA(cudaMemsetAsync(workspace, 0, 4096, (cudaStream_t)stream));
-  void* sc = B > 64 ? nullptr : workspace;
+  void* sc = (B > 64 && precision != TP_PRECISION_BF16) ? nullptr : workspace;   // fp32 split-K scratch is sized for <= 64 rows
   return linear(precision, h_cat, ld_h, w_cat, b_cat, nullptr, 0, feat, 2048, B, 2048, 3 * H, 1.f, 0.f, 1, sc, stream,
                 nullptr, 0, precision == TP_PRECISION_BF16 ? feat_bf16 : nullptr, 2048);
 }
@@ -80,9 +90,7 @@ extern "C" int tp_encoder_heads(int precision, const void* w_fwd, const float* b
                "tp_encoder_heads: workspace too small / misaligned");
   TP_CUDA(cudaMemsetAsync(workspace, 0, 4096, (cudaStream_t)stream));
   void* sc = workspace;
-  if (B > 64) {   // the split-K scratch is sized for <= 64 rows
-    sc = nullptr;
-  }
+  if (B > 64 && P != TP_PRECISION_BF16) sc = nullptr;   // the fp32 split-K scratch is sized for <= 64 rows
   if (!is_train) {
     // (linear_fwd(relu(hF)) + linear_rec(relu(hR))) / 2  -- halving each term first is exact in fp32
     TP_TRY(linear(P, h_fwd, ld_hf, w_fwd, b_fwd, nullptr, 0, feat, 2048, B, 2048, H, 0.5f, 0.f, 1, sc, stream));
@@ -349,7 +357,7 @@ extern "C" int tp_ief_forward(int precision, const tp_ief_weights* w, const floa
   void* psc_lp = P == TP_PRECISION_BF16 ? wsb + 2 * slab_lp : nullptr;
   void* sc = wsb + 2 * slab_lp + slab_p;
   TP_CUDA(cudaMemsetAsync(sc, 0, 4096, (cudaStream_t)stream));
-  if (N > 64) sc = nullptr;
+  if (N > 64 && P != TP_PRECISION_BF16) sc = nullptr;   // fp32 split-K scratch is sized for <= 64 rows
   TP_TRY(linear(P, feat, 2048, w->w1x, w->b1, nullptr, 0, base, 1024, N, 1024, 2048, 1.f, 0.f, 0, sc, stream,
                 P == TP_PRECISION_BF16 ? feat_bf16 : nullptr, 2048));
   k_broadcast_rows<<<(unsigned)ceil_div((int64_t)N * 160, 256), 256, 0, (cudaStream_t)stream>>>(init, psc, N, 160, init_rows);

@@ -166,6 +166,35 @@ def make_state_dict(seed: int = 0, n_layers: int = 1, hidden: int = 2048,
     return sd
 
 
+def make_vibe_state_dict(seed: int = 0, n_layers: int = 2, hidden: int = 1024, add_linear: bool = True,
+                         bidirectional: bool = False) -> dict:
+    """VIBE.state_dict() layout (lib/models/vibe.py:37-49,82-95) minus regressor.smpl.*: encoder.gru.*,
+    encoder.linear.* (when present) and the same regressor.* block as make_state_dict."""
+    g = _rng(seed, 6)
+    H, D = hidden, (2 if bidirectional else 1)
+    kH = 1.0 / math.sqrt(H)
+    sd = {}
+    for layer in range(n_layers):
+        in_sz = FEAT_SIZE if layer == 0 else H * D
+        for sfx in ["", "_reverse"][:D]:
+            p = "encoder.gru."
+            sd[p + f"weight_ih_l{layer}{sfx}"] = _uniform(g, (3 * H, in_sz), kH)
+            sd[p + f"weight_hh_l{layer}{sfx}"] = _uniform(g, (3 * H, H), kH)
+            sd[p + f"bias_ih_l{layer}{sfx}"] = _uniform(g, (3 * H,), kH)
+            sd[p + f"bias_hh_l{layer}{sfx}"] = _uniform(g, (3 * H,), kH)
+    if bidirectional or add_linear:
+        b = 1.0 / math.sqrt(D * H)
+        sd["encoder.linear.weight"] = _uniform(g, (FEAT_SIZE, D * H), b)
+        sd["encoder.linear.bias"] = _uniform(g, (FEAT_SIZE,), b)
+    sd.update({k: v for k, v in make_state_dict(seed, 1, 32).items() if k.startswith("regressor.")})
+    return sd
+
+
+def make_vibe_input(seed: int, batch: int, seqlen: int) -> np.ndarray:
+    """Static features x ~ N(0,1) [B,T,2048] (evaluate.py:233)."""
+    return _rng(seed, 7).standard_normal((batch, seqlen, FEAT_SIZE), dtype=np.float32)
+
+
 def make_input(seed: int, batch: int, seqlen: int) -> np.ndarray:
     """x ~ N(0,1) [B,T,2133] with the newest frame's theta slot zeroed
     (evaluate.py:248-252 leaves input_feat[0,-1,2048:] at zero)."""
@@ -214,3 +243,29 @@ def build_synthetic_model(seed: int, seqlen: int, n_layers: int, hidden: int, pr
         own[k] = torch.as_tensor(v)
     model.load_state_dict(own, strict=True)
     return model.to(device).eval(), sd
+
+
+def build_synthetic_vibe(seed: int, seqlen: int, n_layers: int, hidden: int, add_linear: bool = True,
+                         bidirectional: bool = False, use_residual: bool = True, precision: str = "fp32", device="cpu"):
+    """tepose_b200.vibe.VIBE with the synthetic parameters / SMPL-shaped assets of `seed` loaded.
+    Returns (model.eval() on `device`, state_dict as numpy)."""
+    import tempfile
+    import torch
+    from .vibe import VIBE
+
+    old = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        write_base_data(os.path.join(tmp, "data", "base_data"), seed)      # asset paths are cwd-relative
+        os.chdir(tmp)
+        try:
+            model = VIBE(seqlen=seqlen, n_layers=n_layers, hidden_size=hidden, add_linear=add_linear,
+                         bidirectional=bidirectional, use_residual=use_residual, pretrained="", precision=precision)
+        finally:
+            os.chdir(old)
+    sd = make_vibe_state_dict(seed, n_layers, hidden, add_linear, bidirectional)
+    own = model.state_dict()
+    for k, v in sd.items():
+        assert k in own and tuple(own[k].shape) == tuple(v.shape), k
+        own[k] = torch.as_tensor(v)
+    model.load_state_dict(own, strict=True)
+    return model.eval().to(device), sd

@@ -32,7 +32,63 @@ def _round_up(v, m):
     return (v + m - 1) // m * m
 
 
-class TemporalEncoder(nn.Module):
+class GruKernels:
+    """K1 / K2 launch helpers shared by the encoders (needs self.precision and self.hidden_size)."""
+
+    @staticmethod
+    def _pack_whh(w: torch.Tensor, lp: bool) -> torch.Tensor:
+        """fp32 mode: [3H,H] fp32 as is.  bf16 mode: tensor-core fragment order (tp_pack_whh_bf16)."""
+        w = w.contiguous()
+        if not lp:
+            return w
+        out = torch.empty(w.shape[0], w.shape[1], device=w.device, dtype=torch.bfloat16)
+        nv.check(nv.lib().tp_pack_whh_bf16(nv.ptr(w), nv.ptr(out), w.shape[1], nv.stream()), "tp_pack_whh_bf16")
+        return out
+
+    def _input_proj(self, A, a_rows, W, kp, bias, segs, outs):
+        """K1: outs[i] = A[m-range] . W[n-range]^T + bias[n-range]."""
+        L = nv.lib()
+        if self.precision == "bf16":
+            arr = (nv.GemmSeg * len(segs))()
+            for i, ((m0, mr, n0, nc), out) in enumerate(zip(segs, outs)):
+                arr[i] = nv.GemmSeg(m0, mr, n0, nc, nv.ptr(out), out.shape[1], nv.vp(bias.data_ptr() + 4 * n0))
+            nv.check(L.tp_gemm_bf16_tc(nv.ptr(A), a_rows, nv.ptr(W), W.shape[0], kp, arr, len(segs), nv.stream()),
+                     "tp_gemm_bf16_tc")
+        else:
+            for (m0, mr, n0, nc), out in zip(segs, outs):
+                nv.check(L.tp_gemm_f32(nv.vp(A.data_ptr() + 4 * m0 * kp), kp, nv.vp(W.data_ptr() + 4 * n0 * kp), kp,
+                                       nv.vp(bias.data_ptr() + 4 * n0), nv.vp(0), 0, nv.ptr(out), out.shape[1],
+                                       mr, nc, kp, 1.0, 0.0, 0, nv.stream()), "tp_gemm_f32")
+
+    def _recurrence(self, jobs, B):
+        L = nv.lib()
+        H = self.hidden_size
+        arr = (nv.GruJob * len(jobs))(*jobs)
+        ws = nv.workspace(L.tp_gru_workspace_bytes(len(jobs), B, H), jobs[0]._dev)
+        nv.check(L.tp_gru_recurrence(arr, len(jobs), B, H, nv.PRECISIONS[self.precision], nv.ptr(ws), ws.numel(),
+                                     nv.stream()), "tp_gru_recurrence")
+
+    @staticmethod
+    def _job(dev, gi, col0, w_hh, b_hh, steps, t_in0, t_in_step, h0=None, y=None, ycol=0, y_lp=None,
+             t_out0=0, t_out_step=1, h_final=None, hcol=0):
+        j = nv.GruJob()
+        j.gi = gi.data_ptr() + 4 * col0
+        j.ldg = gi.shape[-1]
+        j.w_hh = w_hh.data_ptr()
+        j.b_hh = b_hh.data_ptr()
+        j.h0 = 0 if h0 is None else h0.data_ptr()
+        j.y = 0 if y is None else y.data_ptr() + 4 * ycol
+        j.ldy = 0 if y is None else y.shape[-1]
+        j.y_lp = 0 if y_lp is None else y_lp.data_ptr() + 2 * ycol
+        j.ldy_lp = 0 if y_lp is None else y_lp.shape[-1]
+        j.h_final = 0 if h_final is None else h_final.data_ptr() + 4 * hcol
+        j.ld_hf = 0 if h_final is None else h_final.stride(0)
+        j.steps, j.t_in0, j.t_in_step, j.t_out0, j.t_out_step = steps, t_in0, t_in_step, t_out0, t_out_step
+        j._dev = dev
+        return j
+
+
+class TemporalEncoder(nn.Module, GruKernels):
     def __init__(self, n_layers=1, seq_len=16, hidden_size=2048, precision="fp32"):
         super().__init__()
         self.gru_fwd = nn.GRU(input_size=INPUT_SIZE, hidden_size=hidden_size, bidirectional=False, num_layers=n_layers)
@@ -106,59 +162,7 @@ class TemporalEncoder(nn.Module):
         self._pack, self._pack_key = pk, key
         return pk
 
-    @staticmethod
-    def _pack_whh(w: torch.Tensor, lp: bool) -> torch.Tensor:
-        """fp32 mode: [3H,H] fp32 as is.  bf16 mode: tensor-core fragment order (tp_pack_whh_bf16)."""
-        w = w.contiguous()
-        if not lp:
-            return w
-        out = torch.empty(w.shape[0], w.shape[1], device=w.device, dtype=torch.bfloat16)
-        nv.check(nv.lib().tp_pack_whh_bf16(nv.ptr(w), nv.ptr(out), w.shape[1], nv.stream()), "tp_pack_whh_bf16")
-        return out
-
     # ------------------------------------------------------------------ kernels
-    def _input_proj(self, A, a_rows, W, kp, bias, segs, outs):
-        """K1: outs[i] = A[m-range] . W[n-range]^T + bias[n-range]."""
-        L = nv.lib()
-        if self.precision == "bf16":
-            arr = (nv.GemmSeg * len(segs))()
-            for i, ((m0, mr, n0, nc), out) in enumerate(zip(segs, outs)):
-                arr[i] = nv.GemmSeg(m0, mr, n0, nc, nv.ptr(out), out.shape[1], nv.vp(bias.data_ptr() + 4 * n0))
-            nv.check(L.tp_gemm_bf16_tc(nv.ptr(A), a_rows, nv.ptr(W), W.shape[0], kp, arr, len(segs), nv.stream()),
-                     "tp_gemm_bf16_tc")
-        else:
-            for (m0, mr, n0, nc), out in zip(segs, outs):
-                nv.check(L.tp_gemm_f32(nv.vp(A.data_ptr() + 4 * m0 * kp), kp, nv.vp(W.data_ptr() + 4 * n0 * kp), kp,
-                                       nv.vp(bias.data_ptr() + 4 * n0), nv.vp(0), 0, nv.ptr(out), out.shape[1],
-                                       mr, nc, kp, 1.0, 0.0, 0, nv.stream()), "tp_gemm_f32")
-
-    def _recurrence(self, jobs, B):
-        L = nv.lib()
-        H = self.hidden_size
-        arr = (nv.GruJob * len(jobs))(*jobs)
-        ws = nv.workspace(L.tp_gru_workspace_bytes(len(jobs), B, H), jobs[0]._dev)
-        nv.check(L.tp_gru_recurrence(arr, len(jobs), B, H, nv.PRECISIONS[self.precision], nv.ptr(ws), ws.numel(),
-                                     nv.stream()), "tp_gru_recurrence")
-
-    @staticmethod
-    def _job(dev, gi, col0, w_hh, b_hh, steps, t_in0, t_in_step, h0=None, y=None, ycol=0, y_lp=None,
-             t_out0=0, t_out_step=1, h_final=None, hcol=0):
-        j = nv.GruJob()
-        j.gi = gi.data_ptr() + 4 * col0
-        j.ldg = gi.shape[-1]
-        j.w_hh = w_hh.data_ptr()
-        j.b_hh = b_hh.data_ptr()
-        j.h0 = 0 if h0 is None else h0.data_ptr()
-        j.y = 0 if y is None else y.data_ptr() + 4 * ycol
-        j.ldy = 0 if y is None else y.shape[-1]
-        j.y_lp = 0 if y_lp is None else y_lp.data_ptr() + 2 * ycol
-        j.ldy_lp = 0 if y_lp is None else y_lp.shape[-1]
-        j.h_final = 0 if h_final is None else h_final.data_ptr() + 4 * hcol
-        j.ld_hf = 0 if h_final is None else h_final.stride(0)
-        j.steps, j.t_in0, j.t_in_step, j.t_out0, j.t_out_step = steps, t_in0, t_in_step, t_out0, t_out_step
-        j._dev = dev
-        return j
-
     def encode_states(self, x: torch.Tensor, h0=None, return_states=False):
         """Runs K1 + K2.  Returns (h_fwd [B,H], h_rec [B,2H]) = (y[-1], y_rec[0]) of
         lib/models/tepose.py:73-80.  h0 = (hF0, hB0) carries state (live-stream mode, L=1);

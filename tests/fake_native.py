@@ -77,6 +77,18 @@ class FakeLib:
         self.calls.append(("pack_rows", rows_b, rows_t, k, kp, prec))
         return 0
 
+    def tp_unpack_rows_residual(self, y, ld_y, x, stride_b, stride_t, rows_b, rows_t, k, out, out_bf16, stream):
+        v = _mat(y, rows_t * rows_b, k, ld_y).clone().reshape(rows_t, rows_b, k).permute(1, 0, 2)
+        if (x.value if isinstance(x, C.c_void_p) else x):
+            flat = _view(x, (rows_b - 1) * stride_b + (rows_t - 1) * stride_t + k, torch.float32)
+            v = v + torch.as_strided(flat, (rows_b, rows_t, k), (stride_b, stride_t, 1))
+        v = v.reshape(rows_b * rows_t, k)
+        _mat(out, rows_b * rows_t, k, k).copy_(v)
+        if (out_bf16.value if isinstance(out_bf16, C.c_void_p) else out_bf16):
+            _mat(out_bf16, rows_b * rows_t, k, k, torch.bfloat16).copy_(v.to(torch.bfloat16))
+        self.calls.append(("unpack_rows_residual", rows_b, rows_t, k))
+        return 0
+
     def tp_gemm_f32(self, A, lda, W, ldw, bias, Cin, ldcin, Cout, ldc, M, N, K, alpha, beta, relu_a, stream):
         a = _mat(A, M, K, lda).clone()
         w = _mat(W, N, K, ldw)

@@ -118,6 +118,8 @@ def test_pipelined_host_buffer_api_matches_direct_forward():
     (2, 256, 6, 32, True, False),      # released depth, train-shaped output (2 rows per sequence)
     (3, 96, 4, 2, False, False),       # three layers, H not a multiple of 128
     (1, 2048, 16, 7, False, False),    # ragged batch at full width
+    (1, 128, 4, 80, False, False),     # more rows than one 64-row chunk of the skinny kernels
+    (1, 128, 3, 40, True, True),       # train-shaped: 80 regressor rows from 40 sequences
 ])
 def test_forward_edge_shapes_against_oracle(L, H, T, B, train, h36m, precision):
     seed = 80 + L + B

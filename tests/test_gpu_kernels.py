@@ -153,6 +153,26 @@ def test_pack_rows():
         assert torch.equal(dst.cpu(), ref.to(dt))          # bit-exact: a copy + RN conversion
 
 
+def test_unpack_rows_residual():
+    """y [T*B, ld] time-major + x [B,T,F] (a strided view) -> [B*T, F]; bit-exact (one fp32 add, RN conversion)."""
+    B, T, F, ld = 3, 5, 2048, 2112
+    y = torch.randn(T * B, ld)
+    xbig = torch.randn(B, 2 * T, F)
+    xs = cu(xbig)[:, ::2]
+    ys = cu(y)
+    for with_x in (True, False):
+        out = torch.full((B * T, F), 7.0, device=DEV)
+        out_lp = torch.full((B * T, F), 7.0, device=DEV, dtype=torch.bfloat16)
+        nv.check(nv.lib().tp_unpack_rows_residual(nv.ptr(ys), ld, nv.vp(xs.data_ptr() if with_x else 0), xs.stride(0),
+                                                  xs.stride(1), B, T, F, nv.ptr(out), nv.ptr(out_lp), nv.stream()))
+        ref = y[:, :F].reshape(T, B, F).permute(1, 0, 2)
+        if with_x:
+            ref = ref + xbig[:, ::2]
+        ref = ref.reshape(B * T, F)
+        assert torch.equal(out.cpu(), ref)
+        assert torch.equal(out_lp.cpu(), ref.to(torch.bfloat16))
+
+
 @pytest.mark.parametrize("rows,wrows,kp", [(8, 192, 128), (512, 768, 2176), (130, 384, 64), (32, 96, 192)])
 def test_gemm_bf16_tcgen05(rows, wrows, kp):
     g = torch.Generator().manual_seed(rows + wrows)
