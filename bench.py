@@ -328,6 +328,23 @@ def main():
         lat = np.array([a.elapsed_time(b_) for a, b_ in lev])
         live = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)), "frames": n_live,
                 "mode": "carried-state causal step, B=1, theta feedback on device, CUDA graph per frame"}
+        # the reference's own loop (evaluate.py:247-269): a full T-frame window from h0 = 0 per frame, thetas fed back
+        from tepose_b200.stream import WindowedTePose
+        ws = WindowedTePose(model, None, batch=1)
+        ws.set_theta(torch.zeros(T - 1, 85))
+        wfeats = torch.from_numpy(synth.make_input(SEED + 8, 1, 64 + T)[:, :, :2048]).to(dev)
+        for i in range(50):
+            ws.step(wfeats[:, i % 64:i % 64 + T])
+        torch.cuda.synchronize(dev)
+        for i in range(n_live):
+            lev[i][0].record()
+            ws.step(wfeats[:, i % 64:i % 64 + T])
+            lev[i][1].record()
+        torch.cuda.synchronize(dev)
+        lat = np.array([a.elapsed_time(b_) for a, b_ in lev])
+        live["windowed"] = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
+                            "mode": f"reference loop: {T}-frame window per frame, B=1, window + theta ring in HBM, "
+                                    "CUDA graph per frame"}
 
     # ---------------------------------------------------------------- SMPL standalone (config 4 shape, this rank's shard)
     smpl_sa = None

@@ -37,6 +37,12 @@ VIBE_CASES = {
     "vibe_L1_H2048_B1_T2_plain": dict(seed=23, batch=1, seqlen=2, n_layers=1, hidden=2048),
 }
 
+# name -> configuration of a live-loop run (VIBE bootstrap + one TePose window per frame, thetas fed back)
+STREAM_CASES = {
+    "stream_T4_N9_L1_H64_vibeL2_H32": dict(seed=31, batch=1, frames=9, seqlen=4, n_layers=1, hidden=64,
+                                           vibe_layers=2, vibe_hidden=32),
+}
+
 
 def edge_rotations() -> np.ndarray:
     """Rotation matrices that hit every branch of lib/utils/geometry.py:191-233:
@@ -64,6 +70,12 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     for name, cfg in VIBE_CASES.items():
         out = ref_harness.run_reference_vibe(**cfg)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"),
+                            cfg=np.array(repr(cfg)), **{k: v.astype(np.float32) for k, v in out.items()})
+        print(name, {k: v.shape for k, v in out.items()})
+    for name, cfg in STREAM_CASES.items():
+        out = ref_harness.run_reference_stream(**cfg)
+        out["verts"] = out["verts"][:, ::4]            # every 4th frame's mesh keeps the fixture small
         np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"),
                             cfg=np.array(repr(cfg)), **{k: v.astype(np.float32) for k, v in out.items()})
         print(name, {k: v.shape for k, v in out.items()})

@@ -213,3 +213,43 @@ def run_reference_vibe(seed, batch, seqlen, n_layers, hidden, add_linear=False, 
         with torch.no_grad():
             out = model(torch.from_numpy(x), J_regressor=Jr)[-1]
     return {k: v.detach().numpy().copy() for k, v in out.items()}
+
+
+def run_reference_stream(seed, batch, frames, seqlen, n_layers, hidden, vibe_layers, vibe_hidden, use_h36m=True):
+    """demo.py:229-252 / evaluate.py:233-269 restated around the UNMODIFIED lib.models.VIBE and lib.models.TePose:
+    VIBE on the first T frames, then one TePose window per frame with the predicted thetas fed back."""
+    import importlib
+    sd_v = synth.make_vibe_state_dict(seed, vibe_layers, vibe_hidden, True, False)
+    sd = synth.make_state_dict(seed, n_layers, hidden)
+    feats = torch.from_numpy(synth.make_vibe_input(seed, batch, frames))
+    T = seqlen
+
+    def load(model, sd_np):
+        own = model.state_dict()
+        for k, v in sd_np.items():
+            assert k in own and tuple(own[k].shape) == tuple(v.shape), k
+            own[k] = torch.as_tensor(v)
+        model.load_state_dict(own, strict=True)
+        return model.eval()
+
+    with reference_env(seed) as mods:
+        vibe = importlib.import_module("lib.models.vibe")
+        model_vibe = load(vibe.VIBE(seqlen=T, n_layers=vibe_layers, hidden_size=vibe_hidden, add_linear=True,
+                                    bidirectional=False, use_residual=True, pretrained=""), sd_v)
+        model = build_reference_model(mods, sd, T, n_layers, hidden)
+        Jr = torch.from_numpy(np.load(os.path.join("data", "base_data", "J_regressor_h36m.npy"))).float() if use_h36m else None
+        keys = ("theta", "verts", "kp_2d", "kp_3d", "rotmat")
+        with torch.no_grad():
+            output = model_vibe(feats[:, :T], J_regressor=Jr)[-1]
+            per = {k: [output[k][:, t] for t in range(T - 1)] for k in keys}
+            theta_input = output["theta"][:, :T - 1].detach().clone()
+            for k in range(frames - T + 1):
+                inp = torch.zeros((batch, T, 2048 + 85)).float()
+                inp[:, :, :2048] = feats[:, k:k + T].clone()
+                inp[:, :T - 1, 2048:] = theta_input.clone()
+                preds = model(inp, J_regressor=Jr, is_train=False)[-1]
+                for kk in keys:
+                    per[kk].append(preds[kk])
+                theta_input[:, :T - 2] = theta_input[:, 1:T - 1].clone()
+                theta_input[:, T - 2] = preds["theta"].clone().detach()
+    return {k: torch.stack(v, dim=1).numpy().copy() for k, v in per.items()}

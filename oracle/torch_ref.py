@@ -312,6 +312,28 @@ def vibe_forward(sd: dict, m: SmplModel, x: torch.Tensor, n_layers: int, hidden:
     }
 
 
+def windowed_stream(sd_vibe: dict, vibe_arch: dict, sd: dict, m: SmplModel, features: torch.Tensor, seqlen: int,
+                    n_layers: int, hidden: int, J_regressor=None, theta_input=None) -> dict:
+    """The live loop of evaluate.py:229-269 (theta ring seeded from VIBE as demo.py:237 does, or from
+    ``theta_input`` [T-1,85] as evaluate.py:219 does).  features [B,N,2048] -> per-frame outputs [B,N,...]."""
+    B, N, T = features.shape[0], features.shape[1], seqlen
+    first = vibe_forward(sd_vibe, m, features[:, :T], J_regressor=J_regressor, **vibe_arch)
+    ring = (first["theta"][:, :T - 1].clone() if theta_input is None
+            else torch.as_tensor(theta_input, dtype=torch.float32).reshape(-1, T - 1, 85).expand(B, -1, -1).clone())
+    frames = {k: [v[:, t] for t in range(T - 1)] for k, v in first.items()}
+    grus = (build_gru(sd, "gru_fwd", n_layers, hidden, False), build_gru(sd, "gru_rec", n_layers, hidden, True))
+    for i in range(N - T + 1):
+        x = torch.zeros(B, T, 2048 + 85)
+        x[:, :, :2048] = features[:, i:i + T]
+        x[:, :T - 1, 2048:] = ring
+        out = tepose_forward(sd, m, x, n_layers, hidden, False, J_regressor, grus)
+        for k in frames:
+            frames[k].append(out[k])
+        ring[:, :T - 2] = ring[:, 1:T - 1].clone()
+        ring[:, T - 2] = out["theta"]
+    return {k: torch.stack(v, dim=1) for k, v in frames.items()}
+
+
 # --------------------------------------------------------------------------- carried state
 def encoder_causal_states(sd: dict, x: torch.Tensor, hidden: int, h0=None):
     """Live-stream oracle (SURVEY.md F3/F4, L=1 only): the encoder restated as three
