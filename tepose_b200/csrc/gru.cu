@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
 }
 
 #include "gru_tma.inl"
+#include "gru_res.inl"
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -468,6 +469,18 @@ static int launch_coop_n(KernelT kfn, const GruParams& p, int stages, int thread
   return TP_OK;
 }
 
+template <typename KernelT>
+static int launch_coop_n2(KernelT kfn, const GruParams& p, int a0, int a1, int threads, int grid, size_t smem, cudaStream_t st) {
+  TP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  TP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem));
+  if (per_sm < 1) return fail(TP_ERR_UNSUPPORTED, "tp_gru_recurrence: kernel does not fit on an SM (smem=%zu)", smem);
+  void* args[] = {(void*)&p, (void*)&a0, (void*)&a1};
+  TP_CUDA(cudaLaunchCooperativeKernel((const void*)kfn, dim3(grid), dim3(threads), args, smem, st));
+  count_launch();
+  return TP_OK;
+}
+
 extern "C" int tp_gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, int H, int precision,
                                  void* workspace, size_t workspace_bytes, void* stream) {
   TP_CHECK_ARG(jobs_in && njobs >= 1 && njobs <= kMaxJobs, "tp_gru_recurrence: njobs=%d out of range [1,%d]", njobs, kMaxJobs);
@@ -509,6 +522,42 @@ extern "C" int tp_gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, in
   static const bool no_tma = getenv("TP_GRU_NO_TMA") != nullptr;
   if (precision == TP_PRECISION_BF16 && !no_tma && n_mat >= 1 && H % 128 == 0 && B <= 32 && n_mat * (H / 32) <= sms) {
     const int NB = B <= 8 ? 8 : 32;
+    // resident-weight variant: part of each CTA's W_hh slice stays in registers / shared memory for all steps
+    // Measured (profiles/r02_gru_resident_ab.txt): at NB = 8 it cuts the windowed live step by 7 %; at NB = 32 the
+    // shared memory the resident chunks take is worth more as ring depth (streaming kernel 175 us, resident 189-203 us),
+    // so NB = 32 stays on k_gru_bf16_tma unless TP_GRU_RES=1 forces the resident kernel.
+    static const bool no_res = getenv("TP_GRU_NO_RES") != nullptr;
+    static const bool force_res = getenv("TP_GRU_RES") != nullptr;
+    if (!no_res && (NB == 8 || force_res)) {
+      static const int ws_env = getenv("TP_GRU_WS") ? atoi(getenv("TP_GRU_WS")) : 0;
+      static const int rs_env = getenv("TP_GRU_RS") ? atoi(getenv("TP_GRU_RS")) : -1;
+      const int nchunks = H / 128;
+      const int RR = NB == 8 ? kResRegChunks1 : kResRegChunks4;
+      const int rr = RR < nchunks ? RR : nchunks;
+      int ws = ws_env > 0 ? (ws_env > 8 ? 8 : ws_env) : 2;
+      cudaFuncAttributes fa;
+      if (NB == 8) TP_CUDA(cudaFuncGetAttributes(&fa, k_gru_bf16_res<1, kResRegChunks1>));
+      else TP_CUDA(cudaFuncGetAttributes(&fa, k_gru_bf16_res<4, kResRegChunks4>));
+      int dev = 0, optin = 0;
+      TP_CUDA(cudaGetDevice(&dev));
+      TP_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+      const long hring = (((long)kResHStages * NB * 256) + 1023) & ~1023L;
+      const long avail = (long)optin - (long)fa.sharedSizeBytes - 512 - hring - (long)ws * kChunkBytes;
+      int rs = avail > 0 ? (int)(avail / kChunkBytes) : 0;
+      if (rs > nchunks - rr) rs = nchunks - rr;
+      if (rs_env >= 0 && rs > rs_env) rs = rs_env;
+      if (avail >= 0) {
+        p.U = 32; p.n_item_jobs = n_mat;
+        int items = 0;
+        for (int j = 0; j < n_mat; ++j) { p.item_begin[j] = items; items += H / 32; }
+        for (int j = n_mat; j <= kMaxJobs; ++j) p.item_begin[j] = items;
+        p.total_items = items;
+        p.lp_tiled = 1; p.lp_slot = (int64_t)32 * H;
+        const size_t smem = (size_t)hring + (size_t)(rs + ws) * kChunkBytes + 512;
+        if (NB == 8) return launch_coop_n2(k_gru_bf16_res<1, kResRegChunks1>, p, rs, ws, kTmaThreads, items, smem, st);
+        return launch_coop_n2(k_gru_bf16_res<4, kResRegChunks4>, p, rs, ws, kTmaThreads, items, smem, st);
+      }
+    }
     const size_t region = ((size_t)4 * 3 * NB * 36 * 4 + 1023) & ~(size_t)1023;     // red only: h rides in the ring
     const size_t budget = 225 * 1024;
     int stages = (int)((budget - region - 256) / kStageBytes);
