@@ -66,8 +66,7 @@ class LiveTePose:
         return out
 
     def _decode(self, h_fwd, h_rec):
-        feat = self.model.encoder.heads(h_fwd, h_rec)
-        out = self.model.regressor(feat, J_regressor=self.J_regressor)[-1]
+        out = self.model.regress_states(h_fwd, h_rec, J_regressor=self.J_regressor)[-1]
         self.x2[:, 0, :FEAT].copy_(self.x2[:, 1, :FEAT])
         self.x2[:, 0, FEAT:].copy_(out["theta"])
         return out

@@ -17,6 +17,26 @@ NPOSE = 24 * 6
 PSC = 160  # pose6d(144) | shape(10) | cam(3) | pad(3)
 
 
+def folded_gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, relu_a: bool) -> torch.Tensor:
+    """out [M,160] = act(a)[M,K] . w[160,K]^T + bias on the fp32 split-K kernel (M small, K long: every SM streams
+    a K slice of the folded matrix)."""
+    L = nv.lib()
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    if M > 64:
+        nv.check(L.tp_gemm_f32(nv.vp(a.data_ptr()), a.stride(0), nv.ptr(w), K, nv.ptr(bias), nv.vp(0), 0, nv.ptr(out), N,
+                               M, N, K, 1.0, 0.0, 1 if relu_a else 0, nv.stream()), "tp_gemm_f32")
+        return out
+    splits = max(1, min(K // 128, 24))
+    ws = nv.workspace(max(int(L.tp_gemm_f32_splitk_workspace_bytes(M, N, splits)), 4096), a.device)
+    ws[:4096].zero_()                                   # ticket area (the kernel leaves it zeroed)
+    nv.check(L.tp_gemm_f32_splitk(nv.vp(a.data_ptr()), a.stride(0), nv.ptr(w), K, nv.ptr(bias), nv.vp(0), 0, nv.ptr(out), N,
+                                  M, N, K, 1.0, 0.0, 1 if relu_a else 0, splits, nv.ptr(ws), ws.numel(), nv.stream()),
+             "tp_gemm_f32_splitk")
+    return out
+
+
 class Regressor(nn.Module):
     def __init__(self, smpl_mean_params=SMPL_MEAN_PARAMS, precision="fp32"):
         super().__init__()
@@ -82,6 +102,58 @@ class Regressor(nn.Module):
             pk["c"] = nv.IefWeights(*[nv.ptr(pk[n]) for n in ("w1x", "b1", "w1p", "w2", "b2", "wdec", "bdec")])
             self._pack, self._pack_key = pk, key
         return self._pack
+
+    # ------------------------------------------------------------------ closed form of the IEF loop
+    def folded(self, n_iter=3):
+        """The IEF loop has NO nonlinearity (lib/models/spin.py:250-261 in eval mode: fc1 -> drop -> fc2 -> drop ->
+        dec*, dropout = identity), so n iterations are one affine map of (feature, initial state):
+
+            p' = p + Wd (W2 (W1x f + W1p p + b1) + b2) + bd  =  A p + Q f + c,     A = I + Wd W2 W1p
+            p_n = A^n p_0 + S_n (Q f + c),                                         S_n = I + A + ... + A^(n-1)
+
+        Returns fp32 tensors {G [160,2048] = S_n Q, g [160] = S_n c, An [160,160] = A^n} composed in float64
+        (rows / columns 157..159 are the zero padding of the [N,160] state).  Opt-in (TePose.fold_linear): the
+        result differs from the layer-by-layer evaluation by fp32 rounding only, but it is a different
+        sequence of floating-point operations than the reference's."""
+        key = (self._key(), int(n_iter))
+        if getattr(self, "_fold_key", None) != key:
+            with torch.no_grad():
+                d = lambda t: t.detach().double()
+                W1 = d(self.fc1.weight)
+                W1x, W1p = W1[:, :2048], W1[:, 2048:]
+                Wd = torch.cat([d(self.decpose.weight), d(self.decshape.weight), d(self.deccam.weight)], dim=0)     # [157,1024]
+                bd = torch.cat([d(self.decpose.bias), d(self.decshape.bias), d(self.deccam.bias)])
+                WdW2 = Wd @ d(self.fc2.weight)
+                A = torch.eye(157, dtype=torch.float64, device=W1.device) + WdW2 @ W1p
+                Q = WdW2 @ W1x
+                c = Wd @ (d(self.fc2.weight) @ d(self.fc1.bias) + d(self.fc2.bias)) + bd
+                S = torch.zeros_like(A)
+                An = torch.eye(157, dtype=torch.float64, device=W1.device)
+                for _ in range(int(n_iter)):
+                    S = S + An
+                    An = An @ A
+                G = torch.zeros(PSC, 2048, dtype=torch.float64, device=W1.device)
+                G[:157] = S @ Q
+                g = torch.zeros(PSC, dtype=torch.float64, device=W1.device)
+                g[:157] = S @ c
+                Anp = torch.zeros(PSC, PSC, dtype=torch.float64, device=W1.device)
+                Anp[:157, :157] = An
+            self._fold = {"G64": G, "g64": g, "An64": Anp, "G": G.float().contiguous(), "g": g.float().contiguous(),
+                          "An": Anp.float().contiguous()}
+            self._fold_key = key
+        return self._fold
+
+    def forward_folded(self, x, n_iter=3, is_train=False, J_regressor=None):
+        """forward() through the closed form: psc = x . G^T + (g + A^n p_0), one fp32 split-K GEMM."""
+        if self.training:
+            raise NotImplementedError("tepose_b200.Regressor implements the inference path; call .eval()")
+        nv.require_cuda(x, "x")
+        pk, fd = self.packed(), self.folded(n_iter)
+        feat = x.detach().contiguous().float()
+        bias = (fd["g64"] + fd["An64"] @ pk["init"][0].double()).float().contiguous()
+        psc = folded_gemm(feat, fd["G"], bias, relu_a=False)
+        nv.mark("k3_ief")
+        return self.decode(psc, is_train=is_train, J_regressor=J_regressor)
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, init_pose=None, init_shape=None, init_cam=None, n_iter=3, is_train=False, J_regressor=None):

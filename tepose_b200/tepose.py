@@ -292,10 +292,11 @@ class TemporalEncoder(nn.Module, GruKernels):
 
 class TePose(nn.Module):
     def __init__(self, seqlen, batch_size=64, n_layers=1, hidden_size=2048,
-                 pretrained=osp.join(BASE_DATA_DIR, 'spin_model_checkpoint.pth.tar'), precision="fp32"):
+                 pretrained=osp.join(BASE_DATA_DIR, 'spin_model_checkpoint.pth.tar'), precision="fp32", fold_linear=False):
         super().__init__()
         if precision not in nv.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(nv.PRECISIONS)}")
+        self.fold_linear = bool(fold_linear)
         self.seqlen = seqlen
         self.batch_size = batch_size
         self.encoder = TemporalEncoder(seq_len=seqlen, n_layers=n_layers, hidden_size=hidden_size, precision=precision)
@@ -316,18 +317,55 @@ class TePose(nn.Module):
         self.encoder.precision = value
         self.regressor.precision = value
 
+    # ------------------------------------------------------------------ heads + IEF as one affine map (opt-in)
+    def folded(self, n_iter=3):
+        """fold_linear: the eval-mode heads (lib/models/tepose.py:79-85) and the IEF loop (lib/models/spin.py:250-261)
+        are both linear AFTER the relu on the encoder states, so
+
+            psc = relu([y[-1] | y_rec[0]]) . (G [0.5 W_fwd | 0.5 W_rec])^T + G (b_fwd + b_rec)/2 + g + A^n p_0
+
+        with G, g, A^n from Regressor.folded().  Composed in float64 at pack time, applied as ONE fp32 GEMM
+        [B,3H] x [3H,160] (2-4 MB of weights instead of 25 MB + 7 MB streamed through 11 dependent layers)."""
+        enc, reg = self.encoder, self.regressor
+        key = (enc._key(), reg._key(), int(n_iter))
+        if getattr(self, "_fold_key", None) != key:
+            fd, pk = reg.folded(n_iter), reg.packed()
+            with torch.no_grad():
+                d = lambda t: t.detach().double()
+                Wcat = torch.cat([0.5 * d(enc.linear_fwd.weight), 0.5 * d(enc.linear_rec.weight)], dim=1)      # [2048,3H]
+                bcat = 0.5 * (d(enc.linear_fwd.bias) + d(enc.linear_rec.bias))
+                Gh = fd["G64"] @ Wcat
+                gh = fd["G64"] @ bcat + fd["g64"] + fd["An64"] @ pk["init"][0].double()
+            self._fold = {"Gh": Gh.float().contiguous(), "gh": gh.float().contiguous()}
+            self._fold_key = key
+        return self._fold
+
+    def regress_states(self, h_fwd, h_rec, is_train=False, J_regressor=None):
+        """K3..K5 from the encoder states (y[-1], y_rec[0]): heads + Regressor, or their folded form."""
+        H = self.encoder.hidden_size
+        adjacent = (h_fwd.stride(0) == 3 * H and h_rec.stride(0) == 3 * H and h_rec.data_ptr() == h_fwd.data_ptr() + 4 * H)
+        if self.fold_linear and not is_train and adjacent:
+            from .spin import folded_gemm
+            fd = self.folded()
+            h_cat = torch.as_strided(h_fwd, (h_fwd.shape[0], 3 * H), (3 * H, 1))
+            psc = folded_gemm(h_cat, fd["Gh"], fd["gh"], relu_a=True)
+            nv.mark("k3_folded")
+            return self.regressor.decode(psc, is_train=False, J_regressor=J_regressor)
+        feature = self.encoder.heads(h_fwd, h_rec, is_train=is_train)
+        lp = getattr(feature, "_tp_bf16", None)
+        feature = feature.reshape(-1, feature.size(-1))
+        if lp is not None:
+            feature._tp_bf16 = lp.reshape(-1, lp.size(-1))
+        return self.regressor(feature, is_train=is_train, J_regressor=J_regressor)
+
     def forward(self, input, is_train=False, J_regressor=None):
         if self.training:
             raise NotImplementedError("tepose_b200.TePose implements the inference path; call .eval() first "
                                       "(train-mode dropout / backward are not implemented yet)")
         batch_size = input.shape[0]
         nv.mark("start")
-        feature = self.encoder(input, is_train=is_train)
-        lp = getattr(feature, "_tp_bf16", None)
-        feature = feature.reshape(-1, feature.size(-1))
-        if lp is not None:
-            feature._tp_bf16 = lp.reshape(-1, lp.size(-1))
-        smpl_output = self.regressor(feature, is_train=is_train, J_regressor=J_regressor)
+        h_fwd, h_rec = self.encoder.encode_states(input)
+        smpl_output = self.regress_states(h_fwd, h_rec, is_train=is_train, J_regressor=J_regressor)
         lead = (batch_size, 2) if is_train else (batch_size,)
         for s in smpl_output:                                  # lib/models/tepose.py:130-145
             s['theta'] = s['theta'].reshape(*lead, -1)

@@ -105,6 +105,12 @@ class FakeLib:
         self.calls.append(("gemm_f32", M, N, K))
         return 0
 
+    def tp_gemm_f32_splitk_workspace_bytes(self, M, N, splits):
+        return 4096 + 4 * M * N * splits
+
+    def tp_gemm_f32_splitk(self, A, lda, W, ldw, bias, Cin, ldcin, Cout, ldc, M, N, K, alpha, beta, relu_a, splits, ws, ws_bytes, stream):
+        return self.tp_gemm_f32(A, lda, W, ldw, bias, Cin, ldcin, Cout, ldc, M, N, K, alpha, beta, relu_a, stream)
+
     def tp_gemm_bf16_tc(self, A, a_rows, W, w_rows, kp, segs, nseg, stream):
         a = _mat(A, a_rows, kp, kp, torch.bfloat16).float()
         w = _mat(W, w_rows, kp, kp, torch.bfloat16).float()

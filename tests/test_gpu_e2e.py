@@ -153,3 +153,42 @@ def test_errors_are_loud():
     model.train()
     with pytest.raises(NotImplementedError):
         model(torch.zeros(2, 4, 2133, device=DEV))
+
+
+# ------------------------------------------------------------------------------------------------ folded heads + IEF
+@pytest.mark.parametrize("fname", sorted(f for f in os.listdir(GOLD) if f.startswith("fwd_") and "train" not in f))
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_folded_forward_against_reference_golden(fname, precision):
+    """fold_linear=True: heads + IEF as one pre-composed affine map (TePose.folded) -- same tolerances."""
+    z = np.load(os.path.join(GOLD, fname))
+    cfg = ast.literal_eval(str(z["cfg"]))
+    model, sd = build_product_model(cfg["seed"], cfg["seqlen"], cfg["n_layers"], cfg["hidden"], precision, DEV)
+    model.fold_linear = True
+    x = torch.from_numpy(synth.make_input(cfg["seed"], cfg["batch"], cfg["seqlen"])).to(DEV)
+    Jr = torch_ref.SmplModel.synthetic(cfg["seed"]).J_regressor_h36m.to(DEV) if cfg.get("use_h36m") else None
+    out = model(x, J_regressor=Jr)[-1]
+    gold = {k: z[k] for k in ("theta", "verts", "kp_2d", "kp_3d", "rotmat")}
+    tol = {} if precision == "fp32" else dict(vert_tol=1e-3, rot_tol=2e-3, kp2d_tol=5e-2)
+    print(fname, precision, compare_outputs(out, gold, label=fname, **tol))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_folded_forward_full_size(precision):
+    from tepose_b200.graph import GraphedTePose
+    seed, L, H, T, B = 47, 1, 2048, 16, 32
+    model, sd = build_product_model(seed, T, L, H, precision, DEV)
+    x = synth.make_input(seed, B, T)
+    ref, m = oracle_forward(seed, sd, x, L, H)
+    xd = torch.from_numpy(x).to(DEV)
+    plain = {k: v.clone() for k, v in model(xd)[-1].items()}
+    model.fold_linear = True
+    out = model(xd)[-1]
+    tol = {} if precision == "fp32" else dict(vert_tol=1e-3, rot_tol=2e-3, kp2d_tol=5e-2)
+    errs = compare_outputs(out, ref, label="folded full", **tol)
+    e_plain = compare_outputs(plain, ref, label="plain full", **tol)
+    print(precision, "folded", errs, "layer-by-layer", e_plain)
+    g = GraphedTePose(model, B, T)
+    rep = g(xd)
+    for k in out:
+        assert torch.equal(rep[k], out[k]), k
+    assert g.launches_per_replay < 12

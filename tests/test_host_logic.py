@@ -138,3 +138,44 @@ def test_live_stream_matches_causal_oracle():
         ref = torch_ref.regressor_forward(sd, m, feat)
         compare_outputs(outs[t], ref, label=f"live frame {t}")
         prev = torch.cat([feats[:, t], ref["theta"]], dim=1)[:, None]
+
+
+# ------------------------------------------------------------------------------------------------ folded heads + IEF
+def test_ief_closed_form_equals_the_loop_in_float64():
+    """Regressor.folded(): n IEF iterations == A^n p0 + S_n (Q f + c) (no nonlinearity: lib/models/spin.py:250-261)."""
+    from oracle import np64
+    model, sd = build_product_model(45, 4, 1, 32)
+    reg = model.regressor
+    feat = np.random.Generator(np.random.PCG64(9)).standard_normal((3, 2048))
+    for n_iter in (1, 3, 4):
+        fd = reg.folded(n_iter)
+        p0 = np.zeros(160)
+        p0[:144] = sd["regressor.init_pose"][0]; p0[144:154] = sd["regressor.init_shape"][0]; p0[154:157] = sd["regressor.init_cam"][0]
+        got = feat @ fd["G64"].numpy().T + fd["g64"].numpy() + fd["An64"].numpy() @ p0
+        pose, shape, cam = np64.ief(sd, feat, n_iter)
+        want = np.concatenate([pose, shape, cam], axis=1)
+        np.testing.assert_allclose(got[:, :157], want, atol=1e-12, rtol=1e-10)
+        assert np.all(got[:, 157:] == 0)
+
+
+@pytest.mark.parametrize("cfg", CASES[:4], ids=lambda c: "L{n_layers}_H{hidden}_B{batch}_T{seqlen}".format(**c))
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_folded_path_matches_oracle(cfg, precision):
+    model, sd = build_product_model(cfg["seed"], cfg["seqlen"], cfg["n_layers"], cfg["hidden"], precision)
+    model.fold_linear = True
+    x = synth.make_input(cfg["seed"], cfg["batch"], cfg["seqlen"])
+    ref, m = oracle_forward(cfg["seed"], sd, x, cfg["n_layers"], cfg["hidden"], False, cfg.get("use_h36m", False))
+    with fake_native.install() as fake:
+        out = model(torch.from_numpy(x), J_regressor=m.J_regressor_h36m if cfg.get("use_h36m") else None)[-1]
+        feat = torch.from_numpy(np.random.Generator(np.random.PCG64(4)).standard_normal((5, 2048)).astype(np.float32))
+        a = model.regressor.forward_folded(feat)[-1]
+        b = model.regressor(feat)[-1]
+    kinds = [c[0] for c in fake.calls]
+    first_smpl = kinds.index("smpl")
+    assert "heads_cat" not in kinds[:first_smpl]                 # one GEMM replaced the heads and the IEF layers
+    assert ("gemm_f32", cfg["batch"], 160, 3 * cfg["hidden"]) in fake.calls
+    if precision == "fp32":
+        compare_outputs(out, ref, label=str(cfg))
+    else:
+        compare_outputs(out, ref, vert_tol=1e-3, rot_tol=2e-3, kp2d_tol=5e-2, label=str(cfg))
+    compare_outputs(a, b, label="regressor folded vs loop", **({} if precision == "fp32" else dict(vert_tol=1e-3, rot_tol=2e-3, kp2d_tol=5e-2)))
