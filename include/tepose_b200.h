@@ -259,6 +259,27 @@ TP_API int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose, int
                     int blend_mode /* 0: fp32 FFMA blend (strict); 1: bf16 tensor-core blend (needs blend_tc) */,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ evaluation metrics (lib/utils/eval_utils.py)
+ * All take fp32 device arrays; pelvis0 / pelvis1 select the root alignment applied to BOTH point sets first
+ * (evaluate.py:420-428): both >= 0: subtract the mean of the two joints (hips 2, 3 of the 14-joint set);
+ * pelvis1 < 0: subtract joint pelvis0 (mpii3d: joint J-3); pelvis0 < 0: none.
+ *
+ * tp_pose_metrics -- pred / target [n, n_joints, 3].  Any output may be NULL:
+ *   aligned  [n, n_joints, 3] = batch_compute_similarity_transform_torch(pred, target)  (eval_utils.py:287-337:
+ *            orthogonal Procrustes, R = V diag(1,1,sign det(U V^T)) U^T from the SVD of X1 X2^T, scale, translation)
+ *   mpjpe    [n] = mean_j ||pred_j - target_j||                     (evaluate.py:433; lib/core/tester.py:286)
+ *   pa_mpjpe [n] = mean_j ||aligned_j - target_j||                  (evaluate.py:435-437; lib/core/tester.py:287-288) */
+TP_API int tp_pose_metrics(const float* pred, const float* target, int n, int n_joints, int pelvis0, int pelvis1,
+                    float* aligned, float* mpjpe, float* pa_mpjpe, void* stream);
+/* tp_accel_error -- pred / target [n_seq, len, n_joints, 3] -> out [n_seq, len-2]:
+ *   out[s,i] = mean_j || (p_i - 2 p_{i+1} + p_{i+2}) - (g_i - 2 g_{i+1} + g_{i+2}) ||   (compute_error_accel_eval /
+ *   compute_error_accel, eval_utils.py:79-138); target NULL: the norm of pred's own acceleration (compute_accel, :53-76). */
+TP_API int tp_accel_error(const float* pred, const float* target, int n_seq, int len, int n_joints, int pelvis0, int pelvis1,
+                   float* out, void* stream);
+/* tp_vertex_error -- verts_a / verts_b [n, n_verts, 3] -> out [n] = mean_v ||a_v - b_v||   (compute_error_verts,
+ * eval_utils.py:141-175; the target mesh comes from tp_smpl_forward with TP_POSE_AXIS_ANGLE).                        */
+TP_API int tp_vertex_error(const float* verts_a, const float* verts_b, int n, int n_verts, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

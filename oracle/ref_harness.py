@@ -253,3 +253,16 @@ def run_reference_stream(seed, batch, frames, seqlen, n_layers, hidden, vibe_lay
                 theta_input[:, :T - 2] = theta_input[:, 1:T - 1].clone()
                 theta_input[:, T - 2] = preds["theta"].clone().detach()
     return {k: torch.stack(v, dim=1).numpy().copy() for k, v in per.items()}
+
+
+def reference_eval_utils():
+    """lib.utils.eval_utils imported unmodified (matplotlib, used only by plot_accel, is stubbed when absent)."""
+    import importlib
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        mpl = types.ModuleType("matplotlib")
+        mpl.pyplot = types.ModuleType("matplotlib.pyplot")
+        sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, mpl.pyplot
+    _install_lib_packages()
+    return importlib.import_module("lib.utils.eval_utils")

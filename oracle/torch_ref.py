@@ -369,3 +369,65 @@ def encoder_from_states(sd, hF, hB, hS):
     b = F.linear(F.relu(torch.cat([hS, hB], dim=1)), _t(sd, "encoder.linear_rec.weight"),
                  _t(sd, "encoder.linear_rec.bias"))
     return (a + b) / 2
+
+
+# --------------------------------------------------------------------------- evaluation metrics (lib/utils/eval_utils.py)
+def procrustes_align(S1: torch.Tensor, S2: torch.Tensor) -> torch.Tensor:
+    """batch_compute_similarity_transform_torch, lib/utils/eval_utils.py:287-337.  S1, S2 [N,J,3] -> S1_hat [N,J,3]
+    (computed in the dtype of the inputs; pass float64 for a tight reference)."""
+    A, B = S1.permute(0, 2, 1), S2.permute(0, 2, 1)
+    mu1, mu2 = A.mean(dim=-1, keepdim=True), B.mean(dim=-1, keepdim=True)
+    X1, X2 = A - mu1, B - mu2
+    var1 = (X1 ** 2).sum(dim=(1, 2))
+    K = X1.bmm(X2.permute(0, 2, 1))
+    U, s, Vh = torch.linalg.svd(K)
+    V = Vh.transpose(1, 2)
+    Z = torch.eye(3, dtype=A.dtype).repeat(A.shape[0], 1, 1)
+    Z[:, -1, -1] *= torch.sign(torch.det(U.bmm(V.permute(0, 2, 1))))
+    R = V.bmm(Z.bmm(U.permute(0, 2, 1)))
+    scale = torch.diagonal(R.bmm(K), dim1=1, dim2=2).sum(-1) / var1
+    t = mu2 - scale[:, None, None] * R.bmm(mu1)
+    return (scale[:, None, None] * R.bmm(A) + t).permute(0, 2, 1)
+
+
+def align_pelvis(j: torch.Tensor, pelvis=(2, 3)) -> torch.Tensor:
+    """evaluate.py:420-428: hip midpoint (2, 3), a single joint (int) or none."""
+    if pelvis is None:
+        return j
+    if isinstance(pelvis, int):
+        return j - j[..., [pelvis], :]
+    return j - (j[..., [pelvis[0]], :] + j[..., [pelvis[1]], :]) / 2.0
+
+
+def pose_metrics(pred: torch.Tensor, target: torch.Tensor, pelvis=(2, 3)) -> dict:
+    """evaluate.py:420-443 for one sequence [N,J,3] (metres)."""
+    P, G = align_pelvis(pred, pelvis), align_pelvis(target, pelvis)
+    mpjpe = torch.sqrt(((P - G) ** 2).sum(-1)).mean(-1)
+    hat = procrustes_align(P, G)
+    pa = torch.sqrt(((hat - G) ** 2).sum(-1)).mean(-1)
+    accel = torch.zeros(P.shape[0], dtype=P.dtype)
+    if P.shape[0] >= 3:
+        accel[1:-1] = accel_error(P, G)
+    return {"mpjpe": mpjpe, "mpjpe_pa": pa, "accel_err": accel, "aligned": hat}
+
+
+def accel_error(pred: torch.Tensor, target=None) -> torch.Tensor:
+    """compute_error_accel_eval (eval_utils.py:110-138, vis=None) on [...,N,J,3] -> [...,N-2]; target None: the norm of
+    pred's own acceleration (compute_accel, :60-63)."""
+    a = pred[..., :-2, :, :] - 2 * pred[..., 1:-1, :, :] + pred[..., 2:, :, :]
+    if target is not None:
+        a = a - (target[..., :-2, :, :] - 2 * target[..., 1:-1, :, :] + target[..., 2:, :, :])
+    return torch.linalg.norm(a, dim=-1).mean(-1)
+
+
+def accel_summary(normed: torch.Tensor, vidlen_each: torch.Tensor, seqlen: int, tail: int, extra: int) -> torch.Tensor:
+    """The reductions of compute_accel (tail 2, extra 1) / compute_error_accel (tail 4, extra 3), eval_utils.py:70-76,104-108."""
+    out = torch.zeros((), dtype=normed.dtype)
+    for i in range(normed.shape[0]):
+        out = out + normed[i, seqlen - 1:int(vidlen_each[i]) - tail].sum()
+    return out / (vidlen_each.sum() - vidlen_each.shape[0] * (seqlen + extra) + 1e-8)
+
+
+def vertex_error(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """compute_error_verts, eval_utils.py:173-175: [N,V,3] x 2 -> [N]."""
+    return torch.sqrt(((a - b) ** 2).sum(dim=2)).mean(dim=1)

@@ -28,6 +28,7 @@ EXPORTS = [
     "tp_pack_whh_bf16", "tp_gru_set_trace", "tp_gru_workspace_bytes", "tp_gru_recurrence",
     "tp_encoder_heads_workspace_bytes", "tp_encoder_heads", "tp_encoder_heads_cat", "tp_ief_workspace_bytes", "tp_ief_forward",
     "tp_smpl_workspace_bytes", "tp_smpl_forward",
+    "tp_pose_metrics", "tp_accel_error", "tp_vertex_error",
 ]
 
 vp, i32, i64, f32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -65,6 +66,9 @@ _SIGNATURES = {
     "tp_batch_rodrigues": (C.c_int, [vp, vp, i64, C.c_int, vp]),
     "tp_projection": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp]),
     "tp_pack_rows": (C.c_int, [vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "tp_pose_metrics": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "tp_accel_error": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "tp_vertex_error": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
     "tp_unpack_rows_residual": (C.c_int, [vp, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "tp_gemm_f32": (C.c_int, [vp, i64, vp, i64, vp, vp, i64, vp, i64, C.c_int, C.c_int, C.c_int, f32, f32, C.c_int, vp]),
     "tp_gemm_f32_splitk_workspace_bytes": (sz, [C.c_int, C.c_int, C.c_int]),

@@ -279,6 +279,39 @@ class FakeLib:
         return 0
 
 
+    # ---- evaluation metrics
+    def tp_pose_metrics(self, pred, target, n, J, p0, p1, aligned, mpjpe, pa, stream):
+        P = _view(pred, n * J * 3, torch.float32).clone().reshape(n, J, 3)
+        G = _view(target, n * J * 3, torch.float32).clone().reshape(n, J, 3)
+        pelvis = None if p0 < 0 else (p0 if p1 < 0 else (p0, p1))
+        m = torch_ref.pose_metrics(P.double(), G.double(), pelvis)
+        for ptr_, key, cnt in ((aligned, "aligned", n * J * 3), (mpjpe, "mpjpe", n), (pa, "mpjpe_pa", n)):
+            v = _view(ptr_, cnt, torch.float32)
+            if v is not None:
+                v.copy_(m[key].float().reshape(-1))
+        self.calls.append(("pose_metrics", n, J, p0, p1))
+        return 0
+
+    def tp_accel_error(self, pred, target, n_seq, ln, J, p0, p1, out, stream):
+        if n_seq == 0 or ln < 3:
+            return 0
+        pelvis = None if p0 < 0 else (p0 if p1 < 0 else (p0, p1))
+        P = torch_ref.align_pelvis(_view(pred, n_seq * ln * J * 3, torch.float32).clone().reshape(n_seq, ln, J, 3).double(), pelvis)
+        G = _view(target, n_seq * ln * J * 3, torch.float32)
+        if G is not None:
+            G = torch_ref.align_pelvis(G.clone().reshape(n_seq, ln, J, 3).double(), pelvis)
+        _view(out, n_seq * (ln - 2), torch.float32).copy_(torch_ref.accel_error(P, G).float().reshape(-1))
+        self.calls.append(("accel_error", n_seq, ln, J))
+        return 0
+
+    def tp_vertex_error(self, a, b, n, V, out, stream):
+        A = _view(a, n * V * 3, torch.float32).clone().reshape(n, V, 3)
+        B = _view(b, n * V * 3, torch.float32).clone().reshape(n, V, 3)
+        _view(out, n, torch.float32).copy_(torch_ref.vertex_error(A, B))
+        self.calls.append(("vertex_error", n, V))
+        return 0
+
+
 class _Patch:
     def __init__(self):
         self.fake = FakeLib()
