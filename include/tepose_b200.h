@@ -239,6 +239,9 @@ typedef struct tp_smpl_model {
    * template_pad: [vp,3] fp32 v_template (zero rows beyond n_verts)                                      */
   const void* blend_tc;
   const float* template_pad;
+  /* blend_km (optional): the same [3*vp, 256] bf16 matrix in plain row-major order, row v*3 + c -- the B operand of the
+   * tcgen05 GEMM that the large-batch path (>= 1024 bodies) runs per chunk of bodies before skinning.     */
+  const void* blend_km;
 } tp_smpl_model;
 
 TP_API size_t tp_smpl_workspace_bytes(const tp_smpl_model* m, int n, int nreg, int blend_mode);

@@ -20,6 +20,7 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 6;
 constexpr int TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK * 2;   // 32 KB
 constexpr int TC_MAX_SEGS = 8;
 constexpr int TC_THREADS = 128;
+constexpr int TC_EPI_PITCH = TC_BN + 4;   // floats per row of the epilogue staging tile (128 x 132 x 4 B = 66 KB of the 192 KB ring)
 
 struct TcParams {
   tp_gemm_seg seg[TC_MAX_SEGS];
@@ -189,33 +190,40 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // ===== epilogue: all four warps, warp w owns TMEM lanes 32w..32w+31 =====
   mbar_wait(tmem_full_bar, 0);
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const int row = m0 + warp * 32 + lane;                 // segment-local output row
-  const bool row_ok = row < sg.m_rows;
-  float* out_row = sg.out + (int64_t)row * sg.ldc;
-  const bool vec_ok = ((sg.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(sg.out) & 15) == 0);
+  // Accumulator rows live one per thread (TMEM lane), but a row-per-thread global store touches 32 different
+  // cache lines per instruction.  The ring stages are idle now (every MMA has completed), so the tile is
+  // transposed through them: thread = row writes its 128 values (pitch 132 floats: conflict-free 16-byte
+  // accesses), then each warp streams ITS 32 rows out with one fully coalesced 512-byte store per row.
+  float* stage = reinterpret_cast<float*>(smem) + (size_t)(warp * 32) * TC_EPI_PITCH;
 #pragma unroll 1
   for (int c0 = 0; c0 < TC_BN; c0 += 32) {
     uint32_t v[32];
     tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-    if (row_ok) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int n = n0 + c0 + q * 4;
-        if (n >= sg.n_cols) break;
-        float4 o;
-        o.x = __uint_as_float(v[q * 4 + 0]); o.y = __uint_as_float(v[q * 4 + 1]);
-        o.z = __uint_as_float(v[q * 4 + 2]); o.w = __uint_as_float(v[q * 4 + 3]);
-        const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + q * 4]);
-        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-        if (n + 3 < sg.n_cols && vec_ok) {
-          *reinterpret_cast<float4*>(out_row + n) = o;
-        } else {
-          const float e[4] = {o.x, o.y, o.z, o.w};
-          for (int i = 0; i < 4; ++i)
-            if (n + i < sg.n_cols) out_row[n + i] = e[i];
-        }
-      }
+    for (int q = 0; q < 8; ++q) {
+      const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + q * 4]);
+      float4 o;
+      o.x = __uint_as_float(v[q * 4 + 0]) + bb.x; o.y = __uint_as_float(v[q * 4 + 1]) + bb.y;
+      o.z = __uint_as_float(v[q * 4 + 2]) + bb.z; o.w = __uint_as_float(v[q * 4 + 3]) + bb.w;
+      *reinterpret_cast<float4*>(stage + (size_t)lane * TC_EPI_PITCH + c0 + q * 4) = o;
+    }
+  }
+  __syncwarp();
+  const bool vec_ok = ((sg.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(sg.out) & 15) == 0);
+  const int n = n0 + lane * 4;
+#pragma unroll 4
+  for (int r = 0; r < 32; ++r) {
+    const int row = m0 + warp * 32 + r;                  // segment-local output row
+    if (row >= sg.m_rows) break;
+    const float4 o = *reinterpret_cast<const float4*>(stage + (size_t)r * TC_EPI_PITCH + lane * 4);
+    float* dst = sg.out + (int64_t)row * sg.ldc + n;
+    if (n + 3 < sg.n_cols && vec_ok) {
+      *reinterpret_cast<float4*>(dst) = o;
+    } else {
+      const float e[4] = {o.x, o.y, o.z, o.w};
+      for (int i = 0; i < 4; ++i)
+        if (n + i < sg.n_cols) dst[i] = e[i];
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");

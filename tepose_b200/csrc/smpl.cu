@@ -337,11 +337,12 @@ constexpr int kTcNB = 32;                    // bodies per group
 constexpr int kTcK = 256;
 constexpr int kTcCsPitch = kTcK + 32;        // bf16 elements per coefficient row (conflict-free 16-byte reads)
 constexpr int kTcAStride = kJ * 12 + 4;      // floats per body in A_s
-constexpr int kTcJtPitch = kTcVT + 1;
+constexpr int kTcJtPitch = kTcVT + 4;     // 16-byte aligned rows: the regressor loop reads float4 (broadcast)
+constexpr int kTcVoPitch = kTcVT * 3 + 4;  // floats per body in vout: 196 = 4 (mod 32) -> conflict-free float4 reads with lane = body
 constexpr size_t kTcSmW = 12 * 8 * 1024;
 constexpr size_t kTcSmC = (size_t)kTcNB * kTcCsPitch * 2;
 constexpr size_t kTcSmA = (size_t)kTcNB * kTcAStride * 4;
-constexpr size_t kTcSmV = (size_t)kTcNB * kTcVT * 3 * 4;
+constexpr size_t kTcSmV = (size_t)kTcNB * kTcVoPitch * 4;
 constexpr size_t kTcSmJ = (size_t)kMaxReg * kTcJtPitch * 4;
 constexpr size_t kTcSmem = kTcSmW + kTcSmC + kTcSmA + kTcSmV + kTcSmJ;
 
@@ -448,7 +449,7 @@ k_smpl_verts_tc(const tp_smpl_model m, int n, const __nv_bfloat16* __restrict__ 
         }
         const int vloc = st * 16 + g + 8 * x;
         const bool vvalid = (v0 + vloc) < m.n_verts;
-        float* o = vout + ((size_t)bl * kTcVT + vloc) * 3;
+        float* o = vout + (size_t)bl * kTcVoPitch + vloc * 3;
         o[0] = vvalid ? (T[0] * px + T[1] * py + T[2] * pz + T[3]) : 0.0f;
         o[1] = vvalid ? (T[4] * px + T[5] * py + T[6] * pz + T[7]) : 0.0f;
         o[2] = vvalid ? (T[8] * px + T[9] * py + T[10] * pz + T[11]) : 0.0f;
@@ -461,28 +462,192 @@ k_smpl_verts_tc(const tp_smpl_model m, int n, const __nv_bfloat16* __restrict__ 
       for (int i = tid; i < kTcNB * (kTcVT * 3 / 2); i += 256) {
         const int b = i / (kTcVT * 3 / 2), q = i - b * (kTcVT * 3 / 2);
         if (body0 + b >= n) continue;
-        const float2 v = *reinterpret_cast<const float2*>(vout + (size_t)b * kTcVT * 3 + q * 2);
+        const float2 v = *reinterpret_cast<const float2*>(vout + (size_t)b * kTcVoPitch + q * 2);
         float* dst = verts + (int64_t)(body0 + b) * nv3 + base + q * 2;
         if (base + q * 2 + 1 < nv3) *reinterpret_cast<float2*>(dst) = v;
         else if (base + q * 2 < nv3) dst[0] = v.x;
       }
     }
-    if (lane < nreg) {
-#pragma unroll
-      for (int bi = 0; bi < kTcNB / 8; ++bi) {
-        const int b = warp * (kTcNB / 8) + bi;
-        if (body0 + b >= n) continue;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        const float* vb = vout + (size_t)b * kTcVT * 3;
-        const float* jr = Jt + lane * kTcJtPitch;
-#pragma unroll 8
-        for (int v = 0; v < kTcVT; ++v) {
-          const float w = jr[v];
-          s0 = fmaf(w, vb[3 * v], s0); s1 = fmaf(w, vb[3 * v + 1], s1); s2 = fmaf(w, vb[3 * v + 2], s2);
-        }
-        float* dst = jpart + (((int64_t)(body0 + b) * ntiles + tile) * nreg + lane) * 3;
+    // joint regressors: lane = body, each warp takes every 8th regressor row; the weights are a broadcast float4,
+    // the body's vertices a conflict-free float4 (body pitch 196 floats) -- every shared-memory wavefront is full
+    for (int r = warp; r < nreg; r += 8) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+      const float4* jr = reinterpret_cast<const float4*>(Jt + r * kTcJtPitch);
+      const float4* vb = reinterpret_cast<const float4*>(vout + (size_t)lane * kTcVoPitch);
+#pragma unroll 4
+      for (int v4 = 0; v4 < kTcVT / 4; ++v4) {
+        const float4 w = jr[v4];
+        const float4 p0 = vb[3 * v4], p1 = vb[3 * v4 + 1], p2 = vb[3 * v4 + 2];      // x0 y0 z0 x1 | y1 z1 x2 y2 | z2 x3 y3 z3
+        s0 = fmaf(w.x, p0.x, s0); s1 = fmaf(w.x, p0.y, s1); s2 = fmaf(w.x, p0.z, s2);
+        s0 = fmaf(w.y, p0.w, s0); s1 = fmaf(w.y, p1.x, s1); s2 = fmaf(w.y, p1.y, s2);
+        s0 = fmaf(w.z, p1.z, s0); s1 = fmaf(w.z, p1.w, s1); s2 = fmaf(w.z, p2.x, s2);
+        s0 = fmaf(w.w, p2.y, s0); s1 = fmaf(w.w, p2.z, s1); s2 = fmaf(w.w, p2.w, s2);
+      }
+      if (body0 + lane < n) {
+        float* dst = jpart + (((int64_t)(body0 + lane) * ntiles + tile) * nreg + r) * 3;
         dst[0] = s0; dst[1] = s1; dst[2] = s2;
       }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Large-batch path (config 4: SMPL standalone at 10^4..10^5 bodies).  The blend contraction
+// [bodies, 256] x [256, 3 vp] runs as a tcgen05 GEMM (tp_gemm_bf16_tc, template as the bias) over a CHUNK of
+// bodies whose fp32 result (<= 64 MB) stays L2-resident, and this kernel skins it straight out of L2:
+// thread = vertex, bodies looped.  All 32 lanes of a warp work on the SAME body, so the per-vertex gathers of the
+// joint transforms hit distinct banks for distinct joints (row pitch 13) or broadcast -- 1.5 wavefronts per
+// (vertex, body), the minimum for 4 x 48 bytes.  Vertices are written once, coalesced; the joint regressors are
+// applied to the tile while it is in shared memory (lane = body, every regressor row per pass).
+constexpr int kSkVT = 128;                         // vertices per CTA
+constexpr int kSkGB = 16;                          // bodies per stage
+constexpr int kSkAPitch = 13;                      // floats per joint row: bank (13 j + q) mod 32 is distinct for distinct joints (scalar loads);
+                                                   // measured: pitch 14 + 8-byte loads has 42 % conflict wavefronts and costs a CTA per SM
+constexpr int kSkABody = kJ * kSkAPitch;           // floats per body in A_s
+constexpr int kSkVoPitch = kSkVT * 3 + 4;          // floats per body in vout (388 = 4 mod 32)
+constexpr int kSkJtPitch = kSkVT + 4;
+constexpr int kSkRC = 9;                           // regressor rows per accumulation pass
+constexpr size_t kSkSmA = (size_t)2 * kSkGB * kSkABody * 4;
+constexpr size_t kSkSmV = (size_t)kSkGB * kSkVoPitch * 4;
+constexpr size_t kSkSmR = (size_t)4 * kSkRC * 3 * kSkGB * 4;
+static size_t skin_smem(int nreg) { return kSkSmA + kSkSmV + kSkSmR + (size_t)(nreg > 0 ? nreg : 1) * kSkJtPitch * 4; }
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
+}
+
+__global__ void __launch_bounds__(kSkVT, 3)
+k_smpl_skin(const tp_smpl_model m, int body_lo, int body_hi, int bodies_per_cta, const float* __restrict__ vposed, int64_t ldv,
+            const float* __restrict__ A, const float* __restrict__ jreg, int nreg, float* __restrict__ verts,
+            float* __restrict__ jpart, int ntiles) {
+  extern __shared__ __align__(16) unsigned char ssm[];
+  float* A_s = reinterpret_cast<float*>(ssm);                                   // [2][GB][24*13]
+  float* vout = reinterpret_cast<float*>(ssm + kSkSmA);                         // [GB][388]
+  float* red = reinterpret_cast<float*>(ssm + kSkSmA + kSkSmV);                 // [4][RC*3][GB]
+  float* Jt = reinterpret_cast<float*>(ssm + kSkSmA + kSkSmV + kSkSmR);         // [nreg][132]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, v0 = tile * kSkVT, v = v0 + tid;
+  const int b_lo = body_lo + blockIdx.y * bodies_per_cta, b_hi = min(body_hi, b_lo + bodies_per_cta);
+  if (b_lo >= b_hi) return;
+  for (int i = tid; i < nreg * kSkVT; i += kSkVT) {
+    const int r = i / kSkVT, vv = i - r * kSkVT;
+    Jt[r * kSkJtPitch + vv] = jreg[(int64_t)r * m.vp + v0 + vv];
+  }
+  int sj[4]; float sw[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    sj[k] = k < m.ks ? m.skin_idx[(int64_t)v * m.ks + k] * kSkAPitch : 0;
+    sw[k] = k < m.ks ? m.skin_w[(int64_t)v * m.ks + k] : 0.0f;
+  }
+  const bool vvalid = v < m.n_verts;
+  const int nstage = (b_hi - b_lo + kSkGB - 1) / kSkGB;
+  auto load_A = [&](int stage) {            // joint transforms of one stage: [GB][24][12] -> row pitch 13, 4-byte async copies
+    float* dst = A_s + (size_t)(stage & 1) * kSkGB * kSkABody;
+    const int bb0 = b_lo + stage * kSkGB;
+    int b = 0, r = tid;                     // r = element index inside a body (24 x 12 = 288)
+#pragma unroll 4
+    for (int it = 0; it < kSkGB * kJ * 12 / kSkVT; ++it) {
+      if (r >= kJ * 12) { r -= kJ * 12; ++b; }
+      const int j = (r * 171) >> 11, q = r - j * 12;             // r / 12 for r < 288
+      const bool ok = bb0 + b < b_hi;
+      cp_async4(dst + b * kSkABody + j * kSkAPitch + q, A + ((int64_t)(ok ? bb0 + b : b_lo) * kJ * 12 + r), ok);
+      r += kSkVT;
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  load_A(0);
+  if (nstage > 1) load_A(1); else asm volatile("cp.async.commit_group;\n" ::);
+  for (int s = 0; s < nstage; ++s) {
+    const int bb0 = b_lo + s * kSkGB;
+    const int nb = min(kSkGB, b_hi - bb0);
+    // blended rest-pose vertices of this stage (L2-resident GEMM output), all loads in flight before A is needed
+    float px[kSkGB], py[kSkGB], pz[kSkGB];
+#pragma unroll
+    for (int b = 0; b < kSkGB; ++b) {
+      px[b] = py[b] = pz[b] = 0.0f;
+      if (b < nb) {
+        const float* src = vposed + (int64_t)(bb0 + b - body_lo) * ldv + (int64_t)v * 3;
+        px[b] = __ldcg(src); py[b] = __ldcg(src + 1); pz[b] = __ldcg(src + 2);
+      }
+    }
+    asm volatile("cp.async.wait_group 1;\n" ::);
+    __syncthreads();
+    const float* As = A_s + (size_t)(s & 1) * kSkGB * kSkABody;
+#pragma unroll
+    for (int b = 0; b < kSkGB; ++b) {
+      float T[12];
+#pragma unroll
+      for (int q = 0; q < 12; ++q) T[q] = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float* Aj = As + b * kSkABody + sj[k];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) T[q] = fmaf(sw[k], Aj[q], T[q]);
+      }
+      float* o = vout + b * kSkVoPitch + tid * 3;
+      o[0] = vvalid ? (T[0] * px[b] + T[1] * py[b] + T[2] * pz[b] + T[3]) : 0.0f;
+      o[1] = vvalid ? (T[4] * px[b] + T[5] * py[b] + T[6] * pz[b] + T[7]) : 0.0f;
+      o[2] = vvalid ? (T[8] * px[b] + T[9] * py[b] + T[10] * pz[b] + T[11]) : 0.0f;
+    }
+    __syncthreads();
+    if (s + 2 < nstage) load_A(s + 2); else asm volatile("cp.async.commit_group;\n" ::);
+    // coalesced vertex store: 1536 contiguous bytes per body, one warp per body
+    if (verts) {
+      const int64_t nv3 = (int64_t)m.n_verts * 3, base = (int64_t)v0 * 3;
+      for (int b = warp; b < nb; b += 4) {
+        const float2* src = reinterpret_cast<const float2*>(vout + b * kSkVoPitch);
+        float* dstb = verts + (int64_t)(bb0 + b) * nv3 + base;
+#pragma unroll
+        for (int k = 0; k < kSkVT * 3 / 64; ++k) {
+          const int q = lane + 32 * k;
+          const float2 val = src[q];
+          if (base + q * 2 + 1 < nv3) *reinterpret_cast<float2*>(dstb + q * 2) = val;
+          else if (base + q * 2 < nv3) dstb[q * 2] = val.x;
+        }
+      }
+    }
+    // joint regressors: lane = (body, vertex half); a warp's 32 vertices are read once per pass of kSkRC rows
+    for (int r0 = 0; r0 < nreg; r0 += kSkRC) {
+      const int bl = lane & 15, vh = lane >> 4;
+      float acc[kSkRC][3];
+#pragma unroll
+      for (int rr = 0; rr < kSkRC; ++rr) acc[rr][0] = acc[rr][1] = acc[rr][2] = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int v4 = warp * 8 + vh * 4 + i;
+        const float4* vb = reinterpret_cast<const float4*>(vout + bl * kSkVoPitch + v4 * 12);
+        const float4 p0 = vb[0], p1 = vb[1], p2 = vb[2];                        // x0 y0 z0 x1 | y1 z1 x2 y2 | z2 x3 y3 z3
+#pragma unroll
+        for (int rr = 0; rr < kSkRC; ++rr) {
+          if (r0 + rr < nreg) {
+            const float4 w = *reinterpret_cast<const float4*>(Jt + (r0 + rr) * kSkJtPitch + v4 * 4);
+            acc[rr][0] = fmaf(w.x, p0.x, acc[rr][0]); acc[rr][1] = fmaf(w.x, p0.y, acc[rr][1]); acc[rr][2] = fmaf(w.x, p0.z, acc[rr][2]);
+            acc[rr][0] = fmaf(w.y, p0.w, acc[rr][0]); acc[rr][1] = fmaf(w.y, p1.x, acc[rr][1]); acc[rr][2] = fmaf(w.y, p1.y, acc[rr][2]);
+            acc[rr][0] = fmaf(w.z, p1.z, acc[rr][0]); acc[rr][1] = fmaf(w.z, p1.w, acc[rr][1]); acc[rr][2] = fmaf(w.z, p2.x, acc[rr][2]);
+            acc[rr][0] = fmaf(w.w, p2.y, acc[rr][0]); acc[rr][1] = fmaf(w.w, p2.z, acc[rr][1]); acc[rr][2] = fmaf(w.w, p2.w, acc[rr][2]);
+          }
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < kSkRC; ++rr)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float t = acc[rr][c] + __shfl_xor_sync(0xffffffffu, acc[rr][c], 16);
+          if (vh == 0) red[(warp * kSkRC * 3 + rr * 3 + c) * kSkGB + bl] = t;
+        }
+      __syncthreads();
+      for (int i = tid; i < kSkRC * 3 * kSkGB; i += kSkVT) {
+        const int rc = i / kSkGB, b = i - rc * kSkGB, rr = rc / 3, c = rc - rr * 3;
+        if (r0 + rr < nreg && b < nb) {
+          const float t = (red[(0 * kSkRC * 3 + rc) * kSkGB + b] + red[(1 * kSkRC * 3 + rc) * kSkGB + b]) +
+                          (red[(2 * kSkRC * 3 + rc) * kSkGB + b] + red[(3 * kSkRC * 3 + rc) * kSkGB + b]);
+          jpart[(((int64_t)(bb0 + b) * ntiles + tile) * nreg + r0 + rr) * 3 + c] = t;
+        }
+      }
+      __syncthreads();
     }
     __syncthreads();
   }
@@ -535,8 +700,12 @@ __global__ void __launch_bounds__(128) k_smpl_finalize(int n, int n_verts, const
 
 static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
-struct SmplPlan { int ntiles, nsplit, tiles_per_split, ngroups; size_t off_A, off_J, off_coef, off_part, off_ctc, total;
-                  int tc, tc_tiles, tc_gsplit, tc_gpc; };
+struct SmplPlan { int ntiles, nsplit, tiles_per_split, ngroups; size_t off_A, off_J, off_coef, off_part, off_ctc, off_vposed, total;
+                  int tc, tc_tiles, tc_gsplit, tc_gpc, split, chunk; };
+
+// large-batch path: from this many bodies on, GEMM + skin over L2-resident chunks replaces the fused kernel
+static int split_min_bodies() { static const int v = getenv("TP_SMPL_SPLIT_MIN") ? atoi(getenv("TP_SMPL_SPLIT_MIN")) : 1024; return v; }
+static int split_chunk_bodies() { static const int v = getenv("TP_SMPL_CHUNK") ? atoi(getenv("TP_SMPL_CHUNK")) : 512; return v < 16 ? 16 : v; }
 
 static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg, int blend_mode) {
   SmplPlan p;
@@ -572,6 +741,9 @@ static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg, int blend_mod
   const int part_tiles = p.tc ? p.tc_tiles : p.nsplit;
   p.off_part = o; o += al256((size_t)n * part_tiles * (nreg > 0 ? nreg : 1) * 3 * 4);
   p.off_ctc = o; o += p.tc ? al256((size_t)n * kTcK * 2) : 0;
+  p.split = (p.tc && m->blend_km && m->vp % kSkVT == 0 && n >= split_min_bodies()) ? 1 : 0;
+  p.chunk = split_chunk_bodies() < n ? split_chunk_bodies() : n;
+  p.off_vposed = o; o += p.split ? al256((size_t)p.chunk * m->vp * 3 * 4) : 0;
   p.total = o;
   return p;
 }
@@ -621,7 +793,30 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
   k_smpl_prepare<<<(unsigned)ceil_div(n, 4), 128, 0, st>>>(*m, n, pa);
   TP_LAUNCH_CHECK();
   const bool need_verts_pass = verts != nullptr || nreg > 0;
-  if (need_verts_pass && pl.tc) {
+  if (need_verts_pass && pl.split) {
+    // chunks of bodies: tcgen05 GEMM (blend + template) into an L2-resident scratch, then the skinning kernel
+    float* vposed = reinterpret_cast<float*>(ws + pl.off_vposed);
+    const int64_t ldv = (int64_t)m->vp * 3;
+    const size_t smem = skin_smem(nreg);
+    TP_CUDA(cudaFuncSetAttribute(k_smpl_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int vt = m->vp / kSkVT, slots = 3 * sm_count();
+    for (int c0 = 0; c0 < n; c0 += pl.chunk) {
+      const int cb = n - c0 < pl.chunk ? n - c0 : pl.chunk;
+      tp_gemm_seg sg;
+      sg.m_start = c0; sg.m_rows = cb; sg.n_start = 0; sg.n_cols = m->vp * 3;
+      sg.out = vposed; sg.ldc = ldv; sg.bias = m->template_pad;
+      int rc = tp_gemm_bf16_tc(pa.coef_tc, n, m->blend_km, m->vp * 3, kTcK, &sg, 1, stream);
+      if (rc != TP_OK) return rc;
+      int splits = slots / vt;                                 // one wave of 3 CTAs per SM
+      const int stages = (cb + kSkGB - 1) / kSkGB;
+      if (splits > stages) splits = stages;
+      if (splits < 1) splits = 1;
+      const int bpc = ((stages + splits - 1) / splits) * kSkGB;
+      dim3 grid((unsigned)vt, (unsigned)((cb + bpc - 1) / bpc));
+      k_smpl_skin<<<grid, kSkVT, smem, st>>>(*m, c0, c0 + cb, bpc, vposed, ldv, pa.A, jreg, nreg, verts, jpart, vt);
+      TP_LAUNCH_CHECK();
+    }
+  } else if (need_verts_pass && pl.tc) {
     TP_CUDA(cudaFuncSetAttribute(k_smpl_verts_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
     dim3 grid((unsigned)pl.tc_tiles, (unsigned)pl.tc_gsplit);
     k_smpl_verts_tc<<<grid, 256, kTcSmem, st>>>(*m, n, pa.coef_tc, pa.A, jreg, nreg, verts, jpart, pl.tc_tiles, pl.tc_gpc);
@@ -636,7 +831,7 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
   }
   if (nj > 0 && (joints || kp2d)) {
     TP_CHECK_ARG(verts != nullptr, "tp_smpl_forward: verts is required when joints are requested (vertex picks read it)");
-    k_smpl_finalize<<<(unsigned)n, 128, 0, st>>>(n, m->n_verts, pa.posedJ, jpart, pl.tc ? pl.tc_tiles : pl.nsplit, nreg, verts, joint_src,
+    k_smpl_finalize<<<(unsigned)n, 128, 0, st>>>(n, m->n_verts, pa.posedJ, jpart, pl.split ? m->vp / kSkVT : (pl.tc ? pl.tc_tiles : pl.nsplit), nreg, verts, joint_src,
                                                 nj, cam, ld_cam, joints, kp2d);
     TP_LAUNCH_CHECK();
   }

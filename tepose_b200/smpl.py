@@ -146,7 +146,7 @@ class PackedSmpl:
         self.skin_w[:V] = wsel
         self.device = device
         # tensor-core blend tables (bf16 mode): [3*vp, 256] rows ((v//16)*3 + c)*16 + v%16
-        self.blend_tc = self.template_pad = None
+        self.blend_tc = self.template_pad = self.blend_km = None
         if ks <= 4:
             S = shapedirs.detach().to(device).float()[:, :, :10]                       # [V,3,10]
             S_hi = S.to(torch.bfloat16).float()
@@ -159,11 +159,12 @@ class PackedSmpl:
             self.blend_tc = torch.empty(nv.lib().tp_pack_mma_a_bytes(vp * 3, 256), dtype=torch.uint8, device=device)
             nv.check(nv.lib().tp_pack_mma_a_bf16(nv.ptr(rows), 256, vp * 3, 256, nv.ptr(self.blend_tc), nv.stream()),
                      "tp_pack_mma_a_bf16")
+            self.blend_km = cols.reshape(vp * 3, 256).to(torch.bfloat16).contiguous()        # row v*3 + c (tcgen05 GEMM operand)
             self.template_pad = torch.zeros(vp, 3, device=device, dtype=torch.float32)
             self.template_pad[:V] = v_template.detach().to(device).float()
         self.c_model = nv.SmplModel(nv.ptr(self.blend), nv.ptr(self.j_template), nv.ptr(self.j_shapedirs),
                                     nv.ptr(self.parents), nv.ptr(self.skin_idx), nv.ptr(self.skin_w),
-                                    ks, V, vp, nv.ptr(self.blend_tc), nv.ptr(self.template_pad))
+                                    ks, V, vp, nv.ptr(self.blend_tc), nv.ptr(self.template_pad), nv.ptr(self.blend_km))
 
 
 def smpl_forward_native(packed: PackedSmpl, pose: torch.Tensor, ld_pose: int, pose_kind: int,

@@ -346,3 +346,28 @@ def test_smpl_size_independent_properties_large_batch():
     Rg = torch_ref.batch_rodrigues_smplx(torch.tensor([[0.3, -0.5, 0.2]]))[0].to(DEV)
     root = torch.einsum("bik,i->bk", v_shaped, m.J_regressor[0].to(DEV))[:, None]
     assert float((out1.vertices - ((out0.vertices - root) @ Rg.t() + root)).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("n", [1024, 1500])
+def test_smpl_large_batch_split_path(n):
+    """>= 1024 bodies in bf16 blend mode: tcgen05 blend GEMM over L2-resident chunks + the skinning kernel.  Checked
+    against the oracle on a sample of bodies and against the fused kernel (same bf16 operands) on all of them."""
+    with base_data_cwd(10):
+        smpl = tepose_b200.SMPL(tepose_b200.SMPL_MODEL_DIR, batch_size=1, create_transl=False).to(DEV)
+    smpl.blend_precision = "bf16"
+    m = torch_ref.SmplModel.synthetic(10)
+    bodies = synth.make_bodies(10, n)
+    aa, betas = torch.from_numpy(bodies["pose_aa"]), torch.from_numpy(bodies["betas"])
+    out = smpl(betas=cu(betas), body_pose=cu(aa[:, 3:]), global_orient=cu(aa[:, :3]), pose2rot=True)
+    pick = torch.tensor([0, 1, 15, 16, 511, 512, 513, 1023, n - 1])
+    v_ref, j_ref, _ = torch_ref.smpl_forward(m, betas[pick], pose_aa=aa[pick])
+    ev = float((out.vertices.cpu()[pick] - v_ref).abs().max())
+    ej = float((out.joints.cpu()[pick] - j_ref).abs().max())
+    assert ev < 1e-4 and ej < 1e-4, (ev, ej)
+    # the fused kernel on sub-batches below the threshold: same operands, fp32 summation order differs only
+    fv, fj = [], []
+    for lo in range(0, n, 512):
+        o = smpl(betas=cu(betas[lo:lo + 512]), body_pose=cu(aa[lo:lo + 512, 3:]), global_orient=cu(aa[lo:lo + 512, :3]), pose2rot=True)
+        fv.append(o.vertices); fj.append(o.joints)
+    assert float((out.vertices - torch.cat(fv)).abs().max()) < 2e-5
+    assert float((out.joints - torch.cat(fj)).abs().max()) < 2e-5
