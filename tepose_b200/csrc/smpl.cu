@@ -495,13 +495,16 @@ k_smpl_verts_tc(const tp_smpl_model m, int n, const __nv_bfloat16* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // Large-batch path (config 4: SMPL standalone at 10^4..10^5 bodies).  The blend contraction
 // [bodies, 256] x [256, 3 vp] runs as a tcgen05 GEMM (tp_gemm_bf16_tc, template as the bias) over a CHUNK of
-// bodies whose fp32 result (<= 64 MB) stays L2-resident, and this kernel skins it straight out of L2:
+// bodies whose fp32 result (85 MB per 1024 bodies) is consumed while most of it is still in L2, and this kernel skins it straight out of L2:
 // thread = vertex, bodies looped.  All 32 lanes of a warp work on the SAME body, so the per-vertex gathers of the
 // joint transforms hit distinct banks for distinct joints (row pitch 13) or broadcast -- 1.5 wavefronts per
 // (vertex, body), the minimum for 4 x 48 bytes.  Vertices are written once, coalesced; the joint regressors are
 // applied to the tile while it is in shared memory (lane = body, every regressor row per pass).
 constexpr int kSkVT = 128;                         // vertices per CTA
-constexpr int kSkGB = 16;                          // bodies per stage
+#ifndef TP_SK_GB
+#define TP_SK_GB 16
+#endif
+constexpr int kSkGB = TP_SK_GB;                    // bodies per stage (8 or 16)
 constexpr int kSkAPitch = 13;                      // floats per joint row: bank (13 j + q) mod 32 is distinct for distinct joints (scalar loads);
                                                    // measured: pitch 14 + 8-byte loads has 42 % conflict wavefronts and costs a CTA per SM
 constexpr int kSkABody = kJ * kSkAPitch;           // floats per body in A_s
@@ -519,7 +522,7 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem, bool val
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
 }
 
-__global__ void __launch_bounds__(kSkVT, 3)
+__global__ void __launch_bounds__(kSkVT, kSkGB == 8 ? 4 : 3)
 k_smpl_skin(const tp_smpl_model m, int body_lo, int body_hi, int bodies_per_cta, const float* __restrict__ vposed, int64_t ldv,
             const float* __restrict__ A, const float* __restrict__ jreg, int nreg, float* __restrict__ verts,
             float* __restrict__ jpart, int ntiles) {
@@ -611,13 +614,14 @@ k_smpl_skin(const tp_smpl_model m, int body_lo, int body_hi, int bodies_per_cta,
     }
     // joint regressors: lane = (body, vertex half); a warp's 32 vertices are read once per pass of kSkRC rows
     for (int r0 = 0; r0 < nreg; r0 += kSkRC) {
-      const int bl = lane & 15, vh = lane >> 4;
+      constexpr int LPB = 32 / kSkGB;                       // lanes per body: each takes 8 / LPB of the warp's 8 vertex quads
+      const int bl = lane % kSkGB, vh = lane / kSkGB;
       float acc[kSkRC][3];
 #pragma unroll
       for (int rr = 0; rr < kSkRC; ++rr) acc[rr][0] = acc[rr][1] = acc[rr][2] = 0.0f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int v4 = warp * 8 + vh * 4 + i;
+      for (int i = 0; i < 8 / LPB; ++i) {
+        const int v4 = warp * 8 + vh * (8 / LPB) + i;
         const float4* vb = reinterpret_cast<const float4*>(vout + bl * kSkVoPitch + v4 * 12);
         const float4 p0 = vb[0], p1 = vb[1], p2 = vb[2];                        // x0 y0 z0 x1 | y1 z1 x2 y2 | z2 x3 y3 z3
 #pragma unroll
@@ -635,7 +639,9 @@ k_smpl_skin(const tp_smpl_model m, int body_lo, int body_hi, int bodies_per_cta,
       for (int rr = 0; rr < kSkRC; ++rr)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float t = acc[rr][c] + __shfl_xor_sync(0xffffffffu, acc[rr][c], 16);
+          float t = acc[rr][c];
+#pragma unroll
+          for (int o = kSkGB; o < 32; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
           if (vh == 0) red[(warp * kSkRC * 3 + rr * 3 + c) * kSkGB + bl] = t;
         }
       __syncthreads();
@@ -705,7 +711,7 @@ struct SmplPlan { int ntiles, nsplit, tiles_per_split, ngroups; size_t off_A, of
 
 // large-batch path: from this many bodies on, GEMM + skin over L2-resident chunks replaces the fused kernel
 static int split_min_bodies() { static const int v = getenv("TP_SMPL_SPLIT_MIN") ? atoi(getenv("TP_SMPL_SPLIT_MIN")) : 1024; return v; }
-static int split_chunk_bodies() { static const int v = getenv("TP_SMPL_CHUNK") ? atoi(getenv("TP_SMPL_CHUNK")) : 512; return v < 16 ? 16 : v; }
+static int split_chunk_bodies() { static const int v = getenv("TP_SMPL_CHUNK") ? atoi(getenv("TP_SMPL_CHUNK")) : 1024; return v < 16 ? 16 : v; }
 
 static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg, int blend_mode) {
   SmplPlan p;
@@ -799,7 +805,9 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
     const int64_t ldv = (int64_t)m->vp * 3;
     const size_t smem = skin_smem(nreg);
     TP_CUDA(cudaFuncSetAttribute(k_smpl_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int vt = m->vp / kSkVT, slots = 3 * sm_count();
+    int per_sm = 1;
+    TP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_smpl_skin, kSkVT, smem));
+    const int vt = m->vp / kSkVT, slots = (per_sm > 0 ? per_sm : 1) * sm_count();
     for (int c0 = 0; c0 < n; c0 += pl.chunk) {
       const int cb = n - c0 < pl.chunk ? n - c0 : pl.chunk;
       tp_gemm_seg sg;
