@@ -218,6 +218,14 @@ TP_API int tp_ief_forward(int precision, const tp_ief_weights* w, const float* f
                    const void* feat_bf16 /* optional bf16 copy of feat (bf16 precision) */, int n_rows, const float* init,
                    int init_rows, int n_iter, float* psc, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Eval-mode heads + IEF as ONE persistent kernel (bf16 operands, n_rows <= 32): tp_encoder_heads_cat's GEMM becomes the
+ * leading layers of the fused IEF kernel (lib/models/tepose.py:79-85 + lib/models/spin.py:250-261).  w_cat / b_cat as for
+ * tp_encoder_heads_cat (packed bf16), h_cat [n_rows, 3H] fp32 (row stride ld_h); workspace: tp_ief_workspace_bytes.   */
+TP_API int tp_heads_ief_forward(const void* w_cat, const float* b_cat, const float* h_cat, int64_t ld_h, int H,
+                         const tp_ief_weights* w, int n_rows, const float* init, int init_rows, int n_iter, float* psc,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+
 /* ------------------------------------------------------------------ SMPL forward (K4 + K5)
  * Packed, device-resident body-model constants (built once by the host, see
  * tepose_b200/smpl.py:pack_smpl_model).                                                    */

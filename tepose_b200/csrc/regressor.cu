@@ -116,12 +116,13 @@ extern "C" int tp_encoder_heads(int precision, const void* w_fwd, const float* b
 // activation block of a layer (kIefRep > 1 would give groups of CTAs their own copy).
 namespace tp {
 
-constexpr int kIefMaxLayers = 12;
+constexpr int kIefMaxLayers = 16;
 constexpr int kIefRep = 1;        // replicas of every inter-layer activation block; >1 spreads the 64 reader CTAs over
                                   // copies (measured: no gain -- the staging phase was bound by constant-cache misses, not L2)
 struct IefLayer {
   const __nv_bfloat16* A; int lda; int K; int rep_in;     // rep_in: element stride between input replicas (0 = single copy)
-  const uint4* Wp; int N;
+  const uint4* Wp; int N; int wkb;                        // wkb: 32-column blocks per 16-row tile of the packed matrix (tile stride)
+  int local_next;                                         // 1: the next layer only consumes what THIS CTA (and thread) wrote -> no grid barrier
   const float* bias; const float* Cin; int ldcin;
   float* C; int ldc; __nv_bfloat16* Clp; int ldclp; int rep_out;   // Clp is written kIefRep times, rep_out elements apart
 };
@@ -131,6 +132,7 @@ struct IefFusedParams {
   unsigned int* barrier;
   const float* feat; const __nv_bfloat16* feat_lp; __nv_bfloat16* feat_cvt;   // feat_cvt: kIefRep bf16 replicas of feat
   const float* init; int init_rows; float* psc; __nv_bfloat16* psc_lp;
+  const float* hcat; int64_t ld_h; int KH; __nv_bfloat16* hcat_cvt;   // fused heads: relu(h_cat [M,KH]) -> bf16 in the prologue
   long long* trace;   // debug: [grid][layers][4] clock stamps
 };
 #define IEF_TRACE(slot) do { if (p.trace && threadIdx.x == 0) p.trace[((size_t)blockIdx.x * kIefMaxLayers + l) * 8 + (slot)] = clock64(); } while (0)
@@ -156,7 +158,14 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
 #pragma unroll
     for (int r = 0; r < kIefRep; ++r) p.psc_lp[(size_t)r * p.M * 160 + i] = __float2bfloat16_rn(v);
   }
+  // fused heads: the encoder states, relu'd, as bf16 rows (lib/models/tepose.py:79-80)
+  if (p.hcat)
+    for (int i = blockIdx.x * kSkThreads + tid; i < p.M * p.KH; i += gridDim.x * kSkThreads) {
+      const int m = i / p.KH, c = i - m * p.KH;
+      p.hcat_cvt[i] = __float2bfloat16_rn(fmaxf(__ldcg(p.hcat + (int64_t)m * p.ld_h + c), 0.0f));
+    }
   // feat (bf16 from the heads, or fp32) -> kIefRep bf16 replicas
+  if (p.feat || p.feat_lp)
   for (int i = blockIdx.x * kSkThreads + tid; i < p.M * 2048; i += gridDim.x * kSkThreads) {
     const __nv_bfloat16 v = p.feat_lp ? p.feat_lp[i] : __float2bfloat16_rn(p.feat[i]);
 #pragma unroll
@@ -168,7 +177,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
   auto prefetch = [&](const IefLayer& L) {
     const int nkb = (L.K + 31) / 32;
     const int b_lo = (warp * nkb) / 8, nb = ((warp + 1) * nkb) / 8 - b_lo;
-    const uint4* wp = L.Wp + ((int64_t)ut * nkb + b_lo) * 64 + lane;
+    const uint4* wp = L.Wp + ((int64_t)ut * L.wkb + b_lo) * 64 + lane;
 #pragma unroll
     for (int q = 0; q < kSkPF; ++q)
       if (q < nb) { wa[q] = ldg_stream16(wp + (int64_t)q * 64); wb[q] = ldg_stream16(wp + (int64_t)q * 64 + 32); }
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
     IEF_TRACE(2);
     if (l + 1 < p.nlayers) {
       if (ut < (sL[l + 1].N + 15) / 16) prefetch(sL[l + 1]);   // weights do not depend on the barrier
-      grid_barrier(p.barrier, ++epoch * gridDim.x);
+      if (!L.local_next) grid_barrier(p.barrier, ++epoch * gridDim.x);
     }
     IEF_TRACE(3);
   }
@@ -276,8 +285,10 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
 
 }  // namespace tp
 
+struct HeadsArgs { const void* w_cat; const float* b_cat; const float* h_cat; int64_t ld_h; int H; };
+
 static int ief_fused(const tp_ief_weights* w, const float* feat, const void* feat_bf16, int N, const float* init,
-                     int init_rows, int n_iter, float* psc, unsigned char* ws, cudaStream_t st) {
+                     int init_rows, int n_iter, float* psc, unsigned char* ws, cudaStream_t st, const HeadsArgs* hd = nullptr) {
   // workspace (see tp_ief_workspace_bytes): [base fp32 | ...per-layer buffers of the unfused path... | scratch];
   // the fused kernel keeps its barrier counter and all replica buffers in the 8 MB scratch region
   const size_t slab = al256((size_t)N * 1024 * sizeof(float));
@@ -290,6 +301,8 @@ static int ief_fused(const tp_ief_weights* w, const float* feat, const void* fea
   __nv_bfloat16* u2_lp = u1_lp + kIefRep * n1024;               // [8][N,1024]
   __nv_bfloat16* psc_lp = u2_lp + kIefRep * n1024;              // [8][N,160]
   __nv_bfloat16* feat_rep = psc_lp + kIefRep * n160;            // [8][N,2048]   (total <= 2.2 MB for N = 32)
+  __nv_bfloat16* hcat_cvt = feat_rep + kIefRep * n2048;         // [N,3H] relu'd encoder states (fused heads)
+  float* featf = reinterpret_cast<float*>(ws + slab);           // [N,2048] fp32 head accumulator (the u1 | u2 slabs of the unfused path)
   IefFusedParams p;
   memset(&p, 0, sizeof(p));
   p.M = N; p.barrier = reinterpret_cast<unsigned int*>(sc);
@@ -300,9 +313,26 @@ static int ief_fused(const tp_ief_weights* w, const float* feat, const void* fea
   auto add = [&](const __nv_bfloat16* A, int lda, int K, size_t rep_in, const void* Wp, int Nn, const float* bias,
                  const float* Cin, int ldcin, float* C, int ldc, __nv_bfloat16* Clp, int ldclp, size_t rep_out) {
     IefLayer& L = p.layer[n++];
-    L.A = A; L.lda = lda; L.K = K; L.rep_in = (int)rep_in; L.Wp = reinterpret_cast<const uint4*>(Wp); L.N = Nn;
+    L.A = A; L.lda = lda; L.K = K; L.rep_in = (int)rep_in; L.Wp = reinterpret_cast<const uint4*>(Wp); L.N = Nn; L.wkb = (K + 31) / 32;
     L.bias = bias; L.Cin = Cin; L.ldcin = ldcin; L.C = C; L.ldc = ldc; L.Clp = Clp; L.ldclp = ldclp; L.rep_out = (int)rep_out;
   };
+  int grid = 64;
+  if (hd) {
+    // eval heads as leading layers: feat = relu(h_cat) . w_cat^T + b_cat, the K = 3H reduction cut into slices of <= 2048
+    // columns that accumulate through the fp32 buffer (one grid barrier each); 2048 output rows = 128 weight tiles
+    const int KH = 3 * hd->H, wkb = KH / 32;
+    p.hcat = hd->h_cat; p.ld_h = hd->ld_h; p.KH = KH; p.hcat_cvt = hcat_cvt;
+    p.feat = nullptr; p.feat_lp = nullptr;
+    const int nsl = (KH + 2047) / 2048;
+    for (int sl = 0; sl < nsl; ++sl) {
+      const int k0 = sl * 2048, kk = KH - k0 < 2048 ? KH - k0 : 2048;
+      add(hcat_cvt + k0, KH, kk, 0, reinterpret_cast<const uint4*>(hd->w_cat) + (size_t)(k0 / 32) * 64, 2048, sl == 0 ? hd->b_cat : nullptr,
+          sl > 0 ? featf : nullptr, 2048, sl + 1 < nsl ? featf : nullptr, 2048, sl + 1 == nsl ? feat_rep : nullptr, 2048, n2048);
+      p.layer[n - 1].wkb = wkb;
+      p.layer[n - 1].local_next = sl + 1 < nsl ? 1 : 0;     // K slices of one output tile accumulate inside the owning CTA
+    }
+    grid = 128;
+  }
   add(feat_rep, 2048, 2048, n2048, w->w1x, 1024, w->b1, nullptr, 0, base, 1024, nullptr, 0, 0);
   for (int it = 0; it < n_iter; ++it) {
     add(psc_lp, 160, 160, n160, w->w1p, 1024, nullptr, base, 1024, nullptr, 0, u1_lp, 1024, n1024);
@@ -316,10 +346,10 @@ static int ief_fused(const tp_ief_weights* w, const float* feat, const void* fea
   void* args[] = {(void*)&p};
   if (nb == 8) {
     TP_CUDA(cudaFuncSetAttribute(tp::k_ief_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TP_CUDA(cudaLaunchCooperativeKernel((const void*)tp::k_ief_fused<1>, dim3(64), dim3(tp::kSkThreads), args, smem, st));
+    TP_CUDA(cudaLaunchCooperativeKernel((const void*)tp::k_ief_fused<1>, dim3(grid), dim3(tp::kSkThreads), args, smem, st));
   } else {
     TP_CUDA(cudaFuncSetAttribute(tp::k_ief_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TP_CUDA(cudaLaunchCooperativeKernel((const void*)tp::k_ief_fused<4>, dim3(64), dim3(tp::kSkThreads), args, smem, st));
+    TP_CUDA(cudaLaunchCooperativeKernel((const void*)tp::k_ief_fused<4>, dim3(grid), dim3(tp::kSkThreads), args, smem, st));
   }
   tp::count_launch();
   return TP_OK;
@@ -372,4 +402,24 @@ extern "C" int tp_ief_forward(int precision, const tp_ief_weights* w, const floa
                   psc_lp, 160));
   }
   return TP_OK;
+}
+
+// Eval heads + IEF in ONE persistent kernel (bf16 mode, <= 32 rows): the heads GEMM becomes the leading layers of
+// k_ief_fused, so the [N,2048] feature never leaves the kernel as a separate launch.
+extern "C" int tp_heads_ief_forward(const void* w_cat, const float* b_cat, const float* h_cat, int64_t ld_h, int H,
+                                    const tp_ief_weights* w, int n_rows, const float* init, int init_rows, int n_iter, float* psc,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  TP_CHECK_ARG(w_cat && b_cat && h_cat && w && init && psc, "tp_heads_ief_forward: null pointer");
+  TP_CHECK_ARG(n_rows >= 1 && n_rows <= 32, "tp_heads_ief_forward: n_rows=%d (1..32; use tp_encoder_heads_cat + tp_ief_forward beyond)", n_rows);
+  TP_CHECK_ARG(H >= 32 && H % 32 == 0, "tp_heads_ief_forward: H=%d must be a multiple of 32", H);
+  TP_CHECK_ARG(n_iter >= 0 && (3 * H + 2047) / 2048 + 1 + 3 * n_iter <= kIefMaxLayers, "tp_heads_ief_forward: too many layers (H=%d, n_iter=%d)", H, n_iter);
+  TP_CHECK_ARG(init_rows == 1 || init_rows == n_rows, "tp_heads_ief_forward: init_rows must be 1 or n_rows");
+  TP_CHECK_ARG(w->w1x && w->b1 && w->w1p && w->w2 && w->b2 && w->wdec && w->bdec, "tp_heads_ief_forward: null weight");
+  TP_CHECK_ARG(workspace && workspace_bytes >= tp_ief_workspace_bytes(n_rows), "tp_heads_ief_forward: workspace too small");
+  TP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "tp_heads_ief_forward: workspace must be 256-byte aligned");
+  TP_CHECK_ARG((size_t)4096 + (size_t)n_rows * (2 * 1024 + 160 + 2048 + 3 * (size_t)H) * 2 <= kSplitScratch, "tp_heads_ief_forward: H too large for the scratch region");
+  if (sm_count() < 128) return fail(TP_ERR_UNSUPPORTED, "tp_heads_ief_forward needs 128 co-resident CTAs");
+  HeadsArgs hd{w_cat, b_cat, h_cat, ld_h, H};
+  return ief_fused(w, nullptr, nullptr, n_rows, init, init_rows, n_iter, psc, reinterpret_cast<unsigned char*>(workspace),
+                   (cudaStream_t)stream, &hd);
 }

@@ -297,6 +297,7 @@ class TePose(nn.Module):
         if precision not in nv.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(nv.PRECISIONS)}")
         self.fold_linear = bool(fold_linear)
+        self.fuse_heads = os.environ.get("TP_NO_FUSED_HEADS") is None     # bf16, B <= 32: heads run as the first layers of the IEF kernel
         self.seqlen = seqlen
         self.batch_size = batch_size
         self.encoder = TemporalEncoder(seq_len=seqlen, n_layers=n_layers, hidden_size=hidden_size, precision=precision)
@@ -350,6 +351,19 @@ class TePose(nn.Module):
             h_cat = torch.as_strided(h_fwd, (h_fwd.shape[0], 3 * H), (3 * H, 1))
             psc = folded_gemm(h_cat, fd["Gh"], fd["gh"], relu_a=True)
             nv.mark("k3_folded")
+            return self.regressor.decode(psc, is_train=False, J_regressor=J_regressor)
+        B = h_fwd.shape[0]
+        if self.precision == "bf16" and not is_train and adjacent and B <= 32 and self.fuse_heads:
+            # heads + IEF in one persistent kernel (the [B,2048] feature stays inside it)
+            from .spin import PSC
+            L = nv.lib()
+            pe, pr = self.encoder.packed(), self.regressor.packed()
+            psc = torch.empty(B, PSC, device=h_fwd.device, dtype=torch.float32)
+            ws = nv.workspace(L.tp_ief_workspace_bytes(B), h_fwd.device)
+            nv.check(L.tp_heads_ief_forward(nv.ptr(pe["w_cat"]), nv.ptr(pe["b_cat"]), nv.vp(h_fwd.data_ptr()), 3 * H, H, pr["c"], B,
+                                            nv.ptr(pr["init"]), 1, 3, nv.ptr(psc), nv.ptr(ws), ws.numel(), nv.stream()),
+                     "tp_heads_ief_forward")
+            nv.mark("k3_heads_ief")
             return self.regressor.decode(psc, is_train=False, J_regressor=J_regressor)
         feature = self.encoder.heads(h_fwd, h_rec, is_train=is_train)
         lp = getattr(feature, "_tp_bf16", None)
