@@ -47,6 +47,9 @@ struct PrepArgs {
 };
 
 __global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int n, const PrepArgs a) {
+  // programmatic dependent launch: the vertex kernel may start now and load its resident blend tile while this
+  // kernel runs; it waits (griddepcontrol.wait) before touching anything written here
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= n) return;                       // whole warp exits together
@@ -387,6 +390,8 @@ k_smpl_verts_tc(const tp_smpl_model m, int n, const __nv_bfloat16* __restrict__ 
     }
   }
 
+  // everything above reads model constants only; the coefficients / transforms come from k_smpl_prepare
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
   const int ngroups = (n + kTcNB - 1) / kTcNB;
   const int g_lo = blockIdx.y * groups_per_cta, g_hi = min(ngroups, g_lo + groups_per_cta);
   for (int grp = g_lo; grp < g_hi; ++grp) {
@@ -827,7 +832,15 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
   } else if (need_verts_pass && pl.tc) {
     TP_CUDA(cudaFuncSetAttribute(k_smpl_verts_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
     dim3 grid((unsigned)pl.tc_tiles, (unsigned)pl.tc_gsplit);
-    k_smpl_verts_tc<<<grid, 256, kTcSmem, st>>>(*m, n, pa.coef_tc, pa.A, jreg, nreg, verts, jpart, pl.tc_tiles, pl.tc_gpc);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = kTcSmem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    TP_CUDA(cudaLaunchKernelEx(&cfg, k_smpl_verts_tc, *m, n, (const __nv_bfloat16*)pa.coef_tc, (const float*)pa.A, jreg, nreg, verts,
+                               jpart, pl.tc_tiles, pl.tc_gpc));
     TP_LAUNCH_CHECK();
   } else if (need_verts_pass) {
     constexpr size_t smem = (size_t)kSmVertsFloats * sizeof(float);
