@@ -392,6 +392,7 @@ k_smpl_verts_tc(const tp_smpl_model m, int n, const __nv_bfloat16* __restrict__ 
 
   // everything above reads model constants only; the coefficients / transforms come from k_smpl_prepare
   asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");      // k_smpl_finalize may be scheduled; it waits for this grid
   const int ngroups = (n + kTcNB - 1) / kTcNB;
   const int g_lo = blockIdx.y * groups_per_cta, g_hi = min(ngroups, g_lo + groups_per_cta);
   for (int grp = g_lo; grp < g_hi; ++grp) {
@@ -669,6 +670,7 @@ __global__ void __launch_bounds__(128) k_smpl_finalize(int n, int n_verts, const
                                                        const float* __restrict__ verts, const int32_t* __restrict__ joint_src,
                                                        int nj, const float* __restrict__ cam, int64_t ld_cam,
                                                        float* __restrict__ joints, float* __restrict__ kp2d) {
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");      // no-op unless launched with programmatic serialization
   __shared__ float Jr[kMaxReg * 3];
   const int b = blockIdx.x, tid = threadIdx.x;
   // regressor partials: one warp per value, lanes stride over the vertex tiles (independent loads in
@@ -852,8 +854,18 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
   }
   if (nj > 0 && (joints || kp2d)) {
     TP_CHECK_ARG(verts != nullptr, "tp_smpl_forward: verts is required when joints are requested (vertex picks read it)");
-    k_smpl_finalize<<<(unsigned)n, 128, 0, st>>>(n, m->n_verts, pa.posedJ, jpart, pl.split ? m->vp / kSkVT : (pl.tc ? pl.tc_tiles : pl.nsplit), nreg, verts, joint_src,
-                                                nj, cam, ld_cam, joints, kp2d);
+    {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)n); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      TP_CUDA(cudaLaunchKernelEx(&cfg, k_smpl_finalize, n, (int)m->n_verts, (const float*)pa.posedJ, (const float*)jpart,
+                                 (int)(pl.split ? m->vp / kSkVT : (pl.tc ? pl.tc_tiles : pl.nsplit)), nreg, (const float*)verts,
+                                 joint_src, nj, cam, ld_cam, joints, kp2d));
+    }
     TP_LAUNCH_CHECK();
   }
   return TP_OK;
