@@ -21,8 +21,25 @@ class PipelinedTePose:
         nv.require_cuda(p, "model parameters")
         self.device, self.depth = p.device, depth
         self.slots = [GraphedTePose(model, batch, seqlen, J_regressor=J_regressor) for _ in range(depth)]
-        self.out_host = [{k: torch.empty_like(s.static_output[k], device="cpu").pin_memory() for k in OUTPUT_KEYS}
-                         for s in self.slots]
+        # the five outputs of a slot are views of one device allocation (smpl_forward_native): mirror it with one pinned
+        # host buffer and move everything with a single D2H copy per step
+        self.dev_flat, self.host_flat, self.out_host = [], [], []
+        for s in self.slots:
+            outs = s.static_output
+            stor = {outs[k].untyped_storage().data_ptr() for k in OUTPUT_KEYS}
+            if len(stor) == 1:
+                st = outs[OUTPUT_KEYS[0]].untyped_storage()
+                dflat = torch.empty(0, dtype=torch.uint8, device=self.device).set_(st)
+                hflat = torch.empty(dflat.numel(), dtype=torch.uint8).pin_memory()
+                views = {}
+                for k in OUTPUT_KEYS:
+                    v = outs[k]
+                    o = v.storage_offset() * 4
+                    views[k] = hflat[o:o + 4 * v.numel()].view(torch.float32).view(v.shape)
+                self.dev_flat.append(dflat); self.host_flat.append(hflat); self.out_host.append(views)
+            else:
+                self.dev_flat.append(None); self.host_flat.append(None)
+                self.out_host.append({k: torch.empty_like(outs[k], device="cpu").pin_memory() for k in OUTPUT_KEYS})
         self.compute = torch.cuda.current_stream(self.device)
         self.h2d = torch.cuda.Stream(device=self.device)
         self.d2h = torch.cuda.Stream(device=self.device)
@@ -49,8 +66,11 @@ class PipelinedTePose:
         self.compute_done[slot].record(self.compute)
         with torch.cuda.stream(self.d2h):
             self.d2h.wait_event(self.compute_done[slot])
-            for k in OUTPUT_KEYS:
-                self.out_host[slot][k].copy_(s.static_output[k], non_blocking=True)
+            if self.dev_flat[slot] is not None:
+                self.host_flat[slot].copy_(self.dev_flat[slot], non_blocking=True)
+            else:
+                for k in OUTPUT_KEYS:
+                    self.out_host[slot][k].copy_(s.static_output[k], non_blocking=True)
             self.d2h_done[slot].record(self.d2h)
         self.count += 1
         return i

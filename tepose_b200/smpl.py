@@ -176,11 +176,24 @@ def smpl_forward_native(packed: PackedSmpl, pose: torch.Tensor, ld_pose: int, po
     dev = packed.device
     nj = int(joint_src.numel())
     nreg = 0 if jreg is None else int(jreg.shape[0])
-    verts = torch.empty(n, packed.n_verts, 3, device=dev, dtype=torch.float32)
-    joints = torch.empty(n, nj, 3, device=dev, dtype=torch.float32)
-    kp2d = torch.empty(n, nj, 2, device=dev, dtype=torch.float32) if cam is not None else None
-    rotmat = torch.empty(n, 24, 3, 3, device=dev, dtype=torch.float32) if want_rotmat else None
-    theta = torch.empty(n, 85, device=dev, dtype=torch.float32) if want_theta else None
+    # all outputs are views of ONE allocation (256-byte aligned pieces): a caller that ships every output to the host
+    # (PipelinedTePose) does it with a single copy
+    shapes = [("verts", (n, packed.n_verts, 3)), ("joints", (n, nj, 3))]
+    if cam is not None:
+        shapes.append(("kp2d", (n, nj, 2)))
+    if want_rotmat:
+        shapes.append(("rotmat", (n, 24, 3, 3)))
+    if want_theta:
+        shapes.append(("theta", (n, 85)))
+    offs, total = {}, 0
+    for name, shp in shapes:
+        offs[name] = total
+        total += (4 * int(torch.Size(shp).numel()) + 255) // 256 * 256
+    flat = torch.empty(max(total, 256), device=dev, dtype=torch.uint8)
+    piece = lambda name, shp: flat[offs[name]:offs[name] + 4 * int(torch.Size(shp).numel())].view(torch.float32).view(shp)
+    outs = {name: piece(name, shp) for name, shp in shapes}
+    verts, joints = outs["verts"], outs["joints"]
+    kp2d, rotmat, theta = outs.get("kp2d"), outs.get("rotmat"), outs.get("theta")
     L = nv.lib()
     if packed.blend_tc is None:
         blend_mode = 0
