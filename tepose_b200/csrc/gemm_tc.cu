@@ -16,11 +16,22 @@
 
 namespace tp {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 6;
-constexpr int TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK * 2;   // 32 KB
+// Tile 128 x BN, BN = 192 or 128 (chosen per launch): the kernel is bound by the L2 -> SM operand stream (every k-step a
+// CTA pulls (128 + BN) x 64 bf16), so a wider tile raises the MACs per byte; BN = 192 also turns the 2.92 waves of the
+// B=32,T=16 input projection (432 tiles of 128 x 128) into 1.95 (288 tiles).  Skinny launches (one wave or less of
+// 128-wide tiles, e.g. the B = 1 live window) stay at BN = 128: they stream weights and want more CTAs.
+constexpr int TC_BM = 128, TC_BK = 64;
+template <int BN> struct TcCfg {
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N / epilogue chunking");
+  static constexpr int STAGE_BYTES = (TC_BM + BN) * TC_BK * 2;        // 40 KB at BN = 192, 32 KB at BN = 128
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;           // 5 / 6
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // power of two >= BN
+  static constexpr int EPI_PITCH = BN + 4;                            // floats per staged row (= 4 mod 32)
+  static_assert((size_t)TC_BM * EPI_PITCH * 4 <= (size_t)STAGES * STAGE_BYTES, "epilogue staging must fit in the ring");
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+};
 constexpr int TC_MAX_SEGS = 8;
 constexpr int TC_THREADS = 128;
-constexpr int TC_EPI_PITCH = TC_BN + 4;   // floats per row of the epilogue staging tile (128 x 132 x 4 B = 66 KB of the 192 KB ring)
 
 struct TcParams {
   tp_gemm_seg seg[TC_MAX_SEGS];
@@ -77,15 +88,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29).
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate) : "memory");
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
@@ -102,8 +112,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
 }
 
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  using Cfg = TcCfg<BN>;
+  constexpr int TC_BN = BN, TC_STAGES = Cfg::STAGES, TC_STAGE_BYTES = Cfg::STAGE_BYTES, TC_TMEM_COLS = Cfg::TMEM_COLS, TC_EPI_PITCH = Cfg::EPI_PITCH;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: [stages][A 16KB | W 16KB] (1024-aligned), then barriers
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -141,9 +154,9 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   // bias of this tile's 128 columns -> shared memory now, so the epilogue does not wait on global loads
   __shared__ float s_bias[TC_BN];
-  s_bias[threadIdx.x] = (sg.bias && n0 + (int)threadIdx.x < sg.n_cols) ? sg.bias[n0 + threadIdx.x] : 0.0f;
+  for (int c = threadIdx.x; c < TC_BN; c += TC_THREADS) s_bias[c] = (sg.bias && n0 + c < sg.n_cols) ? sg.bias[n0 + c] : 0.0f;
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TC_BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TC_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -178,7 +191,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < TC_BK / 16; ++k) {
           // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in 16-byte units
-          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), Cfg::IDESC, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[st]);   // slot reusable once these MMAs have read it
       }
@@ -211,25 +224,28 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   __syncwarp();
   const bool vec_ok = ((sg.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(sg.out) & 15) == 0);
-  const int n = n0 + lane * 4;
-#pragma unroll 4
+#pragma unroll 2
   for (int r = 0; r < 32; ++r) {
     const int row = m0 + warp * 32 + r;                  // segment-local output row
     if (row >= sg.m_rows) break;
-    const float4 o = *reinterpret_cast<const float4*>(stage + (size_t)r * TC_EPI_PITCH + lane * 4);
-    float* dst = sg.out + (int64_t)row * sg.ldc + n;
-    if (n + 3 < sg.n_cols && vec_ok) {
-      *reinterpret_cast<float4*>(dst) = o;
-    } else {
-      const float e[4] = {o.x, o.y, o.z, o.w};
-      for (int i = 0; i < 4; ++i)
-        if (n + i < sg.n_cols) dst[i] = e[i];
+#pragma unroll
+    for (int cc = lane * 4; cc < TC_BN; cc += 128) {     // 512 contiguous bytes per warp store
+      const int n = n0 + cc;
+      const float4 o = *reinterpret_cast<const float4*>(stage + (size_t)r * TC_EPI_PITCH + cc);
+      float* dst = sg.out + (int64_t)row * sg.ldc + n;
+      if (n + 3 < sg.n_cols && vec_ok) {
+        *reinterpret_cast<float4*>(dst) = o;
+      } else {
+        const float e[4] = {o.x, o.y, o.z, o.w};
+        for (int i = 0; i < 4; ++i)
+          if (n + i < sg.n_cols) dst[i] = e[i];
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)TC_BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS));
   }
 }
 
@@ -283,6 +299,11 @@ extern "C" int tp_gemm_bf16_tc(const void* A, int a_rows, const void* W, int w_r
   memset(&p, 0, sizeof(p));
   p.nseg = nseg;
   p.kblocks = kp / TC_BK;
+  // tile width: 192 once the launch has more than one wave of 128-wide tiles, else 128 (skinny launches want CTAs)
+  int tiles128 = 0;
+  for (int i = 0; i < nseg; ++i) tiles128 += (int)(ceil_div(segs[i].m_rows, TC_BM) * ceil_div(segs[i].n_cols, 128));
+  static const int bn_env = getenv("TP_TC_BN") ? atoi(getenv("TP_TC_BN")) : 0;
+  const int bn = bn_env == 128 || bn_env == 192 ? bn_env : (tiles128 > sm_count() ? 192 : 128);
   int tiles = 0;
   for (int i = 0; i < nseg; ++i) {
     const tp_gemm_seg& sg = segs[i];
@@ -291,17 +312,23 @@ extern "C" int tp_gemm_bf16_tc(const void* A, int a_rows, const void* W, int w_r
     TP_CHECK_ARG(sg.n_start >= 0 && sg.n_start + sg.n_cols <= w_rows, "tp_gemm_bf16_tc: segment %d cols out of range", i);
     p.seg[i] = sg;
     p.tile_begin[i] = tiles;
-    tiles += (int)(ceil_div(sg.m_rows, TC_BM) * ceil_div(sg.n_cols, TC_BN));
+    tiles += (int)(ceil_div(sg.m_rows, TC_BM) * ceil_div(sg.n_cols, bn));
   }
   for (int i = nseg; i <= TC_MAX_SEGS; ++i) p.tile_begin[i] = tiles;
   CUtensorMap map_a, map_w;
   int rc = make_map(&map_a, A, a_rows, kp, TC_BM);
   if (rc != TP_OK) return rc;
-  rc = make_map(&map_w, W, w_rows, kp, TC_BN);
+  rc = make_map(&map_w, W, w_rows, kp, bn);
   if (rc != TP_OK) return rc;
-  const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  TP_CUDA(cudaFuncSetAttribute(k_gemm_bf16_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_gemm_bf16_tc<<<(unsigned)tiles, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, p);
+  if (bn == 192) {
+    const size_t smem = (size_t)TcCfg<192>::STAGES * TcCfg<192>::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    TP_CUDA(cudaFuncSetAttribute(k_gemm_bf16_tc<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gemm_bf16_tc<192><<<(unsigned)tiles, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, p);
+  } else {
+    const size_t smem = (size_t)TcCfg<128>::STAGES * TcCfg<128>::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    TP_CUDA(cudaFuncSetAttribute(k_gemm_bf16_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gemm_bf16_tc<128><<<(unsigned)tiles, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, p);
+  }
   TP_LAUNCH_CHECK();
   return TP_OK;
 }
