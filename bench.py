@@ -102,6 +102,39 @@ def oracle_step_fn(threads):
     return step
 
 
+def cpu_other_configs(threads):
+    """the same CPU port on BASELINE configs[0] (one sequence, B=1,T=16: the live-loop frame) and on the
+    SMPL-standalone shape (4096 bodies, axis-angle in, as lib/utils/eval_utils.py:164 chunks them); best of 5 after 2 warm-ups."""
+    from oracle import synth, torch_ref
+    torch.set_num_threads(threads)
+    sd = {k: torch.as_tensor(v) for k, v in synth.make_state_dict(SEED, L, H).items()}
+    m = torch_ref.SmplModel.synthetic(SEED)
+    grus = (torch_ref.build_gru(sd, "gru_fwd", L, H, False), torch_ref.build_gru(sd, "gru_rec", L, H, True))
+    x1 = torch.from_numpy(synth.make_input(SEED, 1, T))
+    bod = synth.make_bodies(SEED, 4096)
+    aa, betas = torch.from_numpy(bod["pose_aa"]), torch.from_numpy(bod["betas"])
+
+    def best(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return min(ts), float(np.median(ts))
+    with torch.no_grad():
+        b1 = best(lambda: torch_ref.tepose_forward(sd, m, x1, L, H, grus=grus))
+        sm = best(lambda: torch_ref.smpl_forward(m, betas, pose_aa=aa), reps=3, warm=1)
+    model = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            model = next((ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name")), "")
+    except OSError:
+        pass
+    return {"B1_T16_ms": {"best": 1e3 * b1[0], "median": 1e3 * b1[1]},
+            "smpl_4096_bodies": {"best_ms": 1e3 * sm[0], "median_ms": 1e3 * sm[1], "bodies_per_s": 4096 / sm[1]},
+            "cpu_model": model, "threads": threads}
+
+
 def time_cpu(step, budget_s, min_iters=2, warm=1):
     for i in range(warm):
         step(i)
@@ -287,6 +320,7 @@ def main():
 
     # ---------------------------------------------------------------- per-kernel timing (roofline)
     stage_ms = {}
+    lib.tp_set_pdl(0)             # events between kernels need plain stream order: no programmatic overlap in this pass
     with torch.no_grad():
         for i in range(min(args.steps, 20)):
             flush.zero_()
@@ -297,6 +331,7 @@ def main():
             torch.cuda.synchronize(dev)
             for (n0, a), (n1, b_) in zip(marks[:-1], marks[1:]):
                 stage_ms.setdefault(n1, []).append(a.elapsed_time(b_))
+    lib.tp_set_pdl(1)
     stage_avg = {k: float(np.mean(v)) for k, v in stage_ms.items()}
     hbm_peak, tf_peak, peak_src = peaks()
     wbytes = 2 if args.precision == "bf16" else 4
@@ -422,6 +457,8 @@ def main():
         cpu_baseline = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
                         "sample": f"{len(times)} forwards of the full B=32,T=16 batch, median "
                                   f"{1e3 * float(np.median(times)):.1f} ms (oracle/torch_ref.py on torch {torch.__version__} CPU)"}
+        if args.cpu_budget >= 4:
+            cpu_baseline["other_configs"] = cpu_other_configs(cores)
 
     if rank == 0:
         line = {

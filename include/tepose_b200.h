@@ -58,6 +58,10 @@ TP_API int tp_version(void);
 TP_API const char* tp_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 TP_API unsigned long long tp_launch_count(void);
+/* Programmatic dependent launch between the kernels of a forward (each kernel's set-up overlaps the tail of its
+ * predecessor).  On by default; profiling passes that bracket single kernels with events switch it off.  Returns the
+ * previous setting. */
+TP_API int tp_set_pdl(int enable);
 /* host out-params; any may be NULL */
 TP_API int tp_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_per_block_optin);
 
@@ -176,6 +180,12 @@ TP_API size_t tp_gru_workspace_bytes(int njobs, int B, int H);
  * H % 32 == 0.  workspace must be 256-byte aligned.                                        */
 TP_API int tp_gru_recurrence(const tp_gru_job* jobs, int njobs, int B, int H, int precision,
                       void* workspace, size_t workspace_bytes, void* stream);
+/* Same, with the grid-barrier word supplied by the caller: `barrier` (16-byte aligned, >= 16 bytes) must be ZERO when the
+ * kernel starts -- zeroed by an operation ordered BEFORE the previous kernel in the stream, so that no memset node
+ * separates this launch from its programmatic-dependent-launch predecessor (the input-projection GEMM).  NULL = the
+ * plain entry point's behaviour (barrier inside the workspace, zeroed by a memset right before the launch).          */
+TP_API int tp_gru_recurrence_ex(const tp_gru_job* jobs, int njobs, int B, int H, int precision,
+                         void* workspace, size_t workspace_bytes, void* barrier, void* stream);
 
 /* ------------------------------------------------------------------ Regressor (K3)
  * Linear heads of the encoder (lib/models/tepose.py:79-85):
@@ -223,7 +233,8 @@ TP_API int tp_ief_forward(int precision, const tp_ief_weights* w, const float* f
  * tp_encoder_heads_cat (packed bf16), h_cat [n_rows, 3H] fp32 (row stride ld_h); workspace: tp_ief_workspace_bytes.   */
 TP_API int tp_heads_ief_forward(const void* w_cat, const float* b_cat, const float* h_cat, int64_t ld_h, int H,
                          const tp_ief_weights* w, int n_rows, const float* init, int init_rows, int n_iter, float* psc,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         void* workspace, size_t workspace_bytes, void* barrier /* as for tp_gru_recurrence_ex, or NULL */,
+                         void* stream);
 
 
 /* ------------------------------------------------------------------ SMPL forward (K4 + K5)

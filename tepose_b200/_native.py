@@ -21,11 +21,11 @@ PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16}
 
 # every symbol include/tepose_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "tp_version", "tp_last_error", "tp_launch_count", "tp_device_info",
+    "tp_version", "tp_last_error", "tp_launch_count", "tp_set_pdl", "tp_device_info",
     "tp_rot6d_to_rotmat", "tp_rotmat_to_angle_axis", "tp_batch_rodrigues", "tp_projection",
     "tp_pack_rows", "tp_unpack_rows_residual", "tp_gemm_f32", "tp_gemm_f32_splitk_workspace_bytes", "tp_gemm_f32_splitk",
     "tp_pack_mma_a_bytes", "tp_pack_mma_a_bf16", "tp_skinny_bf16_workspace_bytes", "tp_skinny_bf16", "tp_skinny_bf16_ex", "tp_gemm_bf16_tc",
-    "tp_pack_whh_bf16", "tp_gru_set_trace", "tp_gru_workspace_bytes", "tp_gru_recurrence",
+    "tp_pack_whh_bf16", "tp_gru_set_trace", "tp_gru_workspace_bytes", "tp_gru_recurrence", "tp_gru_recurrence_ex",
     "tp_encoder_heads_workspace_bytes", "tp_encoder_heads", "tp_encoder_heads_cat", "tp_ief_workspace_bytes", "tp_ief_forward", "tp_heads_ief_forward",
     "tp_smpl_workspace_bytes", "tp_smpl_forward",
     "tp_pose_metrics", "tp_accel_error", "tp_vertex_error",
@@ -60,13 +60,14 @@ _SIGNATURES = {
     "tp_version": (C.c_int, []),
     "tp_last_error": (C.c_char_p, []),
     "tp_launch_count": (C.c_ulonglong, []),
+    "tp_set_pdl": (C.c_int, [C.c_int]),
     "tp_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(sz)]),
     "tp_rot6d_to_rotmat": (C.c_int, [vp, vp, i64, vp]),
     "tp_rotmat_to_angle_axis": (C.c_int, [vp, vp, i64, vp]),
     "tp_batch_rodrigues": (C.c_int, [vp, vp, i64, C.c_int, vp]),
     "tp_projection": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp]),
     "tp_pack_rows": (C.c_int, [vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
-    "tp_heads_ief_forward": (C.c_int, [vp, vp, vp, i64, C.c_int, C.POINTER(IefWeights), C.c_int, vp, C.c_int, C.c_int, vp, vp, sz, vp]),
+    "tp_heads_ief_forward": (C.c_int, [vp, vp, vp, i64, C.c_int, C.POINTER(IefWeights), C.c_int, vp, C.c_int, C.c_int, vp, vp, sz, vp, vp]),
     "tp_pose_metrics": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
     "tp_accel_error": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "tp_vertex_error": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
@@ -87,6 +88,7 @@ _SIGNATURES = {
     "tp_gru_set_trace": (None, [vp]),
     "tp_gru_workspace_bytes": (sz, [C.c_int, C.c_int, C.c_int]),
     "tp_gru_recurrence": (C.c_int, [C.POINTER(GruJob), C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, vp]),
+    "tp_gru_recurrence_ex": (C.c_int, [C.POINTER(GruJob), C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, vp, vp]),
     "tp_encoder_heads_workspace_bytes": (sz, [C.c_int]),
     "tp_encoder_heads": (C.c_int, [C.c_int, vp, vp, vp, vp, vp, i64, vp, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp, sz, vp]),
     "tp_encoder_heads_cat": (C.c_int, [C.c_int, vp, vp, vp, i64, C.c_int, C.c_int, vp, vp, vp, sz, vp]),

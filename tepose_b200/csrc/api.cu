@@ -29,6 +29,10 @@ static long long* g_trace = nullptr;
 long long* trace_ptr() { return g_trace; }
 void set_trace_ptr(long long* p) { g_trace = p; }
 
+static std::atomic<int> g_pdl{1};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+void set_pdl(int on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -43,6 +47,9 @@ int sm_count() {
 }  // namespace tp
 
 extern "C" int tp_version(void) { return 100; }
+
+namespace tp { void set_pdl(int on); }
+extern "C" int tp_set_pdl(int enable) { const int was = tp::pdl_enabled() ? 1 : 0; tp::set_pdl(enable); return was; }
 
 namespace tp { unsigned long long launches(); }
 extern "C" unsigned long long tp_launch_count(void) { return tp::launches(); }

@@ -40,12 +40,39 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int sm_count();  // of the current device (cached)
+
+bool pdl_enabled();            // tp_set_pdl(); default on
+// launch configuration with programmatic stream serialization (and, optionally, a cooperative grid)
+struct PdlConfig {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  PdlConfig(dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool cooperative = false) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = 1;
+    if (cooperative) {
+      attr[1].id = cudaLaunchAttributeCooperative;
+      attr[1].val.cooperative = 1;
+      cfg.numAttrs = 2;
+    }
+    cfg.attrs = attr;
+  }
+};
 void count_launch();
 long long* trace_ptr();          // debug stamp buffer (tp_gru_set_trace), or null
 void set_trace_ptr(long long* p);  // bumps the counter behind tp_launch_count()
 
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (PDL).  A kernel launched with pdl_config() may be scheduled as soon as every CTA of
+// its predecessor in the stream has called pdl_launch_dependents() (or exited); it must call pdl_wait() before it
+// touches anything the predecessor wrote (the wait returns when the predecessor grid has completed and flushed).
+// Both are no-ops for kernels launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 // Grid barrier for a co-resident (cooperatively launched) grid: one arrival per CTA on a
 // monotonic counter, release/acquire at gpu scope (the release is cumulative over the CTA's
 // writes that thread 0 observed through bar.sync).  CONTRACT: after this barrier, data written by

@@ -163,6 +163,9 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: barriers, TMEM and the tensor maps were set up while the producer of A (the pack kernel) was still running
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (elect_one()) {  // ===== TMA producer =====
@@ -323,11 +326,13 @@ extern "C" int tp_gemm_bf16_tc(const void* A, int a_rows, const void* W, int w_r
   if (bn == 192) {
     const size_t smem = (size_t)TcCfg<192>::STAGES * TcCfg<192>::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     TP_CUDA(cudaFuncSetAttribute(k_gemm_bf16_tc<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_gemm_bf16_tc<192><<<(unsigned)tiles, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, p);
+    PdlConfig lc(dim3((unsigned)tiles), dim3(TC_THREADS), smem, (cudaStream_t)stream);
+    TP_CUDA(cudaLaunchKernelEx(&lc.cfg, k_gemm_bf16_tc<192>, map_a, map_w, p));
   } else {
     const size_t smem = (size_t)TcCfg<128>::STAGES * TcCfg<128>::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     TP_CUDA(cudaFuncSetAttribute(k_gemm_bf16_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_gemm_bf16_tc<128><<<(unsigned)tiles, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, p);
+    PdlConfig lc(dim3((unsigned)tiles), dim3(TC_THREADS), smem, (cudaStream_t)stream);
+    TP_CUDA(cudaLaunchKernelEx(&lc.cfg, k_gemm_bf16_tc<128>, map_a, map_w, p));
   }
   TP_LAUNCH_CHECK();
   return TP_OK;

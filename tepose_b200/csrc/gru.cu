@@ -463,8 +463,8 @@ static int launch_coop_n(KernelT kfn, const GruParams& p, int stages, int thread
   int per_sm = 0;
   TP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem));
   if (per_sm < 1) return fail(TP_ERR_UNSUPPORTED, "tp_gru_recurrence: kernel does not fit on an SM (smem=%zu)", smem);
-  void* args[] = {(void*)&p, (void*)&stages};
-  TP_CUDA(cudaLaunchCooperativeKernel((const void*)kfn, dim3(grid), dim3(threads), args, smem, st));
+  PdlConfig lc(dim3(grid), dim3(threads), smem, st, /*cooperative=*/true);
+  TP_CUDA(cudaLaunchKernelEx(&lc.cfg, kfn, p, stages));
   count_launch();
   return TP_OK;
 }
@@ -475,14 +475,28 @@ static int launch_coop_n2(KernelT kfn, const GruParams& p, int a0, int a1, int t
   int per_sm = 0;
   TP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem));
   if (per_sm < 1) return fail(TP_ERR_UNSUPPORTED, "tp_gru_recurrence: kernel does not fit on an SM (smem=%zu)", smem);
-  void* args[] = {(void*)&p, (void*)&a0, (void*)&a1};
-  TP_CUDA(cudaLaunchCooperativeKernel((const void*)kfn, dim3(grid), dim3(threads), args, smem, st));
+  PdlConfig lc(dim3(grid), dim3(threads), smem, st, /*cooperative=*/true);
+  TP_CUDA(cudaLaunchKernelEx(&lc.cfg, kfn, p, a0, a1));
   count_launch();
   return TP_OK;
 }
 
+static int gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, int H, int precision, void* workspace,
+                          size_t workspace_bytes, void* barrier, void* stream);
+
 extern "C" int tp_gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, int H, int precision,
                                  void* workspace, size_t workspace_bytes, void* stream) {
+  return gru_recurrence(jobs_in, njobs, B, H, precision, workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" int tp_gru_recurrence_ex(const tp_gru_job* jobs_in, int njobs, int B, int H, int precision,
+                                    void* workspace, size_t workspace_bytes, void* barrier, void* stream) {
+  TP_CHECK_ARG(!barrier || (reinterpret_cast<uintptr_t>(barrier) & 15) == 0, "tp_gru_recurrence_ex: barrier must be 16-byte aligned");
+  return gru_recurrence(jobs_in, njobs, B, H, precision, workspace, workspace_bytes, barrier, stream);
+}
+
+static int gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, int H, int precision, void* workspace,
+                          size_t workspace_bytes, void* barrier, void* stream) {
   TP_CHECK_ARG(jobs_in && njobs >= 1 && njobs <= kMaxJobs, "tp_gru_recurrence: njobs=%d out of range [1,%d]", njobs, kMaxJobs);
   TP_CHECK_ARG(B >= 1 && H >= 32 && H % 32 == 0, "tp_gru_recurrence: need B>=1 and H a multiple of 32 (B=%d H=%d)", B, H);
   TP_CHECK_ARG(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "tp_gru_recurrence: workspace must be 256-byte aligned");
@@ -508,14 +522,15 @@ extern "C" int tp_gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, in
     if (jb.h0) p.any_h0 = 1;
   }
   size_t per = (size_t)njobs * 2 * B * H;
-  p.barrier = reinterpret_cast<unsigned int*>(workspace);
+  p.barrier = reinterpret_cast<unsigned int*>(barrier ? barrier : workspace);
   p.hbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 256);
   p.hbuf_lp = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(workspace) + 256 + align_up(per * sizeof(float), 256));
   const size_t per_lp = (size_t)njobs * 2 * (B < 32 ? 32 : B) * H;
   p.lp_rep_stride = align_up(per_lp * sizeof(__nv_bfloat16), 256) / sizeof(__nv_bfloat16);
   p.lp_slot = (int64_t)B * H; p.lp_tiled = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  TP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+  if (!barrier) TP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));      // a caller-provided barrier word is already zero (and keeps
+                                                                      // the memset node from sitting between this kernel and its PDL predecessor)
   const int sms = sm_count();
 
   // ---- bf16 fast path: TMA-fed ring, one item per CTA

@@ -53,6 +53,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_res(const GruParams
   for (int i = tid; i < (int)(sizeof(tp_gru_job) * kMaxJobs / 4); i += kTmaThreads)
     reinterpret_cast<int*>(sjobs)[i] = reinterpret_cast<const int*>(p.jobs)[i];
   __syncthreads();
+  // PDL: everything above ran while the input-projection GEMM was draining; gi is read from here on
+  pdl_wait();
+  pdl_launch_dependents();
 
   for (int je = p.n_item_jobs; je < p.njobs; ++je)
     for (int64_t i = blockIdx.x * (int64_t)kTmaThreads + tid; i < (int64_t)B * H; i += (int64_t)gridDim.x * kTmaThreads) {

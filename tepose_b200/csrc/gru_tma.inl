@@ -69,6 +69,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
   for (int i = tid; i < (int)(sizeof(tp_gru_job) * kMaxJobs / 4); i += kTmaThreads)
     reinterpret_cast<int*>(sjobs)[i] = reinterpret_cast<const int*>(p.jobs)[i];
   __syncthreads();
+  // PDL: everything above ran while the input-projection GEMM was draining; gi is read from here on
+  pdl_wait();
+  pdl_launch_dependents();
 
   // step-0-only jobs without an initial state have no matmul at all: plain gate math, grid-strided
   for (int je = p.n_item_jobs; je < p.njobs; ++je)

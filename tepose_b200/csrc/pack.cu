@@ -6,6 +6,7 @@ namespace tp {
 template <typename OutT>
 __global__ void k_pack_rows(const float* __restrict__ src, int64_t stride_b, int64_t stride_t,
                             int rows_b, int rows_t, int k, OutT* __restrict__ dst, int kp, int relu) {
+  pdl_launch_dependents();            // the GEMM that consumes dst may set itself up now (it waits before reading)
   int row = blockIdx.x;               // t * rows_b + b
   int t = row / rows_b, b = row - t * rows_b;
   const float* s = src + (int64_t)b * stride_b + (int64_t)t * stride_t;

@@ -150,6 +150,8 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
   for (int i = tid; i < (int)(sizeof(IefLayer) * kIefMaxLayers / 4); i += kSkThreads)
     reinterpret_cast<int*>(sL)[i] = reinterpret_cast<const int*>(p.layer)[i];
   __syncthreads();
+  pdl_wait();                    // PDL: the encoder states / features come from the previous kernel
+  pdl_launch_dependents();
 
   // prologue: IEF state <- init (fp32 + bf16 copy), optional feat conversion
   for (int i = blockIdx.x * kSkThreads + tid; i < p.M * 160; i += gridDim.x * kSkThreads) {
@@ -288,7 +290,8 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
 struct HeadsArgs { const void* w_cat; const float* b_cat; const float* h_cat; int64_t ld_h; int H; };
 
 static int ief_fused(const tp_ief_weights* w, const float* feat, const void* feat_bf16, int N, const float* init,
-                     int init_rows, int n_iter, float* psc, unsigned char* ws, cudaStream_t st, const HeadsArgs* hd = nullptr) {
+                     int init_rows, int n_iter, float* psc, unsigned char* ws, cudaStream_t st, const HeadsArgs* hd = nullptr,
+                     void* barrier = nullptr) {
   // workspace (see tp_ief_workspace_bytes): [base fp32 | ...per-layer buffers of the unfused path... | scratch];
   // the fused kernel keeps its barrier counter and all replica buffers in the 8 MB scratch region
   const size_t slab = al256((size_t)N * 1024 * sizeof(float));
@@ -305,7 +308,7 @@ static int ief_fused(const tp_ief_weights* w, const float* feat, const void* fea
   float* featf = reinterpret_cast<float*>(ws + slab);           // [N,2048] fp32 head accumulator (the u1 | u2 slabs of the unfused path)
   IefFusedParams p;
   memset(&p, 0, sizeof(p));
-  p.M = N; p.barrier = reinterpret_cast<unsigned int*>(sc);
+  p.M = N; p.barrier = reinterpret_cast<unsigned int*>(barrier ? barrier : sc);
   p.feat = feat; p.feat_lp = reinterpret_cast<const __nv_bfloat16*>(feat_bf16); p.feat_cvt = feat_rep;
   p.init = init; p.init_rows = init_rows; p.psc = psc; p.psc_lp = psc_lp;
   p.trace = tp::trace_ptr();
@@ -340,16 +343,17 @@ static int ief_fused(const tp_ief_weights* w, const float* feat, const void* fea
     add(u2_lp, 1024, 1024, n1024, w->wdec, 160, w->bdec, psc, 160, psc, 160, psc_lp, 160, n160);
   }
   p.nlayers = n;
-  TP_CUDA(cudaMemsetAsync(sc, 0, 256, st));
+  if (!barrier) TP_CUDA(cudaMemsetAsync(sc, 0, 256, st));
   const int nb = N <= 8 ? 8 : 32;
   const size_t smem = (size_t)nb * (2048 + 32) * 2 + (size_t)8 * nb * 17 * 4;
-  void* args[] = {(void*)&p};
   if (nb == 8) {
     TP_CUDA(cudaFuncSetAttribute(tp::k_ief_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TP_CUDA(cudaLaunchCooperativeKernel((const void*)tp::k_ief_fused<1>, dim3(grid), dim3(tp::kSkThreads), args, smem, st));
+    tp::PdlConfig lc(dim3(grid), dim3(tp::kSkThreads), smem, st, /*cooperative=*/true);
+    TP_CUDA(cudaLaunchKernelEx(&lc.cfg, tp::k_ief_fused<1>, p));
   } else {
     TP_CUDA(cudaFuncSetAttribute(tp::k_ief_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TP_CUDA(cudaLaunchCooperativeKernel((const void*)tp::k_ief_fused<4>, dim3(grid), dim3(tp::kSkThreads), args, smem, st));
+    tp::PdlConfig lc(dim3(grid), dim3(tp::kSkThreads), smem, st, /*cooperative=*/true);
+    TP_CUDA(cudaLaunchKernelEx(&lc.cfg, tp::k_ief_fused<4>, p));
   }
   tp::count_launch();
   return TP_OK;
@@ -408,7 +412,7 @@ extern "C" int tp_ief_forward(int precision, const tp_ief_weights* w, const floa
 // k_ief_fused, so the [N,2048] feature never leaves the kernel as a separate launch.
 extern "C" int tp_heads_ief_forward(const void* w_cat, const float* b_cat, const float* h_cat, int64_t ld_h, int H,
                                     const tp_ief_weights* w, int n_rows, const float* init, int init_rows, int n_iter, float* psc,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+                                    void* workspace, size_t workspace_bytes, void* barrier, void* stream) {
   TP_CHECK_ARG(w_cat && b_cat && h_cat && w && init && psc, "tp_heads_ief_forward: null pointer");
   TP_CHECK_ARG(n_rows >= 1 && n_rows <= 32, "tp_heads_ief_forward: n_rows=%d (1..32; use tp_encoder_heads_cat + tp_ief_forward beyond)", n_rows);
   TP_CHECK_ARG(H >= 32 && H % 32 == 0, "tp_heads_ief_forward: H=%d must be a multiple of 32", H);
@@ -421,5 +425,5 @@ extern "C" int tp_heads_ief_forward(const void* w_cat, const float* b_cat, const
   if (sm_count() < 128) return fail(TP_ERR_UNSUPPORTED, "tp_heads_ief_forward needs 128 co-resident CTAs");
   HeadsArgs hd{w_cat, b_cat, h_cat, ld_h, H};
   return ief_fused(w, nullptr, nullptr, n_rows, init, init_rows, n_iter, psc, reinterpret_cast<unsigned char*>(workspace),
-                   (cudaStream_t)stream, &hd);
+                   (cudaStream_t)stream, &hd, barrier);
 }

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int
   // programmatic dependent launch: the vertex kernel may start now and load its resident blend tile while this
   // kernel runs; it waits (griddepcontrol.wait) before touching anything written here
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  pdl_wait();                                                             // pose / betas / cam may come from a PDL predecessor (the IEF kernel)
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= n) return;                       // whole warp exits together
@@ -803,7 +804,10 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
   pa.coef_tc = pl.tc ? reinterpret_cast<__nv_bfloat16*>(ws + pl.off_ctc) : nullptr;
   float* jpart = reinterpret_cast<float*>(ws + pl.off_part);
 
-  k_smpl_prepare<<<(unsigned)ceil_div(n, 4), 128, 0, st>>>(*m, n, pa);
+  {
+    PdlConfig lc(dim3((unsigned)ceil_div(n, 4)), dim3(128), 0, st);
+    TP_CUDA(cudaLaunchKernelEx(&lc.cfg, k_smpl_prepare, *m, n, pa));
+  }
   TP_LAUNCH_CHECK();
   const bool need_verts_pass = verts != nullptr || nreg > 0;
   if (need_verts_pass && pl.split) {

@@ -60,13 +60,21 @@ class GruKernels:
                                        nv.vp(bias.data_ptr() + 4 * n0), nv.vp(0), 0, nv.ptr(out), out.shape[1],
                                        mr, nc, kp, 1.0, 0.0, 0, nv.stream()), "tp_gemm_f32")
 
-    def _recurrence(self, jobs, B):
+    def _recurrence(self, jobs, B, barrier=None):
+        """barrier: a zeroed 256-byte slice (see sync_words) -> no memset between this launch and the GEMM before it."""
         L = nv.lib()
         H = self.hidden_size
         arr = (nv.GruJob * len(jobs))(*jobs)
         ws = nv.workspace(L.tp_gru_workspace_bytes(len(jobs), B, H), jobs[0]._dev)
-        nv.check(L.tp_gru_recurrence(arr, len(jobs), B, H, nv.PRECISIONS[self.precision], nv.ptr(ws), ws.numel(),
-                                     nv.stream()), "tp_gru_recurrence")
+        nv.check(L.tp_gru_recurrence_ex(arr, len(jobs), B, H, nv.PRECISIONS[self.precision], nv.ptr(ws), ws.numel(),
+                                        nv.vp(0 if barrier is None else barrier.data_ptr()), nv.stream()), "tp_gru_recurrence")
+
+    @staticmethod
+    def sync_words(device, n):
+        """n zeroed 256-byte grid-barrier slots in ONE fill, issued at the top of a forward: every persistent kernel of
+        the step gets its own slot, and no memset node has to sit right in front of those kernels (it would cut the
+        programmatic-dependent-launch edge to the kernel before)."""
+        return torch.zeros(n, 64, device=device, dtype=torch.int32)
 
     @staticmethod
     def _job(dev, gi, col0, w_hh, b_hh, steps, t_in0, t_in_step, h0=None, y=None, ycol=0, y_lp=None,
@@ -183,6 +191,8 @@ class TemporalEncoder(nn.Module, GruKernels):
             x = x.contiguous()
         if (h0 is not None or return_states) and Ln != 1:
             raise ValueError("carried state is only defined for n_layers == 1 (SURVEY.md H5)")
+        sync = self.sync_words(dev, Ln + 1)          # one slot per layer's recurrence + one for the heads/IEF kernel
+        self._sync_tail = sync[Ln]
         seq_f = torch.empty(T, B, H, device=dev, dtype=torch.float32) if return_states else None
         seq_b = torch.empty(T, B, H, device=dev, dtype=torch.float32) if return_states else None
         h_cat = torch.empty(B, 3 * H, device=dev, dtype=torch.float32)     # [y[-1] | y_rec[0]]
@@ -254,7 +264,7 @@ class TemporalEncoder(nn.Module, GruKernels):
                               t_out0=T - 1, t_out_step=-1),
                     self._job(dev, gi_s, c_s, w[2], b[2], T, s_in[0], s_in[1], y=ny_r, ycol=0, y_lp=ny_r_lp),
                 ]
-            self._recurrence(jobs, B)
+            self._recurrence(jobs, B, barrier=sync[l])
             nv.mark(f"k2_recurrence_l{l}")
             if not last:
                 y_f, y_r, y_f_lp, y_r_lp = ny_f, ny_r, ny_f_lp, ny_r_lp
@@ -360,8 +370,11 @@ class TePose(nn.Module):
             pe, pr = self.encoder.packed(), self.regressor.packed()
             psc = torch.empty(B, PSC, device=h_fwd.device, dtype=torch.float32)
             ws = nv.workspace(L.tp_ief_workspace_bytes(B), h_fwd.device)
+            bar = getattr(self.encoder, "_sync_tail", None)      # zeroed at the top of encode_states (same stream, same step)
+            self.encoder._sync_tail = None                       # one use per fill
             nv.check(L.tp_heads_ief_forward(nv.ptr(pe["w_cat"]), nv.ptr(pe["b_cat"]), nv.vp(h_fwd.data_ptr()), 3 * H, H, pr["c"], B,
-                                            nv.ptr(pr["init"]), 1, 3, nv.ptr(psc), nv.ptr(ws), ws.numel(), nv.stream()),
+                                            nv.ptr(pr["init"]), 1, 3, nv.ptr(psc), nv.ptr(ws), ws.numel(),
+                                            nv.vp(0 if bar is None else bar.data_ptr()), nv.stream()),
                      "tp_heads_ief_forward")
             nv.mark("k3_heads_ief")
             return self.regressor.decode(psc, is_train=False, J_regressor=J_regressor)

@@ -201,7 +201,10 @@ class FakeLib:
         self.calls.append(("heads_cat", B, H))
         return 0
 
-    def tp_heads_ief_forward(self, w_cat, b_cat, h_cat, ld_h, H, w, n_rows, init, init_rows, n_iter, psc, ws, ws_bytes, stream):
+    def tp_gru_recurrence_ex(self, jobs, njobs, B, H, precision, ws, ws_bytes, barrier, stream):
+        return self.tp_gru_recurrence(jobs, njobs, B, H, precision, ws, ws_bytes, stream)
+
+    def tp_heads_ief_forward(self, w_cat, b_cat, h_cat, ld_h, H, w, n_rows, init, init_rows, n_iter, psc, ws, ws_bytes, barrier, stream):
         P = nv.PRECISION_BF16
         feat = torch.empty(n_rows, 2048)
         self.tp_encoder_heads_cat(P, w_cat, b_cat, h_cat, ld_h, n_rows, H, C.c_void_p(feat.data_ptr()), None, ws, ws_bytes, stream)
