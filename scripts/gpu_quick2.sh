@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_e2e.py tests/test_gpu_kernels.py -m gpu -q --no-header -p no:cacheprovider -k "smpl or golden or full_size or graph or pipeline or live or gemm or tcgen05 or edge" > gpurun_out/e2e.log 2>&1; echo "tests exit=$? $(tail -1 gpurun_out/e2e.log)"
+timeout 900 python -m pytest tests/test_gpu_e2e.py tests/test_gpu_kernels.py -m gpu -q --no-header -p no:cacheprovider -k "smpl or golden or full_size or graph or pipeline or live or gemm or tcgen05 or edge or gru" > gpurun_out/e2e.log 2>&1; echo "tests exit=$? $(tail -1 gpurun_out/e2e.log)"
 grep -E "^FAILED|^ERROR|Error:" gpurun_out/e2e.log | head -10
 timeout 600 python bench.py --steps 50 --warmup 5 --no-smpl --no-fold --cpu-budget 1 > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err; echo "bench exit=$?"; tail -2 gpurun_out/bench_q.err
 python - <<'PY'

@@ -53,19 +53,6 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_res(const GruParams
   for (int i = tid; i < (int)(sizeof(tp_gru_job) * kMaxJobs / 4); i += kTmaThreads)
     reinterpret_cast<int*>(sjobs)[i] = reinterpret_cast<const int*>(p.jobs)[i];
   __syncthreads();
-  // PDL: everything above ran while the input-projection GEMM was draining; gi is read from here on
-  pdl_wait();
-  pdl_launch_dependents();
-
-  for (int je = p.n_item_jobs; je < p.njobs; ++je)
-    for (int64_t i = blockIdx.x * (int64_t)kTmaThreads + tid; i < (int64_t)B * H; i += (int64_t)gridDim.x * kTmaThreads) {
-      const int b = (int)(i / H), u = (int)(i - (int64_t)b * H);
-      gru_finalize<true>(p, sjobs[je], je, 0, b, u, gate_fetch(p, sjobs[je], je, 0, b, u), 0.f, 0.f, 0.f);
-    }
-
-  unsigned int epoch = 0;
-  if (p.any_h0) { seed_h0(p); grid_barrier(p.barrier, ++epoch * gridDim.x); }
-
   int j, u0;
   locate_item(p, blockIdx.x, j, u0);
   const tp_gru_job& jb = sjobs[j];
@@ -140,6 +127,26 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_res(const GruParams
   };
   // k-th chunk in consumption order -> chunk index
   auto chunk_of = [&](int k) { return k < nstream ? rr + rs + k : (k < nstream + rs ? rr + (k - nstream) : k - nstream - rs); };
+
+  // W_hh does not depend on anything the previous kernel writes: the resident fills above and, when step 0 has no
+  // matmul (h0 = 0), the W ring for step 1 are issued before the PDL wait, while the input-projection GEMM drains
+  if (producer && jb.h0 == nullptr && jb.steps > 1) {
+    const int n = ws < nstream ? ws : nstream;
+    for (int k = 0; k < n; ++k) issue_w(chunk_of(k));
+    prefetched = n;
+  }
+  // PDL: everything above ran while the input-projection GEMM was draining; gi is read from here on
+  pdl_wait();
+  pdl_launch_dependents();
+
+  for (int je = p.n_item_jobs; je < p.njobs; ++je)
+    for (int64_t i = blockIdx.x * (int64_t)kTmaThreads + tid; i < (int64_t)B * H; i += (int64_t)gridDim.x * kTmaThreads) {
+      const int b = (int)(i / H), u = (int)(i - (int64_t)b * H);
+      gru_finalize<true>(p, sjobs[je], je, 0, b, u, gate_fetch(p, sjobs[je], je, 0, b, u), 0.f, 0.f, 0.f);
+    }
+
+  unsigned int epoch = 0;
+  if (p.any_h0) { seed_h0(p); grid_barrier(p.barrier, ++epoch * gridDim.x); }
 
   for (int s = 0; s < p.max_steps; ++s) {
     TP_TRACE(0);

@@ -69,20 +69,6 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
   for (int i = tid; i < (int)(sizeof(tp_gru_job) * kMaxJobs / 4); i += kTmaThreads)
     reinterpret_cast<int*>(sjobs)[i] = reinterpret_cast<const int*>(p.jobs)[i];
   __syncthreads();
-  // PDL: everything above ran while the input-projection GEMM was draining; gi is read from here on
-  pdl_wait();
-  pdl_launch_dependents();
-
-  // step-0-only jobs without an initial state have no matmul at all: plain gate math, grid-strided
-  for (int je = p.n_item_jobs; je < p.njobs; ++je)
-    for (int64_t i = blockIdx.x * (int64_t)kTmaThreads + tid; i < (int64_t)B * H; i += (int64_t)gridDim.x * kTmaThreads) {
-      const int b = (int)(i / H), u = (int)(i - (int64_t)b * H);
-      gru_finalize<true>(p, sjobs[je], je, 0, b, u, gate_fetch(p, sjobs[je], je, 0, b, u), 0.f, 0.f, 0.f);
-    }
-
-  unsigned int epoch = 0;
-  if (p.any_h0) { seed_h0(p); grid_barrier(p.barrier, ++epoch * gridDim.x); }
-
   int j, u0;
   locate_item(p, blockIdx.x, j, u0);          // exactly one item per CTA on this path
   const tp_gru_job& jb = sjobs[j];
@@ -123,6 +109,27 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_tma(const GruParams
     }
     ++hprod;
   };
+
+  // W_hh does not depend on anything the previous kernel writes: when step 0 has no matmul (h0 = 0) the producer fills
+  // the ring for step 1 right away -- before the PDL wait, i.e. while the input-projection GEMM is still draining
+  if (producer && jb.h0 == nullptr && jb.steps > 1) {
+    const int n = stages < nchunks ? stages : nchunks;
+    for (int c = 0; c < n; ++c) issue_w(c);
+    prefetched = n;
+  }
+  // PDL: everything above ran while the input-projection GEMM was draining; gi is read from here on
+  pdl_wait();
+  pdl_launch_dependents();
+
+  // step-0-only jobs without an initial state have no matmul at all: plain gate math, grid-strided
+  for (int je = p.n_item_jobs; je < p.njobs; ++je)
+    for (int64_t i = blockIdx.x * (int64_t)kTmaThreads + tid; i < (int64_t)B * H; i += (int64_t)gridDim.x * kTmaThreads) {
+      const int b = (int)(i / H), u = (int)(i - (int64_t)b * H);
+      gru_finalize<true>(p, sjobs[je], je, 0, b, u, gate_fetch(p, sjobs[je], je, 0, b, u), 0.f, 0.f, 0.f);
+    }
+
+  unsigned int epoch = 0;
+  if (p.any_h0) { seed_h0(p); grid_barrier(p.barrier, ++epoch * gridDim.x); }
 
   for (int s = 0; s < p.max_steps; ++s) {
     TP_TRACE(0);
