@@ -180,8 +180,8 @@ TP_API size_t tp_gru_workspace_bytes(int njobs, int B, int H);
  * H % 32 == 0.  workspace must be 256-byte aligned.                                        */
 TP_API int tp_gru_recurrence(const tp_gru_job* jobs, int njobs, int B, int H, int precision,
                       void* workspace, size_t workspace_bytes, void* stream);
-/* Same, with the grid-barrier word supplied by the caller: `barrier` (16-byte aligned, >= 16 bytes) must be ZERO when the
- * kernel starts -- zeroed by an operation ordered BEFORE the previous kernel in the stream, so that no memset node
+/* Same, with the grid-barrier slot supplied by the caller: `barrier` (128-byte aligned, 1024 bytes = 8 sharded counters
+ * on their own cache lines) must be ZERO when the kernel starts -- zeroed by an operation ordered BEFORE the previous kernel in the stream, so that no memset node
  * separates this launch from its programmatic-dependent-launch predecessor (the input-projection GEMM).  NULL = the
  * plain entry point's behaviour (barrier inside the workspace, zeroed by a memset right before the launch).          */
 TP_API int tp_gru_recurrence_ex(const tp_gru_job* jobs, int njobs, int B, int H, int precision,

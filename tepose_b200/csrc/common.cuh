@@ -99,6 +99,29 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
+// Sharded variant: `shards` counters 128 bytes apart (base + 32 k); CTA c arrives on counter c % shards and lanes
+// 0..shards-1 of warp 0 each poll one counter, so the arrivals are `shards` short chains of same-address atomics instead
+// of one long one.  shards == 1 is grid_barrier().  epoch counts the barriers of this launch from 1.
+constexpr int kBarrierShards = 8;
+__device__ __forceinline__ void grid_barrier_sh(unsigned int* base, unsigned int epoch, int shards) {
+  __syncthreads();
+  if ((int)threadIdx.x < shards) {
+    const unsigned int k = threadIdx.x;
+    unsigned int* ctr = base + 32 * k;
+    if (k == blockIdx.x % (unsigned)shards) asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(ctr) : "memory");
+    const unsigned int pop = gridDim.x / (unsigned)shards + (k < gridDim.x % (unsigned)shards ? 1u : 0u);
+    const unsigned int target = epoch * pop;
+    unsigned int seen;
+    do {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(ctr) : "memory");
+    } while (seen < target);
+#ifdef TP_BARRIER_ACQUIRE_FENCE
+    asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+#endif
+  }
+  __syncthreads();
+}
+
 #endif
 
 }  // namespace tp

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_res(const GruParams
     }
 
   unsigned int epoch = 0;
-  if (p.any_h0) { seed_h0(p); grid_barrier(p.barrier, ++epoch * gridDim.x); }
+  if (p.any_h0) { seed_h0(p); grid_barrier_sh(p.barrier, ++epoch, p.barrier_shards); }
 
   for (int s = 0; s < p.max_steps; ++s) {
     TP_TRACE(0);
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_gru_bf16_res(const GruParams
     }
     if (s + 1 < p.max_steps) {
       TP_TRACE(4);
-      grid_barrier(p.barrier, ++epoch * gridDim.x);
+      grid_barrier_sh(p.barrier, ++epoch, p.barrier_shards);
       TP_TRACE(5);
     }
   }

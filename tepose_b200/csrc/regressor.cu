@@ -129,7 +129,7 @@ struct IefLayer {
 struct IefFusedParams {
   IefLayer layer[kIefMaxLayers];
   int nlayers, M;
-  unsigned int* barrier;
+  unsigned int* barrier; int barrier_shards;
   const float* feat; const __nv_bfloat16* feat_lp; __nv_bfloat16* feat_cvt;   // feat_cvt: kIefRep bf16 replicas of feat
   const float* init; int init_rows; float* psc; __nv_bfloat16* psc_lp;
   const float* hcat; int64_t ld_h; int KH; __nv_bfloat16* hcat_cvt;   // fused heads: relu(h_cat [M,KH]) -> bf16 in the prologue
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
 #pragma unroll
     for (int r = 0; r < kIefRep; ++r) p.feat_cvt[(size_t)r * p.M * 2048 + i] = v;
   }
-  grid_barrier(p.barrier, ++epoch * gridDim.x);
+  grid_barrier_sh(p.barrier, ++epoch, p.barrier_shards);
 
   uint4 wa[kSkPF], wb[kSkPF];
   auto prefetch = [&](const IefLayer& L) {
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
     IEF_TRACE(2);
     if (l + 1 < p.nlayers) {
       if (ut < (sL[l + 1].N + 15) / 16) prefetch(sL[l + 1]);   // weights do not depend on the barrier
-      if (!L.local_next) grid_barrier(p.barrier, ++epoch * gridDim.x);
+      if (!L.local_next) grid_barrier_sh(p.barrier, ++epoch, p.barrier_shards);
     }
     IEF_TRACE(3);
   }
@@ -309,6 +309,8 @@ static int ief_fused(const tp_ief_weights* w, const float* feat, const void* fea
   IefFusedParams p;
   memset(&p, 0, sizeof(p));
   p.M = N; p.barrier = reinterpret_cast<unsigned int*>(barrier ? barrier : sc);
+  static const int shards_env = getenv("TP_BARRIER_SHARDS") ? atoi(getenv("TP_BARRIER_SHARDS")) : 1;
+  p.barrier_shards = barrier ? (shards_env >= 1 && shards_env <= tp::kBarrierShards ? shards_env : 1) : 1;
   p.feat = feat; p.feat_lp = reinterpret_cast<const __nv_bfloat16*>(feat_bf16); p.feat_cvt = feat_rep;
   p.init = init; p.init_rows = init_rows; p.psc = psc; p.psc_lp = psc_lp;
   p.trace = tp::trace_ptr();

@@ -71,10 +71,10 @@ class GruKernels:
 
     @staticmethod
     def sync_words(device, n):
-        """n zeroed 256-byte grid-barrier slots in ONE fill, issued at the top of a forward: every persistent kernel of
+        """n zeroed 1 KB grid-barrier slots (8 sharded counters each) in ONE fill, issued at the top of a forward: every persistent kernel of
         the step gets its own slot, and no memset node has to sit right in front of those kernels (it would cut the
         programmatic-dependent-launch edge to the kernel before)."""
-        return torch.zeros(n, 64, device=device, dtype=torch.int32)
+        return torch.zeros(n, 256, device=device, dtype=torch.int32)
 
     @staticmethod
     def _job(dev, gi, col0, w_hh, b_hh, steps, t_in0, t_in_step, h0=None, y=None, ycol=0, y_lp=None,
