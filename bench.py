@@ -332,7 +332,7 @@ def main():
             for (n0, a), (n1, b_) in zip(marks[:-1], marks[1:]):
                 stage_ms.setdefault(n1, []).append(a.elapsed_time(b_))
     lib.tp_set_pdl(1)
-    stage_avg = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+    stage_avg = {k: float(np.median(v)) for k, v in stage_ms.items()}     # median: an allocator cudaMalloc in one iteration must not skew a stage
     hbm_peak, tf_peak, peak_src = peaks()
     wbytes = 2 if args.precision == "bf16" else 4
     k2_ms = stage_avg.get("k2_recurrence_l0", float("nan"))
