@@ -130,6 +130,7 @@ struct IefFusedParams {
   IefLayer layer[kIefMaxLayers];
   int nlayers, M;
   unsigned int* barrier; int barrier_shards;
+  int direct_kb;      // layers with at most this many 32-column blocks load their B fragments straight into registers (0 = never)
   const float* feat; const __nv_bfloat16* feat_lp; __nv_bfloat16* feat_cvt;   // feat_cvt: kIefRep bf16 replicas of feat
   const float* init; int init_rows; float* psc; __nv_bfloat16* psc_lp;
   const float* hcat; int64_t ld_h; int KH; __nv_bfloat16* hcat_cvt;   // fused heads: relu(h_cat [M,KH]) -> bf16 in the prologue
@@ -207,6 +208,33 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
       }
       // activations of this layer (bf16 rows written by the previous layer / the prologue): own replica
       const __nv_bfloat16* Ain = L.A + (size_t)(blockIdx.x % kIefRep) * L.rep_in;
+      float acc[NT][4];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.0f;
+      if (nkb <= p.direct_kb) {
+        // K <= 1024: a warp's B fragments are <= 4 k-blocks x NT row groups of 16 bytes -- load them straight from L2
+        // into registers (one round trip), no shared-memory staging and no CTA-wide sync before the MMAs
+        uint4 bv[4][NT];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int n = 0; n < NT; ++n) {
+            const int r = n * 8 + g;
+            bv[q][n] = make_uint4(0u, 0u, 0u, 0u);
+            if (q < nb && r < p.M) bv[q][n] = __ldcg(reinterpret_cast<const uint4*>(Ain + (int64_t)r * L.lda + (b_lo + q) * 32 + 8 * t));
+          }
+        IEF_TRACE(1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q < nb) {
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+              mma16816(acc[n], wa[q], bv[q][n].x, bv[q][n].y);
+              mma16816(acc[n], wb[q], bv[q][n].z, bv[q][n].w);
+            }
+          }
+        }
+      } else {
       // every thread keeps ALL its 16-byte loads of a half block in flight before the first store:
       // this phase is a pure L2 round trip, so bytes in flight decide its duration
       const int c8n = nkb * 4;                                  // 16-byte groups per row
@@ -238,9 +266,6 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
       IEF_TRACE(6);                              // this warp done staging
       __syncthreads();
       IEF_TRACE(1);
-      float acc[NT][4];
-#pragma unroll
-      for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.0f;
 #pragma unroll
       for (int q = 0; q < kSkPF; ++q) {
         if (q < nb) {
@@ -251,6 +276,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
             mma16816(acc[n], wb[q], bv.z, bv.w);
           }
         }
+      }
       }
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
@@ -314,6 +340,8 @@ static int ief_fused(const tp_ief_weights* w, const float* feat, const void* fea
   p.feat = feat; p.feat_lp = reinterpret_cast<const __nv_bfloat16*>(feat_bf16); p.feat_cvt = feat_rep;
   p.init = init; p.init_rows = init_rows; p.psc = psc; p.psc_lp = psc_lp;
   p.trace = tp::trace_ptr();
+  static const bool no_direct = getenv("TP_IEF_NO_DIRECT") != nullptr;
+  p.direct_kb = no_direct ? 0 : 32;
   int n = 0;
   auto add = [&](const __nv_bfloat16* A, int lda, int K, size_t rep_in, const void* Wp, int Nn, const float* bias,
                  const float* Cin, int ldcin, float* C, int ldc, __nv_bfloat16* Clp, int ldclp, size_t rep_out) {
