@@ -423,6 +423,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
 
 #include "gru_tma.inl"
 #include "gru_res.inl"
+#include "gru_dual.inl"
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -538,6 +539,23 @@ static int gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, int H, in
 
   // ---- bf16 fast path: TMA-fed ring, one item per CTA
   static const bool no_tma = getenv("TP_GRU_NO_TMA") != nullptr;
+  // ---- two matmul jobs at batch 9..32 (the two causal directions of the encoder): interleaved teams, one CTA per 16 units
+  static const bool no_dual = getenv("TP_GRU_NO_DUAL") != nullptr;
+  if (precision == TP_PRECISION_BF16 && !no_tma && !no_dual && n_mat == 2 && !p.any_h0 && H % 128 == 0 && B > 8 && B <= 32 &&
+      H / 16 <= sms) {
+    p.U = 16; p.n_item_jobs = n_mat;
+    p.total_items = H / 16;
+    p.lp_tiled = 1; p.lp_slot = (int64_t)32 * H;
+    TP_CUDA(cudaFuncSetAttribute(k_gru_bf16_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDualSmem));
+    int per_sm = 0;
+    TP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gru_bf16_dual, kDualThreads, kDualSmem));
+    if (per_sm >= 1) {
+      PdlConfig lc(dim3(H / 16), dim3(kDualThreads), kDualSmem, st, /*cooperative=*/true);
+      TP_CUDA(cudaLaunchKernelEx(&lc.cfg, k_gru_bf16_dual, p));
+      count_launch();
+      return TP_OK;
+    }
+  }
   if (precision == TP_PRECISION_BF16 && !no_tma && n_mat >= 1 && H % 128 == 0 && B <= 32 && n_mat * (H / 32) <= sms) {
     const int NB = B <= 8 ? 8 : 32;
     // resident-weight variant: part of each CTA's W_hh slice stays in registers / shared memory for all steps

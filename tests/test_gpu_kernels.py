@@ -371,3 +371,40 @@ def test_smpl_large_batch_split_path(n):
         fv.append(o.vertices); fj.append(o.joints)
     assert float((out.vertices - torch.cat(fv)).abs().max()) < 2e-5
     assert float((out.joints - torch.cat(fj)).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("B,T0,T1,H", [(32, 16, 16, 2048), (9, 5, 3, 128), (17, 2, 6, 1024), (32, 1, 4, 256)])
+def test_gru_recurrence_two_interleaved_directions(B, T0, T1, H):
+    """bf16, exactly two matmul jobs without h0 at batch 9..32 -> k_gru_bf16_dual (independent 5-warp teams per direction,
+    different step counts allowed) + one single-step job handled as plain gate math; also with a caller-provided barrier."""
+    L = nv.lib()
+    cases = [_gru_case(B, T0, H, "bf16", 11, False, False), _gru_case(B, T1, H, "bf16", 12, False, True),
+             _gru_case(B, 1, H, "bf16", 13, False, False)]
+    for use_slot in (False, True):
+        keep, jobs, outs = [], [], []
+        for i, (gi, w, b, h0, ys, hT) in enumerate(cases):
+            Tj = gi.shape[0]
+            rev = i == 1
+            d = dict(gi=gi.to(DEV), w=_dev_whh(w, "bf16"), b=cu(b), y=torch.zeros(Tj, B, H, device=DEV),
+                     ylp=torch.zeros(Tj, B, H, device=DEV, dtype=torch.bfloat16), hf=torch.zeros(B, H, device=DEV))
+            keep.append(d)
+            j = nv.GruJob()
+            j.gi, j.ldg, j.w_hh, j.b_hh = d["gi"].data_ptr(), 3 * H, d["w"].data_ptr(), d["b"].data_ptr()
+            j.h0 = 0
+            j.y, j.ldy, j.y_lp, j.ldy_lp = d["y"].data_ptr(), H, d["ylp"].data_ptr(), H
+            j.h_final, j.ld_hf = d["hf"].data_ptr(), H
+            j.steps = Tj
+            j.t_in0, j.t_in_step = (Tj - 1, -1) if rev else (0, 1)
+            j.t_out0, j.t_out_step = (Tj - 1, -1) if rev else (0, 1)
+            jobs.append(j)
+            outs.append((ys, hT))
+        arr = (nv.GruJob * 3)(*jobs)
+        ws = nv.workspace(L.tp_gru_workspace_bytes(3, B, H), DEV)
+        slot = torch.zeros(256, device=DEV, dtype=torch.int32)
+        nv.check(L.tp_gru_recurrence_ex(arr, 3, B, H, nv.PRECISION_BF16, nv.ptr(ws), ws.numel(),
+                                        nv.vp(slot.data_ptr() if use_slot else 0), nv.stream()))
+        torch.cuda.synchronize()
+        for d, (ys, hT) in zip(keep, outs):
+            assert float((d["y"].cpu().double() - ys).abs().max()) < 2e-4
+            assert float((d["hf"].cpu().double() - hT).abs().max()) < 2e-4
+            assert float((d["ylp"].float().cpu().double() - ys).abs().max()) < 1e-2
