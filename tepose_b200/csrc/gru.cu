@@ -36,6 +36,7 @@ struct GruParams {
                             //    (one contiguous 8 KB block per ring stage of k_gru_bf16_tma); 0: row-major [B][H]
   unsigned int* barrier;    // monotonic grid-barrier counters (zeroed before launch), barrier_shards of them 128 B apart
   int barrier_shards;
+  int dual_skew;            // k_gru_bf16_dual: SM cycles team 1 waits before its first step (de-phases the two teams)
   long long* trace;         // debug: [gridDim][max_steps][8] SM-clock stamps (tp_gru_set_trace), or null
 };
 
@@ -543,6 +544,8 @@ static int gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, int H, in
   static const bool no_dual = getenv("TP_GRU_NO_DUAL") != nullptr;
   if (precision == TP_PRECISION_BF16 && !no_tma && !no_dual && n_mat == 2 && !p.any_h0 && H % 128 == 0 && B > 8 && B <= 32 &&
       H / 16 <= sms) {
+    static const int skew_env = getenv("TP_GRU_DUAL_SKEW") ? atoi(getenv("TP_GRU_DUAL_SKEW")) : 0;
+    p.dual_skew = skew_env;
     p.U = 16; p.n_item_jobs = n_mat;
     p.total_items = H / 16;
     p.lp_tiled = 1; p.lp_slot = (int64_t)32 * H;

@@ -10,12 +10,18 @@
 // per step next to the 393 KB of W_hh).
 //
 // Ring stage of a team: 12 KB W (3 gate tiles x 4 column blocks, fragment-packed) + 8 KB h slice (tiled, swizzled).
+// The h parts are empty whenever the team is in its gate phase (h_t does not exist yet), so the cross-warp reduction
+// buffer lives there (2048 floats per stage) and all of shared memory goes to ring depth: 5 stages per team.
 constexpr int kDualThreads = 320;                         // 2 teams x (4 consumer warps + 1 producer warp)
 constexpr int kDualWBytes = 3 * kChunkBlocks * 1024;      // 12 KB
 constexpr int kDualStageBytes = kDualWBytes + kHChunkBytes;   // 20 KB
-constexpr int kDualStages = 4;
+#ifndef TP_DUAL_STAGES
+#define TP_DUAL_STAGES 5
+#endif
+constexpr int kDualStages = TP_DUAL_STAGES;
 constexpr int kDualRedFloats = 4 * 3 * 32 * 20;           // [KG][3][NB = 32][RP = 16 + 4]
-constexpr size_t kDualSmem = (size_t)2 * kDualStages * kDualStageBytes + (size_t)2 * kDualRedFloats * 4 + 512;
+static_assert(kDualStages >= 4 && 3 * 32 * 20 <= kHChunkBytes / 4, "K group k's reduction slab lives in the h part of ring stage k");
+constexpr size_t kDualSmem = (size_t)2 * kDualStages * kDualStageBytes + 512;
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
 
@@ -32,8 +38,9 @@ __global__ void __launch_bounds__(kDualThreads, 1) k_gru_bf16_dual(const GruPara
   const int kg = warp & 3;                                  // consumers: K group
   const int ctid = tid - d * 128;                           // consumers: thread index inside the team (0..127)
   unsigned char* ring = smem_d + (size_t)d * kDualStages * kDualStageBytes;
-  float* red = reinterpret_cast<float*>(smem_d + (size_t)2 * kDualStages * kDualStageBytes) + (size_t)d * kDualRedFloats;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_d + (size_t)2 * kDualStages * kDualStageBytes + (size_t)2 * kDualRedFloats * 4);
+  // reduction buffer: K group k's slab [3][NB][RP] (1920 floats) lives in the h part (2048 floats) of ring stage k
+  auto redk = [&](int k) { return reinterpret_cast<float*>(ring + (size_t)k * kDualStageBytes + kDualWBytes); };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_d + (size_t)2 * kDualStages * kDualStageBytes);
   uint64_t* full = bars + d * 16;                           // [stages]: W arrival + h arrival
   uint64_t* empty = full + 8;                               // [stages]: 4 consumer warps
 
@@ -98,7 +105,12 @@ __global__ void __launch_bounds__(kDualThreads, 1) k_gru_bf16_dual(const GruPara
   auto ldnc = [](const float* ptr) { float v; asm volatile("ld.global.nc.f32 %0, [%1];\n" : "=f"(v) : "l"(ptr)); return v; };
   auto ldcg = [](const float* ptr) { float v; asm volatile("ld.global.cg.f32 %0, [%1];\n" : "=f"(v) : "l"(ptr)); return v; };
 
+  if (d == 1 && p.dual_skew > 0) {                          // optional phase offset between the teams
+    const long long t0 = clock64();
+    while (clock64() - t0 < p.dual_skew) { }
+  }
   for (int s = 0; s < jb.steps; ++s) {
+    TP_TRACE(0);
     const bool have_prev = s > 0;                           // jobs with h0 do not take this kernel
     if (producer) {
       if (have_prev) {
@@ -144,6 +156,7 @@ __global__ void __launch_bounds__(kDualThreads, 1) k_gru_bf16_dual(const GruPara
           for (int n = 0; n < NT; ++n)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[i][n][e] = 0.0f;
+        TP_TRACE(1);
         for (int c = 0; c < nchunks; ++c) {
           const int st = c_stage;
           mb_wait(&full[st], c_phase);
@@ -168,17 +181,20 @@ __global__ void __launch_bounds__(kDualThreads, 1) k_gru_bf16_dual(const GruPara
           if (lane == 0) mb_arrive(&empty[st]);
           if (++c_stage == kDualStages) { c_stage = 0; c_phase ^= 1; }
         }
+        TP_TRACE(2);
+        bar_sync(3 + d, 128);                                // every warp of the team is done with the h slices
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
           for (int n = 0; n < NT; ++n) {
-            float* r0 = red + ((size_t)(kg * 3 + i) * NB + n * 8 + 2 * t) * RP + g;
+            float* r0 = redk(kg) + (size_t)(i * NB + n * 8 + 2 * t) * RP + g;
             r0[0] = acc[i][n][0];
             r0[RP] = acc[i][n][1];
             r0[8] = acc[i][n][2];
             r0[RP + 8] = acc[i][n][3];
           }
         bar_sync(3 + d, 128);
+        TP_TRACE(3);
       }
 #pragma unroll
       for (int e = 0; e < GE; ++e) {
@@ -188,9 +204,10 @@ __global__ void __launch_bounds__(kDualThreads, 1) k_gru_bf16_dual(const GruPara
         if (have_prev) {
 #pragma unroll
           for (int k = 0; k < KG; ++k) {
-            ar += red[((size_t)(k * 3 + 0) * NB + bb) * RP + uu];
-            az += red[((size_t)(k * 3 + 1) * NB + bb) * RP + uu];
-            an += red[((size_t)(k * 3 + 2) * NB + bb) * RP + uu];
+            const float* rk = redk(k);
+            ar += rk[(0 * NB + bb) * RP + uu];
+            az += rk[(1 * NB + bb) * RP + uu];
+            an += rk[(2 * NB + bb) * RP + uu];
           }
         }
         gru_finalize<true>(p, jb, d, s, bb, u0 + uu, gin[e], ar, az, an);
@@ -198,6 +215,7 @@ __global__ void __launch_bounds__(kDualThreads, 1) k_gru_bf16_dual(const GruPara
     }
     if (s + 1 < jb.steps) {
       // grid barrier of this direction only: all CTAs' teams d.  Same release / relaxed-poll protocol as grid_barrier().
+      TP_TRACE(4);
       bar_sync(1 + d, 160);
       if (!producer && ctid == 0) {
         const unsigned int target = ++epoch * gridDim.x;
@@ -208,6 +226,7 @@ __global__ void __launch_bounds__(kDualThreads, 1) k_gru_bf16_dual(const GruPara
         } while (seen < target);
       }
       bar_sync(1 + d, 160);
+      TP_TRACE(5);
     }
   }
 }
