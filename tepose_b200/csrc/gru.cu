@@ -542,22 +542,23 @@ static int gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, int H, in
   static const bool no_tma = getenv("TP_GRU_NO_TMA") != nullptr;
   // ---- two matmul jobs at batch 9..32 (the two causal directions of the encoder): interleaved teams, one CTA per 16 units
   static const bool no_dual = getenv("TP_GRU_NO_DUAL") != nullptr;
-  if (precision == TP_PRECISION_BF16 && !no_tma && !no_dual && n_mat == 2 && !p.any_h0 && H % 128 == 0 && B > 8 && B <= 32 &&
-      H / 16 <= sms) {
+  if (precision == TP_PRECISION_BF16 && !no_tma && !no_dual && n_mat == 2 && !p.any_h0 && H % 128 == 0 && B <= 32 && H / 16 <= sms) {
     static const int skew_env = getenv("TP_GRU_DUAL_SKEW") ? atoi(getenv("TP_GRU_DUAL_SKEW")) : 0;
     p.dual_skew = skew_env;
     p.U = 16; p.n_item_jobs = n_mat;
     p.total_items = H / 16;
     p.lp_tiled = 1; p.lp_slot = (int64_t)32 * H;
-    TP_CUDA(cudaFuncSetAttribute(k_gru_bf16_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDualSmem));
-    int per_sm = 0;
-    TP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gru_bf16_dual, kDualThreads, kDualSmem));
-    if (per_sm >= 1) {
+    auto launch = [&](auto kfn) -> int {
+      TP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDualSmem));
+      int per_sm = 0;
+      TP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kDualThreads, kDualSmem));
+      if (per_sm < 1) return fail(TP_ERR_UNSUPPORTED, "tp_gru_recurrence: dual kernel does not fit on an SM");
       PdlConfig lc(dim3(H / 16), dim3(kDualThreads), kDualSmem, st, /*cooperative=*/true);
-      TP_CUDA(cudaLaunchKernelEx(&lc.cfg, k_gru_bf16_dual, p));
+      TP_CUDA(cudaLaunchKernelEx(&lc.cfg, kfn, p));
       count_launch();
       return TP_OK;
-    }
+    };
+    return B <= 8 ? launch(k_gru_bf16_dual<1>) : launch(k_gru_bf16_dual<4>);
   }
   if (precision == TP_PRECISION_BF16 && !no_tma && n_mat >= 1 && H % 128 == 0 && B <= 32 && n_mat * (H / 32) <= sms) {
     const int NB = B <= 8 ? 8 : 32;

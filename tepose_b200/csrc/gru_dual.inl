@@ -25,8 +25,10 @@ constexpr size_t kDualSmem = (size_t)2 * kDualStages * kDualStageBytes + 512;
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
 
+template <int NT>
 __global__ void __launch_bounds__(kDualThreads, 1) k_gru_bf16_dual(const GruParams p) {
-  constexpr int NT = 4, NB = 32, U = 16, KG = 4, RP = U + 4, GE = 4;     // 512 gate elements per team / 128 threads
+  constexpr int NB = NT * 8, U = 16, KG = 4, RP = U + 4, GE = NT;        // NB x 16 gate elements per team / 128 threads
+  constexpr uint32_t kHB = NB * 256;                                      // bytes of an h slice that are read (NB rows x 128 bf16)
   extern __shared__ __align__(1024) unsigned char smem_d[];
   const int H = p.H, B = p.B;
   const int nblk = H / 32, nchunks = nblk / kChunkBlocks;
@@ -75,8 +77,8 @@ __global__ void __launch_bounds__(kDualThreads, 1) k_gru_bf16_dual(const GruPara
   auto issue_h = [&](int c, const __nv_bfloat16* hprev) {
     const int st = hprod % kDualStages;
     if (lane == 3) {
-      mb_expect_tx(&full[st], kHChunkBytes);
-      bulk_g2s(ring + (size_t)st * kDualStageBytes + kDualWBytes, hprev + (size_t)c * 32 * 128, kHChunkBytes, &full[st]);
+      mb_expect_tx(&full[st], kHB);
+      bulk_g2s(ring + (size_t)st * kDualStageBytes + kDualWBytes, hprev + (size_t)c * 32 * 128, kHB, &full[st]);
     }
     ++hprod;
   };

@@ -373,9 +373,9 @@ def test_smpl_large_batch_split_path(n):
     assert float((out.joints - torch.cat(fj)).abs().max()) < 2e-5
 
 
-@pytest.mark.parametrize("B,T0,T1,H", [(32, 16, 16, 2048), (9, 5, 3, 128), (17, 2, 6, 1024), (32, 1, 4, 256)])
+@pytest.mark.parametrize("B,T0,T1,H", [(32, 16, 16, 2048), (9, 5, 3, 128), (17, 2, 6, 1024), (32, 1, 4, 256), (1, 16, 16, 2048), (5, 3, 4, 256)])
 def test_gru_recurrence_two_interleaved_directions(B, T0, T1, H):
-    """bf16, exactly two matmul jobs without h0 at batch 9..32 -> k_gru_bf16_dual (independent 5-warp teams per direction,
+    """bf16, exactly two matmul jobs without h0 at batch <= 32 -> k_gru_bf16_dual (independent 5-warp teams per direction,
     different step counts allowed) + one single-step job handled as plain gate math; also with a caller-provided barrier."""
     L = nv.lib()
     cases = [_gru_case(B, T0, H, "bf16", 11, False, False), _gru_case(B, T1, H, "bf16", 12, False, True),
