@@ -340,12 +340,17 @@ def main():
     k1_ms = stage_avg.get("k1_input_proj_l0", float("nan"))
     k1_flops = 2.0 * (2 * B * T + B) * 2133 * 3 * H
     roofline = {
-        "kernel": "k_gru_bf16_tma (K2 recurrence)" if args.precision == "bf16" else "k_gru_f32 (K2 recurrence)",
+        "kernel": "k_gru_bf16_dual (K2 recurrence)" if args.precision == "bf16" else "k_gru_f32 (K2 recurrence)",
         "bound": "hbm", "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
         "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / hbm_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-        # (profiles/r01_ncu_k_gru_bf16_tma.txt: 76.4 MB + 2.6 MB; = W_hh once + the K1 gate pre-activations once)
-        "traffic": 79.0e6 if args.precision == "bf16" else None, "peak_source": peak_src,
+        # (profiles/r02_ncu_k_gru_bf16_dual.txt: 76.4 MB + 2.4 MB; = W_hh once + the K1 gate pre-activations once)
+        "traffic": 78.9e6 if args.precision == "bf16" else None, "peak_source": peak_src,
+        # what actually bounds it: W_hh is re-streamed from L2 every step (it cannot stay on chip: 50.3 MB vs 33.6 MB of
+        # shared memory).  L2 -> SM bytes per launch from the same capture (lts__t_sectors_srcunit_tex_op_read x 32 B)
+        # against the L2 streaming rate scripts/micro/l2bw.cu reaches with 128 CTAs (profiles/r01_l2bw_micro.txt)
+        "l2_stream": ({"bytes_per_launch": 1.0325e9, "achieved_GBps": 1.0325e9 / (k2_ms * 1e-3) / 1e9, "micro_ceiling_GBps": 6900.0,
+                       "frac": 1.0325e9 / (k2_ms * 1e-3) / 1e9 / 6900.0} if args.precision == "bf16" else None),
         "algorithmic_bytes": k2_bytes, "avg_ms": k2_ms,
         "secondary": {"kernel": "k_gemm_bf16_tc (K1 input projection)" if args.precision == "bf16" else "k_gemm_f32 (K1)",
                       "bound": "tensor", "achieved": k1_flops / (k1_ms * 1e-3) / 1e12, "peak": tf_peak,
