@@ -674,17 +674,24 @@ __global__ void __launch_bounds__(128) k_smpl_finalize(int n, int n_verts, const
   asm volatile("griddepcontrol.wait;\n" ::: "memory");      // no-op unless launched with programmatic serialization
   __shared__ float Jr[kMaxReg * 3];
   const int b = blockIdx.x, tid = threadIdx.x;
-  // regressor partials: one warp per value, lanes stride over the vertex tiles (independent loads in
-  // flight), fixed-shape shuffle tree -> deterministic
+  // regressor partials [tile][value]: warp w takes tiles w, w+4, ...; lane = value, so a tile is one contiguous
+  // coalesced read and all of a warp's loads are independent (a few L2 round trips in total).  The four warp sums
+  // are added in a fixed order -> deterministic.
   {
-    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    for (int i = warp; i < nreg * 3; i += nwarps) {
-      float s = 0.0f;
-      for (int sp = lane; sp < nsplit; sp += 32) s += __ldcg(&jpart[((int64_t)b * nsplit + sp) * nreg * 3 + i]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) Jr[i] = s;
+    __shared__ float Jw[4][kMaxReg * 3];
+    const int warp = tid >> 5, lane = tid & 31, nval = nreg * 3;
+    const float* base = jpart + (int64_t)b * nsplit * nval;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 4
+    for (int sp = warp; sp < nsplit; sp += 4) {
+      const float* row = base + (int64_t)sp * nval;
+      if (lane < nval) a0 += __ldcg(row + lane);
+      if (lane + 32 < nval) a1 += __ldcg(row + lane + 32);
+      if (lane + 64 < nval) a2 += __ldcg(row + lane + 64);
     }
+    if (warp < 4) { Jw[warp][lane] = a0; Jw[warp][lane + 32] = a1; Jw[warp][lane + 64] = a2; }
+    __syncthreads();
+    for (int i = tid; i < nval; i += blockDim.x) Jr[i] = (Jw[0][i] + Jw[1][i]) + (Jw[2][i] + Jw[3][i]);
   }
   __syncthreads();
   for (int o = tid; o < nj; o += blockDim.x) {
