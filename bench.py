@@ -356,6 +356,25 @@ def main():
                       "bound": "tensor", "achieved": k1_flops / (k1_ms * 1e-3) / 1e12, "peak": tf_peak,
                       "unit": "TFLOP/s", "frac": k1_flops / (k1_ms * 1e-3) / 1e12 / tf_peak, "avg_ms": k1_ms},
     }
+    # every stage against the roofline that bounds it: algorithmic bytes / flops per launch over its average time
+    def _hbm(name, nbytes, what):
+        ms = stage_avg.get(name)
+        return None if not ms else {"stage": name, "bound": "hbm", "what": what, "algorithmic_bytes": nbytes, "avg_ms": ms,
+                                    "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                    "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak}
+    k3_w = (3 * H * 2048 + 2048 * 1024 + 3 * (160 * 1024 + 1024 * 1024 + 1024 * 160)) * wbytes     # heads + fc1 feature part + 3 IEF iterations
+    k3_ms = (stage_avg.get("k3_heads_ief") or (stage_avg.get("k3_heads", 0.0) + stage_avg.get("k3_ief", 0.0))) or None
+    roofline["stages"] = [x for x in (
+        _hbm("pack", B * T * 2133 * 4 + B * T * 2176 * wbytes, "x fp32 in, padded time-major operand out"),
+        {"stage": "k1_input_proj_l0", "bound": "tensor", "achieved": k1_flops / (k1_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+         "frac": k1_flops / (k1_ms * 1e-3) / 1e12 / tf_peak, "avg_ms": k1_ms, "what": "minimal FLOPs of the three directions' input projection"},
+        {"stage": "k2_recurrence_l0", "bound": "hbm", "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+         "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / hbm_peak, "avg_ms": k2_ms, "what": "W_hh of both directions read once (see l2_stream)"},
+        None if not k3_ms else {"stage": "k3_heads_ief", "bound": "hbm", "what": "every Linear weight of the heads and the IEF read once (a 14-layer dependent chain)",
+                                "algorithmic_bytes": k3_w, "avg_ms": k3_ms, "achieved": k3_w / (k3_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                "unit": "GB/s", "frac": k3_w / (k3_ms * 1e-3) / 1e9 / hbm_peak},
+        _hbm("k45_smpl", B * 85780, "916 B in + 84 864 B out per body (SURVEY 8d)"),
+    ) if x]
 
     # ---------------------------------------------------------------- live-stream latency (config 3, rank 0)
     live = None
