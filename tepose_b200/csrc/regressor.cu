@@ -326,10 +326,10 @@ static int ief_fused(const tp_ief_weights* w, const float* feat, const void* fea
   unsigned char* sc = ws + 3 * slab + 2 * slab_lp + slab_p;
   const size_t n1024 = (size_t)N * 1024, n160 = (size_t)N * 160, n2048 = (size_t)N * 2048;
   __nv_bfloat16* rep = reinterpret_cast<__nv_bfloat16*>(sc + 4096);
-  __nv_bfloat16* u1_lp = rep;                                   // [8][N,1024]
-  __nv_bfloat16* u2_lp = u1_lp + kIefRep * n1024;               // [8][N,1024]
-  __nv_bfloat16* psc_lp = u2_lp + kIefRep * n1024;              // [8][N,160]
-  __nv_bfloat16* feat_rep = psc_lp + kIefRep * n160;            // [8][N,2048]   (total <= 2.2 MB for N = 32)
+  __nv_bfloat16* u1_lp = rep;                                   // [kIefRep][N,1024]
+  __nv_bfloat16* u2_lp = u1_lp + kIefRep * n1024;               // [kIefRep][N,1024]
+  __nv_bfloat16* psc_lp = u2_lp + kIefRep * n1024;              // [kIefRep][N,160]
+  __nv_bfloat16* feat_rep = psc_lp + kIefRep * n160;            // [kIefRep][N,2048]
   __nv_bfloat16* hcat_cvt = feat_rep + kIefRep * n2048;         // [N,3H] relu'd encoder states (fused heads)
   float* featf = reinterpret_cast<float*>(ws + slab);           // [N,2048] fp32 head accumulator (the u1 | u2 slabs of the unfused path)
   IefFusedParams p;
