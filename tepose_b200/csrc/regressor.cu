@@ -212,25 +212,32 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
 #pragma unroll
       for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.0f;
       if (nkb <= p.direct_kb) {
-        // K <= 1024: a warp's B fragments are <= 4 k-blocks x NT row groups of 16 bytes -- load them straight from L2
-        // into registers (one round trip), no shared-memory staging and no CTA-wide sync before the MMAs
-        uint4 bv[4][NT];
+        // a warp's B fragments are <= 8 k-blocks x NT row groups of 16 bytes -- load them straight from L2 into
+        // registers (one round trip per 4 k-blocks), no shared-memory staging and no CTA-wide sync before the MMAs
+        // (two rounds of <= 4 k-blocks per warp, so K = 2048 layers take this path too)
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int h = 0; h < 2; ++h) {
+          if (h * 4 < nb) {
+            uint4 bv[4][NT];
 #pragma unroll
-          for (int n = 0; n < NT; ++n) {
-            const int r = n * 8 + g;
-            bv[q][n] = make_uint4(0u, 0u, 0u, 0u);
-            if (q < nb && r < p.M) bv[q][n] = __ldcg(reinterpret_cast<const uint4*>(Ain + (int64_t)r * L.lda + (b_lo + q) * 32 + 8 * t));
-          }
-        IEF_TRACE(1);
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (q < nb) {
+              for (int n = 0; n < NT; ++n) {
+                const int r = n * 8 + g;
+                bv[q][n] = make_uint4(0u, 0u, 0u, 0u);
+                if (h * 4 + q < nb && r < p.M)
+                  bv[q][n] = __ldcg(reinterpret_cast<const uint4*>(Ain + (int64_t)r * L.lda + (b_lo + h * 4 + q) * 32 + 8 * t));
+              }
+            if (h == 0) IEF_TRACE(1);
 #pragma unroll
-            for (int n = 0; n < NT; ++n) {
-              mma16816(acc[n], wa[q], bv[q][n].x, bv[q][n].y);
-              mma16816(acc[n], wb[q], bv[q][n].z, bv[q][n].w);
+            for (int q = 0; q < 4; ++q) {
+              if (h * 4 + q < nb) {
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                  mma16816(acc[n], wa[h * 4 + q], bv[q][n].x, bv[q][n].y);
+                  mma16816(acc[n], wb[h * 4 + q], bv[q][n].z, bv[q][n].w);
+                }
+              }
             }
           }
         }
@@ -341,7 +348,8 @@ static int ief_fused(const tp_ief_weights* w, const float* feat, const void* fea
   p.init = init; p.init_rows = init_rows; p.psc = psc; p.psc_lp = psc_lp;
   p.trace = tp::trace_ptr();
   static const bool no_direct = getenv("TP_IEF_NO_DIRECT") != nullptr;
-  p.direct_kb = no_direct ? 0 : 32;
+  static const int direct_env = getenv("TP_IEF_DIRECT_KB") ? atoi(getenv("TP_IEF_DIRECT_KB")) : 32;
+  p.direct_kb = no_direct ? 0 : direct_env;     // 32: layers with K <= 1024 load their B fragments straight from L2 (64 = K <= 2048 too: measured, no difference)
   int n = 0;
   auto add = [&](const __nv_bfloat16* A, int lda, int K, size_t rep_in, const void* Wp, int Nn, const float* bias,
                  const float* Cin, int ldcin, float* C, int ldc, __nv_bfloat16* Clp, int ldclp, size_t rep_out) {
