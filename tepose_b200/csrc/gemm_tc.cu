@@ -21,13 +21,15 @@ namespace tp {
 // B=32,T=16 input projection (432 tiles of 128 x 128) into 1.95 (288 tiles).  Skinny launches (one wave or less of
 // 128-wide tiles, e.g. the B = 1 live window) stay at BN = 128: they stream weights and want more CTAs.
 constexpr int TC_BM = 128, TC_BK = 64;
-template <int BN> struct TcCfg {
-  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N / epilogue chunking");
-  static constexpr int STAGE_BYTES = (TC_BM + BN) * TC_BK * 2;        // 40 KB at BN = 192, 32 KB at BN = 128
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;           // 5 / 6
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // power of two >= BN
+template <int BN, int BMH> struct TcCfg {                             // BMH: 128-row accumulators per CTA (1 or 2)
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256 && (BMH == 1 || BMH == 2), "UMMA N / epilogue chunking");
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;                   // one 128-row A block of a k-step: 16 KB
+  static constexpr int STAGE_BYTES = BMH * A_BYTES + BN * TC_BK * 2;  // 56 KB at (192, 2), 32 KB at (128, 1)
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;           // 3 / 6
+  static constexpr int TMEM_COLS = BMH * BN <= 32 ? 32 : BMH * BN <= 64 ? 64 : BMH * BN <= 128 ? 128 : BMH * BN <= 256 ? 256 : 512;
   static constexpr int EPI_PITCH = BN + 4;                            // floats per staged row (= 4 mod 32)
   static_assert((size_t)TC_BM * EPI_PITCH * 4 <= (size_t)STAGES * STAGE_BYTES, "epilogue staging must fit in the ring");
+  static_assert(BMH * BN <= 512, "TMEM has 512 columns");
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 };
 constexpr int TC_MAX_SEGS = 8;
@@ -36,6 +38,7 @@ constexpr int TC_THREADS = 128;
 struct TcParams {
   tp_gemm_seg seg[TC_MAX_SEGS];
   int tile_begin[TC_MAX_SEGS + 1];
+  int halves[TC_MAX_SEGS];          // 128-row accumulators per tile of this segment (2: 256-row tiles, every W tile loaded half as often)
   int nseg, kblocks;
 };
 
@@ -112,10 +115,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
 }
 
-template <int BN>
+template <int BN, int BMH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, BMH>;
   constexpr int TC_BN = BN, TC_STAGES = Cfg::STAGES, TC_STAGE_BYTES = Cfg::STAGE_BYTES, TC_TMEM_COLS = Cfg::TMEM_COLS, TC_EPI_PITCH = Cfg::EPI_PITCH;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: [stages][A 16KB | W 16KB] (1024-aligned), then barriers
@@ -134,14 +137,16 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (q < p.nseg && (int)blockIdx.x >= p.tile_begin[q]) s = q;
   // static-index select: a dynamic index into the kernel parameters costs a constant-cache miss per field
   tp_gemm_seg sg = p.seg[0];
-  int tile0 = p.tile_begin[0];
+  int tile0 = p.tile_begin[0], halves = p.halves[0];
 #pragma unroll
   for (int q = 1; q < TC_MAX_SEGS; ++q)
-    if (q == s) { sg = p.seg[q]; tile0 = p.tile_begin[q]; }
+    if (q == s) { sg = p.seg[q]; tile0 = p.tile_begin[q]; halves = p.halves[q]; }
+  if (BMH == 1) halves = 1;
   const int local = blockIdx.x - tile0;
-  const int m_tiles = (sg.m_rows + TC_BM - 1) / TC_BM;
+  const int bm = TC_BM * halves;                        // rows of this tile: 128 or 256
+  const int m_tiles = (sg.m_rows + bm - 1) / bm;
   const int n_tile = local / m_tiles, m_tile = local - n_tile * m_tiles;
-  const int m0 = m_tile * TC_BM, n0 = n_tile * TC_BN;   // segment-local
+  const int m0 = m_tile * bm, n0 = n_tile * TC_BN;      // segment-local
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -174,9 +179,10 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t ph = (kb / TC_STAGES) & 1;
         mbar_wait(&empty_bar[st], ph ^ 1);
         unsigned char* a_dst = smem + st * TC_STAGE_BYTES;
-        unsigned char* w_dst = a_dst + TC_BM * TC_BK * 2;
-        mbar_expect_tx(&full_bar[st], TC_STAGE_BYTES);
+        unsigned char* w_dst = a_dst + BMH * Cfg::A_BYTES;
+        mbar_expect_tx(&full_bar[st], (uint32_t)(halves * Cfg::A_BYTES + TC_BN * TC_BK * 2));
         tma_load_2d(a_dst, &map_a, &full_bar[st], kb * TC_BK, sg.m_start + m0);
+        if (BMH == 2 && halves == 2) tma_load_2d(a_dst + Cfg::A_BYTES, &map_a, &full_bar[st], kb * TC_BK, sg.m_start + m0 + TC_BM);
         tma_load_2d(w_dst, &map_w, &full_bar[st], kb * TC_BK, sg.n_start + n0);
       }
     }
@@ -189,12 +195,19 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(&full_bar[st], ph);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const uint32_t a_addr = smem_u32(smem + st * TC_STAGE_BYTES);
-        const uint32_t w_addr = a_addr + TC_BM * TC_BK * 2;
-        const uint64_t da = umma_desc_sw128(a_addr), db = umma_desc_sw128(w_addr);
+        const uint32_t w_addr = a_addr + BMH * Cfg::A_BYTES;
+        const uint64_t db = umma_desc_sw128(w_addr);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in 16-byte units
-          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), Cfg::IDESC, (kb | k) != 0 ? 1u : 0u);
+        for (int h = 0; h < BMH; ++h) {
+          if (h < halves) {
+            const uint64_t da = umma_desc_sw128(a_addr + h * Cfg::A_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in 16-byte units;
+              // accumulator h lives TC_BN TMEM columns further
+              umma_f16(tmem_base + (uint32_t)(h * TC_BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), Cfg::IDESC, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
         }
         umma_commit(&empty_bar[st]);   // slot reusable once these MMAs have read it
       }
@@ -211,10 +224,13 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // transposed through them: thread = row writes its 128 values (pitch 132 floats: conflict-free 16-byte
   // accesses), then each warp streams ITS 32 rows out with one fully coalesced 512-byte store per row.
   float* stage = reinterpret_cast<float*>(smem) + (size_t)(warp * 32) * TC_EPI_PITCH;
+  const bool vec_ok = ((sg.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(sg.out) & 15) == 0);
+#pragma unroll 1
+  for (int h = 0; h < halves; ++h) {
 #pragma unroll 1
   for (int c0 = 0; c0 < TC_BN; c0 += 32) {
     uint32_t v[32];
-    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(h * TC_BN + c0), v);
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -226,10 +242,9 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   }
   __syncwarp();
-  const bool vec_ok = ((sg.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(sg.out) & 15) == 0);
 #pragma unroll 2
   for (int r = 0; r < 32; ++r) {
-    const int row = m0 + warp * 32 + r;                  // segment-local output row
+    const int row = m0 + h * TC_BM + warp * 32 + r;      // segment-local output row
     if (row >= sg.m_rows) break;
 #pragma unroll
     for (int cc = lane * 4; cc < TC_BN; cc += 128) {     // 512 contiguous bytes per warp store
@@ -244,6 +259,8 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (n + i < sg.n_cols) dst[i] = e[i];
       }
     }
+  }
+  __syncwarp();                                          // the staging rows are rewritten by the next half
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
@@ -302,10 +319,15 @@ extern "C" int tp_gemm_bf16_tc(const void* A, int a_rows, const void* W, int w_r
   memset(&p, 0, sizeof(p));
   p.nseg = nseg;
   p.kblocks = kp / TC_BK;
-  // tile width: 192 once the launch has more than one wave of 128-wide tiles, else 128 (skinny launches want CTAs)
+  // tile shape: once the launch has more than one wave of 128 x 128 tiles it is bound by the L2 -> SM operand stream, so
+  // tiles get wider (192) and, for segments whose row count is a multiple of 256, twice as tall (two TMEM accumulators
+  // share every W tile); skinny launches stay at 128 x 128: they stream weights and want CTAs.
   int tiles128 = 0;
   for (int i = 0; i < nseg; ++i) tiles128 += (int)(ceil_div(segs[i].m_rows, TC_BM) * ceil_div(segs[i].n_cols, 128));
   static const int bn_env = getenv("TP_TC_BN") ? atoi(getenv("TP_TC_BN")) : 0;
+  // 256-row tiles (two TMEM accumulators sharing each W tile) cost ring depth -- 3 stages of 56 KB instead of 5 of 40 KB --
+  // and measured slower on the B=32,T=16 input projection (55 us vs 47 us): opt-in only (TP_TC_TALL=1)
+  static const bool tall = getenv("TP_TC_TALL") != nullptr;
   const int bn = bn_env == 128 || bn_env == 192 ? bn_env : (tiles128 > sm_count() ? 192 : 128);
   int tiles = 0;
   for (int i = 0; i < nseg; ++i) {
@@ -314,8 +336,9 @@ extern "C" int tp_gemm_bf16_tc(const void* A, int a_rows, const void* W, int w_r
     TP_CHECK_ARG(sg.m_start >= 0 && sg.m_start + sg.m_rows <= a_rows, "tp_gemm_bf16_tc: segment %d rows out of range", i);
     TP_CHECK_ARG(sg.n_start >= 0 && sg.n_start + sg.n_cols <= w_rows, "tp_gemm_bf16_tc: segment %d cols out of range", i);
     p.seg[i] = sg;
+    p.halves[i] = (bn == 192 && tall && sg.m_rows % (2 * TC_BM) == 0) ? 2 : 1;
     p.tile_begin[i] = tiles;
-    tiles += (int)(ceil_div(sg.m_rows, TC_BM) * ceil_div(sg.n_cols, bn));
+    tiles += (int)(ceil_div(sg.m_rows, TC_BM * p.halves[i]) * ceil_div(sg.n_cols, bn));
   }
   for (int i = nseg; i <= TC_MAX_SEGS; ++i) p.tile_begin[i] = tiles;
   CUtensorMap map_a, map_w;
@@ -323,16 +346,24 @@ extern "C" int tp_gemm_bf16_tc(const void* A, int a_rows, const void* W, int w_r
   if (rc != TP_OK) return rc;
   rc = make_map(&map_w, W, w_rows, kp, bn);
   if (rc != TP_OK) return rc;
-  if (bn == 192) {
-    const size_t smem = (size_t)TcCfg<192>::STAGES * TcCfg<192>::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-    TP_CUDA(cudaFuncSetAttribute(k_gemm_bf16_tc<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (bn == 192 && tall) {
+    using Cfg = TcCfg<192, 2>;
+    const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    TP_CUDA(cudaFuncSetAttribute(k_gemm_bf16_tc<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PdlConfig lc(dim3((unsigned)tiles), dim3(TC_THREADS), smem, (cudaStream_t)stream);
-    TP_CUDA(cudaLaunchKernelEx(&lc.cfg, k_gemm_bf16_tc<192>, map_a, map_w, p));
+    TP_CUDA(cudaLaunchKernelEx(&lc.cfg, k_gemm_bf16_tc<192, 2>, map_a, map_w, p));
+  } else if (bn == 192) {
+    using Cfg = TcCfg<192, 1>;
+    const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    TP_CUDA(cudaFuncSetAttribute(k_gemm_bf16_tc<192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PdlConfig lc(dim3((unsigned)tiles), dim3(TC_THREADS), smem, (cudaStream_t)stream);
+    TP_CUDA(cudaLaunchKernelEx(&lc.cfg, k_gemm_bf16_tc<192, 1>, map_a, map_w, p));
   } else {
-    const size_t smem = (size_t)TcCfg<128>::STAGES * TcCfg<128>::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-    TP_CUDA(cudaFuncSetAttribute(k_gemm_bf16_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    using Cfg = TcCfg<128, 1>;
+    const size_t smem = (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    TP_CUDA(cudaFuncSetAttribute(k_gemm_bf16_tc<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PdlConfig lc(dim3((unsigned)tiles), dim3(TC_THREADS), smem, (cudaStream_t)stream);
-    TP_CUDA(cudaLaunchKernelEx(&lc.cfg, k_gemm_bf16_tc<128>, map_a, map_w, p));
+    TP_CUDA(cudaLaunchKernelEx(&lc.cfg, k_gemm_bf16_tc<128, 1>, map_a, map_w, p));
   }
   TP_LAUNCH_CHECK();
   return TP_OK;
