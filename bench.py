@@ -466,6 +466,30 @@ def main():
         model.fold_linear = False
         del g2
 
+    # ---------------------------------------------------------------- second shape: the released checkpoint's architecture
+    released = None
+    if rank == 0 and not args.no_graph and not args.no_fold:
+        Lr, Hr, Tr = 2, 1024, 6
+        m2, _ = build_product_model(SEED + 1, Tr, Lr, Hr, args.precision, dev)
+        g3 = GraphedTePose(m2, B, Tr)
+        xr = torch.from_numpy(synth.make_input(SEED + 9, B, Tr)).to(dev)
+        rev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        with torch.no_grad():
+            for i in range(args.warmup):
+                g3.static_input.copy_(xr); g3.replay()
+            torch.cuda.synchronize(dev)
+            for i in range(args.steps):
+                g3.static_input.copy_(xr)
+                flush.zero_()
+                rev[i][0].record()
+                g3.replay()
+                rev[i][1].record()
+            torch.cuda.synchronize(dev)
+        r_ms = float(np.mean([a.elapsed_time(b_) for a, b_ in rev]))
+        released = {"config": {"batch": B, "seqlen": Tr, "n_layers": Lr, "hidden": Hr}, "ms_per_step": r_ms,
+                    "frames_per_s": B / (r_ms * 1e-3), "launches_per_step": g3.launches_per_replay}
+        del g3, m2
+
     # ---------------------------------------------------------------- aggregate over ranks
     from tepose_b200 import shard as _sh
     dev_ms_max, e2e_ms_max = _sh.max_over_ranks([dev_ms_total, e2e_ms_total], dev)
@@ -503,6 +527,7 @@ def main():
             "stages_ms": stage_avg,
             "live": live,
             "folded": folded,
+            "released_config": released,
             "smpl_standalone": smpl_sa,
             "step_ms": {"min": float(step_ms.min()), "median": float(np.median(step_ms)), "max": float(step_ms.max())},
             "wall_s_timed_region": t_wall,
