@@ -192,3 +192,44 @@ def test_folded_forward_full_size(precision):
     for k in out:
         assert torch.equal(rep[k], out[k]), k
     assert g.launches_per_replay < 12
+
+
+# ------------------------------------------------------------------------------------------------ launch structure
+@pytest.mark.parametrize("B,T,L,H", [(32, 16, 1, 2048), (1, 16, 1, 2048), (32, 6, 2, 1024)])
+def test_programmatic_dependent_launch_does_not_change_results(B, T, L, H):
+    """Every kernel of a forward is PDL-linked to its predecessor (set-up overlaps the predecessor's tail, then
+    griddepcontrol.wait).  A kernel that touched its inputs before the wait would race: results with the overlap on
+    (eager and graph replay, repeated) must be bit-identical to the fully serialised run."""
+    from tepose_b200 import _native as nv
+    from tepose_b200.graph import GraphedTePose
+    model, _ = build_product_model(95, T, L, H, "bf16", DEV)
+    x = torch.from_numpy(synth.make_input(95, B, T)).to(DEV)
+    was = nv.lib().tp_set_pdl(0)
+    try:
+        ref = {k: v.clone() for k, v in model(x)[-1].items()}
+    finally:
+        nv.lib().tp_set_pdl(1)
+    assert was == 1
+    g = GraphedTePose(model, B, T)
+    for rep in range(5):
+        out = model(x)[-1]
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), ("eager", rep, k)
+        out = g(x)
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), ("graph", rep, k)
+
+
+def test_fused_heads_ief_kernel_against_separate_kernels():
+    """tp_heads_ief_forward (heads as leading layers of the persistent IEF kernel) vs tp_encoder_heads_cat + tp_ief_forward."""
+    model, _ = build_product_model(96, 16, 1, 2048, "bf16", DEV)
+    x = torch.from_numpy(synth.make_input(96, 32, 16)).to(DEV)
+    fused = {k: v.clone() for k, v in model(x)[-1].items()}
+    model.fuse_heads = False
+    try:
+        sep = model(x)[-1]
+    finally:
+        model.fuse_heads = True
+    # same bf16 operands, fp32 accumulation in a different order (K slices / split-K)
+    assert float((fused["theta"] - sep["theta"]).abs().max()) < 2e-4
+    assert float((fused["verts"] - sep["verts"]).abs().max()) < 1e-4
