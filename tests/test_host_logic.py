@@ -179,3 +179,18 @@ def test_folded_path_matches_oracle(cfg, precision):
     else:
         compare_outputs(out, ref, vert_tol=1e-3, rot_tol=2e-3, kp2d_tol=5e-2, label=str(cfg))
     compare_outputs(a, b, label="regressor folded vs loop", **({} if precision == "fp32" else dict(vert_tol=1e-3, rot_tol=2e-3, kp2d_tol=5e-2)))
+
+
+def test_large_batches_run_as_balanced_groups():
+    """bf16 mode, B > 32: the encoder + heads/IEF run per group of <= 32 sequences (their fast kernels hold one 32-row
+    tile), the SMPL pass once over all rows; results must not depend on the grouping."""
+    cfg = dict(seed=27, batch=70, seqlen=3, n_layers=1, hidden=32)
+    model, sd = build_product_model(cfg["seed"], cfg["seqlen"], cfg["n_layers"], cfg["hidden"], "bf16")
+    x = synth.make_input(cfg["seed"], cfg["batch"], cfg["seqlen"])
+    ref, m = oracle_forward(cfg["seed"], sd, x, cfg["n_layers"], cfg["hidden"])
+    with fake_native.install() as fake:
+        out = model(torch.from_numpy(x))[-1]
+    compare_outputs(out, ref, vert_tol=1e-3, rot_tol=2e-3, kp2d_tol=5e-2, label="grouped")
+    grus = [c for c in fake.calls if c[0] == "gru"]
+    assert [c[2] for c in grus] == [24, 24, 22]                    # balanced groups of the 70 sequences
+    assert [c[0] for c in fake.calls].count("smpl") == 1 and out["verts"].shape[0] == 70
