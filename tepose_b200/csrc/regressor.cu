@@ -130,6 +130,8 @@ struct IefFusedParams {
   IefLayer layer[kIefMaxLayers];
   int nlayers, M;
   unsigned int* barrier; int barrier_shards;
+  int narrow_from, narrow_ctas;   // layers >= narrow_from need only the first narrow_ctas CTAs: the others leave, and the
+                                  // barriers of that phase count narrow_ctas arrivals on a second counter (barrier + 32)
   int direct_kb;      // layers with at most this many 32-column blocks load their B fragments straight into registers (0 = never)
   const float* feat; const __nv_bfloat16* feat_lp; __nv_bfloat16* feat_cvt;   // feat_cvt: kIefRep bf16 replicas of feat
   const float* init; int init_rows; float* psc; __nv_bfloat16* psc_lp;
@@ -187,7 +189,22 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
   };
   if (ut < (sL[0].N + 15) / 16) prefetch(sL[0]);
 
+  unsigned int epoch2 = 0;
+  auto barrier_narrow = [&]() {          // grid_barrier() among the first narrow_ctas CTAs
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int* ctr = p.barrier + 32;
+      const unsigned int target = ++epoch2 * (unsigned int)p.narrow_ctas;
+      unsigned int seen;
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(ctr) : "memory");
+      do {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(ctr) : "memory");
+      } while (seen < target);
+    }
+    __syncthreads();
+  };
   for (int l = 0; l < p.nlayers; ++l) {
+    if (l == p.narrow_from && (int)blockIdx.x >= p.narrow_ctas) return;      // no work left for this CTA
     const IefLayer L = sL[l];
     IEF_TRACE(0);
     if (ut < (L.N + 15) / 16) {
@@ -312,7 +329,10 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
     IEF_TRACE(2);
     if (l + 1 < p.nlayers) {
       if (ut < (sL[l + 1].N + 15) / 16) prefetch(sL[l + 1]);   // weights do not depend on the barrier
-      if (!L.local_next) grid_barrier_sh(p.barrier, ++epoch, p.barrier_shards);
+      if (!L.local_next) {
+        if (l + 1 > p.narrow_from) barrier_narrow();      // producer and consumers of layer l's output are all narrow-phase CTAs
+        else grid_barrier_sh(p.barrier, ++epoch, p.barrier_shards);
+      }
     }
     IEF_TRACE(3);
   }
@@ -358,6 +378,7 @@ static int ief_fused(const tp_ief_weights* w, const float* feat, const void* fea
     L.bias = bias; L.Cin = Cin; L.ldcin = ldcin; L.C = C; L.ldc = ldc; L.Clp = Clp; L.ldclp = ldclp; L.rep_out = (int)rep_out;
   };
   int grid = 64;
+  p.narrow_from = 0; p.narrow_ctas = 64;
   if (hd) {
     // eval heads as leading layers: feat = relu(h_cat) . w_cat^T + b_cat, the K = 3H reduction cut into slices of <= 2048
     // columns that accumulate through the fp32 buffer (one grid barrier each); 2048 output rows = 128 weight tiles
@@ -373,6 +394,9 @@ static int ief_fused(const tp_ief_weights* w, const float* feat, const void* fea
       p.layer[n - 1].local_next = sl + 1 < nsl ? 1 : 0;     // K slices of one output tile accumulate inside the owning CTA
     }
     grid = 128;
+    static const bool no_narrow = getenv("TP_IEF_NO_NARROW") != nullptr;
+    p.narrow_from = n;                     // the IEF layers proper (1024 or 160 output rows) live on CTAs 0..63
+    if (no_narrow) p.narrow_ctas = 128;
   }
   add(feat_rep, 2048, 2048, n2048, w->w1x, 1024, w->b1, nullptr, 0, base, 1024, nullptr, 0, 0);
   for (int it = 0; it < n_iter; ++it) {
