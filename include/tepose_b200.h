@@ -82,6 +82,10 @@ TP_API int tp_projection(const float* joints, const float* cam, float* kp2d, int
  * Replaces x.permute(1,0,2) (lib/models/tepose.py:73,76).  kp >= k, kp % 8 == 0.        */
 TP_API int tp_pack_rows(const float* src, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t, int k,
                  void* dst, int kp, int dst_precision, int relu, void* stream);
+/* Same; additionally clears `zero_bytes` bytes at `zero` (the grid-barrier slots of the persistent kernels that follow in
+ * the step: tp_gru_recurrence_ex, tp_heads_ief_forward), so the step needs no separate fill.  zero may be NULL.           */
+TP_API int tp_pack_rows_ex(const float* src, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t, int k,
+                    void* dst, int kp, int dst_precision, int relu, void* zero, size_t zero_bytes, void* stream);
 /* The way back, with the residual of lib/models/vibe.py:60-63 folded in (y + x, then TNF -> NTF):
  * out[b*rows_t + t, c] = y[(t*rows_b + b)*ld_y + c] + x[b*stride_b + t*stride_t + c]   (x may be NULL: no residual).
  * out is dense [rows_b*rows_t, k] fp32; out_bf16 (optional) receives the same rows in bf16.  k even.              */

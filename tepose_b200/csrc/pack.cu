@@ -5,8 +5,12 @@ namespace tp {
 
 template <typename OutT>
 __global__ void k_pack_rows(const float* __restrict__ src, int64_t stride_b, int64_t stride_t,
-                            int rows_b, int rows_t, int k, OutT* __restrict__ dst, int kp, int relu) {
+                            int rows_b, int rows_t, int k, OutT* __restrict__ dst, int kp, int relu,
+                            unsigned int* __restrict__ zero, int zero_words) {
   pdl_launch_dependents();            // the GEMM that consumes dst may set itself up now (it waits before reading)
+  // first kernel of a step: it also clears the grid-barrier slots of the persistent kernels that follow (saves a fill node)
+  if (zero && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < zero_words; i += blockDim.x) zero[i] = 0u;
   int row = blockIdx.x;               // t * rows_b + b
   int t = row / rows_b, b = row - t * rows_b;
   const float* s = src + (int64_t)b * stride_b + (int64_t)t * stride_t;
@@ -47,20 +51,35 @@ __global__ void k_unpack_rows_residual(const float* __restrict__ y, int64_t ld_y
 
 }  // namespace tp
 
+extern "C" int tp_pack_rows_ex(const float* src, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t,
+                               int k, void* dst, int kp, int dst_precision, int relu, void* zero, size_t zero_bytes, void* stream);
+
 extern "C" int tp_pack_rows(const float* src, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t,
                             int k, void* dst, int kp, int dst_precision, int relu, void* stream) {
+  return tp_pack_rows_ex(src, stride_b, stride_t, rows_b, rows_t, k, dst, kp, dst_precision, relu, nullptr, 0, stream);
+}
+
+extern "C" int tp_pack_rows_ex(const float* src, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t,
+                               int k, void* dst, int kp, int dst_precision, int relu, void* zero, size_t zero_bytes, void* stream) {
   using namespace tp;
+  TP_CHECK_ARG(!zero || ((reinterpret_cast<uintptr_t>(zero) & 3) == 0 && zero_bytes % 4 == 0 && zero_bytes <= (1u << 20)),
+               "tp_pack_rows_ex: zero region must be 4-byte aligned, a multiple of 4 bytes and <= 1 MB");
+  unsigned int* zp = reinterpret_cast<unsigned int*>(zero);
+  const int zw = zero ? (int)(zero_bytes / 4) : 0;
   TP_CHECK_ARG(rows_b >= 0 && rows_t >= 0 && k >= 0 && kp >= k, "tp_pack_rows: bad sizes");
   TP_CHECK_ARG(kp % 8 == 0, "tp_pack_rows: kp=%d must be a multiple of 8", kp);
-  if (rows_b == 0 || rows_t == 0 || kp == 0) return TP_OK;
+  if (rows_b == 0 || rows_t == 0 || kp == 0) {
+    if (zero && zw) TP_CUDA(cudaMemsetAsync(zero, 0, zero_bytes, (cudaStream_t)stream));
+    return TP_OK;
+  }
   TP_CHECK_ARG(src && dst, "tp_pack_rows: null pointer");
   unsigned grid = (unsigned)(rows_b * rows_t);
   if (dst_precision == TP_PRECISION_BF16)
     k_pack_rows<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, stride_b, stride_t, rows_b, rows_t, k,
-                                                                      (__nv_bfloat16*)dst, kp, relu);
+                                                                      (__nv_bfloat16*)dst, kp, relu, zp, zw);
   else
     k_pack_rows<float><<<grid, 256, 0, (cudaStream_t)stream>>>(src, stride_b, stride_t, rows_b, rows_t, k,
-                                                              (float*)dst, kp, relu);
+                                                              (float*)dst, kp, relu, zp, zw);
   TP_LAUNCH_CHECK();
   return TP_OK;
 }

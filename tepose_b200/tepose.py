@@ -61,7 +61,8 @@ class GruKernels:
                                        mr, nc, kp, 1.0, 0.0, 0, nv.stream()), "tp_gemm_f32")
 
     def _recurrence(self, jobs, B, barrier=None):
-        """barrier: a zeroed 256-byte slice (see sync_words) -> no memset between this launch and the GEMM before it."""
+        """barrier: a zeroed 1 KB slot (cleared by the pack kernel at the top of the step) -> no memset node between this
+        launch and the GEMM before it, so the two stay linked by programmatic dependent launch."""
         L = nv.lib()
         H = self.hidden_size
         arr = (nv.GruJob * len(jobs))(*jobs)
@@ -69,12 +70,6 @@ class GruKernels:
         nv.check(L.tp_gru_recurrence_ex(arr, len(jobs), B, H, nv.PRECISIONS[self.precision], nv.ptr(ws), ws.numel(),
                                         nv.vp(0 if barrier is None else barrier.data_ptr()), nv.stream()), "tp_gru_recurrence")
 
-    @staticmethod
-    def sync_words(device, n):
-        """n zeroed 1 KB grid-barrier slots (8 sharded counters each) in ONE fill, issued at the top of a forward: every persistent kernel of
-        the step gets its own slot, and no memset node has to sit right in front of those kernels (it would cut the
-        programmatic-dependent-launch edge to the kernel before)."""
-        return torch.zeros(n, 256, device=device, dtype=torch.int32)
 
     @staticmethod
     def _job(dev, gi, col0, w_hh, b_hh, steps, t_in0, t_in_step, h0=None, y=None, ycol=0, y_lp=None,
@@ -191,7 +186,8 @@ class TemporalEncoder(nn.Module, GruKernels):
             x = x.contiguous()
         if (h0 is not None or return_states) and Ln != 1:
             raise ValueError("carried state is only defined for n_layers == 1 (SURVEY.md H5)")
-        sync = self.sync_words(dev, Ln + 1)          # one slot per layer's recurrence + one for the heads/IEF kernel
+        # grid-barrier slots: one per layer's recurrence + one for the heads/IEF kernel; cleared by the pack kernel
+        sync = torch.empty(Ln + 1, 256, device=dev, dtype=torch.int32)
         self._sync_tail = sync[Ln]
         seq_f = torch.empty(T, B, H, device=dev, dtype=torch.float32) if return_states else None
         seq_b = torch.empty(T, B, H, device=dev, dtype=torch.float32) if return_states else None
@@ -204,8 +200,8 @@ class TemporalEncoder(nn.Module, GruKernels):
             if l == 0:
                 kp = d["kpf"]
                 xp = torch.empty(T * B, kp, device=dev, dtype=adt)
-                nv.check(L.tp_pack_rows(nv.vp(x.data_ptr()), x.stride(0), x.stride(1), B, T, INPUT_SIZE, nv.ptr(xp), kp,
-                                        prec, 0, nv.stream()), "tp_pack_rows")
+                nv.check(L.tp_pack_rows_ex(nv.vp(x.data_ptr()), x.stride(0), x.stride(1), B, T, INPUT_SIZE, nv.ptr(xp), kp,
+                                           prec, 0, nv.ptr(sync), sync.numel() * 4, nv.stream()), "tp_pack_rows")
                 nv.mark("pack")
                 if last:
                     gi = torch.empty(T * B, 6 * H, device=dev, dtype=torch.float32)      # [fwd | rec-backward]

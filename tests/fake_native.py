@@ -77,6 +77,12 @@ class FakeLib:
         self.calls.append(("pack_rows", rows_b, rows_t, k, kp, prec))
         return 0
 
+    def tp_pack_rows_ex(self, src, stride_b, stride_t, rows_b, rows_t, k, dst, kp, prec, relu, zero, zero_bytes, stream):
+        z = _view(zero, zero_bytes, torch.uint8)
+        if z is not None:
+            z.zero_()
+        return self.tp_pack_rows(src, stride_b, stride_t, rows_b, rows_t, k, dst, kp, prec, relu, stream)
+
     def tp_unpack_rows_residual(self, y, ld_y, x, stride_b, stride_t, rows_b, rows_t, k, out, out_bf16, stream):
         v = _mat(y, rows_t * rows_b, k, ld_y).clone().reshape(rows_t, rows_b, k).permute(1, 0, 2)
         if (x.value if isinstance(x, C.c_void_p) else x):
