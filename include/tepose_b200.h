@@ -169,11 +169,19 @@ typedef struct tp_gru_job {
   int32_t steps;
   int32_t t_in0, t_in_step;
   int32_t t_out0, t_out_step;
+  const void* w_hh_umma; /* optional (bf16 mode): tp_pack_whh_umma image of the same weight_hh -> the tcgen05 kernel
+                            with W_hh resident in TMEM + shared memory takes jobs that provide it; NULL = not provided */
 } tp_gru_job;
 
 /* Packs weight_hh [3H,H] fp32 into the bf16 tensor-core fragment order the bf16 recurrence
  * streams (3*H*H bf16 = 6*H*H bytes at dst, 16-byte aligned).  Done once per weight update.  */
 TP_API int tp_pack_whh_bf16(const float* w_hh, void* dst, int H, void* stream);
+/* Packs weight_hh [3H,H] fp32 (H % 128 == 0) into the per-CTA images k_gru_umma keeps resident: for each of the H/32
+ * CTAs of a direction, tile 1 (128 rows: r,z,n of 32 units + r of the next 32) for K < 896 in TMEM row order, its K tail
+ * and tile 2 (z,n of the second 32 units) as UMMA 128-byte-swizzle K-major shared-memory images; CTA 2p+k holds the K
+ * half k of pair p's 64 units.  tp_whh_umma_bytes(H) = 6 H^2 bytes at dst (16-byte aligned); 0 if H is unsupported. */
+TP_API size_t tp_whh_umma_bytes(int H);
+TP_API int tp_pack_whh_umma(const float* w_hh, void* dst, int H, void* stream);
 /* debug hook: when non-NULL, the bf16 recurrence kernel writes SM-clock stamps
  * [grid][max_steps][8] (int64) into this device buffer; NULL (default) disables it. */
 TP_API void tp_gru_set_trace(void* device_buffer);

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "--- D2 lane mode (default)"; timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -k "umma" -q --no-header -p no:cacheprovider -x 2>&1 | tail -3
+echo "--- D2 own columns"; TP_UM_D2=0 timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -k "umma" -q --no-header -p no:cacheprovider -x 2>&1 | tail -3
+for acq in 0 1 2; do echo "--- trace acq=$acq"; TP_UM_ACQ=$acq timeout 300 python scripts/umma_trace.py 2>&1 | tail -4; done
+echo "--- trace D2=0"; TP_UM_D2=0 timeout 300 python scripts/umma_trace.py 2>&1 | tail -3
+timeout 600 python bench.py --steps 20 --warmup 5 --cpu-budget 1 --no-live --no-fold --no-smpl > gpurun_out/bench_umma.json 2> gpurun_out/bench_umma.err; echo "bench exit=$?"
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/bench_umma.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d.get("stages_ms"))
+PY

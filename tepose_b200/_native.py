@@ -43,7 +43,7 @@ class GruJob(C.Structure):
     _fields_ = [("gi", vp), ("ldg", i64), ("w_hh", vp), ("b_hh", vp), ("h0", vp),
                 ("y", vp), ("ldy", i64), ("y_lp", vp), ("ldy_lp", i64),
                 ("h_final", vp), ("ld_hf", i64), ("steps", i32),
-                ("t_in0", i32), ("t_in_step", i32), ("t_out0", i32), ("t_out_step", i32)]
+                ("t_in0", i32), ("t_in_step", i32), ("t_out0", i32), ("t_out_step", i32), ("w_hh_umma", vp)]
 
 
 class IefWeights(C.Structure):
@@ -86,6 +86,8 @@ _SIGNATURES = {
                                     C.c_int, C.c_int, C.c_int, vp, sz, vp]),
     "tp_gemm_bf16_tc": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.POINTER(GemmSeg), C.c_int, vp]),
     "tp_pack_whh_bf16": (C.c_int, [vp, vp, C.c_int, vp]),
+    "tp_whh_umma_bytes": (sz, [C.c_int]),
+    "tp_pack_whh_umma": (C.c_int, [vp, vp, C.c_int, vp]),
     "tp_gru_set_trace": (None, [vp]),
     "tp_gru_workspace_bytes": (sz, [C.c_int, C.c_int, C.c_int]),
     "tp_gru_recurrence": (C.c_int, [C.POINTER(GruJob), C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, vp]),

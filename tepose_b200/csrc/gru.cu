@@ -14,6 +14,7 @@
 //          shared memory, 8 warps split K (x M) and reduce through shared memory.
 //          State, gates and accumulation stay fp32.
 #include "common.cuh"
+#include "umma.cuh"
 #include <stdlib.h>
 
 namespace tp {
@@ -425,6 +426,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) k_gru_bf16(const GruParams p) 
 #include "gru_tma.inl"
 #include "gru_res.inl"
 #include "gru_dual.inl"
+#include "gru_umma.inl"
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -437,6 +439,18 @@ extern "C" int tp_pack_whh_bf16(const float* w_hh, void* dst, int H, void* strea
   // [3H,H] row-major: the generic fragment packing with 16-row tiles ordered gate-major is exactly
   // the [gate][unit_tile][k block][q][lane][word] order k_gru_bf16 streams.
   return tp_pack_mma_a_bf16(w_hh, H, 3 * H, H, dst, stream);
+}
+
+extern "C" size_t tp_whh_umma_bytes(int H) { return H >= 128 && H % 128 == 0 ? (size_t)6 * H * H : 0; }
+
+extern "C" int tp_pack_whh_umma(const float* w_hh, void* dst, int H, void* stream) {
+  TP_CHECK_ARG(w_hh && dst && H >= 128 && H % 128 == 0, "tp_pack_whh_umma: need non-null pointers and H %% 128 == 0 (H=%d)", H);
+  TP_CHECK_ARG(aligned16(w_hh) && aligned16(dst), "tp_pack_whh_umma: pointers must be 16-byte aligned");
+  const size_t chunks = (size_t)6 * H * H / 16;
+  const unsigned grid = (unsigned)(chunks / 256 < 4096 ? (chunks + 255) / 256 : 4096);
+  k_pack_whh_umma<<<grid, 256, 0, (cudaStream_t)stream>>>(w_hh, reinterpret_cast<uint4*>(dst), H, um_cfg().max_tmem_k);
+  TP_LAUNCH_CHECK();
+  return TP_OK;
 }
 
 extern "C" void tp_gru_set_trace(void* device_buffer) { tp::set_trace_ptr(reinterpret_cast<long long*>(device_buffer)); }
@@ -537,6 +551,64 @@ static int gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, int H, in
   if (!barrier) TP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));      // a caller-provided barrier word is already zero (and keeps
                                                                       // the memset node from sitting between this kernel and its PDL predecessor)
   const int sms = sm_count();
+
+  // ---- bf16, W_hh resident in TMEM + shared memory, tcgen05 (gru_umma.inl): every matmul job has a tp_pack_whh_umma image
+  static const bool no_umma = getenv("TP_GRU_NO_UMMA") != nullptr;
+  if (precision == TP_PRECISION_BF16 && !no_umma && n_mat >= 1 && !p.any_h0 && H % 128 == 0 && B <= 32 && n_mat * (H / 32) <= sms) {
+    bool have_img = true;
+    for (int j = 0; j < n_mat; ++j) have_img = have_img && jobs[j].w_hh_umma != nullptr;
+    const UmGeom geo = um_geom(H, um_cfg().max_tmem_k);
+    int dev = 0, optin = 0;
+    TP_CUDA(cudaGetDevice(&dev));
+    TP_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cudaFuncAttributes fa;
+    TP_CUDA(cudaFuncGetAttributes(&fa, k_gru_umma));
+    if (have_img && geo.smem_bytes + fa.sharedSizeBytes <= (size_t)optin) {
+      UmParams up;
+      memset(&up, 0, sizeof(up));
+      p.n_item_jobs = n_mat;
+      p.lp_tiled = 2; p.lp_slot = (int64_t)32 * H;
+      up.g = p;
+      up.max_tmem_k = um_cfg().max_tmem_k; up.sync_mode = um_cfg().sync_mode; up.trace_set = um_cfg().trace_set;
+      for (int j = 0; j < n_mat; ++j) {
+        TP_CHECK_ARG(aligned16(jobs[j].w_hh_umma), "tp_gru_recurrence: w_hh_umma must be 16-byte aligned");
+        TP_CHECK_ARG(aligned16(jobs[j].gi) && jobs[j].ldg % 4 == 0, "tp_gru_recurrence: gi must be 16-byte aligned with ldg %% 4 == 0");
+        up.w_img[j] = reinterpret_cast<const unsigned char*>(jobs[j].w_hh_umma);
+      }
+      TP_CUDA(cudaFuncSetAttribute(k_gru_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes));
+      cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+      cudaLaunchAttribute attr[3];
+      cfg.gridDim = dim3((unsigned)(n_mat * (H / 32))); cfg.blockDim = dim3(kUmThreads);
+      cfg.dynamicSmemBytes = geo.smem_bytes; cfg.stream = st;
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+      attr[2].id = cudaLaunchAttributeCooperative;
+      attr[2].val.cooperative = 1;
+      cfg.attrs = attr;
+      // co-residency: every cluster of the grid must be resident at once (the kernel spins on grid barriers)
+      cfg.numAttrs = 1;
+      int max_clusters = 0;
+      TP_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, k_gru_umma, &cfg));
+      if (max_clusters * 2 >= (int)cfg.gridDim.x) {
+        static int coop_ok = getenv("TP_UM_NOCOOP") ? 0 : -1;   // cooperative + cluster launches: probed once, plain cluster launch otherwise (TP_UM_NOCOOP: profilers)
+        cfg.numAttrs = coop_ok == 0 ? 2 : 3;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_gru_umma, up);
+        if (e != cudaSuccess && cfg.numAttrs == 3) {
+          (void)cudaGetLastError();
+          coop_ok = 0;
+          cfg.numAttrs = 2;
+          e = cudaLaunchKernelEx(&cfg, k_gru_umma, up);
+        } else if (e == cudaSuccess && coop_ok < 0) {
+          coop_ok = 1;
+        }
+        if (e != cudaSuccess) return fail(TP_ERR_CUDA, "k_gru_umma launch failed: %s", cudaGetErrorString(e));
+        count_launch();
+        return TP_OK;
+      }
+    }
+  }
 
   // ---- bf16 fast path: TMA-fed ring, one item per CTA
   static const bool no_tma = getenv("TP_GRU_NO_TMA") != nullptr;

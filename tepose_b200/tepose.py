@@ -45,6 +45,19 @@ class GruKernels:
         nv.check(nv.lib().tp_pack_whh_bf16(nv.ptr(w), nv.ptr(out), w.shape[1], nv.stream()), "tp_pack_whh_bf16")
         return out
 
+    @staticmethod
+    def _pack_whh_umma(w: torch.Tensor, lp: bool):
+        """bf16 mode, H % 128 == 0: the per-CTA images the tcgen05 recurrence keeps resident in TMEM + shared memory
+        (tp_pack_whh_umma); None otherwise (the streaming kernels take the job)."""
+        H = w.shape[1]
+        nbytes = nv.lib().tp_whh_umma_bytes(H) if lp else 0
+        if nbytes == 0:
+            return None
+        w = w.contiguous()
+        out = torch.empty(nbytes, device=w.device, dtype=torch.uint8)
+        nv.check(nv.lib().tp_pack_whh_umma(nv.ptr(w), nv.ptr(out), H, nv.stream()), "tp_pack_whh_umma")
+        return out
+
     def _input_proj(self, A, a_rows, W, kp, bias, segs, outs):
         """K1: outs[i] = A[m-range] . W[n-range]^T + bias[n-range]."""
         L = nv.lib()
@@ -73,8 +86,9 @@ class GruKernels:
 
     @staticmethod
     def _job(dev, gi, col0, w_hh, b_hh, steps, t_in0, t_in_step, h0=None, y=None, ycol=0, y_lp=None,
-             t_out0=0, t_out_step=1, h_final=None, hcol=0):
+             t_out0=0, t_out_step=1, h_final=None, hcol=0, w_umma=None):
         j = nv.GruJob()
+        j.w_hh_umma = 0 if w_umma is None else w_umma.data_ptr()
         j.gi = gi.data_ptr() + 4 * col0
         j.ldg = gi.shape[-1]
         j.w_hh = w_hh.data_ptr()
@@ -152,6 +166,9 @@ class TemporalEncoder(nn.Module, GruKernels):
             d["w_hh"] = [self._pack_whh(g(self.gru_fwd, f"weight_hh_l{l}"), lp),
                          self._pack_whh(g(self.gru_rec, f"weight_hh_l{l}_reverse"), lp),
                          self._pack_whh(g(self.gru_rec, f"weight_hh_l{l}"), lp)]
+            d["w_um"] = [self._pack_whh_umma(g(self.gru_fwd, f"weight_hh_l{l}"), lp),
+                         self._pack_whh_umma(g(self.gru_rec, f"weight_hh_l{l}_reverse"), lp),
+                         self._pack_whh_umma(g(self.gru_rec, f"weight_hh_l{l}"), lp) if Ln > 1 and l < Ln - 1 else None]
             d["b_hh"] = [g(self.gru_fwd, f"bias_hh_l{l}").contiguous(),
                          g(self.gru_rec, f"bias_hh_l{l}_reverse").contiguous(),
                          g(self.gru_rec, f"bias_hh_l{l}").contiguous()]
@@ -243,11 +260,11 @@ class TemporalEncoder(nn.Module, GruKernels):
                 ny_r_lp = torch.zeros(T * B, kpn_r, device=dev, dtype=torch.bfloat16) if lp else None
             nv.mark(f"k1_input_proj_l{l}")
             hF0, hB0 = (None, None) if h0 is None else h0
-            w, b = d["w_hh"], d["b_hh"]
+            w, b, wu = d["w_hh"], d["b_hh"], d["w_um"]
             if last:
                 jobs = [
-                    self._job(dev, gi_f, c_f, w[0], b[0], T, f_in[0], f_in[1], h0=hF0, h_final=h_fwd, hcol=0, y=seq_f),
-                    self._job(dev, gi_b, c_b, w[1], b[1], T, b_in[0], b_in[1], h0=hB0, h_final=h_rec, hcol=H, y=seq_b),
+                    self._job(dev, gi_f, c_f, w[0], b[0], T, f_in[0], f_in[1], h0=hF0, h_final=h_fwd, hcol=0, y=seq_f, w_umma=wu[0]),
+                    self._job(dev, gi_b, c_b, w[1], b[1], T, b_in[0], b_in[1], h0=hB0, h_final=h_rec, hcol=H, y=seq_b, w_umma=wu[1]),
                     self._job(dev, gi_s, c_s, w[2], b[2], 1, s_in[0] if gi_s.shape[0] != B else 0, s_in[1],
                               h_final=h_rec, hcol=0),
                 ]
@@ -255,10 +272,10 @@ class TemporalEncoder(nn.Module, GruKernels):
                 # outputs of gru_rec are stored by x_rec index tau: forward dir writes tau = s,
                 # backward dir writes tau = T-1-s
                 jobs = [
-                    self._job(dev, gi_f, c_f, w[0], b[0], T, f_in[0], f_in[1], y=ny_f, y_lp=ny_f_lp),
+                    self._job(dev, gi_f, c_f, w[0], b[0], T, f_in[0], f_in[1], y=ny_f, y_lp=ny_f_lp, w_umma=wu[0]),
                     self._job(dev, gi_b, c_b, w[1], b[1], T, b_in[0], b_in[1], y=ny_r, ycol=H, y_lp=ny_r_lp,
-                              t_out0=T - 1, t_out_step=-1),
-                    self._job(dev, gi_s, c_s, w[2], b[2], T, s_in[0], s_in[1], y=ny_r, ycol=0, y_lp=ny_r_lp),
+                              t_out0=T - 1, t_out_step=-1, w_umma=wu[1]),
+                    self._job(dev, gi_s, c_s, w[2], b[2], T, s_in[0], s_in[1], y=ny_r, ycol=0, y_lp=ny_r_lp, w_umma=wu[2]),
                 ]
             self._recurrence(jobs, B, barrier=sync[l])
             nv.mark(f"k2_recurrence_l{l}")

@@ -409,3 +409,56 @@ def test_gru_recurrence_two_interleaved_directions(B, T0, T1, H):
             assert float((d["y"].cpu().double() - ys).abs().max()) < 2e-4
             assert float((d["hf"].cpu().double() - hT).abs().max()) < 2e-4
             assert float((d["ylp"].float().cpu().double() - ys).abs().max()) < 1e-2
+
+
+def _dev_whh_umma(w):
+    wf = w.float().to(DEV).contiguous()
+    out = torch.empty(nv.lib().tp_whh_umma_bytes(wf.shape[1]), device=DEV, dtype=torch.uint8)
+    nv.check(nv.lib().tp_pack_whh_umma(nv.ptr(wf), nv.ptr(out), wf.shape[1], nv.stream()))
+    return out
+
+
+@pytest.mark.parametrize("B,steps,H", [(32, (16, 16), 2048), (1, (16, 16), 2048), (9, (5, 3), 128), (17, (2, 6, 4), 1024),
+                                       (32, (1, 4), 256), (5, (3, 4, 2, 5), 384), (32, (7,), 2048), (3, (6, 6), 640)])
+def test_gru_recurrence_umma(B, steps, H):
+    """bf16, every matmul job carries a tp_pack_whh_umma image -> k_gru_umma (tcgen05, W_hh resident in TMEM + shared
+    memory, cluster pairs splitting K); 1..4 matmul jobs with different step counts + one single-step job as plain gate
+    math (only when a job slot is left); ragged batch rows, strided outputs, caller-provided barrier slot.  Same tolerance
+    as the mma.sync kernels against the float64 cell with the state re-quantised to bf16 per step."""
+    L = nv.lib()
+    cases = [_gru_case(B, t, H, "bf16", 21 + i, False, i % 2 == 1) for i, t in enumerate(steps)]
+    if len(cases) < 4:
+        cases.append(_gru_case(B, 1, H, "bf16", 29, False, False))
+    n = len(cases)
+    for use_slot in (False, True):
+        keep, jobs, outs = [], [], []
+        for i, (gi, w, b, h0, ys, hT) in enumerate(cases):
+            Tj = gi.shape[0]
+            rev = i % 2 == 1 and i < len(steps)
+            d = dict(gi=gi.to(DEV), w=_dev_whh(w, "bf16"), wu=_dev_whh_umma(w), b=cu(b), y=torch.zeros(Tj, B, H + 8, device=DEV),
+                     ylp=torch.zeros(Tj, B, H, device=DEV, dtype=torch.bfloat16), hf=torch.zeros(B, 2 * H, device=DEV))
+            keep.append(d)
+            j = nv.GruJob()
+            j.gi, j.ldg, j.w_hh, j.b_hh = d["gi"].data_ptr(), 3 * H, d["w"].data_ptr(), d["b"].data_ptr()
+            j.w_hh_umma = d["wu"].data_ptr()
+            j.h0 = 0
+            j.y, j.ldy, j.y_lp, j.ldy_lp = d["y"].data_ptr(), H + 8, d["ylp"].data_ptr(), H
+            j.h_final, j.ld_hf = d["hf"].data_ptr() + 4 * H, 2 * H
+            j.steps = Tj
+            j.t_in0, j.t_in_step = (Tj - 1, -1) if rev else (0, 1)
+            j.t_out0, j.t_out_step = (Tj - 1, -1) if rev else (0, 1)
+            jobs.append(j)
+            outs.append((ys, hT))
+        arr = (nv.GruJob * n)(*jobs)
+        ws = nv.workspace(L.tp_gru_workspace_bytes(n, B, H), DEV)
+        slot = torch.zeros(256, device=DEV, dtype=torch.int32)
+        nv.check(L.tp_gru_recurrence_ex(arr, n, B, H, nv.PRECISION_BF16, nv.ptr(ws), ws.numel(),
+                                        nv.vp(slot.data_ptr() if use_slot else 0), nv.stream()))
+        torch.cuda.synchronize()
+        for i, (d, (ys, hT)) in enumerate(zip(keep, outs)):
+            y = d["y"][:, :, :H].cpu().double()
+            assert float((y - ys).abs().max()) < 2e-4, (i, float((y - ys).abs().max()))
+            assert float(d["y"][:, :, H:].abs().max()) == 0.0
+            assert float((d["hf"][:, H:].cpu().double() - hT).abs().max()) < 2e-4
+            assert float(d["hf"][:, :H].abs().max()) == 0.0
+            assert float((d["ylp"].float().cpu().double() - ys).abs().max()) < 1e-2
