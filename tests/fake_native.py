@@ -133,6 +133,9 @@ class FakeLib:
     def tp_skinny_bf16_workspace_bytes(self, M, N, splits):
         return 4096
 
+    def tp_whh_umma_bytes(self, H):
+        return 0        # the fake has no tcgen05 kernel: the host layer then leaves w_hh_umma NULL
+
     def tp_pack_whh_bf16(self, w_hh, dst, H, stream):
         # the emulation keeps W_hh row-major bf16 (the fragment order only matters to the CUDA kernel)
         _mat(dst, 3 * H, H, H, torch.bfloat16).copy_(_mat(w_hh, 3 * H, H, H).to(torch.bfloat16))
