@@ -188,6 +188,37 @@ def run_reference(seed, batch, seqlen, n_layers, hidden, is_train=False, use_h36
     return {k: v.detach().numpy().copy() for k, v in out.items()}
 
 
+def run_reference_train(seed, batch, seqlen, n_layers, hidden):
+    """The unmodified reference in TRAIN mode (lib/core/trainer.py:137,203: `generator.train()`,
+    `generator(inp, is_train=True)`), one synthetic-loss backward.  nn.Dropout draws its masks from torch's RNG; to make the
+    run reproducible from numpy seeds the given masks are forced through forward hooks on `regressor.drop1/drop2`
+    (the hook returns input * mask / (1 - p), i.e. what nn.Dropout computes for that mask).  Returns outputs, loss and
+    every parameter's gradient."""
+    from . import train_ref
+    sd = synth.make_state_dict(seed, n_layers, hidden)
+    x = synth.make_input(seed, batch, seqlen)
+    masks = torch.from_numpy(train_ref.make_masks(seed, 2 * batch))
+    tgt = train_ref.make_targets(seed, 2 * batch)
+    with reference_env(seed) as mods:
+        model = build_reference_model(mods, sd, seqlen, n_layers, hidden).train()
+        calls = {"drop1": 0, "drop2": 0}
+
+        def hook(which, col):
+            def fn(module, inp, out):
+                i = calls[which]
+                calls[which] += 1
+                return inp[0] * masks[i, col] / (1.0 - module.p)
+            return fn
+        model.regressor.drop1.register_forward_hook(hook("drop1", 0))
+        model.regressor.drop2.register_forward_hook(hook("drop2", 1))
+        out = model(torch.from_numpy(x), is_train=True)[-1]
+        loss = train_ref.synthetic_loss(out, tgt)
+        model.zero_grad()
+        loss.backward()
+        grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    return {k: v.detach().numpy().copy() for k, v in out.items()}, float(loss.detach()), grads
+
+
 def run_reference_vibe(seed, batch, seqlen, n_layers, hidden, add_linear=False, bidirectional=False, use_residual=True,
                        use_h36m=False, x=None):
     """The unmodified lib/models/vibe.py VIBE on the synthetic parameters of `seed`."""

@@ -13,14 +13,15 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t db, uint
 }
 
 // MODE 0: TS M=128; 1: SS M=128; 2: SS M=64; 3: alternate TS M=128 / SS M=64 (k_gru_umma pattern, NACC chains each)
-template <int MODE, int N, int NACC>
+template <int MODE, int N, int NACC, int COMMIT = 0>
 __global__ void __launch_bounds__(128, 1) k_lat(long long* out) {
   extern __shared__ __align__(1024) unsigned char raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[16];
   __shared__ uint32_t slot;
   for (int i = threadIdx.x; i < 96 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+  if (threadIdx.x == 0) { for (int i = 0; i < 16; ++i) mbar_init(&bar2[i], 1); mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
   if (threadIdx.x < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&slot)), "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(128, 1) k_lat(long long* out) {
               else umma_f16(tm + (uint32_t)((NACC + (i >> 1) % NACC) * N), da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc64, acc);
             }
           }
+          if (COMMIT) umma_commit(&bar2[blk]);
         }
         __syncwarp();
       }
@@ -72,11 +74,11 @@ __global__ void __launch_bounds__(128, 1) k_lat(long long* out) {
 }
 
 static long long* d_out;
-template <int MODE, int N, int NACC>
+template <int MODE, int N, int NACC, int COMMIT = 0>
 void run(const char* name) {
   const int smem = 100 * 1024;
-  cudaFuncSetAttribute(k_lat<MODE, N, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  k_lat<MODE, N, NACC><<<1, 128, smem>>>(d_out);
+  cudaFuncSetAttribute(k_lat<MODE, N, NACC, COMMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  k_lat<MODE, N, NACC, COMMIT><<<1, 128, smem>>>(d_out);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[2] = {0, 0};
   cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost);
@@ -89,6 +91,7 @@ int main() {
   run<0, 16, 1>("TS M128"); run<0, 64, 1>("TS M128"); run<0, 64, 2>("TS M128"); run<0, 128, 1>("TS M128"); run<0, 128, 2>("TS M128"); run<0, 256, 1>("TS M128");
   run<1, 32, 1>("SS M128"); run<1, 32, 2>("SS M128"); run<1, 32, 4>("SS M128"); run<1, 128, 1>("SS M128"); run<1, 256, 1>("SS M128");
   run<2, 32, 1>("SS M64"); run<2, 32, 2>("SS M64"); run<2, 32, 4>("SS M64"); run<2, 8, 1>("SS M64"); run<2, 128, 1>("SS M64");
+  run<3, 32, 1, 1>("mix+commit/32"); run<0, 32, 1, 1>("TS+commit/32");
   run<3, 32, 1>("TS128+SS64"); run<3, 32, 2>("TS128+SS64"); run<3, 32, 4>("TS128+SS64");
   return 0;
 }
