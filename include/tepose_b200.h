@@ -169,6 +169,8 @@ typedef struct tp_gru_job {
   int32_t steps;
   int32_t t_in0, t_in_step;
   int32_t t_out0, t_out_step;
+  float* gates;          /* optional [T,B,4H] fp32 (indexed like y): r | z | n | (W_hn h + b_hn) of every step, saved for the
+                            backward pass (tp_gru_cell_backward); NULL = not stored                                      */
   const void* w_hh_umma; /* optional (bf16 mode): tp_pack_whh_umma image of the same weight_hh -> the tcgen05 kernel
                             with W_hh resident in TMEM + shared memory takes jobs that provide it; NULL = not provided */
 } tp_gru_job;
@@ -313,6 +315,47 @@ TP_API int tp_accel_error(const float* pred, const float* target, int n_seq, int
 /* tp_vertex_error -- verts_a / verts_b [n, n_verts, 3] -> out [n] = mean_v ||a_v - b_v||   (compute_error_verts,
  * eval_utils.py:141-175; the target mesh comes from tp_smpl_forward with TP_POSE_AXIS_ANGLE).                        */
 TP_API int tp_vertex_error(const float* verts_a, const float* verts_b, int n, int n_verts, float* out, void* stream);
+
+/* ------------------------------------------------------------------ training step: backward kernels
+ * The reference trains through torch.autograd (lib/core/trainer.py:203,235-237); these are the adjoints of the path's
+ * stages.  GEMM-shaped adjoints (dX = dY.W, dW = dY^T.X) run on tp_gemm_f32 / tp_gemm_bf16_tc over operands transposed by
+ * tp_transpose_f32.  All arrays fp32 device memory unless noted.                                                         */
+/* dst[c][r] = src[r][c] (max(.,0) first when relu) for r < rows, c < cols; dst has dst_rows rows (>= cols, extra rows zero)
+ * of ld_dst elements (columns rows..ld_dst-1 zero); dst_precision selects fp32 or bf16 output.                            */
+TP_API int tp_transpose_f32(const float* src, int64_t ld_src, int rows, int cols, void* dst, int64_t ld_dst, int dst_rows,
+                     int dst_precision, int relu, void* stream);
+/* out[c] = beta*out[c] + sum_r A[r][c]  (bias gradients; fixed summation order) */
+TP_API int tp_colsum_f32(const float* A, int64_t lda, int rows, int cols, float* out, float beta, void* stream);
+/* a *= mask * scale  (nn.Dropout with the mask as an input: forward and backward are the same op; spin.py:216-218,256-258) */
+TP_API int tp_mask_scale(float* a, int64_t ld, const float* mask, int64_t ldm, int rows, int cols, float scale, void* stream);
+/* g = h > 0 ? g : 0  (F.relu backward, lib/models/tepose.py:79-80) */
+TP_API int tp_relu_backward(float* g, int64_t ld, const float* h, int64_t ldh, int rows, int cols, void* stream);
+/* dst = alpha*src + beta*dst */
+TP_API int tp_axpby_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, float alpha, float beta, void* stream);
+/* One step of back-propagation through time of a torch.nn.GRU direction: g_h [B,H] holds dL/dh_t on entry and
+ * dL/dh_t * z_t on exit (add d_gh . W_hh for the full dL/dh_{t-1}); gates = the [B,4H] block tp_gru_recurrence saved for
+ * the step; h_prev = h_{t-1} [B,H] or NULL for zeros; d_gi / d_gh [B,3H] = gradients w.r.t. the input-side and
+ * hidden-side gate pre-activations (r|z|n).                                                                              */
+TP_API int tp_gru_cell_backward(float* g_h, int64_t ldg, const float* gates, int64_t ld_gates, const float* h_prev, int64_t ldh,
+                         float* d_gi, int64_t ld_dgi, float* d_gh, int64_t ld_dgh, int B, int H, void* stream);
+/* adjoint of rot6d_to_rotmat (lib/utils/geometry.py:330-343): x6 [n,6], g_R [n,9] -> g_x6 [n,6] */
+TP_API int tp_rot6d_backward(const float* x6, const float* g_R, float* g_x6, int64_t n, void* stream);
+/* adjoint of rotation_matrix_to_angle_axis (lib/utils/geometry.py:68-233): R [n,9]; rotation i takes its gradient from
+ * g_aa + (i / per_row) * ld_gaa + 3 * (i % per_row)  (theta rows: per_row = 24, ld_gaa = 85); g_R [n,9] is overwritten or
+ * accumulated into.                                                                                                       */
+TP_API int tp_rotmat_to_angle_axis_backward(const float* R, const float* g_aa, int64_t ld_gaa, int per_row, float* g_R, int64_t n,
+                                     int accumulate, void* stream);
+/* Adjoint of tp_smpl_forward with pose_kind = rotation matrices (SMPL lbs + joint selection + projection):
+ *   inputs  R [n,24,9], betas, cam (as in the forward), jreg / joint_src (as in the forward), joints [n,nj,3] = the forward's
+ *           joint output; gradients g_verts [n,n_verts,3], g_joints [n,nj,3], g_kp2d [n,nj,2], g_R_extra [n,24,9] (any NULL)
+ *   outputs g_R [n,24,9] (= LBS + pose-blend + chain terms + g_R_extra), g_betas [n,10], g_cam [n,3] (NULL without cam).
+ * Four launches: chain recompute + projection adjoint, skinning adjoint (v_posed recomputed, per-joint sums reduced in a
+ * fixed order), one GEMM against the blend table for the pose-feature / shape gradients, kinematic-chain adjoint.       */
+TP_API size_t tp_smpl_backward_workspace_bytes(const tp_smpl_model* m, int n);
+TP_API int tp_smpl_backward(const tp_smpl_model* m, int n, const float* R, const float* betas, int64_t ld_betas, const float* cam,
+                     int64_t ld_cam, const float* jreg, int nreg, const int32_t* joint_src, int nj, const float* joints,
+                     const float* g_verts, const float* g_joints, const float* g_kp2d, const float* g_R_extra,
+                     float* g_R, float* g_betas, float* g_cam, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,8 @@ EXPORTS = [
     "tp_encoder_heads_workspace_bytes", "tp_encoder_heads", "tp_encoder_heads_cat", "tp_ief_workspace_bytes", "tp_ief_forward", "tp_heads_ief_forward",
     "tp_smpl_workspace_bytes", "tp_smpl_forward",
     "tp_pose_metrics", "tp_accel_error", "tp_vertex_error",
+    "tp_transpose_f32", "tp_colsum_f32", "tp_mask_scale", "tp_relu_backward", "tp_axpby_f32", "tp_gru_cell_backward",
+    "tp_rot6d_backward", "tp_rotmat_to_angle_axis_backward", "tp_smpl_backward_workspace_bytes", "tp_smpl_backward",
 ]
 
 vp, i32, i64, f32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -43,7 +45,7 @@ class GruJob(C.Structure):
     _fields_ = [("gi", vp), ("ldg", i64), ("w_hh", vp), ("b_hh", vp), ("h0", vp),
                 ("y", vp), ("ldy", i64), ("y_lp", vp), ("ldy_lp", i64),
                 ("h_final", vp), ("ld_hf", i64), ("steps", i32),
-                ("t_in0", i32), ("t_in_step", i32), ("t_out0", i32), ("t_out_step", i32), ("w_hh_umma", vp)]
+                ("t_in0", i32), ("t_in_step", i32), ("t_out0", i32), ("t_out_step", i32), ("gates", vp), ("w_hh_umma", vp)]
 
 
 class IefWeights(C.Structure):
@@ -97,6 +99,17 @@ _SIGNATURES = {
     "tp_encoder_heads_cat": (C.c_int, [C.c_int, vp, vp, vp, i64, C.c_int, C.c_int, vp, vp, vp, sz, vp]),
     "tp_ief_workspace_bytes": (sz, [C.c_int]),
     "tp_ief_forward": (C.c_int, [C.c_int, C.POINTER(IefWeights), vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, sz, vp]),
+    "tp_transpose_f32": (C.c_int, [vp, i64, C.c_int, C.c_int, vp, i64, C.c_int, C.c_int, C.c_int, vp]),
+    "tp_colsum_f32": (C.c_int, [vp, i64, C.c_int, C.c_int, vp, f32, vp]),
+    "tp_mask_scale": (C.c_int, [vp, i64, vp, i64, C.c_int, C.c_int, f32, vp]),
+    "tp_relu_backward": (C.c_int, [vp, i64, vp, i64, C.c_int, C.c_int, vp]),
+    "tp_axpby_f32": (C.c_int, [vp, i64, vp, i64, C.c_int, C.c_int, f32, f32, vp]),
+    "tp_gru_cell_backward": (C.c_int, [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, C.c_int, C.c_int, vp]),
+    "tp_rot6d_backward": (C.c_int, [vp, vp, vp, i64, vp]),
+    "tp_rotmat_to_angle_axis_backward": (C.c_int, [vp, vp, i64, C.c_int, vp, i64, C.c_int, vp]),
+    "tp_smpl_backward_workspace_bytes": (sz, [C.POINTER(SmplModel), C.c_int]),
+    "tp_smpl_backward": (C.c_int, [C.POINTER(SmplModel), C.c_int, vp, vp, i64, vp, i64, vp, C.c_int, vp, C.c_int, vp,
+                                   vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "tp_smpl_workspace_bytes": (sz, [C.POINTER(SmplModel), C.c_int, C.c_int, C.c_int]),
     "tp_smpl_forward": (C.c_int, [C.POINTER(SmplModel), C.c_int, vp, i64, C.c_int, vp, i64, vp, i64,
                                   vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, sz, vp]),

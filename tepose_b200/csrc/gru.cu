@@ -131,6 +131,10 @@ __device__ __forceinline__ void gru_finalize(const GruParams& p, const tp_gru_jo
   if (jb.y) jb.y[((int64_t)t_out * B + b) * jb.ldy + u] = h;
   if (jb.y_lp) reinterpret_cast<__nv_bfloat16*>(jb.y_lp)[((int64_t)t_out * B + b) * jb.ldy_lp + u] = __float2bfloat16_rn(h);
   if (jb.h_final && s == jb.steps - 1) jb.h_final[(int64_t)b * jb.ld_hf + u] = h;
+  if (jb.gates) {                 // saved for tp_gru_cell_backward
+    float* gt = jb.gates + ((int64_t)t_out * B + b) * 4 * H;
+    gt[u] = r; gt[H + u] = z; gt[2 * H + u] = n; gt[3 * H + u] = acc_n + g.bn;
+  }
 }
 
 __device__ __forceinline__ void locate_item(const GruParams& p, int item, int& j, int& u0) {

@@ -436,6 +436,10 @@ __global__ void __launch_bounds__(kUmThreads, 1) k_gru_umma(const UmParams up) {
         const float z = um_sigmoid(gi[H + u] + js.b_hh[H + u]);
         const float n = um_tanh(gi[2 * H + u] + r * js.b_hh[2 * H + u]);
         const float h = (1.0f - z) * n;
+        if (js.gates) {
+          float* gt = js.gates + ((int64_t)js.t_out0 * B + b) * 4 * H;
+          gt[u] = r; gt[H + u] = z; gt[2 * H + u] = n; gt[3 * H + u] = js.b_hh[2 * H + u];
+        }
         if (js.y) js.y[((int64_t)js.t_out0 * B + b) * js.ldy + u] = h;
         if (js.y_lp) reinterpret_cast<__nv_bfloat16*>(js.y_lp)[((int64_t)js.t_out0 * B + b) * js.ldy_lp + u] = __float2bfloat16_rn(h);
         if (js.h_final) js.h_final[(int64_t)b * js.ld_hf + u] = h;
@@ -530,6 +534,10 @@ __global__ void __launch_bounds__(kUmThreads, 1) k_gru_umma(const UmParams up) {
         const float n = um_tanh(gin[2][j] + r * (acc[2][j] + bh[2]));
         hn[j] = b0 + j < B ? (1.0f - z) * n + z * hp[j] : 0.0f;
         hp[j] = hn[j];
+        if (jb.gates && b0 + j < B) {       // saved for tp_gru_cell_backward
+          float* gt = jb.gates + ((int64_t)(jb.t_out0 + s * jb.t_out_step) * B + b0 + j) * 4 * H;
+          gt[U] = r; gt[H + U] = z; gt[2 * H + U] = n; gt[3 * H + U] = acc[2][j] + bh[2];
+        }
       }
       if (s + 1 < steps) {
         __nv_bfloat16* hw = hlp + (int64_t)(s & 1) * p.lp_slot;

@@ -86,9 +86,10 @@ class GruKernels:
 
     @staticmethod
     def _job(dev, gi, col0, w_hh, b_hh, steps, t_in0, t_in_step, h0=None, y=None, ycol=0, y_lp=None,
-             t_out0=0, t_out_step=1, h_final=None, hcol=0, w_umma=None):
+             t_out0=0, t_out_step=1, h_final=None, hcol=0, w_umma=None, gates=None):
         j = nv.GruJob()
         j.w_hh_umma = 0 if w_umma is None else w_umma.data_ptr()
+        j.gates = 0 if gates is None else gates.data_ptr()
         j.gi = gi.data_ptr() + 4 * col0
         j.ldg = gi.shape[-1]
         j.w_hh = w_hh.data_ptr()
@@ -183,11 +184,12 @@ class TemporalEncoder(nn.Module, GruKernels):
         return pk
 
     # ------------------------------------------------------------------ kernels
-    def encode_states(self, x: torch.Tensor, h0=None, return_states=False):
+    def encode_states(self, x: torch.Tensor, h0=None, return_states=False, train_ctx=None):
         """Runs K1 + K2.  Returns (h_fwd [B,H], h_rec [B,2H]) = (y[-1], y_rec[0]) of
         lib/models/tepose.py:73-80.  h0 = (hF0, hB0) carries state (live-stream mode, L=1);
         with return_states the per-step states (yF [T,B,H], yB [T,B,H]) of the two causal
-        directions are returned as well."""
+        directions are returned as well.  train_ctx (a dict, training path): the per-step states, the gate activations of every
+        step (tp_gru_job.gates) and an fp32 copy of the packed input are stored into it for the backward pass."""
         nv.require_cuda(x, "input")
         if x.dim() != 3 or x.shape[2] != INPUT_SIZE:
             raise ValueError(f"expected input [B,T,{INPUT_SIZE}], got {tuple(x.shape)}")
@@ -206,8 +208,16 @@ class TemporalEncoder(nn.Module, GruKernels):
         # grid-barrier slots: one per layer's recurrence + one for the heads/IEF kernel; cleared by the pack kernel
         sync = torch.empty(Ln + 1, 256, device=dev, dtype=torch.int32)
         self._sync_tail = sync[Ln]
-        seq_f = torch.empty(T, B, H, device=dev, dtype=torch.float32) if return_states else None
-        seq_b = torch.empty(T, B, H, device=dev, dtype=torch.float32) if return_states else None
+        keep = return_states or train_ctx is not None
+        seq_f = torch.empty(T, B, H, device=dev, dtype=torch.float32) if keep else None
+        seq_b = torch.empty(T, B, H, device=dev, dtype=torch.float32) if keep else None
+        gates_f = gates_b = gates_s = None
+        if train_ctx is not None:
+            if Ln != 1:
+                raise NotImplementedError("training path: n_layers == 1 only")
+            gates_f = torch.empty(T, B, 4 * H, device=dev, dtype=torch.float32)
+            gates_b = torch.empty(T, B, 4 * H, device=dev, dtype=torch.float32)
+            gates_s = torch.empty(1, B, 4 * H, device=dev, dtype=torch.float32)
         h_cat = torch.empty(B, 3 * H, device=dev, dtype=torch.float32)     # [y[-1] | y_rec[0]]
         h_fwd, h_rec = h_cat[:, :H], h_cat[:, H:]
         y_f = y_r = y_f_lp = y_r_lp = None
@@ -220,6 +230,14 @@ class TemporalEncoder(nn.Module, GruKernels):
                 nv.check(L.tp_pack_rows_ex(nv.vp(x.data_ptr()), x.stride(0), x.stride(1), B, T, INPUT_SIZE, nv.ptr(xp), kp,
                                            prec, 0, nv.ptr(sync), sync.numel() * 4, nv.stream()), "tp_pack_rows")
                 nv.mark("pack")
+                if train_ctx is not None:
+                    if lp:      # the weight-gradient GEMM reads the packed input in fp32
+                        xp32 = torch.empty(T * B, kp, device=dev, dtype=torch.float32)
+                        nv.check(L.tp_pack_rows(nv.vp(x.data_ptr()), x.stride(0), x.stride(1), B, T, INPUT_SIZE, nv.ptr(xp32), kp,
+                                                nv.PRECISION_FP32, 0, nv.stream()), "tp_pack_rows")
+                        train_ctx["xp"] = xp32
+                    else:
+                        train_ctx["xp"] = xp
                 if last:
                     gi = torch.empty(T * B, 6 * H, device=dev, dtype=torch.float32)      # [fwd | rec-backward]
                     gs = torch.empty(B, 3 * H, device=dev, dtype=torch.float32)          # rec-forward, newest frame only
@@ -263,10 +281,12 @@ class TemporalEncoder(nn.Module, GruKernels):
             w, b, wu = d["w_hh"], d["b_hh"], d["w_um"]
             if last:
                 jobs = [
-                    self._job(dev, gi_f, c_f, w[0], b[0], T, f_in[0], f_in[1], h0=hF0, h_final=h_fwd, hcol=0, y=seq_f, w_umma=wu[0]),
-                    self._job(dev, gi_b, c_b, w[1], b[1], T, b_in[0], b_in[1], h0=hB0, h_final=h_rec, hcol=H, y=seq_b, w_umma=wu[1]),
+                    self._job(dev, gi_f, c_f, w[0], b[0], T, f_in[0], f_in[1], h0=hF0, h_final=h_fwd, hcol=0, y=seq_f, w_umma=wu[0],
+                              gates=gates_f),
+                    self._job(dev, gi_b, c_b, w[1], b[1], T, b_in[0], b_in[1], h0=hB0, h_final=h_rec, hcol=H, y=seq_b, w_umma=wu[1],
+                              gates=gates_b),
                     self._job(dev, gi_s, c_s, w[2], b[2], 1, s_in[0] if gi_s.shape[0] != B else 0, s_in[1],
-                              h_final=h_rec, hcol=0),
+                              h_final=h_rec, hcol=0, gates=gates_s),
                 ]
             else:
                 # outputs of gru_rec are stored by x_rec index tau: forward dir writes tau = s,
@@ -281,6 +301,8 @@ class TemporalEncoder(nn.Module, GruKernels):
             nv.mark(f"k2_recurrence_l{l}")
             if not last:
                 y_f, y_r, y_f_lp, y_r_lp = ny_f, ny_r, ny_f_lp, ny_r_lp
+        if train_ctx is not None:
+            train_ctx.update(seq_f=seq_f, seq_b=seq_b, gates_f=gates_f, gates_b=gates_b, gates_s=gates_s)
         if return_states:
             return h_fwd, h_rec, seq_f, seq_b
         return h_fwd, h_rec
@@ -413,10 +435,15 @@ class TePose(nn.Module):
     # hold one 32-row batch tile; larger batches run as balanced groups and share ONE SMPL pass
     GROUP = 32
 
-    def forward(self, input, is_train=False, J_regressor=None):
+    def forward(self, input, is_train=False, J_regressor=None, dropout_masks=None):
         if self.training:
-            raise NotImplementedError("tepose_b200.TePose implements the inference path; call .eval() first "
-                                      "(train-mode dropout / backward are not implemented yet)")
+            # lib/core/trainer.py:137,203: generator.train(); generator(inp, is_train=True) -- dropout active, outputs [B,2,...],
+            # gradients to every encoder / regressor parameter through the hand-written backward (tepose_b200/train.py)
+            if not is_train:
+                raise NotImplementedError("tepose_b200.TePose in .train() mode implements the reference's training call "
+                                          "(is_train=True); call .eval() for inference")
+            from .train import train_forward
+            return train_forward(self, input, dropout_masks)
         batch_size = input.shape[0]
         nv.mark("start")
         smpl_output = None

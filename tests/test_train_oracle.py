@@ -58,3 +58,29 @@ def test_masks_are_inputs_and_scale_like_nn_dropout():
     a = torch.nn.functional.linear(xc, W["fc1.weight"], W["fc1.bias"]) * 2.0
     a = torch.nn.functional.linear(a, W["fc2.weight"], W["fc2.bias"]) * 2.0
     assert torch.allclose(p, torch.nn.functional.linear(a, W["decpose.weight"], W["decpose.bias"]), atol=1e-5)
+
+
+def test_smpl_backward_decomposition_matches_autograd():
+    """The stage-by-stage backward the CUDA kernels implement (oracle/smpl_backward_proto.py) against torch.autograd through
+    the oracle's SMPL forward + projection, in float64 (tight) -- verifies the kernel's algebra on the CPU."""
+    from oracle import smpl_backward_proto as proto, torch_ref
+    m = torch_ref.SmplModel.synthetic(5, dtype=torch.float64)
+    g = torch.Generator().manual_seed(3)
+    N = 3
+    betas = torch.randn(N, 10, generator=g, dtype=torch.float64).requires_grad_(True)
+    x6 = torch.randn(N, 144, generator=g, dtype=torch.float64)
+    R = torch_ref.rot6d_to_rotmat(x6).reshape(N, 24, 3, 3).detach().requires_grad_(True)
+    cam = (torch.tensor([0.9, 0.0, 0.0], dtype=torch.float64) + 0.1 * torch.randn(N, 3, generator=g, dtype=torch.float64)).requires_grad_(True)
+    verts, j49, _ = torch_ref.smpl_forward(m, betas, R=R)
+    kp2d = torch_ref.projection(j49, cam)
+    gv = torch.randn(verts.shape, generator=g, dtype=torch.float64) * 0.01
+    gj = torch.randn(j49.shape, generator=g, dtype=torch.float64)
+    gk = torch.randn(kp2d.shape, generator=g, dtype=torch.float64)
+    gRx = torch.randn(R.shape, generator=g, dtype=torch.float64)
+    loss = (verts * gv).sum() + (j49 * gj).sum() + (kp2d * gk).sum() + (R * gRx).sum()
+    loss.backward()
+    g_R, g_b, g_c = proto.smpl_backward(m, torch_ref.JOINT_SOURCE_49, betas.detach(), R.detach(), cam.detach(), gv, gj, gk, gRx)
+    rel = lambda a, b: float((a - b).abs().max() / (b.abs().max() + 1e-30))
+    assert rel(g_R, R.grad) < 1e-10
+    assert rel(g_b, betas.grad) < 1e-10
+    assert rel(g_c, cam.grad) < 1e-10
