@@ -29,7 +29,8 @@ def test_rot6d_backward_matches_autograd():
     gR = torch.randn(200, 9, generator=g, dtype=torch.float64)
     (torch_ref.rot6d_to_rotmat(x).reshape(200, 9) * gR).sum().backward()
     out = torch.empty(200, 6, device=DEV)
-    nv.check(nv.lib().tp_rot6d_backward(nv.ptr(cu(x.detach())), nv.ptr(cu(gR)), nv.ptr(out), 200, nv.stream()))
+    xd, gd = cu(x.detach()), cu(gR)                    # keep the device copies alive across the launch
+    nv.check(nv.lib().tp_rot6d_backward(nv.ptr(xd), nv.ptr(gd), nv.ptr(out), 200, nv.stream()))
     assert rel_err(out, x.grad) < 2e-5
 
 
@@ -41,8 +42,8 @@ def test_rotmat_to_angle_axis_backward_matches_autograd():
     out_aa = torch_ref.rotmat_to_angle_axis(R).reshape(10, 72)
     (out_aa * gaa[:, 3:75]).sum().backward()
     gR = torch.zeros(240, 9, device=DEV)
-    gth = cu(gaa)
-    nv.check(nv.lib().tp_rotmat_to_angle_axis_backward(nv.ptr(cu(R.detach().reshape(240, 9))), nv.vp(gth.data_ptr() + 12), 85, 24,
+    gth, Rd = cu(gaa), cu(R.detach().reshape(240, 9))
+    nv.check(nv.lib().tp_rotmat_to_angle_axis_backward(nv.ptr(Rd), nv.vp(gth.data_ptr() + 12), 85, 24,
                                                        nv.ptr(gR), 240, 0, nv.stream()))
     assert rel_err(gR, R.grad.reshape(240, 9)) < 2e-4
 
@@ -61,7 +62,8 @@ def test_gru_cell_backward_matches_autograd():
     gates = cu(torch.cat([r, z, n, gh[:, 2 * H:]], dim=1).detach())
     gbuf = cu(gout)
     dgi, dgh = torch.empty(B, 3 * H, device=DEV), torch.empty(B, 3 * H, device=DEV)
-    nv.check(nv.lib().tp_gru_cell_backward(nv.ptr(gbuf), H, nv.ptr(gates), 4 * H, nv.ptr(cu(h.detach())), H, nv.ptr(dgi), 3 * H,
+    hd = cu(h.detach())
+    nv.check(nv.lib().tp_gru_cell_backward(nv.ptr(gbuf), H, nv.ptr(gates), 4 * H, nv.ptr(hd), H, nv.ptr(dgi), 3 * H,
                                            nv.ptr(dgh), 3 * H, B, H, nv.stream()))
     assert rel_err(dgi, gi.grad) < 1e-5 and rel_err(dgh, gh.grad) < 1e-5 and rel_err(gbuf, h.grad) < 1e-5
 
@@ -115,7 +117,7 @@ def test_train_step_forward_and_gradients_match_oracle(seed, B, T, H):
     loss.backward()
     orc = train_ref.TrainOracle(sd, seed, 1, H)
     ref_out, ref_loss, ref_grads = orc.loss_and_grads(x, masks, tgt)
-    assert abs(float(loss) - ref_loss) < 1e-4 * max(1.0, abs(ref_loss))
+    assert abs(float(loss.detach()) - ref_loss) < 1e-4 * max(1.0, abs(ref_loss))
     for k in ("kp_2d", "kp_3d", "rotmat", "verts"):
         assert float((out[k].detach().cpu() - ref_out[k]).abs().max()) < (1e-3 if k == "kp_2d" else 1e-4), k
     params = dict(model.named_parameters())
