@@ -32,7 +32,14 @@ if ROOT not in sys.path:
 B, T, L, H = 32, 16, 1, 2048
 SEED = 0
 METRIC = "output frames/s at B=32,T=16 (TePose encoder + IEF Regressor + SMPL)"
+TRAIN_METRIC = "training sequences/s at B=32,T=16 per GPU (forward + backward + gradient all-reduce + Adam)"
+TRAIN_WORKLOAD = "BASELINE.json configs[4]: training step B=32,T=16, L=1,H=2048 (encoder + Regressor + SMPL), data-parallel replicas"
 WORKLOAD = "BASELINE.json configs[1]: 3DPW-eval-shaped batched inference B=32,T=16, L=1,H=2048, 2133-d inputs"
+
+
+def active_switches():
+    """TP_* environment switches that change which kernel runs (recorded in the bench line's config)."""
+    return {k: v for k, v in sorted(os.environ.items()) if k.startswith("TP_")}
 
 
 def peaks():
@@ -205,6 +212,101 @@ def run_reference_gpu(args, rank):
           flush=True)
 
 
+def run_train_reference(args, rank):
+    """--config train --impl reference: the training step of the reference path on the host CPU (oracle/train_ref.py: the torch
+    ops the reference runs + torch.autograd + torch.optim.Adam, lib/core/trainer.py:203,235-237), all host threads.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import synth, train_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.make_state_dict(SEED, L, H)
+    orc = train_ref.TrainOracle(sd, SEED, L, H)
+    params = [p for _, p in orc.named_parameters()]
+    opt = torch.optim.Adam(params, lr=5e-5)
+    x = synth.make_input(SEED, B, T)
+    masks = train_ref.make_masks(SEED, 2 * B)
+    tgt = train_ref.make_targets(SEED, 2 * B)
+
+    def step():
+        orc.loss_and_grads(x, masks, tgt)
+        opt.step()
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    n = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    dt = (time.perf_counter() - t0) / n
+    line = {"impl": "reference", "metric": TRAIN_METRIC, "value": B / dt, "unit": "sequences/s", "n_gpus": args.gpus, "steps": n,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": TRAIN_WORKLOAD, "batch": B, "seqlen": T, "n_layers": L, "hidden": H},
+            "cpu_baseline": {"value": B / dt, "unit": "sequences/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} training steps of the full B=32,T=16 batch (oracle/train_ref.py, torch {torch.__version__} CPU autograd + Adam)"},
+            "e2e": {"value": B / dt, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def measure_training(args, rank, world, dev, dist, steps, warmup, precision="fp32", tensor_core_grads=False):
+    """BASELINE.json configs[4]: forward + backward + (for world > 1) NCCL gradient all-reduce + Adam step, B=32,T=16 per GPU.
+    Returns a dict (rank-aggregated: max over ranks of the CUDA-event time).  The step is measured twice when world > 1:
+    with the all-reduce and with it switched off, which gives the exposed-communication share."""
+    from tepose_b200 import synthetic as synth
+    from tepose_b200.synthetic import build_synthetic_model
+    from tepose_b200.train import DataParallel, path_parameters, make_dropout_masks
+    from tepose_b200 import shard as _sh
+    import tepose_b200._native as nv
+    model, _ = build_synthetic_model(SEED, T, L, H, precision, dev)
+    model.train()
+    model.train_tensor_core_grads = bool(tensor_core_grads)
+    params = [p for _, p in path_parameters(model)]
+    opt = torch.optim.Adam(params, lr=5e-5, fused=True)          # lib/utils/utils.py:145-152, lr of configs/*.yaml
+    dp = DataParallel(model, opt)
+    xs = [torch.from_numpy(synth.make_input(SEED + 100 * rank + i, B, T)).pin_memory() for i in range(2)]
+    tgt = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_train_targets(SEED + rank, 2 * B).items()}
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+    loss_fn = lambda out: synth.synthetic_train_loss(out, tgt)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(n, use_sync):
+        real_world = dp.sync.world
+        if not use_sync:
+            dp.sync.world = 1
+        launches0 = nv.lib().tp_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        last = None
+        for i in range(n):
+            x = xs[i % 2].to(dev, non_blocking=True)            # host -> device copy of the step's input inside the timed region
+            last = dp.step(x, loss_fn, make_dropout_masks(2 * B, dev, generator=gen))
+        loss_host = float(last)                                  # device -> host read of the step's result
+        e1.record()
+        barrier()
+        dp.sync.world = real_world
+        ms = e0.elapsed_time(e1)
+        return _sh.max_over_ranks([ms], dev)[0] / n, loss_host, int(nv.lib().tp_launch_count() - launches0) // max(n, 1)
+
+    timed(max(warmup, 3), True)
+    ms_sync, loss, launches = timed(steps, True)
+    out = {"ms_per_step": ms_sync, "sequences_per_s": B * world / (ms_sync * 1e-3), "loss": loss, "launches_per_step": launches,
+           "precision": precision, "tensor_core_weight_grads": bool(tensor_core_grads), "optimizer": "torch.optim.Adam(fused=True), lr 5e-5",
+           "params": int(sum(p.numel() for p in params)), "h2d_bytes_per_step": int(xs[0].numel() * 4), "d2h_bytes_per_step": 4}
+    if world > 1:
+        ms_nosync, _, _ = timed(steps, False)
+        out.update(allreduce_bytes_per_step=int(dp.sync.bytes) if dp.sync.bytes else int(sum(p.numel() for p in params) * 4),
+                   ms_per_step_without_allreduce=ms_nosync, exposed_comm_frac=max(0.0, (ms_sync - ms_nosync) / ms_sync),
+                   collective="ncclAllReduce(sum) per gradient bucket on a side stream, issued from inside the backward; 1/world scale")
+    del dp, opt, model
+    torch.cuda.empty_cache()
+    return out
+
+
 def _shard_max(v, dev):
     from tepose_b200 import shard as _sh
     return _sh.max_over_ranks([v], dev)[0]
@@ -224,6 +326,12 @@ def main():
     ap.add_argument("--no-live", action="store_true", help="skip the live-stream latency measurement")
     ap.add_argument("--no-fold", action="store_true", help="skip the fold_linear measurement")
     ap.add_argument("--no-smpl", action="store_true", help="skip the SMPL-standalone (65,536 bodies) measurement")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step block of the default line")
+    ap.add_argument("--config", default="infer", choices=["infer", "train"],
+                    help="train: BASELINE.json configs[4] (training step, NCCL gradient all-reduce when launched with torchrun) "
+                         "as the headline of the printed line")
+    ap.add_argument("--train-precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--tc-grads", action="store_true", help="training: weight-gradient GEMMs in bf16 on the tcgen05 GEMM")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
 
@@ -231,7 +339,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        if args.config == "train":
+            run_train_reference(args, rank)
+        else:
+            run_reference(args, rank, world)
         return
     if args.impl == "reference-gpu":
         run_reference_gpu(args, rank)
@@ -262,6 +373,37 @@ def main():
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
+
+    if args.config == "train":
+        sampler = ClockSampler(local_rank); sampler.start()
+        tr = measure_training(args, rank, world, dev, dist, args.steps, args.warmup, args.train_precision, args.tc_grads)
+        clocks = sampler.finish()
+        if rank == 0:
+            cpu_baseline = None
+            if world == 1 and args.cpu_budget > 0:
+                from oracle import synth as osynth, train_ref
+                cores = os.cpu_count() or 1
+                torch.set_num_threads(cores)
+                orc = train_ref.TrainOracle(osynth.make_state_dict(SEED, L, H), SEED, L, H)
+                opt = torch.optim.Adam([p for _, p in orc.named_parameters()], lr=5e-5)
+                xo, mo, to = osynth.make_input(SEED, B, T), train_ref.make_masks(SEED, 2 * B), train_ref.make_targets(SEED, 2 * B)
+                times = time_cpu(lambda i: (orc.loss_and_grads(xo, mo, to), opt.step()), min(args.cpu_budget, 15.0))
+                cpu_baseline = {"value": B / float(np.median(times)), "unit": "sequences/s", "cores": cores, "kind": "port",
+                                "sample": f"{len(times)} training steps of the full batch, median {1e3 * float(np.median(times)):.0f} ms "
+                                          f"(oracle/train_ref.py: torch {torch.__version__} CPU autograd + Adam)"}
+            line = {"metric": TRAIN_METRIC, "value": tr["sequences_per_s"], "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "f32" if args.train_precision == "fp32" else "bf16", "data": "synthetic",
+                    "config": {"workload": TRAIN_WORKLOAD, "batch_per_gpu": B, "seqlen": T, "n_layers": L, "hidden": H,
+                               "precision": args.train_precision, "parallelism": f"dp{world}", "switches": active_switches()},
+                    "e2e": {"value": tr["sequences_per_s"], "unit": "sequences/s", "h2d_bytes_per_step": tr["h2d_bytes_per_step"],
+                            "d2h_bytes_per_step": tr["d2h_bytes_per_step"],
+                            "note": "the timed step copies its input from pinned host memory and reads the loss back"},
+                    "gpu_launches": tr["launches_per_step"] * args.steps, "clocks": clocks, "training": tr, "cpu_baseline": cpu_baseline}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     model, _ = build_product_model(SEED, T, L, H, args.precision, dev)
     n_inputs = 4
@@ -500,6 +642,11 @@ def main():
                     "frames_per_s": B / (r_ms * 1e-3), "launches_per_step": g3.launches_per_replay}
         del g3, m2
 
+    # ---------------------------------------------------------------- training step (configs[4]; all ranks: it holds the all-reduce)
+    training = None
+    if not args.no_train:
+        training = measure_training(args, rank, world, dev, dist, min(args.steps, 10), 3, "fp32", False)
+
     # ---------------------------------------------------------------- aggregate over ranks
     from tepose_b200 import shard as _sh
     dev_ms_max, e2e_ms_max = _sh.max_over_ranks([dev_ms_total, e2e_ms_total], dev)
@@ -525,7 +672,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "seqlen": T, "n_layers": L, "hidden": H,
-                       "precision": args.precision, "cuda_graph": not args.no_graph,
+                       "precision": args.precision, "cuda_graph": not args.no_graph, "switches": active_switches(),
                        "l2": "256 MiB memset between steps, outside the per-step event pairs",
                        "parallelism": f"batch-sharded x{world}, no collective"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
@@ -539,6 +686,7 @@ def main():
             "folded": folded,
             "released_config": released,
             "smpl_standalone": smpl_sa,
+            "training": training,
             "step_ms": {"min": float(step_ms.min()), "median": float(np.median(step_ms)), "max": float(step_ms.max())},
             "wall_s_timed_region": t_wall,
         }

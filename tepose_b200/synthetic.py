@@ -215,6 +215,26 @@ def make_bodies(seed: int, n: int, pose_scale: float = 0.3) -> dict:
     }
 
 
+def make_train_targets(seed: int, n_rows: int) -> dict:
+    """Synthetic regression targets for the outputs that carry gradient in TePoseLoss (lib/core/loss.py:93-131):
+    kp_2d [n,49,2], the 14 common 3-D joints [n,14,3], theta [n,85]."""
+    g = _rng(seed, 901)
+    return {"kp_2d": g.standard_normal((n_rows, 49, 2)).astype(np.float32) * 0.5,
+            "kp_3d": g.standard_normal((n_rows, 14, 3)).astype(np.float32) * 0.3,
+            "theta": g.standard_normal((n_rows, 85)).astype(np.float32) * 0.2}
+
+
+def synthetic_train_loss(out: dict, tgt: dict):
+    """Stand-in for TePoseLoss on the same outputs (its data terms need the licensed datasets): MSE on kp_2d, on
+    kp_3d[:, 25:39] (lib/core/loss.py:99) and on theta.  Plain torch ops: the loss is the caller's code, as in the reference."""
+    import torch
+    t = lambda k: torch.as_tensor(tgt[k], dtype=out[k].dtype, device=out[k].device)
+    kp2 = out["kp_2d"].reshape(-1, 49, 2)
+    kp3 = out["kp_3d"].reshape(-1, 49, 3)[:, 25:39]
+    th = out["theta"].reshape(-1, 85)
+    return ((kp2 - t("kp_2d")) ** 2).mean() + ((kp3 - t("kp_3d")) ** 2).mean() * 10.0 + ((th - t("theta")) ** 2).mean()
+
+
 def build_synthetic_model(seed: int, seqlen: int, n_layers: int, hidden: int, precision: str = "fp32", device="cpu"):
     """tepose_b200.TePose with the synthetic parameters / SMPL-shaped assets of `seed` loaded.
     Returns (model.eval() on `device`, state_dict as numpy)."""
