@@ -33,13 +33,22 @@ __global__ void k_transpose(const float* __restrict__ src, int64_t ld_src, int r
   }
 }
 
-// out[c] = beta * out[c] + sum_r A[r][c]   (bias gradients); one warp-wide column strip per block, fixed summation order
+// out[c] = beta * out[c] + sum_r A[r][c]   (bias gradients).  Block = 32 columns x 8 row groups; every thread sums its rows in
+// order, the 8 partial sums are added in a fixed order (deterministic).
 __global__ void k_colsum(const float* __restrict__ A, int64_t lda, int rows, int cols, float* __restrict__ out, float beta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.0f;
-  for (int r = 0; r < rows; ++r) s += A[(int64_t)r * lda + c];
-  out[c] = beta != 0.0f ? beta * out[c] + s : s;
+  if (c < cols)
+    for (int r = threadIdx.y; r < rows; r += 8) s += A[(int64_t)r * lda + c];
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += part[q][threadIdx.x];
+    out[c] = beta != 0.0f ? beta * out[c] + t : t;
+  }
 }
 
 // a[r][c] *= mask[r][c] * scale   (dropout forward and backward: the same op)
@@ -419,7 +428,7 @@ extern "C" int tp_transpose_f32(const float* src, int64_t ld_src, int rows, int 
 extern "C" int tp_colsum_f32(const float* A, int64_t lda, int rows, int cols, float* out, float beta, void* stream) {
   TP_CHECK_ARG(A && out && rows >= 0 && cols >= 0 && lda >= cols, "tp_colsum_f32: bad arguments");
   if (cols == 0) return TP_OK;
-  k_colsum<<<(unsigned)ceil_div(cols, 128), 128, 0, (cudaStream_t)stream>>>(A, lda, rows, cols, out, beta);
+  k_colsum<<<(unsigned)ceil_div(cols, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(A, lda, rows, cols, out, beta);
   TP_LAUNCH_CHECK();
   return TP_OK;
 }

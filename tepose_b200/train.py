@@ -324,6 +324,14 @@ def _train_backward(model, sv, g_theta, g_verts, g_kp2d, g_kp3d, g_rotmat):
         gates = {"f": sv["gates_f"], "b": sv["gates_b"], "s": sv["gates_s"]}
         g_h = {"f": g_hcat[:, :H].contiguous(), "s": g_hcat[:, H:2 * H].contiguous(), "b": g_hcat[:, 2 * H:].contiguous()}
         whhT = {"f": _Ops.transpose(f32(enc.gru_fwd.weight_hh_l0)), "b": _Ops.transpose(f32(enc.gru_rec.weight_hh_l0_reverse))}
+        # mixed precision (precision='bf16' models): the per-step dL/dh += d_gh . W_hh runs on the skinny tensor-core GEMM over a
+        # fragment-packed bf16 copy of W_hh^T (25 MB streamed per step instead of 50 MB of fp32 through the FFMA GEMM)
+        whh_lp = None
+        if model.precision == "bf16" and B <= 64 and H % 16 == 0:
+            whh_lp = {d: nv.pack_linear(whhT[d][:, :3 * H], "bf16") for d in ("f", "b")}
+            sk_splits = 8                                  # 128-row groups x 8 K slices: 128 CTAs stream W_hh^T at H = 2048
+            sk_ws = nv.workspace(int(L.tp_skinny_bf16_workspace_bytes(B, H, sk_splits)), dev)
+            sk_ws[:4096].zero_()
         dgi = {d: torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32) for d in ("f", "b")}
         dgh = {d: torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32) for d in ("f", "b")}
         dgi["s"] = torch.empty(B, 3 * H, device=dev, dtype=torch.float32)
@@ -339,7 +347,10 @@ def _train_backward(model, sv, g_theta, g_verts, g_kp2d, g_kp3d, g_rotmat):
         for s in range(T - 1, -1, -1):
             for d in ("f", "b"):
                 cell(d, s, seq[d][s - 1] if s > 0 else None)
-                if s > 0:
+                if s > 0 and whh_lp is not None:
+                    nv.check(L.tp_skinny_bf16(P(dgh[d][s * B:(s + 1) * B]), 3 * H, B, 3 * H, nv.ptr(whh_lp[d]), H, nv.vp(0), P(g_h[d]), H,
+                                              P(g_h[d]), H, 1.0, 1.0, 0, sk_splits, nv.ptr(sk_ws), sk_ws.numel(), nv.stream()), "tp_skinny_bf16")
+                elif s > 0:
                     _Ops.gemm(dgh[d][s * B:(s + 1) * B], whhT[d], out=g_h[d], cin=g_h[d], beta=1.0)
         # hidden-side weights: dW_hh = sum_t d_gh[t]^T h[t-1]  (rows B.. of d_gh against rows ..(T-1)B of the states)
         names = {"f": "gru_fwd.{}_l0", "b": "gru_rec.{}_l0_reverse", "s": "gru_rec.{}_l0"}
@@ -372,36 +383,44 @@ def _train_backward(model, sv, g_theta, g_verts, g_kp2d, g_kp3d, g_rotmat):
 
 # ------------------------------------------------------------------------------------------------------------ data parallel
 class GradSync:
-    """Bucketed NCCL all-reduce (sum, then 1 / world_size) of the gradients, issued from inside the backward on a side stream
-    as soon as a bucket is complete: the regressor / heads bucket overlaps the BPTT, the W_hh bucket overlaps the dW_ih GEMMs."""
+    """Bucketed all-reduce (sum, then 1 / world_size) of the gradients, issued from inside the backward as soon as a bucket is
+    complete: the regressor / heads bucket overlaps the BPTT, the W_hh bucket overlaps the dW_ih GEMMs.  On CUDA tensors the
+    collective (NCCL) runs on a side stream; on CPU tensors (gloo, the world-size-2 tests) it runs inline."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
         self.dist, self.group = dist, group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.stream = torch.cuda.Stream()
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.stream = None
         self.bytes = 0
         self.flat = []
 
     def ready(self, named):
-        """named: [(parameter name, gradient tensor)] that are final.  The bucket is flattened and reduced on the side stream."""
-        if self.world == 1:
+        """named: [(parameter name, gradient tensor)] that are final.  The bucket is flattened and reduced."""
+        if self.world == 1 or not named:
             return
         flat = torch.cat([t.reshape(-1) for _, t in named])
-        ev = torch.cuda.Event()
-        ev.record()
-        with torch.cuda.stream(self.stream):
-            self.stream.wait_event(ev)
+        if flat.is_cuda:
+            if self.stream is None:
+                self.stream = torch.cuda.Stream(device=flat.device)
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ev)
+                self.dist.all_reduce(flat, group=self.group)
+                flat.mul_(1.0 / self.world)
+        else:
             self.dist.all_reduce(flat, group=self.group)
             flat.mul_(1.0 / self.world)
-        self.bytes += flat.numel() * 4
+        self.bytes += flat.numel() * flat.element_size()
         self.flat.append((flat, [(k, t.numel()) for k, t in named]))
 
     def finish(self, params: dict):
         """After loss.backward(): waits for the collectives and writes the averaged values into the parameters' .grad."""
         if self.world == 1:
             return
-        torch.cuda.current_stream().wait_stream(self.stream)
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
         for flat, pieces in self.flat:
             off = 0
             for name, n in pieces:

@@ -142,3 +142,52 @@ def test_train_mode_refuses_eval_style_call_and_generates_masks():
     assert out["theta"].shape == (2, 2, 85) and out["kp_3d"].shape == (2, 2, 49, 3) and out["verts"].requires_grad
     out["kp_2d"].square().mean().backward()
     assert model.encoder.gru_fwd.weight_hh_l0.grad is not None
+
+
+def test_train_step_full_size_gradients_match_oracle():
+    """BASELINE configs[4] shape: B=32, T=16, H=2048, fp32.  Every parameter gradient (93.16 M values) against torch.autograd
+    through the oracle on the CPU."""
+    seed, B, T, H = 0, 32, 16, 2048
+    model, sd = build_product_model(seed, T, 1, H, "fp32", DEV)
+    model.train()
+    x = synth.make_input(seed, B, T)
+    masks = train_ref.make_masks(seed, 2 * B)
+    tgt = train_ref.make_targets(seed, 2 * B)
+    out = model(torch.from_numpy(x).to(DEV), is_train=True, dropout_masks=torch.from_numpy(masks).to(DEV))[-1]
+    loss = train_ref.synthetic_loss(out, tgt)
+    loss.backward()
+    orc = train_ref.TrainOracle(sd, seed, 1, H)
+    ref_out, ref_loss, ref_grads = orc.loss_and_grads(x, masks, tgt)
+    assert abs(float(loss.detach()) - ref_loss) < 1e-4 * max(1.0, abs(ref_loss))
+    params = dict(model.named_parameters())
+    worst = {name: rel_err(params[name].grad, g_ref) for name, g_ref in ref_grads.items()}
+    print("full-size gradient errors (max-norm relative):", {k: f"{v:.1e}" for k, v in sorted(worst.items(), key=lambda kv: -kv[1])[:6]})
+    assert max(worst.values()) < 1e-4, worst
+
+
+@pytest.mark.parametrize("tc", [False, True])
+def test_train_step_mixed_precision_gradients_are_close(tc):
+    """precision='bf16' model in train mode: bf16 operands in the encoder forward (tcgen05 K1 / K2, fp32 accumulation and state),
+    fp32 backward (optionally the weight-gradient GEMMs on the tcgen05 GEMM with bf16 operands).  Gradients are compared with the
+    fp32 oracle direction-wise: cosine >= 0.98 and max-norm relative error <= 0.2 per tensor (the state is re-quantised to bf16 as
+    MMA operand at every step of the forward and d_gh at every step of the backward: ~1 % of gradient noise at this size)."""
+    seed, B, T, H = 44, 4, 6, 256
+    model, sd = build_product_model(seed, T, 1, H, "bf16", DEV)
+    model.train()
+    model.train_tensor_core_grads = tc
+    x = synth.make_input(seed, B, T)
+    masks = train_ref.make_masks(seed, 2 * B)
+    tgt = train_ref.make_targets(seed, 2 * B)
+    out = model(torch.from_numpy(x).to(DEV), is_train=True, dropout_masks=torch.from_numpy(masks).to(DEV))[-1]
+    train_ref.synthetic_loss(out, tgt).backward()
+    _, _, ref_grads = train_ref.TrainOracle(sd, seed, 1, H).loss_and_grads(x, masks, tgt)
+    params = dict(model.named_parameters())
+    for name, g_ref in ref_grads.items():
+        g = params[name].grad.detach().cpu().double().reshape(-1)
+        r = g_ref.double().reshape(-1)
+        if float(r.abs().max()) == 0.0:
+            assert float(g.abs().max()) == 0.0, name
+            continue
+        cos = float((g * r).sum() / (g.norm() * r.norm() + 1e-30))
+        assert cos > 0.98, (name, cos)
+        assert rel_err(params[name].grad, g_ref) < 0.2, name
