@@ -309,6 +309,10 @@ def _train_backward(model, sv, g_theta, g_verts, g_kp2d, g_kp3d, g_rotmat):
         _Ops.gemm(g_f, _Ops.transpose(f32(enc.linear_fwd.weight)), out=g_hcat[:, :H])
         _Ops.gemm(g_r, _Ops.transpose(f32(enc.linear_rec.weight)), out=g_hcat[:, H:])
         _Ops.relu_backward(g_hcat, h_cat)
+        dbg = getattr(model, "_debug_capture", None)
+        if dbg is not None:
+            dbg.update(g_hcat=g_hcat.clone(), h_cat=h_cat.clone(), g_feat=g_feat.clone(), seq_f=sv["seq_f"].clone(), seq_b=sv["seq_b"].clone(),
+                       gates_f=sv["gates_f"].clone(), gates_b=sv["gates_b"].clone())
         for name, g_rows, lo, hi in (("linear_fwd", g_f, 0, H), ("linear_rec", g_r, H, 3 * H)):
             dw = torch.empty(2048, hi - lo, device=dev, dtype=torch.float32)
             gT = _Ops.transpose(g_rows, B, 2048)
@@ -327,7 +331,7 @@ def _train_backward(model, sv, g_theta, g_verts, g_kp2d, g_kp3d, g_rotmat):
         # mixed precision (precision='bf16' models): the per-step dL/dh += d_gh . W_hh runs on the skinny tensor-core GEMM over a
         # fragment-packed bf16 copy of W_hh^T (25 MB streamed per step instead of 50 MB of fp32 through the FFMA GEMM)
         whh_lp = None
-        if model.precision == "bf16" and B <= 64 and H % 16 == 0:
+        if model.precision == "bf16" and B <= 64 and H % 16 == 0 and not getattr(model, "train_fp32_bptt", False):
             whh_lp = {d: nv.pack_linear(whhT[d][:, :3 * H], "bf16") for d in ("f", "b")}
             sk_splits = 8                                  # 128-row groups x 8 K slices: 128 CTAs stream W_hh^T at H = 2048
             sk_ws = nv.workspace(int(L.tp_skinny_bf16_workspace_bytes(B, H, sk_splits)), dev)
@@ -352,6 +356,8 @@ def _train_backward(model, sv, g_theta, g_verts, g_kp2d, g_kp3d, g_rotmat):
                                               P(g_h[d]), H, 1.0, 1.0, 0, sk_splits, nv.ptr(sk_ws), sk_ws.numel(), nv.stream()), "tp_skinny_bf16")
                 elif s > 0:
                     _Ops.gemm(dgh[d][s * B:(s + 1) * B], whhT[d], out=g_h[d], cin=g_h[d], beta=1.0)
+        if dbg is not None:
+            dbg.update(dgi_f=dgi["f"].clone(), dgi_b=dgi["b"].clone(), dgh_f=dgh["f"].clone(), dgh_b=dgh["b"].clone())
         # hidden-side weights: dW_hh = sum_t d_gh[t]^T h[t-1]  (rows B.. of d_gh against rows ..(T-1)B of the states)
         names = {"f": "gru_fwd.{}_l0", "b": "gru_rec.{}_l0_reverse", "s": "gru_rec.{}_l0"}
         late = []
