@@ -275,6 +275,10 @@ typedef struct tp_smpl_model {
   /* blend_km (optional): the same [3*vp, 256] bf16 matrix in plain row-major order, row v*3 + c -- the B operand of the
    * tcgen05 GEMM that the large-batch path (>= 1024 bodies) runs per chunk of bodies before skinning.     */
   const void* blend_km;
+  /* blend_um (optional): the same bf16 matrix as the A-operand image of the fused tcgen05 blend + skinning kernel of the
+   * large-batch path: [vertex tile of 128][plane c 3][K block of 64: 4][row 128][128 B], the eight 16-byte chunks of a row
+   * stored at position chunk ^ (row & 7).  NULL: the large-batch path runs the GEMM + skinning pair instead.             */
+  const void* blend_um;
 } tp_smpl_model;
 
 TP_API size_t tp_smpl_workspace_bytes(const tp_smpl_model* m, int n, int nreg, int blend_mode);

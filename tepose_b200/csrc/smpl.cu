@@ -15,6 +15,7 @@
 //  k_smpl_finalize per body: reduce regressor partials, compose the output joint set, project.
 #include "rotations.cuh"
 #include "skinny.cuh"
+#include "umma.cuh"
 
 namespace tp {
 
@@ -44,7 +45,15 @@ struct PrepArgs {
   float* rotmat;   // [n][24][9] or null
   float* theta;    // [n][85] or null
   __nv_bfloat16* coef_tc;  // [n][256] bf16: pf(207) | beta_hi(10) | beta_lo(10) | beta_hi(10) | 0   (tensor-core path) or null
+  unsigned char* coef_um;  // the same rows as the tcgen05 B-operand image [group of 32 bodies][K block 4][row 32][128 B, 16-byte chunks
+                           // XOR-swizzled by row & 7] (k_smpl_lbs_um) or null; bodies n..n_pad-1 get zero rows and zero transforms
+  int n_pad;
 };
+
+// byte offset of coefficient k of body b inside the tcgen05 B-operand image
+__device__ __forceinline__ size_t coef_um_offset(int b, int k) {
+  return (size_t)(b >> 5) * 16384 + (size_t)(k >> 6) * 4096 + (size_t)(b & 31) * 128 + (size_t)((((k & 63) >> 3) ^ (b & 7)) << 4) + (size_t)(k & 7) * 2;
+}
 
 __global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int n, const PrepArgs a) {
   // programmatic dependent launch: the vertex kernel may start now and load its resident blend tile while this
@@ -53,7 +62,14 @@ __global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int
   pdl_wait();                                                             // pose / betas / cam may come from a PDL predecessor (the IEF kernel)
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (b >= n) return;                       // whole warp exits together
+  if (b >= n) {                             // whole warp exits together
+    if (a.coef_um && b < a.n_pad) {         // padding bodies of the last group: zero operand rows, zero transforms
+      *reinterpret_cast<uint4*>(a.coef_um + (size_t)(b >> 5) * 16384 + (size_t)(lane >> 3) * 4096 + (size_t)(b & 31) * 128 + (size_t)(lane & 7) * 16) =
+          make_uint4(0u, 0u, 0u, 0u);
+      for (int i = lane; i < kJ * 12; i += 32) a.A[(int64_t)b * kJ * 12 + i] = 0.0f;
+    }
+    return;
+  }
   const int j = lane < kJ ? lane : kJ - 1;  // idle lanes shadow joint 23 (never written)
   const bool active = lane < kJ;
 
@@ -165,6 +181,24 @@ __global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int
         ct[207 + l] = hi; ct[217 + l] = lo; ct[227 + l] = hi;
       }
       for (int k = 237; k < 256; ++k) ct[k] = __float2bfloat16_rn(0.0f);
+    }
+  }
+  if (a.coef_um) {
+    if (j >= 1) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        *reinterpret_cast<__nv_bfloat16*>(a.coef_um + coef_um_offset(b, (j - 1) * 9 + k)) =
+            __float2bfloat16_rn(R[k] - ((k == 0 || k == 4 || k == 8) ? 1.0f : 0.0f));
+    } else {
+#pragma unroll
+      for (int l = 0; l < 10; ++l) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(beta[l]);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(beta[l] - __bfloat162float(hi));
+        *reinterpret_cast<__nv_bfloat16*>(a.coef_um + coef_um_offset(b, 207 + l)) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(a.coef_um + coef_um_offset(b, 217 + l)) = lo;
+        *reinterpret_cast<__nv_bfloat16*>(a.coef_um + coef_um_offset(b, 227 + l)) = hi;
+      }
+      for (int k = 237; k < 256; ++k) *reinterpret_cast<__nv_bfloat16*>(a.coef_um + coef_um_offset(b, k)) = __float2bfloat16_rn(0.0f);
     }
   }
   if (a.rotmat) {
@@ -666,6 +700,8 @@ k_smpl_skin(const tp_smpl_model m, int body_lo, int body_hi, int bodies_per_cta,
   }
 }
 
+#include "smpl_um.inl"
+
 __global__ void __launch_bounds__(128) k_smpl_finalize(int n, int n_verts, const float* __restrict__ posedJ,
                                                        const float* __restrict__ jpart, int nsplit, int nreg,
                                                        const float* __restrict__ verts, const int32_t* __restrict__ joint_src,
@@ -721,11 +757,13 @@ __global__ void __launch_bounds__(128) k_smpl_finalize(int n, int n_verts, const
 
 static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
-struct SmplPlan { int ntiles, nsplit, tiles_per_split, ngroups; size_t off_A, off_J, off_coef, off_part, off_ctc, off_vposed, total;
-                  int tc, tc_tiles, tc_gsplit, tc_gpc, split, chunk; };
+struct SmplPlan { int ntiles, nsplit, tiles_per_split, ngroups; size_t off_A, off_J, off_coef, off_part, off_ctc, off_vposed, off_um, total;
+                  int tc, tc_tiles, tc_gsplit, tc_gpc, split, chunk, um, n_pad; };
 
 // large-batch path: from this many bodies on, GEMM + skin over L2-resident chunks replaces the fused kernel
 static int split_min_bodies() { static const int v = getenv("TP_SMPL_SPLIT_MIN") ? atoi(getenv("TP_SMPL_SPLIT_MIN")) : 1024; return v; }
+// fused tcgen05 blend + skinning kernel (k_smpl_lbs_um) for the large-batch path; TP_SMPL_UM=0 falls back to GEMM + k_smpl_skin
+static int um_enabled() { static const int v = getenv("TP_SMPL_UM") ? atoi(getenv("TP_SMPL_UM")) : 1; return v; }
 static int split_chunk_bodies() { static const int v = getenv("TP_SMPL_CHUNK") ? atoi(getenv("TP_SMPL_CHUNK")) : 1024; return v < 16 ? 16 : v; }
 
 static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg, int blend_mode) {
@@ -755,16 +793,20 @@ static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg, int blend_mod
   if (want > p.ntiles) want = p.ntiles;
   p.tiles_per_split = (p.ntiles + want - 1) / want;
   p.nsplit = (p.ntiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.split = (p.tc && m->blend_km && m->vp % kSkVT == 0 && n >= split_min_bodies()) ? 1 : 0;
+  p.um = (p.tc && m->blend_um && m->vp % kUsVT == 0 && nreg <= 16 && n >= split_min_bodies() && um_enabled()) ? 1 : 0;
+  if (p.um) p.split = 0;
+  p.n_pad = p.um ? (n + kUsGB - 1) / kUsGB * kUsGB : n;
   size_t o = 0;
-  p.off_A = o; o += al256((size_t)n * kJ * 12 * 4);
+  p.off_A = o; o += al256((size_t)p.n_pad * kJ * 12 * 4);
   p.off_J = o; o += al256((size_t)n * kJ * 3 * 4);
   p.off_coef = o; o += al256((size_t)n * kCoefLd * 4);
-  const int part_tiles = p.tc ? p.tc_tiles : p.nsplit;
+  const int part_tiles = p.um ? m->vp / kUsVT : (p.tc ? p.tc_tiles : p.nsplit);
   p.off_part = o; o += al256((size_t)n * part_tiles * (nreg > 0 ? nreg : 1) * 3 * 4);
   p.off_ctc = o; o += p.tc ? al256((size_t)n * kTcK * 2) : 0;
-  p.split = (p.tc && m->blend_km && m->vp % kSkVT == 0 && n >= split_min_bodies()) ? 1 : 0;
   p.chunk = split_chunk_bodies() < n ? split_chunk_bodies() : n;
   p.off_vposed = o; o += p.split ? al256((size_t)p.chunk * m->vp * 3 * 4) : 0;
+  p.off_um = o; o += p.um ? al256((size_t)(p.n_pad / kUsGB) * kUsBBytes) : 0;
   p.total = o;
   return p;
 }
@@ -808,16 +850,28 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
   pa.posedJ = reinterpret_cast<float*>(ws + pl.off_J);
   pa.coef = reinterpret_cast<float*>(ws + pl.off_coef);
   pa.rotmat = rotmat; pa.theta = theta;
-  pa.coef_tc = pl.tc ? reinterpret_cast<__nv_bfloat16*>(ws + pl.off_ctc) : nullptr;
+  pa.coef_tc = (pl.tc && !pl.um) ? reinterpret_cast<__nv_bfloat16*>(ws + pl.off_ctc) : nullptr;
+  pa.coef_um = pl.um ? ws + pl.off_um : nullptr;
+  pa.n_pad = pl.n_pad;
   float* jpart = reinterpret_cast<float*>(ws + pl.off_part);
 
   {
-    PdlConfig lc(dim3((unsigned)ceil_div(n, 4)), dim3(128), 0, st);
+    PdlConfig lc(dim3((unsigned)ceil_div(pl.n_pad, 4)), dim3(128), 0, st);
     TP_CUDA(cudaLaunchKernelEx(&lc.cfg, k_smpl_prepare, *m, n, pa));
   }
   TP_LAUNCH_CHECK();
   const bool need_verts_pass = verts != nullptr || nreg > 0;
-  if (need_verts_pass && pl.split) {
+  if (need_verts_pass && pl.um) {
+    UsParams up;
+    up.m = *m; up.n = n; up.ngroups = pl.n_pad / kUsGB; up.ntiles = m->vp / kUsVT; up.nreg = nreg;
+    up.coef_img = ws + pl.off_um; up.A = pa.A; up.jreg = jreg; up.verts = verts; up.jpart = jpart;
+    TP_CUDA(cudaFuncSetAttribute(k_smpl_lbs_um, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUsSmem));
+    const long long items = (long long)up.ntiles * up.ngroups;
+    const int grid = (int)(items < sm_count() ? items : sm_count());
+    PdlConfig lc(dim3((unsigned)grid), dim3(kUsThreads), kUsSmem, st);
+    TP_CUDA(cudaLaunchKernelEx(&lc.cfg, k_smpl_lbs_um, up));
+    TP_LAUNCH_CHECK();
+  } else if (need_verts_pass && pl.split) {
     // chunks of bodies: tcgen05 GEMM (blend + template) into an L2-resident scratch, then the skinning kernel
     float* vposed = reinterpret_cast<float*>(ws + pl.off_vposed);
     const int64_t ldv = (int64_t)m->vp * 3;
@@ -874,7 +928,7 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
       TP_CUDA(cudaLaunchKernelEx(&cfg, k_smpl_finalize, n, (int)m->n_verts, (const float*)pa.posedJ, (const float*)jpart,
-                                 (int)(pl.split ? m->vp / kSkVT : (pl.tc ? pl.tc_tiles : pl.nsplit)), nreg, (const float*)verts,
+                                 (int)((pl.split || pl.um) ? m->vp / kSkVT : (pl.tc ? pl.tc_tiles : pl.nsplit)), nreg, (const float*)verts,
                                  joint_src, nj, cam, ld_cam, joints, kp2d));
     }
     TP_LAUNCH_CHECK();

@@ -146,7 +146,7 @@ class PackedSmpl:
         self.skin_w[:V] = wsel
         self.device = device
         # tensor-core blend tables (bf16 mode): [3*vp, 256] rows ((v//16)*3 + c)*16 + v%16
-        self.blend_tc = self.template_pad = self.blend_km = None
+        self.blend_tc = self.template_pad = self.blend_km = self.blend_um = None
         if ks <= 4:
             S = shapedirs.detach().to(device).float()[:, :, :10]                       # [V,3,10]
             S_hi = S.to(torch.bfloat16).float()
@@ -162,9 +162,15 @@ class PackedSmpl:
             self.blend_km = cols.reshape(vp * 3, 256).to(torch.bfloat16).contiguous()        # row v*3 + c (tcgen05 GEMM operand)
             self.template_pad = torch.zeros(vp, 3, device=device, dtype=torch.float32)
             self.template_pad[:V] = v_template.detach().to(device).float()
+            # A-operand image of the fused tcgen05 blend + skinning kernel: [tile 128 v][plane][K block 64][row][8 chunks of 8 bf16],
+            # chunk q of row r stored at position q ^ (r & 7) (the 128-byte swizzle the shared-memory staging is read back with)
+            img = cols.to(torch.bfloat16).reshape(vp // 128, 128, 3, 4, 8, 8).permute(0, 2, 3, 1, 4, 5)     # t, c, kb, r, q, e
+            sw = (torch.arange(8, device=device)[None, :] ^ (torch.arange(128, device=device) % 8)[:, None])   # [r, q'] -> source chunk
+            self.blend_um = torch.gather(img, 4, sw[None, None, None, :, :, None].expand(vp // 128, 3, 4, 128, 8, 8)).contiguous()
         self.c_model = nv.SmplModel(nv.ptr(self.blend), nv.ptr(self.j_template), nv.ptr(self.j_shapedirs),
                                     nv.ptr(self.parents), nv.ptr(self.skin_idx), nv.ptr(self.skin_w),
-                                    ks, V, vp, nv.ptr(self.blend_tc), nv.ptr(self.template_pad), nv.ptr(self.blend_km))
+                                    ks, V, vp, nv.ptr(self.blend_tc), nv.ptr(self.template_pad), nv.ptr(self.blend_km),
+                                    nv.ptr(self.blend_um))
 
 
 def smpl_forward_native(packed: PackedSmpl, pose: torch.Tensor, ld_pose: int, pose_kind: int,
