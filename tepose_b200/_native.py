@@ -162,6 +162,34 @@ def stream() -> vp:
     return vp(torch.cuda.current_stream().cuda_stream)
 
 
+def device_guard(fn):
+    """Decorator for the public entry points: makes the device of the first CUDA tensor argument (else of the module's own
+    parameters / buffers) the CURRENT device for the duration of the call.  The C ABI takes raw pointers and a stream; the stream
+    (`stream()`), the workspaces, the SM count and the occupancy queries behind the cooperative launches all refer to the current
+    device, so a model on cuda:1 called while cuda:0 is current would otherwise launch on the wrong device (ATen guards this for
+    torch modules; the reference's modules therefore work in that situation, and so must their drop-ins)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if torch.is_tensor(a) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None and args and isinstance(args[0], torch.nn.Module):
+            t = next(iter(args[0].parameters()), None)
+            if t is None:
+                t = next(iter(args[0].buffers()), None)
+            if t is not None and t.is_cuda:
+                dev = t.device
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 def workspace(nbytes: int, device) -> torch.Tensor:
     """256-byte aligned scratch (torch's caching allocator aligns to 512 B)."""
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

@@ -22,6 +22,7 @@ constexpr int kUsGB = 32;                       // bodies per group (MMA N)
 constexpr int kUsVT = 128;                      // vertices per tile (MMA M)
 constexpr int kUsK = 256;
 constexpr int kUsBStages = 3;
+constexpr int kUsChunkGroups = 128;            // bodies per L2-resident chunk / 32
 constexpr int kUsBBytes = kUsGB * kUsK * 2;                 // 16 KB coefficient image of one group
 constexpr int kUsTBytes = kUsGB * kJ * 12 * 4;              // 36 KB joint transforms of one group
 constexpr int kUsSlabPitch = 100;                           // floats per body in a warp's slab (96 + 4: 16-byte rows, bank shift 4)
@@ -139,22 +140,26 @@ __global__ void __launch_bounds__(kUsThreads, 1) k_smpl_lbs_um(const UsParams p)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 96;     // 3 x 32 accumulator columns, then 3 planes x 128 columns of A
 
-  // this CTA's contiguous range of (tile, group) items
-  const long long total = (long long)p.ntiles * p.ngroups;
-  long long it = total * blockIdx.x / gridDim.x;
-  const long long it_hi = total * (blockIdx.x + 1) / gridDim.x;
-
+  // Work order: bodies are taken in CHUNKS of kUsChunkGroups groups (4096 bodies: 6.8 MB of coefficient rows + transforms, which
+  // stay in L2 while the 54 vertex tiles re-read them); inside a chunk the (tile, group) items are cut into equal contiguous
+  // ranges, one per CTA, in tile-major order.
   pdl_wait();                       // coefficient image / transforms come from k_smpl_prepare
   pdl_launch_dependents();
 
   uint32_t ngrp = 0;                // groups this CTA has been through (ring stage / parity bookkeeping, all roles in step)
   uint32_t nfill = 0;
   const int q = warp & 3, sset = warp >> 2;                    // epilogue: TMEM lane quadrant, body set
+  for (int chunk0 = 0; chunk0 < p.ngroups; chunk0 += kUsChunkGroups) {
+  const int cgroups = p.ngroups - chunk0 < kUsChunkGroups ? p.ngroups - chunk0 : kUsChunkGroups;
+  const long long total = (long long)p.ntiles * cgroups;
+  long long it = total * blockIdx.x / gridDim.x;
+  const long long it_hi = total * (blockIdx.x + 1) / gridDim.x;
   while (it < it_hi) {
-    const int tile = (int)(it / p.ngroups);
-    const int g0 = (int)(it - (long long)tile * p.ngroups);
+    const int tile = (int)(it / cgroups);
+    const int gl0 = (int)(it - (long long)tile * cgroups);
     const long long left = it_hi - it;
-    const int g1 = (long long)(p.ngroups - g0) < left ? p.ngroups : g0 + (int)left;
+    const int gl1 = (long long)(cgroups - gl0) < left ? cgroups : gl0 + (int)left;
+    const int g0 = chunk0 + gl0, g1 = chunk0 + gl1;
     const int v0 = tile * kUsVT;
 
     // ------------------------------------------------------------------ tile set-up (everyone; the pipeline is drained)
@@ -257,6 +262,21 @@ __global__ void __launch_bounds__(kUsThreads, 1) k_smpl_lbs_um(const UsParams p)
       const uint32_t t_lane = (uint32_t)(q * 32) << 16;
       const int64_t nv3 = (int64_t)p.m.n_verts * 3;
       const int gq = lane >> 2, tq = lane & 3;
+      // per-tile store bounds of this lane's two float2 slots (only the last tile is ragged)
+      const int64_t vbase = (int64_t)(v0 + q * 32) * 3;
+      const int64_t vrem = nv3 - vbase;
+      const bool st_a2 = lane * 2 + 1 < vrem, st_a1 = lane * 2 < vrem;
+      const bool st_b2 = lane < 16 && 64 + lane * 2 + 1 < vrem, st_b1 = lane < 16 && 64 + lane * 2 < vrem;
+      // partial-sum slots this thread adds up after the regressor MMAs: value i = row * 24 + body * 3 + coordinate
+      int js_off[3]; bool js_ok[3]; int js_bi[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int i = q * 32 + lane + 128 * k;
+        const int r = i / 24, col = i - r * 24, bi = col / 3, c = col - bi * 3;
+        js_ok[k] = i < p.nreg * 24;
+        js_bi[k] = bi;
+        js_off[k] = ((bi * p.ntiles + tile) * p.nreg + r) * 3 + c;
+      }
       for (int g = g0; g < g1; ++g, ++ngrp) {
         float px[8], py[8], pz[8];
         mbar_wait(acc_full, ngrp & 1u);
@@ -300,23 +320,20 @@ __global__ void __launch_bounds__(kUsThreads, 1) k_smpl_lbs_um(const UsParams p)
         __syncwarp();
         if (lane == 0) us_mb_arrive(&t_empty[stt]);
         const int body0 = g * kUsGB + sset * 8;
-        // coalesced vertex store: 384 contiguous bytes per (warp, body)
+        const int nvalid = p.n - body0;                       // bodies of this set that exist (>= 8 except in the last group)
+        // coalesced vertex store: 384 contiguous bytes per (warp, body); the per-lane bounds were settled once per tile
         if (p.verts) {
-          const int64_t base = (int64_t)(v0 + q * 32) * 3;
+          float* dstb = p.verts + (int64_t)body0 * nv3 + vbase;
 #pragma unroll
           for (int bi = 0; bi < 8; ++bi) {
-            if (body0 + bi < p.n) {
-              float* dstb = p.verts + (int64_t)(body0 + bi) * nv3 + base;
+            if (bi < nvalid) {
               const float2* src = reinterpret_cast<const float2*>(slab + bi * kUsSlabPitch);
-              const float2 a = src[lane];
-              if (base + lane * 2 + 1 < nv3) *reinterpret_cast<float2*>(dstb + lane * 2) = a;
-              else if (base + lane * 2 < nv3) dstb[lane * 2] = a.x;
-              if (lane < 16) {
-                const float2 b2 = src[32 + lane];
-                if (base + 64 + lane * 2 + 1 < nv3) *reinterpret_cast<float2*>(dstb + 64 + lane * 2) = b2;
-                else if (base + 64 + lane * 2 < nv3) dstb[64 + lane * 2] = b2.x;
-              }
+              if (st_a2) *reinterpret_cast<float2*>(dstb + lane * 2) = src[lane];
+              else if (st_a1) dstb[lane * 2] = src[lane].x;
+              if (st_b2) *reinterpret_cast<float2*>(dstb + 64 + lane * 2) = src[32 + lane];
+              else if (st_b1) dstb[64 + lane * 2] = src[32 + lane].x;
             }
+            dstb += nv3;
           }
         }
         // joint regressors on the tile while it is on chip: D[row 16, (body, coord) 24] += J[16, 32 v] . V[32 v, 24], 3xTF32
@@ -350,12 +367,12 @@ __global__ void __launch_bounds__(kUsThreads, 1) k_smpl_lbs_um(const UsParams p)
           }
           asm volatile("bar.sync %0, 128;\n" ::"r"(1 + sset) : "memory");
           {
-            const float* s0 = s_slab + (size_t)(sset * 4) * kUsSlabFloats;
-            for (int i = q * 32 + lane; i < p.nreg * 24; i += 128) {
-              const float sum = (s0[i] + s0[kUsSlabFloats + i]) + (s0[2 * kUsSlabFloats + i] + s0[3 * kUsSlabFloats + i]);
-              const int r = i / 24, col = i - r * 24, bi = col / 3, c = col - bi * 3;
-              if (body0 + bi < p.n)
-                p.jpart[(((int64_t)(body0 + bi) * p.ntiles + tile) * p.nreg + r) * 3 + c] = sum;
+            const float* s0 = s_slab + (size_t)(sset * 4) * kUsSlabFloats + q * 32 + lane;
+            float* jp = p.jpart + (int64_t)body0 * p.ntiles * p.nreg * 3;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              if (js_ok[k] && js_bi[k] < nvalid)
+                jp[js_off[k]] = (s0[128 * k] + s0[kUsSlabFloats + 128 * k]) + (s0[2 * kUsSlabFloats + 128 * k] + s0[3 * kUsSlabFloats + 128 * k]);
             }
           }
           asm volatile("bar.sync %0, 128;\n" ::"r"(1 + sset) : "memory");
@@ -365,6 +382,7 @@ __global__ void __launch_bounds__(kUsThreads, 1) k_smpl_lbs_um(const UsParams p)
       }
     }
     it += g1 - g0;
+  }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();

@@ -38,6 +38,9 @@ def _pelvis(pelvis):
     return int(pelvis[0]), int(pelvis[1])
 
 
+@nv.device_guard
+
+
 def pose_metrics(pred_j3ds, target_j3ds, pelvis=(2, 3), want_aligned=False):
     """evaluate.py:420-443 for one sequence: root-align both joint sets, then per-frame MPJPE, Procrustes-aligned
     MPJPE and acceleration error (zeros at the first / last frame, evaluate.py:441-442), all in metres.
@@ -83,6 +86,9 @@ def batch_compute_similarity_transform_torch(S1, S2):
     return out if transposed else out.permute(0, 2, 1)
 
 
+@nv.device_guard
+
+
 def compute_error_accel_eval(joints_gt, joints_pred, vis=None):
     """[N,J,3] x 2 -> [N-2] (visible entries only when vis [N] is given: a frame counts if it and its two
     successors are visible, eval_utils.py:128-136)."""
@@ -107,6 +113,9 @@ def _masked_mean(normed: torch.Tensor, vidlen_each, lo: int, tail: int, extra: i
     return total / (vl.sum() - vl.shape[0] * (lo + 1 + extra) + 1e-8)
 
 
+@nv.device_guard
+
+
 def compute_accel(joints, vidlen_each, seqlen):
     """joints [S,L,J,3] -> scalar mean acceleration norm over frames seqlen-1 .. vidlen-3 of every sequence."""
     P = _dev_f32(joints)
@@ -114,6 +123,9 @@ def compute_accel(joints, vidlen_each, seqlen):
     normed = torch.empty(S, max(Ln - 2, 0), device=P.device)
     nv.check(nv.lib().tp_accel_error(nv.ptr(P), nv.vp(0), S, Ln, J, -1, -1, nv.ptr(normed), nv.stream()), "tp_accel_error")
     return _masked_mean(normed, vidlen_each, seqlen - 1, 2, 1)
+
+
+@nv.device_guard
 
 
 def compute_error_accel(joints_gt, joints_pred, vidlen_each, seqlen, vis=None):
@@ -126,6 +138,9 @@ def compute_error_accel(joints_gt, joints_pred, vidlen_each, seqlen, vis=None):
     normed = torch.empty(S, max(Ln - 2, 0), device=P.device)
     nv.check(nv.lib().tp_accel_error(nv.ptr(P), nv.ptr(G), S, Ln, J, -1, -1, nv.ptr(normed), nv.stream()), "tp_accel_error")
     return _masked_mean(normed, vidlen_each, seqlen - 1, 4, 3)
+
+
+@nv.device_guard
 
 
 def compute_error_verts(pred_verts, target_verts=None, target_theta=None, device=None, smpl=None):

@@ -12,12 +12,18 @@ def _prep(x: torch.Tensor, width: int) -> torch.Tensor:
     return x.reshape(-1, width).contiguous().float()
 
 
+@nv.device_guard
+
+
 def rot6d_to_rotmat(x: torch.Tensor) -> torch.Tensor:
     """lib/utils/geometry.py:330-343.  [...,6k] -> [N,3,3] (x is viewed as (-1,3,2))."""
     flat = _prep(x, 6)
     out = torch.empty(flat.shape[0], 3, 3, device=flat.device, dtype=torch.float32)
     nv.check(nv.lib().tp_rot6d_to_rotmat(nv.ptr(flat), nv.ptr(out), flat.shape[0], nv.stream()), "tp_rot6d_to_rotmat")
     return out
+
+
+@nv.device_guard
 
 
 def rotation_matrix_to_angle_axis(rotation_matrix: torch.Tensor) -> torch.Tensor:
@@ -31,6 +37,9 @@ def rotation_matrix_to_angle_axis(rotation_matrix: torch.Tensor) -> torch.Tensor
     return out
 
 
+@nv.device_guard
+
+
 def batch_rodrigues(axisang: torch.Tensor, form: str = "quat") -> torch.Tensor:
     """form='quat': lib/utils/geometry.py:22-34 (returns [N,9] like the reference);
     form='smplx': smplx.lbs.batch_rodrigues (returns [N,3,3])."""
@@ -39,6 +48,9 @@ def batch_rodrigues(axisang: torch.Tensor, form: str = "quat") -> torch.Tensor:
     code = nv.RODRIGUES_QUAT if form == "quat" else nv.RODRIGUES_SMPLX
     nv.check(nv.lib().tp_batch_rodrigues(nv.ptr(flat), nv.ptr(out), flat.shape[0], code, nv.stream()), "tp_batch_rodrigues")
     return out.reshape(-1, 9) if form == "quat" else out
+
+
+@nv.device_guard
 
 
 def projection(pred_joints: torch.Tensor, pred_camera: torch.Tensor) -> torch.Tensor:

@@ -37,9 +37,13 @@ class GraphedTePose:
             self.static_output = self.model(self.static_input, is_train=is_train, J_regressor=self.J_regressor)[-1]
         self.launches_per_replay = int(nv.lib().tp_launch_count() - before)
 
+    @nv.device_guard
+
     def replay(self):
         self.graph.replay()
         return self.static_output
+
+    @nv.device_guard
 
     def __call__(self, x: torch.Tensor):
         self.static_input.copy_(x, non_blocking=True)

@@ -72,6 +72,7 @@ class LiveTePose:
         return out
 
     @torch.no_grad()
+    @nv.device_guard
     def step(self, features: torch.Tensor):
         """features [B,2048] (CUDA or pinned host).  Returns {theta, verts, kp_2d, kp_3d, rotmat} for
         the newest frame (tensors are reused by the next call when graphs are on)."""

@@ -51,6 +51,8 @@ class PipelinedTePose:
         self.h2d_bytes = self.slots[0].static_input.numel() * 4
         self.d2h_bytes = sum(v.numel() * 4 for v in self.out_host[0].values())
 
+    @nv.device_guard
+
     def submit(self, x_host: torch.Tensor) -> int:
         i, slot = self.count, self.count % self.depth
         s = self.slots[slot]

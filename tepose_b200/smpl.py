@@ -294,6 +294,7 @@ class SMPL(nn.Module):
         return hit
 
     # ------------------------------------------------------------------ forward
+    @nv.device_guard
     def forward(self, betas=None, body_pose=None, global_orient=None, transl=None, pose2rot=True, **kwargs):
         p = self.packed()
         betas = self.betas if betas is None else betas

@@ -143,6 +143,8 @@ class Regressor(nn.Module):
             self._fold_key = key
         return self._fold
 
+    @nv.device_guard
+
     def forward_folded(self, x, n_iter=3, is_train=False, J_regressor=None):
         """forward() through the closed form: psc = x . G^T + (g + A^n p_0), one fp32 split-K GEMM."""
         if self.training:
@@ -156,6 +158,7 @@ class Regressor(nn.Module):
         return self.decode(psc, is_train=is_train, J_regressor=J_regressor)
 
     # ------------------------------------------------------------------ forward
+    @nv.device_guard
     def forward(self, x, init_pose=None, init_shape=None, init_cam=None, n_iter=3, is_train=False, J_regressor=None):
         if self.training:
             raise NotImplementedError(
@@ -187,6 +190,8 @@ class Regressor(nn.Module):
                                   nv.ptr(ws), ws.numel(), nv.stream()), "tp_ief_forward")
         nv.mark("k3_ief")
         return self.decode(psc, is_train=is_train, J_regressor=J_regressor)
+
+    @nv.device_guard
 
     def decode(self, psc: torch.Tensor, is_train=False, J_regressor=None):
         """rot6d -> R, SMPL, (H36M regression), projection, R -> axis-angle, theta

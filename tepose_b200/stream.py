@@ -77,6 +77,7 @@ class WindowedTePose:
         return out
 
     @torch.no_grad()
+    @nv.device_guard
     def step(self, window_feats: torch.Tensor):
         """window_feats [B,T,2048] (CUDA or pinned host): the static features of the T newest frames.
         Returns the prediction for the newest one (tensors are reused by the next call when graphs are on)."""

@@ -52,8 +52,13 @@ def _rng(seed: int, stream: int) -> np.random.Generator:
     return np.random.Generator(np.random.PCG64([int(seed), int(stream)]))
 
 
-def make_smpl_model(seed: int = 0) -> dict:
-    """SMPL-shaped random body model (float32 arrays, pkl-style key names)."""
+def make_smpl_model(seed: int = 0, skinning: str = "random") -> dict:
+    """SMPL-shaped random body model (float32 arrays, pkl-style key names).
+
+    skinning="random" (default; what every golden was generated with): each vertex is bound to 4 joints drawn uniformly --
+    no locality at all, the worst case for any kernel that shares joint transforms between neighbouring vertices.
+    skinning="coherent": the locality of the licensed SMPL asset (consecutive vertex ids belong to the same body part): runs of
+    vertices share a primary joint and take the other three from its kinematic neighbourhood (parent, children, grandparent)."""
     g = _rng(seed, 1)
     V, J = NUM_VERTS, NUM_JOINTS
     v_template = (0.3 * g.standard_normal((V, 3))).astype(np.float32)
@@ -68,6 +73,19 @@ def make_smpl_model(seed: int = 0) -> dict:
 
     weights = np.zeros((V, J), dtype=np.float32)
     cols = np.stack([g.permutation(J)[:4] for _ in range(V)])
+    if skinning == "coherent":
+        par = SMPL_PARENTS
+        neigh = []
+        for j in range(J):
+            cand = [j] + ([int(par[j])] if par[j] >= 0 else []) + [c for c in range(J) if par[c] == j]
+            if par[j] >= 0 and par[int(par[j])] >= 0:
+                cand.append(int(par[int(par[j])]))
+            cand += [c for c in range(J) if c not in cand]            # pad (leaf joints have few neighbours)
+            neigh.append(cand[:4])
+        run = V // J + 1                                              # ~288 consecutive vertices per body part
+        cols = np.stack([np.array(neigh[min(v // run, J - 1)]) for v in range(V)])
+    elif skinning != "random":
+        raise ValueError(f"skinning must be 'random' or 'coherent', got {skinning!r}")
     w = g.random((V, 4)).astype(np.float32) + 0.05
     w = w / w.sum(axis=1, keepdims=True)
     np.put_along_axis(weights, cols, w, axis=1)
@@ -108,11 +126,11 @@ def make_mean_params() -> dict:
     return {"pose": pose, "shape": shape, "cam": cam}
 
 
-def write_base_data(dirname: str, seed: int = 0) -> str:
+def write_base_data(dirname: str, seed: int = 0, skinning: str = "random") -> str:
     """Materialise ``data/base_data`` the way lib/core/config.py:31 expects it."""
     os.makedirs(dirname, exist_ok=True)
     with open(os.path.join(dirname, "SMPL_NEUTRAL.pkl"), "wb") as fh:
-        pickle.dump(make_smpl_model(seed), fh)
+        pickle.dump(make_smpl_model(seed, skinning), fh)
     ex = make_extra_regressors(seed)
     np.save(os.path.join(dirname, "J_regressor_extra.npy"), ex["J_regressor_extra"])
     np.save(os.path.join(dirname, "J_regressor_h36m.npy"), ex["J_regressor_h36m"])
@@ -235,7 +253,8 @@ def synthetic_train_loss(out: dict, tgt: dict):
     return ((kp2 - t("kp_2d")) ** 2).mean() + ((kp3 - t("kp_3d")) ** 2).mean() * 10.0 + ((th - t("theta")) ** 2).mean()
 
 
-def build_synthetic_model(seed: int, seqlen: int, n_layers: int, hidden: int, precision: str = "fp32", device="cpu"):
+def build_synthetic_model(seed: int, seqlen: int, n_layers: int, hidden: int, precision: str = "fp32", device="cpu",
+                          skinning: str = "random"):
     """tepose_b200.TePose with the synthetic parameters / SMPL-shaped assets of `seed` loaded.
     Returns (model.eval() on `device`, state_dict as numpy)."""
     import contextlib
@@ -253,7 +272,7 @@ def build_synthetic_model(seed: int, seqlen: int, n_layers: int, hidden: int, pr
             os.chdir(old)
 
     with tempfile.TemporaryDirectory() as tmp:
-        write_base_data(os.path.join(tmp, "data", "base_data"), seed)      # asset paths are cwd-relative
+        write_base_data(os.path.join(tmp, "data", "base_data"), seed, skinning)      # asset paths are cwd-relative
         with _cwd(tmp):
             model = TePose(seqlen=seqlen, n_layers=n_layers, hidden_size=hidden, pretrained="", precision=precision)
     sd = make_state_dict(seed, n_layers, hidden)

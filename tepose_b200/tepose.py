@@ -45,6 +45,14 @@ class GruKernels:
         nv.check(nv.lib().tp_pack_whh_bf16(nv.ptr(w), nv.ptr(out), w.shape[1], nv.stream()), "tp_pack_whh_bf16")
         return out
 
+    def uses_umma(self, batch: int) -> bool:
+        """Whether tp_gru_recurrence takes the tcgen05 resident-weight kernel (k_gru_umma) for this model's two full directions at
+        this batch: the host-side mirror of the dispatch conditions in csrc/gru.cu (for reporting; the library decides)."""
+        import os
+        H = self.hidden_size
+        return (self.precision == "bf16" and H % 128 == 0 and batch <= 32 and 2 * (H // 32) <= 148
+                and "TP_GRU_NO_UMMA" not in os.environ and self.n_layers == 1)
+
     @staticmethod
     def _pack_whh_umma(w: torch.Tensor, lp: bool):
         """bf16 mode, H % 128 == 0: the per-CTA images the tcgen05 recurrence keeps resident in TMEM + shared memory
@@ -330,6 +338,8 @@ class TemporalEncoder(nn.Module, GruKernels):
         nv.mark("k3_heads")
         return feat
 
+    @nv.device_guard
+
     def forward(self, x, is_train=False):
         h_fwd, h_rec = self.encode_states(x)
         return self.heads(h_fwd, h_rec, is_train=is_train)
@@ -434,6 +444,8 @@ class TePose(nn.Module):
     # sequences per pass of the encoder + regressor kernels: their fast paths (interleaved recurrence, fused heads + IEF)
     # hold one 32-row batch tile; larger batches run as balanced groups and share ONE SMPL pass
     GROUP = 32
+
+    @nv.device_guard
 
     def forward(self, input, is_train=False, J_regressor=None, dropout_masks=None):
         if self.training:

@@ -89,6 +89,7 @@ class TemporalEncoder(nn.Module, GruKernels):
         return pk
 
     # ------------------------------------------------------------------ forward
+    @nv.device_guard
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x [B,T,2048] -> [B,T,F] (lib/models/vibe.py:52-65); F = 2048 with a linear layer, else D*H."""
         nv.require_cuda(x, "input")
@@ -168,6 +169,8 @@ class VIBE(nn.Module):
             pretrained_dict = torch.load(pretrained)['model']
             self.regressor.load_state_dict(pretrained_dict, strict=False)
             print(f'=> loaded pretrained model from \'{pretrained}\'')
+
+    @nv.device_guard
 
     def forward(self, input, J_regressor=None):
         if self.training:

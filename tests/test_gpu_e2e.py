@@ -233,3 +233,24 @@ def test_fused_heads_ief_kernel_against_separate_kernels():
     # same bf16 operands, fp32 accumulation in a different order (K slices / split-K)
     assert float((fused["theta"] - sep["theta"]).abs().max()) < 2e-4
     assert float((fused["verts"] - sep["verts"]).abs().max()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_forward_on_a_non_current_device():
+    """A model and input on cuda:1 while cuda:0 is the current device: the entry points switch the current device
+    themselves, the outputs live on cuda:1 and match the same forward run with cuda:1 current."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from tepose_b200 import synthetic as psynth
+    x = torch.from_numpy(psynth.make_input(3, 4, 8))
+    torch.cuda.set_device(1)
+    model, _ = psynth.build_synthetic_model(3, 8, 1, 256, "bf16", "cuda:1")
+    with torch.no_grad():
+        want = model(x.to("cuda:1"))[-1]
+    torch.cuda.set_device(0)
+    with torch.no_grad():
+        got = model(x.to("cuda:1"))[-1]
+    torch.cuda.synchronize("cuda:1")
+    for k in want:
+        assert got[k].device == want[k].device == torch.device("cuda:1")
+        assert torch.equal(got[k], want[k]), k

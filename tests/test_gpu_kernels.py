@@ -374,6 +374,40 @@ def test_smpl_large_batch_split_path(n):
     assert float((out.joints - torch.cat(fj)).abs().max()) < 2e-5
 
 
+@pytest.mark.parametrize("skinning", ["random", "coherent"])
+def test_smpl_config3_65536_bodies(skinning):
+    """BASELINE.json configs[3] at its full size: 65,536 bodies through the fused tcgen05 blend + skinning kernel (k_smpl_lbs_um).
+    256 sampled bodies against the oracle (<= 1e-4 m), and ALL bodies against the small-batch fused kernel (k_smpl_verts_tc, same
+    bf16 blend operands, different summation order) in chunks of 512.  Both skinning layouts of the synthetic body model: 4 random
+    joints per vertex (no locality) and SMPL-like runs of vertices that share their joints."""
+    from tepose_b200 import synthetic as psynth
+    n = 65536
+    model, _ = psynth.build_synthetic_model(10, 16, 1, 64, "bf16", "cuda:0", skinning=skinning)
+    smpl = model.regressor.smpl
+    smpl.blend_precision = "bf16"
+    bodies = synth.make_bodies(11, n)
+    aa, betas = torch.from_numpy(bodies["pose_aa"]), torch.from_numpy(bodies["betas"])
+    aa_d, betas_d = cu(aa), cu(betas)
+    out = smpl(betas=betas_d, body_pose=aa_d[:, 3:], global_orient=aa_d[:, :3], pose2rot=True)
+    assert tuple(out.vertices.shape) == (n, 6890, 3) and tuple(out.joints.shape) == (n, 49, 3)
+    assert bool(torch.isfinite(out.vertices).all())
+    g = torch.Generator().manual_seed(5)
+    pick = torch.cat([torch.tensor([0, 1, 31, 32, 33, n - 33, n - 32, n - 1]), torch.randint(0, n, (248,), generator=g)])
+    sm = psynth.make_smpl_model(10, skinning)
+    m = torch_ref.SmplModel.synthetic(10)
+    m.lbs_weights = torch.from_numpy(sm["weights"])
+    v_ref, j_ref, _ = torch_ref.smpl_forward(m, betas[pick], pose_aa=aa[pick])
+    ev = float((out.vertices[pick.to(DEV)].cpu() - v_ref).abs().max())
+    ej = float((out.joints[pick.to(DEV)].cpu() - j_ref).abs().max())
+    assert ev < 1e-4 and ej < 1e-4, (ev, ej)
+    worst_v = worst_j = 0.0
+    for lo in range(0, n, 512):
+        o = smpl(betas=betas_d[lo:lo + 512], body_pose=aa_d[lo:lo + 512, 3:], global_orient=aa_d[lo:lo + 512, :3], pose2rot=True)
+        worst_v = max(worst_v, float((out.vertices[lo:lo + 512] - o.vertices).abs().max()))
+        worst_j = max(worst_j, float((out.joints[lo:lo + 512] - o.joints).abs().max()))
+    assert worst_v < 3e-5 and worst_j < 3e-5, (worst_v, worst_j)
+
+
 @pytest.mark.parametrize("B,T0,T1,H", [(32, 16, 16, 2048), (9, 5, 3, 128), (17, 2, 6, 1024), (32, 1, 4, 256), (1, 16, 16, 2048), (5, 3, 4, 256)])
 def test_gru_recurrence_two_interleaved_directions(B, T0, T1, H):
     """bf16, exactly two matmul jobs without h0 at batch <= 32 -> k_gru_bf16_dual (independent 5-warp teams per direction,

@@ -194,3 +194,19 @@ def test_large_batches_run_as_balanced_groups():
     grus = [c for c in fake.calls if c[0] == "gru"]
     assert [c[2] for c in grus] == [24, 24, 22]                    # balanced groups of the 70 sequences
     assert [c[0] for c in fake.calls].count("smpl") == 1 and out["verts"].shape[0] == 70
+
+
+def test_device_guard_is_transparent_without_cuda_tensors():
+    """nv.device_guard (every public entry point runs with its tensors' device current) must not touch CUDA when no
+    CUDA tensor is involved, and must keep signature / return value."""
+    import tepose_b200._native as nv
+    calls = []
+
+    @nv.device_guard
+    def f(a, b=2):
+        calls.append((a, b))
+        return a
+
+    t = torch.zeros(2)
+    assert f(t, b=3) is t and calls == [(t, 3)]
+    assert f.__name__ == "f"
