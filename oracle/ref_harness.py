@@ -28,11 +28,44 @@ import torch
 
 from . import synth, torch_ref
 
-REFERENCE_ROOT = "/root/reference"
+# The reference tree: /root/reference in the authoring container.  On the GPU box that path does not exist; what travels there is
+# oracle/_ref/ (git-ignored, NOT gpurun-ignored): the handful of UNMODIFIED reference module files of the path, staged by
+# stage_reference() from __graft_entry__.build() -- the Python counterpart of a compiled oracle/_ref/*.so.  Only bench.py's
+# --impl reference arm and its cpu_baseline leg execute them there.
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED_ROOT = os.path.join(_HERE, "_ref")
+STAGED_FILES = ("lib/models/tepose.py", "lib/models/spin.py", "lib/models/smpl.py", "lib/utils/geometry.py", "lib/core/config.py")
+
+
+def _pick_root() -> str:
+    if os.environ.get("TEPOSE_REF_ROOT"):                       # tests: force the staged copy
+        return os.environ["TEPOSE_REF_ROOT"]
+    if os.path.isfile(os.path.join("/root/reference", "lib", "models", "tepose.py")):
+        return "/root/reference"
+    return STAGED_ROOT
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "lib", "models", "tepose.py"))
+
+
+def stage_reference(src: str = "/root/reference") -> bool:
+    """Copies the path's reference modules, byte for byte, into oracle/_ref/ (outputs only under oracle/_ref/, which is
+    git-ignored: reference sources never enter the repository's history).  Returns False when `src` is absent."""
+    import shutil
+    if not os.path.isfile(os.path.join(src, "lib", "models", "tepose.py")):
+        return False
+    for rel in STAGED_FILES:
+        dst = os.path.join(STAGED_ROOT, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(src, rel), dst)
+    with open(os.path.join(STAGED_ROOT, "README"), "w") as fh:
+        fh.write("Unmodified copies of the reference's hot-path modules (staged by oracle/ref_harness.stage_reference from "
+                 "/root/reference); executed only by bench.py --impl reference / cpu_baseline.  Not tracked by git.\n")
+    return True
 
 
 def _install_yacs_stub():
