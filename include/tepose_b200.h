@@ -40,6 +40,11 @@ extern "C" {
 
 #define TP_PRECISION_FP32 0 /* fp32 operands, FFMA, fp32 accumulate (strict parity mode)   */
 #define TP_PRECISION_BF16 1 /* bf16 operands on tensor cores, fp32 accumulate + fp32 state */
+#define TP_PRECISION_BF16X3 2 /* tp_gru_recurrence only: fp32-grade recurrent matmul on tensor cores.  Both operands are split
+                                 x = hi + lo with hi = bf16(x), lo = bf16(x - hi); h.W^T = hi.W_hi + lo.W_hi + hi.W_lo (the lo.lo
+                                 term, 2^-18 relative, is dropped) runs as ONE bf16 contraction over the K-concatenated operands
+                                 [h_hi | h_lo | h_hi] x [W_hi | W_hi | W_lo]: w_hh is tp_pack_mma_a_bf16 of that [3H, 3H] matrix.
+                                 State, gates and accumulation stay fp32 (exact expf / tanhf).                                 */
 
 #define TP_POSE_ROTMAT 0     /* [n,24,3,3]  (smplx pose2rot=False, lib/models/spin.py:265-270) */
 #define TP_POSE_AXIS_ANGLE 1 /* [n,72]      (smplx pose2rot=True,  lib/utils/eval_utils.py:168) */
@@ -86,6 +91,9 @@ TP_API int tp_pack_rows(const float* src, int64_t stride_b, int64_t stride_t, in
  * the step: tp_gru_recurrence_ex, tp_heads_ief_forward), so the step needs no separate fill.  zero may be NULL.           */
 TP_API int tp_pack_rows_ex(const float* src, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t, int k,
                     void* dst, int kp, int dst_precision, int relu, void* zero, size_t zero_bytes, void* stream);
+/* dst [rows, 3 k] bf16 = [hi | lo | hi] of src [rows, k] fp32 (row stride ld_src): the A operand of a bf16 x 3 contraction whose
+ * weight side is [W_hi | W_hi | W_lo] (see TP_PRECISION_BF16X3).  k % 8 == 0.                                             */
+TP_API int tp_split3_bf16(const float* src, int64_t ld_src, int rows, int k, void* dst, void* stream);
 /* The way back, with the residual of lib/models/vibe.py:60-63 folded in (y + x, then TNF -> NTF):
  * out[b*rows_t + t, c] = y[(t*rows_b + b)*ld_y + c] + x[b*stride_b + t*stride_t + c]   (x may be NULL: no residual).
  * out is dense [rows_b*rows_t, k] fp32; out_bf16 (optional) receives the same rows in bf16.  k even.              */

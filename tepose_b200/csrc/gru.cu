@@ -28,6 +28,8 @@ struct GruParams {
   tp_gru_job jobs[kMaxJobs];
   int item_begin[kMaxJobs + 1];
   int njobs, B, H, U, max_steps, total_items, any_h0;
+  int K;                    // reduction length of the recurrent matmul: H, or 3 H in TP_PRECISION_BF16X3 (operands [hi | lo | hi])
+  int split3;               // TP_PRECISION_BF16X3: the bf16 operand copy of h_t is written as hi at column u, lo at H + u, hi at 2 H + u
   int n_item_jobs;          // jobs [0, n_item_jobs) are cut into items; the rest are step-0-only elementwise jobs
   float* hbuf;              // [njobs][2][B][H]  fp32 state ping-pong
   __nv_bfloat16* hbuf_lp;   // [kHRep][njobs][2][B][H]  bf16 copies (MMA operand of the next step)
@@ -77,7 +79,7 @@ __device__ __forceinline__ void mma_bf16(float* c, uint32_t a0, uint32_t a1, uin
 
 // element index of (batch b, unit u) inside one [B,H] bf16 state slot
 __device__ __forceinline__ int64_t lp_index(const GruParams& p, int b, int u) {
-  if (!p.lp_tiled) return (int64_t)b * p.H + u;
+  if (!p.lp_tiled) return (int64_t)b * p.K + u;
   const int chunk = u >> 7, c = u & 127;
   return ((int64_t)chunk * 32 + b) * 128 + ((((c >> 3) ^ ((b & 1) << 2)) << 3) | (c & 7));
 }
@@ -123,9 +125,15 @@ __device__ __forceinline__ void gru_finalize(const GruParams& p, const tp_gru_jo
   p.hbuf[slot] = h;
   {
     const __nv_bfloat16 hb = __float2bfloat16_rn(h);
-    const int64_t lp = (int64_t)(j * 2 + (s & 1)) * p.lp_slot + lp_index(p, b, u);
+    const int64_t base = (int64_t)(j * 2 + (s & 1)) * p.lp_slot;
+    const int64_t lp = base + lp_index(p, b, u);
 #pragma unroll
     for (int r = 0; r < kHRep; ++r) p.hbuf_lp[(size_t)r * p.lp_rep_stride + lp] = hb;
+    if (p.split3) {
+      const __nv_bfloat16 lo = __float2bfloat16_rn(h - __bfloat162float(hb));
+      p.hbuf_lp[base + lp_index(p, b, H + u)] = lo;
+      p.hbuf_lp[base + lp_index(p, b, 2 * H + u)] = hb;
+    }
   }
   const int t_out = jb.t_out0 + s * jb.t_out_step;
   if (jb.y) jb.y[((int64_t)t_out * B + b) * jb.ldy + u] = h;
@@ -461,7 +469,7 @@ extern "C" void tp_gru_set_trace(void* device_buffer) { tp::set_trace_ptr(reinte
 
 extern "C" size_t tp_gru_workspace_bytes(int njobs, int B, int H) {
   size_t per = (size_t)njobs * 2 * B * H;
-  size_t per_lp = (size_t)njobs * 2 * (B < 32 ? 32 : B) * H;      // the tiled layout pads a slot to 32 rows
+  size_t per_lp = (size_t)njobs * 2 * (B < 32 ? 32 : B) * 3 * H;  // the tiled layout pads a slot to 32 rows; x3: the [hi | lo | hi] operand of TP_PRECISION_BF16X3
   return 256 + align_up(per * sizeof(float), 256) + kHRep * align_up(per_lp * sizeof(__nv_bfloat16), 256);
 }
 
@@ -522,7 +530,7 @@ static int gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, int H, in
   TP_CHECK_ARG(B >= 1 && H >= 32 && H % 32 == 0, "tp_gru_recurrence: need B>=1 and H a multiple of 32 (B=%d H=%d)", B, H);
   TP_CHECK_ARG(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "tp_gru_recurrence: workspace must be 256-byte aligned");
   TP_CHECK_ARG(workspace_bytes >= tp_gru_workspace_bytes(njobs, B, H), "tp_gru_recurrence: workspace too small");
-  TP_CHECK_ARG(precision == TP_PRECISION_FP32 || precision == TP_PRECISION_BF16, "tp_gru_recurrence: bad precision");
+  TP_CHECK_ARG(precision == TP_PRECISION_FP32 || precision == TP_PRECISION_BF16 || precision == TP_PRECISION_BF16X3, "tp_gru_recurrence: bad precision");
   // jobs with a recurrent matmul first; single-step jobs from a zero state are pure gate math
   tp_gru_job jobs[kMaxJobs];
   int n_mat = 0;
@@ -534,6 +542,8 @@ static int gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, int H, in
   GruParams p;
   memset(&p, 0, sizeof(p));
   p.njobs = njobs; p.B = B; p.H = H; p.trace = trace_ptr();
+  p.K = precision == TP_PRECISION_BF16X3 ? 3 * H : H;
+  p.split3 = precision == TP_PRECISION_BF16X3 ? 1 : 0;
   for (int j = 0; j < njobs; ++j) {
     const tp_gru_job& jb = jobs[j];
     TP_CHECK_ARG(jb.gi && jb.w_hh && jb.b_hh && jb.steps >= 1, "tp_gru_recurrence: a job has null gi/w_hh/b_hh or steps<1");
@@ -548,7 +558,7 @@ static int gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, int H, in
   p.barrier_shards = barrier ? (shards_env >= 1 && shards_env <= kBarrierShards ? shards_env : 1) : 1;   // a caller-provided slot is kBarrierShards x 128 zeroed bytes
   p.hbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 256);
   p.hbuf_lp = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(workspace) + 256 + align_up(per * sizeof(float), 256));
-  const size_t per_lp = (size_t)njobs * 2 * (B < 32 ? 32 : B) * H;
+  const size_t per_lp = (size_t)njobs * 2 * (B < 32 ? 32 : B) * 3 * H;
   p.lp_rep_stride = align_up(per_lp * sizeof(__nv_bfloat16), 256) / sizeof(__nv_bfloat16);
   p.lp_slot = (int64_t)B * H; p.lp_tiled = 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -618,12 +628,13 @@ static int gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, int H, in
   static const bool no_tma = getenv("TP_GRU_NO_TMA") != nullptr;
   // ---- two matmul jobs at batch 9..32 (the two causal directions of the encoder): interleaved teams, one CTA per 16 units
   static const bool no_dual = getenv("TP_GRU_NO_DUAL") != nullptr;
-  if (precision == TP_PRECISION_BF16 && !no_tma && !no_dual && n_mat == 2 && !p.any_h0 && H % 128 == 0 && B <= 32 && H / 16 <= sms) {
+  if ((precision == TP_PRECISION_BF16 || precision == TP_PRECISION_BF16X3) && !no_tma && !no_dual && n_mat == 2 && !p.any_h0 && H % 128 == 0 &&
+      B <= 32 && H / 16 <= sms) {
     static const int skew_env = getenv("TP_GRU_DUAL_SKEW") ? atoi(getenv("TP_GRU_DUAL_SKEW")) : 0;
     p.dual_skew = skew_env;
     p.U = 16; p.n_item_jobs = n_mat;
     p.total_items = H / 16;
-    p.lp_tiled = 1; p.lp_slot = (int64_t)32 * H;
+    p.lp_tiled = 1; p.lp_slot = (int64_t)32 * p.K;
     auto launch = [&](auto kfn) -> int {
       TP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDualSmem));
       int per_sm = 0;
@@ -636,6 +647,9 @@ static int gru_recurrence(const tp_gru_job* jobs_in, int njobs, int B, int H, in
     };
     return B <= 8 ? launch(k_gru_bf16_dual<1>) : launch(k_gru_bf16_dual<4>);
   }
+  if (precision == TP_PRECISION_BF16X3)
+    return fail(TP_ERR_UNSUPPORTED, "tp_gru_recurrence(BF16X3): only exactly two matmul jobs without h0 at B <= 32, H %% 128 == 0 (the encoder's "
+                                    "two full directions) are built; use TP_PRECISION_FP32 for this job set");
   if (precision == TP_PRECISION_BF16 && !no_tma && n_mat >= 1 && H % 128 == 0 && B <= 32 && n_mat * (H / 32) <= sms) {
     const int NB = B <= 8 ? 8 : 32;
     // resident-weight variant: part of each CTA's W_hh slice stays in registers / shared memory for all steps

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(kDualThreads, 1) k_gru_bf16_dual(const GruPara
   constexpr uint32_t kHB = NB * 256;                                      // bytes of an h slice that are read (NB rows x 128 bf16)
   extern __shared__ __align__(1024) unsigned char smem_d[];
   const int H = p.H, B = p.B;
-  const int nblk = H / 32, nchunks = nblk / kChunkBlocks;
+  const int nblk = p.K / 32, nchunks = nblk / kChunkBlocks;       // K = H, or 3 H for the [hi | lo | hi] operands of TP_PRECISION_BF16X3
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   // team d = direction / job d: consumer warps 4d..4d+3, producer warp 8+d
@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(kDualThreads, 1) k_gru_bf16_dual(const GruPara
   for (int je = p.n_item_jobs; je < p.njobs; ++je)
     for (int64_t i = blockIdx.x * (int64_t)kDualThreads + tid; i < (int64_t)B * H; i += (int64_t)gridDim.x * kDualThreads) {
       const int b = (int)(i / H), u = (int)(i - (int64_t)b * H);
-      gru_finalize<true>(p, sjobs[je], je, 0, b, u, gate_fetch(p, sjobs[je], je, 0, b, u), 0.f, 0.f, 0.f);
+      if (p.split3) gru_finalize<false>(p, sjobs[je], je, 0, b, u, gate_fetch(p, sjobs[je], je, 0, b, u), 0.f, 0.f, 0.f);
+      else gru_finalize<true>(p, sjobs[je], je, 0, b, u, gate_fetch(p, sjobs[je], je, 0, b, u), 0.f, 0.f, 0.f);
     }
 
   // from here on the two teams never meet: named barriers 1 + d (team, 160 threads) and 3 + d (consumers, 128 threads)
@@ -212,7 +213,8 @@ __global__ void __launch_bounds__(kDualThreads, 1) k_gru_bf16_dual(const GruPara
             an += rk[(2 * NB + bb) * RP + uu];
           }
         }
-        gru_finalize<true>(p, jb, d, s, bb, u0 + uu, gin[e], ar, az, an);
+        if (p.split3) gru_finalize<false>(p, jb, d, s, bb, u0 + uu, gin[e], ar, az, an);     // fp32-grade mode: exact expf / tanhf
+        else gru_finalize<true>(p, jb, d, s, bb, u0 + uu, gin[e], ar, az, an);
       }
     }
     if (s + 1 < jb.steps) {

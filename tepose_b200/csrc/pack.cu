@@ -84,6 +84,34 @@ extern "C" int tp_pack_rows_ex(const float* src, int64_t stride_b, int64_t strid
   return TP_OK;
 }
 
+namespace tp {
+__global__ void k_split3(const float* __restrict__ src, int64_t ld, int rows, int k, __nv_bfloat16* __restrict__ dst) {
+  const int64_t n4 = (int64_t)rows * (k / 4);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (k / 4)), c = (int)(i - (int64_t)r * (k / 4)) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(src + (int64_t)r * ld + c);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { hi[e] = __float2bfloat16_rn(x[e]); lo[e] = __float2bfloat16_rn(x[e] - __bfloat162float(hi[e])); }
+    __nv_bfloat16* d = dst + (int64_t)r * 3 * k + c;
+    *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(d + k) = *reinterpret_cast<const uint2*>(lo);
+    *reinterpret_cast<uint2*>(d + 2 * k) = *reinterpret_cast<const uint2*>(hi);
+  }
+}
+}  // namespace tp
+
+extern "C" int tp_split3_bf16(const float* src, int64_t ld_src, int rows, int k, void* dst, void* stream) {
+  TP_CHECK_ARG(src && dst && rows > 0 && k > 0 && k % 8 == 0 && ld_src % 4 == 0, "tp_split3_bf16: need k %% 8 == 0, ld %% 4 == 0 (rows=%d k=%d)", rows, k);
+  TP_CHECK_ARG(tp::aligned16(src) && tp::aligned16(dst), "tp_split3_bf16: pointers must be 16-byte aligned");
+  const int64_t n4 = (int64_t)rows * (k / 4);
+  const unsigned grid = (unsigned)(n4 / 256 + 1 < 2048 ? n4 / 256 + 1 : 2048);
+  tp::k_split3<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, rows, k, reinterpret_cast<__nv_bfloat16*>(dst));
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}
+
 extern "C" int tp_unpack_rows_residual(const float* y, int64_t ld_y, const float* x, int64_t stride_b, int64_t stride_t,
                                        int rows_b, int rows_t, int k, float* out, void* out_bf16, void* stream) {
   using namespace tp;

@@ -39,8 +39,6 @@ def _pelvis(pelvis):
 
 
 @nv.device_guard
-
-
 def pose_metrics(pred_j3ds, target_j3ds, pelvis=(2, 3), want_aligned=False):
     """evaluate.py:420-443 for one sequence: root-align both joint sets, then per-frame MPJPE, Procrustes-aligned
     MPJPE and acceleration error (zeros at the first / last frame, evaluate.py:441-442), all in metres.
@@ -87,8 +85,6 @@ def batch_compute_similarity_transform_torch(S1, S2):
 
 
 @nv.device_guard
-
-
 def compute_error_accel_eval(joints_gt, joints_pred, vis=None):
     """[N,J,3] x 2 -> [N-2] (visible entries only when vis [N] is given: a frame counts if it and its two
     successors are visible, eval_utils.py:128-136)."""
@@ -114,8 +110,6 @@ def _masked_mean(normed: torch.Tensor, vidlen_each, lo: int, tail: int, extra: i
 
 
 @nv.device_guard
-
-
 def compute_accel(joints, vidlen_each, seqlen):
     """joints [S,L,J,3] -> scalar mean acceleration norm over frames seqlen-1 .. vidlen-3 of every sequence."""
     P = _dev_f32(joints)
@@ -126,8 +120,6 @@ def compute_accel(joints, vidlen_each, seqlen):
 
 
 @nv.device_guard
-
-
 def compute_error_accel(joints_gt, joints_pred, vidlen_each, seqlen, vis=None):
     """[S,L,J,3] x 2 -> scalar mean acceleration error over frames seqlen-1 .. vidlen-5 (eval_utils.py:79-108)."""
     if vis is not None:
@@ -141,8 +133,6 @@ def compute_error_accel(joints_gt, joints_pred, vidlen_each, seqlen, vis=None):
 
 
 @nv.device_guard
-
-
 def compute_error_verts(pred_verts, target_verts=None, target_theta=None, device=None, smpl=None):
     """Mean per-vertex distance per body [N] (eval_utils.py:141-175).  Without target_verts the target mesh is
     built from target_theta [N,85] (cam | axis-angle pose | betas) with the SMPL forward (pose2rot=True), in

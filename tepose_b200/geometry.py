@@ -13,8 +13,6 @@ def _prep(x: torch.Tensor, width: int) -> torch.Tensor:
 
 
 @nv.device_guard
-
-
 def rot6d_to_rotmat(x: torch.Tensor) -> torch.Tensor:
     """lib/utils/geometry.py:330-343.  [...,6k] -> [N,3,3] (x is viewed as (-1,3,2))."""
     flat = _prep(x, 6)
@@ -24,8 +22,6 @@ def rot6d_to_rotmat(x: torch.Tensor) -> torch.Tensor:
 
 
 @nv.device_guard
-
-
 def rotation_matrix_to_angle_axis(rotation_matrix: torch.Tensor) -> torch.Tensor:
     """lib/utils/geometry.py:68-97.  [N,3,3] (or [N,3,4], last column ignored) -> [N,3]."""
     if rotation_matrix.shape[-2:] == (3, 4):
@@ -38,8 +34,6 @@ def rotation_matrix_to_angle_axis(rotation_matrix: torch.Tensor) -> torch.Tensor
 
 
 @nv.device_guard
-
-
 def batch_rodrigues(axisang: torch.Tensor, form: str = "quat") -> torch.Tensor:
     """form='quat': lib/utils/geometry.py:22-34 (returns [N,9] like the reference);
     form='smplx': smplx.lbs.batch_rodrigues (returns [N,3,3])."""
@@ -51,8 +45,6 @@ def batch_rodrigues(axisang: torch.Tensor, form: str = "quat") -> torch.Tensor:
 
 
 @nv.device_guard
-
-
 def projection(pred_joints: torch.Tensor, pred_camera: torch.Tensor) -> torch.Tensor:
     """lib/models/spin.py:307-320.  joints [N,J,3], camera [N,3] -> [N,J,2]."""
     nv.require_cuda(pred_joints, "pred_joints")

@@ -38,13 +38,11 @@ class GraphedTePose:
         self.launches_per_replay = int(nv.lib().tp_launch_count() - before)
 
     @nv.device_guard
-
     def replay(self):
         self.graph.replay()
         return self.static_output
 
     @nv.device_guard
-
     def __call__(self, x: torch.Tensor):
         self.static_input.copy_(x, non_blocking=True)
         return self.replay()

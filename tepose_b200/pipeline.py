@@ -52,7 +52,6 @@ class PipelinedTePose:
         self.d2h_bytes = sum(v.numel() * 4 for v in self.out_host[0].values())
 
     @nv.device_guard
-
     def submit(self, x_host: torch.Tensor) -> int:
         i, slot = self.count, self.count % self.depth
         s = self.slots[slot]

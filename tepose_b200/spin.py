@@ -144,7 +144,6 @@ class Regressor(nn.Module):
         return self._fold
 
     @nv.device_guard
-
     def forward_folded(self, x, n_iter=3, is_train=False, J_regressor=None):
         """forward() through the closed form: psc = x . G^T + (g + A^n p_0), one fp32 split-K GEMM."""
         if self.training:
@@ -192,7 +191,6 @@ class Regressor(nn.Module):
         return self.decode(psc, is_train=is_train, J_regressor=J_regressor)
 
     @nv.device_guard
-
     def decode(self, psc: torch.Tensor, is_train=False, J_regressor=None):
         """rot6d -> R, SMPL, (H36M regression), projection, R -> axis-angle, theta
         (lib/models/spin.py:263-291) in one tp_smpl_forward call on the IEF state [N,160]."""

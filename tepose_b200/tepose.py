@@ -69,7 +69,7 @@ class GruKernels:
     def _input_proj(self, A, a_rows, W, kp, bias, segs, outs):
         """K1: outs[i] = A[m-range] . W[n-range]^T + bias[n-range]."""
         L = nv.lib()
-        if self.precision == "bf16":
+        if self.precision == "bf16" or A.dtype == torch.bfloat16:      # bf16 mode, or the [hi | lo | hi] operands of fp32_tc
             arr = (nv.GemmSeg * len(segs))()
             for i, ((m0, mr, n0, nc), out) in enumerate(zip(segs, outs)):
                 arr[i] = nv.GemmSeg(m0, mr, n0, nc, nv.ptr(out), out.shape[1], nv.vp(bias.data_ptr() + 4 * n0))
@@ -81,14 +81,14 @@ class GruKernels:
                                        nv.vp(bias.data_ptr() + 4 * n0), nv.vp(0), 0, nv.ptr(out), out.shape[1],
                                        mr, nc, kp, 1.0, 0.0, 0, nv.stream()), "tp_gemm_f32")
 
-    def _recurrence(self, jobs, B, barrier=None):
+    def _recurrence(self, jobs, B, barrier=None, precision=None):
         """barrier: a zeroed 1 KB slot (cleared by the pack kernel at the top of the step) -> no memset node between this
         launch and the GEMM before it, so the two stay linked by programmatic dependent launch."""
         L = nv.lib()
         H = self.hidden_size
         arr = (nv.GruJob * len(jobs))(*jobs)
         ws = nv.workspace(L.tp_gru_workspace_bytes(len(jobs), B, H), jobs[0]._dev)
-        nv.check(L.tp_gru_recurrence_ex(arr, len(jobs), B, H, nv.PRECISIONS[self.precision], nv.ptr(ws), ws.numel(),
+        nv.check(L.tp_gru_recurrence_ex(arr, len(jobs), B, H, nv.PRECISIONS[self.precision] if precision is None else precision, nv.ptr(ws), ws.numel(),
                                         nv.vp(0 if barrier is None else barrier.data_ptr()), nv.stream()), "tp_gru_recurrence")
 
 
@@ -175,6 +175,20 @@ class TemporalEncoder(nn.Module, GruKernels):
             d["w_hh"] = [self._pack_whh(g(self.gru_fwd, f"weight_hh_l{l}"), lp),
                          self._pack_whh(g(self.gru_rec, f"weight_hh_l{l}_reverse"), lp),
                          self._pack_whh(g(self.gru_rec, f"weight_hh_l{l}"), lp)]
+            if self.precision == "fp32_tc" and l == 0 and Ln == 1 and H % 128 == 0:
+                # fp32-grade tensor-core operands (TP_PRECISION_BF16X3): [W_hi | W_hi | W_lo] against [x_hi | x_lo | x_hi]
+                def split3(w):
+                    hi = w.to(torch.bfloat16)
+                    lo = (w - hi.float()).to(torch.bfloat16)
+                    return torch.cat([hi, hi, lo], dim=1).contiguous()
+                d["w_ih3"] = split3(d["w_ih"])
+                d["w_hh3"] = []
+                for w in (g(self.gru_fwd, "weight_hh_l0"), g(self.gru_rec, "weight_hh_l0_reverse")):
+                    w3 = split3(w).float()
+                    out = torch.empty(nv.lib().tp_pack_mma_a_bytes(3 * H, 3 * H), dtype=torch.uint8, device=dev)
+                    nv.check(nv.lib().tp_pack_mma_a_bf16(nv.ptr(w3), 3 * H, 3 * H, 3 * H, nv.ptr(out), nv.stream()), "tp_pack_mma_a_bf16")
+                    d["w_hh3"].append(out)
+                    del w3
             d["w_um"] = [self._pack_whh_umma(g(self.gru_fwd, f"weight_hh_l{l}"), lp),
                          self._pack_whh_umma(g(self.gru_rec, f"weight_hh_l{l}_reverse"), lp),
                          self._pack_whh_umma(g(self.gru_rec, f"weight_hh_l{l}"), lp) if Ln > 1 and l < Ln - 1 else None]
@@ -249,8 +263,14 @@ class TemporalEncoder(nn.Module, GruKernels):
                 if last:
                     gi = torch.empty(T * B, 6 * H, device=dev, dtype=torch.float32)      # [fwd | rec-backward]
                     gs = torch.empty(B, 3 * H, device=dev, dtype=torch.float32)          # rec-forward, newest frame only
-                    self._input_proj(xp, T * B, d["w_ih"], kp, d["b_ih"],
-                                     [(0, T * B, 0, 6 * H), ((T - 1) * B, B, 6 * H, 3 * H)], [gi, gs])
+                    if "w_ih3" in d:             # fp32_tc: x -> [hi | lo | hi] bf16, one tcgen05 GEMM over K = 3 kp
+                        xp3 = torch.empty(T * B, 3 * kp, device=dev, dtype=torch.bfloat16)
+                        nv.check(L.tp_split3_bf16(nv.ptr(xp), kp, T * B, kp, nv.ptr(xp3), nv.stream()), "tp_split3_bf16")
+                        self._input_proj(xp3, T * B, d["w_ih3"], 3 * kp, d["b_ih"],
+                                         [(0, T * B, 0, 6 * H), ((T - 1) * B, B, 6 * H, 3 * H)], [gi, gs])
+                    else:
+                        self._input_proj(xp, T * B, d["w_ih"], kp, d["b_ih"],
+                                         [(0, T * B, 0, 6 * H), ((T - 1) * B, B, 6 * H, 3 * H)], [gi, gs])
                     gi_f, c_f, gi_b, c_b, gi_s, c_s = gi, 0, gi, 3 * H, gs, 0
                     s_t0 = 0     # gs holds a single time block
                 else:
@@ -287,6 +307,10 @@ class TemporalEncoder(nn.Module, GruKernels):
             nv.mark(f"k1_input_proj_l{l}")
             hF0, hB0 = (None, None) if h0 is None else h0
             w, b, wu = d["w_hh"], d["b_hh"], d["w_um"]
+            k2_prec = None
+            if last and "w_hh3" in d and h0 is None and B <= 32 and H // 16 <= 148 and "TP_FP32TC_NO_K2" not in os.environ:
+                w = [d["w_hh3"][0], d["w_hh3"][1], w[2]]           # the single-step direction has no recurrent matmul
+                k2_prec = nv.PRECISION_BF16X3
             if last:
                 jobs = [
                     self._job(dev, gi_f, c_f, w[0], b[0], T, f_in[0], f_in[1], h0=hF0, h_final=h_fwd, hcol=0, y=seq_f, w_umma=wu[0],
@@ -305,7 +329,7 @@ class TemporalEncoder(nn.Module, GruKernels):
                               t_out0=T - 1, t_out_step=-1, w_umma=wu[1]),
                     self._job(dev, gi_s, c_s, w[2], b[2], T, s_in[0], s_in[1], y=ny_r, ycol=0, y_lp=ny_r_lp, w_umma=wu[2]),
                 ]
-            self._recurrence(jobs, B, barrier=sync[l])
+            self._recurrence(jobs, B, barrier=sync[l], precision=k2_prec)
             nv.mark(f"k2_recurrence_l{l}")
             if not last:
                 y_f, y_r, y_f_lp, y_r_lp = ny_f, ny_r, ny_f_lp, ny_r_lp
@@ -339,7 +363,6 @@ class TemporalEncoder(nn.Module, GruKernels):
         return feat
 
     @nv.device_guard
-
     def forward(self, x, is_train=False):
         h_fwd, h_rec = self.encode_states(x)
         return self.heads(h_fwd, h_rec, is_train=is_train)
@@ -446,7 +469,6 @@ class TePose(nn.Module):
     GROUP = 32
 
     @nv.device_guard
-
     def forward(self, input, is_train=False, J_regressor=None, dropout_masks=None):
         if self.training:
             # lib/core/trainer.py:137,203: generator.train(); generator(inp, is_train=True) -- dropout active, outputs [B,2,...],

@@ -171,7 +171,6 @@ class VIBE(nn.Module):
             print(f'=> loaded pretrained model from \'{pretrained}\'')
 
     @nv.device_guard
-
     def forward(self, input, J_regressor=None):
         if self.training:
             raise NotImplementedError("tepose_b200.VIBE implements the inference path; call .eval() first")

@@ -83,6 +83,13 @@ class FakeLib:
             z.zero_()
         return self.tp_pack_rows(src, stride_b, stride_t, rows_b, rows_t, k, dst, kp, prec, relu, stream)
 
+    def tp_split3_bf16(self, src, ld_src, rows, k, dst, stream):
+        v = _mat(src, rows, k, ld_src).clone()
+        hi = v.to(torch.bfloat16)
+        lo = (v - hi.float()).to(torch.bfloat16)
+        _mat(dst, rows, 3 * k, 3 * k, torch.bfloat16).copy_(torch.cat([hi, lo, hi], dim=1))
+        return 0
+
     def tp_unpack_rows_residual(self, y, ld_y, x, stride_b, stride_t, rows_b, rows_t, k, out, out_bf16, stream):
         v = _mat(y, rows_t * rows_b, k, ld_y).clone().reshape(rows_t, rows_b, k).permute(1, 0, 2)
         if (x.value if isinstance(x, C.c_void_p) else x):

@@ -16,7 +16,7 @@ DEV = "cuda:0"
 
 
 @pytest.mark.parametrize("fname", sorted(f for f in os.listdir(GOLD) if f.startswith("fwd_")))
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp32_tc"])
 def test_forward_against_reference_golden(fname, precision):
     z = np.load(os.path.join(GOLD, fname))
     cfg = ast.literal_eval(str(z["cfg"]))
@@ -25,14 +25,14 @@ def test_forward_against_reference_golden(fname, precision):
     Jr = torch_ref.SmplModel.synthetic(cfg["seed"]).J_regressor_h36m.to(DEV) if cfg.get("use_h36m") else None
     out = model(x, is_train=cfg.get("is_train", False), J_regressor=Jr)[-1]
     gold = {k: z[k] for k in ("theta", "verts", "kp_2d", "kp_3d", "rotmat")}
-    if precision == "fp32":   # north_star: <= 1e-4 m on verts / joints in fp32
+    if precision in ("fp32", "fp32_tc"):   # north_star: <= 1e-4 m on verts / joints in fp32 (fp32_tc: K1 / K2 as 3-term bf16 splits on tensor cores)
         errs = compare_outputs(out, gold, label=fname)
     else:                     # north_star: <= 1 mm in bf16
         errs = compare_outputs(out, gold, vert_tol=1e-3, rot_tol=2e-3, kp2d_tol=5e-2, label=fname)
     print(fname, precision, errs)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp32_tc"])
 @pytest.mark.parametrize("L,H,T,B", [(1, 2048, 16, 32), (2, 1024, 6, 32), (1, 2048, 16, 1)])
 def test_forward_full_size_against_oracle(L, H, T, B, precision):
     """BASELINE configs at full size (defaults L=1,H=2048,T=16; released L=2,H=1024,T=6)."""
@@ -41,7 +41,7 @@ def test_forward_full_size_against_oracle(L, H, T, B, precision):
     x = synth.make_input(seed, B, T)
     ref, m = oracle_forward(seed, sd, x, L, H)
     out = model(torch.from_numpy(x).to(DEV))[-1]
-    if precision == "fp32":
+    if precision in ("fp32", "fp32_tc"):
         errs = compare_outputs(out, ref, label=f"L{L}H{H}")
     else:
         errs = compare_outputs(out, ref, vert_tol=1e-3, rot_tol=2e-3, kp2d_tol=5e-2, label=f"L{L}H{H}")
