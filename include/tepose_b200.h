@@ -91,6 +91,10 @@ TP_API int tp_pack_rows(const float* src, int64_t stride_b, int64_t stride_t, in
  * the step: tp_gru_recurrence_ex, tp_heads_ief_forward), so the step needs no separate fill.  zero may be NULL.           */
 TP_API int tp_pack_rows_ex(const float* src, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t, int k,
                     void* dst, int kp, int dst_precision, int relu, void* zero, size_t zero_bytes, void* stream);
+/* tp_pack_rows_ex for a float16 source (strides in elements): the reference's datasets keep features and thetas as float16 on
+ * the host (lib/dataset/dataset_3d.py:244-248), so a caller may ship them as they are -- half the host -> device bytes.   */
+TP_API int tp_pack_rows_f16(const void* src_f16, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t, int k,
+                     void* dst, int kp, int dst_precision, int relu, void* zero, size_t zero_bytes, void* stream);
 /* dst [rows, 3 k] bf16 = [hi | lo | hi] of src [rows, k] fp32 (row stride ld_src): the A operand of a bf16 x 3 contraction whose
  * weight side is [W_hi | W_hi | W_lo] (see TP_PRECISION_BF16X3).  k % 8 == 0.                                             */
 TP_API int tp_split3_bf16(const float* src, int64_t ld_src, int rows, int k, void* dst, void* stream);

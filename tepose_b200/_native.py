@@ -25,7 +25,7 @@ PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16, "fp32_tc": PRECISI
 EXPORTS = [
     "tp_version", "tp_last_error", "tp_launch_count", "tp_set_pdl", "tp_device_info",
     "tp_rot6d_to_rotmat", "tp_rotmat_to_angle_axis", "tp_batch_rodrigues", "tp_projection",
-    "tp_pack_rows", "tp_pack_rows_ex", "tp_split3_bf16", "tp_unpack_rows_residual", "tp_gemm_f32", "tp_gemm_f32_splitk_workspace_bytes", "tp_gemm_f32_splitk",
+    "tp_pack_rows", "tp_pack_rows_ex", "tp_pack_rows_f16", "tp_split3_bf16", "tp_unpack_rows_residual", "tp_gemm_f32", "tp_gemm_f32_splitk_workspace_bytes", "tp_gemm_f32_splitk",
     "tp_pack_mma_a_bytes", "tp_pack_mma_a_bf16", "tp_skinny_bf16_workspace_bytes", "tp_skinny_bf16", "tp_skinny_bf16_ex", "tp_gemm_bf16_tc",
     "tp_pack_whh_bf16", "tp_whh_umma_bytes", "tp_pack_whh_umma", "tp_gru_set_trace", "tp_gru_workspace_bytes", "tp_gru_recurrence", "tp_gru_recurrence_ex",
     "tp_encoder_heads_workspace_bytes", "tp_encoder_heads", "tp_encoder_heads_cat", "tp_ief_workspace_bytes", "tp_ief_forward", "tp_heads_ief_forward",
@@ -70,6 +70,7 @@ _SIGNATURES = {
     "tp_rotmat_to_angle_axis": (C.c_int, [vp, vp, i64, vp]),
     "tp_batch_rodrigues": (C.c_int, [vp, vp, i64, C.c_int, vp]),
     "tp_projection": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp]),
+    "tp_pack_rows_f16": (C.c_int, [vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, sz, vp]),
     "tp_split3_bf16": (C.c_int, [vp, i64, C.c_int, C.c_int, vp, vp]),
     "tp_pack_rows": (C.c_int, [vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
     "tp_pack_rows_ex": (C.c_int, [vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, sz, vp]),

@@ -1,10 +1,14 @@
 // Operand packing: [B,T,K] fp32 -> time-major, zero-padded [T*B, Kp] fp32 / bf16.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace tp {
 
-template <typename OutT>
-__global__ void k_pack_rows(const float* __restrict__ src, int64_t stride_b, int64_t stride_t,
+__device__ __forceinline__ float in_f32(float v) { return v; }
+__device__ __forceinline__ float in_f32(__half v) { return __half2float(v); }
+
+template <typename OutT, typename InT = float>
+__global__ void k_pack_rows(const InT* __restrict__ src, int64_t stride_b, int64_t stride_t,
                             int rows_b, int rows_t, int k, OutT* __restrict__ dst, int kp, int relu,
                             unsigned int* __restrict__ zero, int zero_words) {
   pdl_launch_dependents();            // the GEMM that consumes dst may set itself up now (it waits before reading)
@@ -13,18 +17,18 @@ __global__ void k_pack_rows(const float* __restrict__ src, int64_t stride_b, int
     for (int i = threadIdx.x; i < zero_words; i += blockDim.x) zero[i] = 0u;
   int row = blockIdx.x;               // t * rows_b + b
   int t = row / rows_b, b = row - t * rows_b;
-  const float* s = src + (int64_t)b * stride_b + (int64_t)t * stride_t;
+  const InT* s = src + (int64_t)b * stride_b + (int64_t)t * stride_t;
   OutT* d = dst + (int64_t)row * kp;
   if constexpr (sizeof(OutT) == 2) {
     // two columns per thread: one 4-byte store instead of two 2-byte stores (kp is even)
     for (int c = 2 * threadIdx.x; c < kp; c += 2 * blockDim.x) {
-      float v0 = (c < k) ? s[c] : 0.0f, v1 = (c + 1 < k) ? s[c + 1] : 0.0f;
+      float v0 = (c < k) ? in_f32(s[c]) : 0.0f, v1 = (c + 1 < k) ? in_f32(s[c + 1]) : 0.0f;
       if (relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
       *reinterpret_cast<__nv_bfloat162*>(d + c) = __floats2bfloat162_rn(v0, v1);
     }
   } else {
     for (int c = threadIdx.x; c < kp; c += blockDim.x) {
-      float v = (c < k) ? s[c] : 0.0f;
+      float v = (c < k) ? in_f32(s[c]) : 0.0f;
       if (relu) v = fmaxf(v, 0.0f);
       d[c] = v;
     }
@@ -59,8 +63,9 @@ extern "C" int tp_pack_rows(const float* src, int64_t stride_b, int64_t stride_t
   return tp_pack_rows_ex(src, stride_b, stride_t, rows_b, rows_t, k, dst, kp, dst_precision, relu, nullptr, 0, stream);
 }
 
-extern "C" int tp_pack_rows_ex(const float* src, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t,
-                               int k, void* dst, int kp, int dst_precision, int relu, void* zero, size_t zero_bytes, void* stream) {
+template <typename InT>
+static int pack_rows_impl(const InT* src, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t,
+                          int k, void* dst, int kp, int dst_precision, int relu, void* zero, size_t zero_bytes, void* stream) {
   using namespace tp;
   TP_CHECK_ARG(!zero || ((reinterpret_cast<uintptr_t>(zero) & 3) == 0 && zero_bytes % 4 == 0 && zero_bytes <= (1u << 20)),
                "tp_pack_rows_ex: zero region must be 4-byte aligned, a multiple of 4 bytes and <= 1 MB");
@@ -75,13 +80,24 @@ extern "C" int tp_pack_rows_ex(const float* src, int64_t stride_b, int64_t strid
   TP_CHECK_ARG(src && dst, "tp_pack_rows: null pointer");
   unsigned grid = (unsigned)(rows_b * rows_t);
   if (dst_precision == TP_PRECISION_BF16)
-    k_pack_rows<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, stride_b, stride_t, rows_b, rows_t, k,
-                                                                      (__nv_bfloat16*)dst, kp, relu, zp, zw);
+    k_pack_rows<__nv_bfloat16, InT><<<grid, 256, 0, (cudaStream_t)stream>>>(src, stride_b, stride_t, rows_b, rows_t, k,
+                                                                           (__nv_bfloat16*)dst, kp, relu, zp, zw);
   else
-    k_pack_rows<float><<<grid, 256, 0, (cudaStream_t)stream>>>(src, stride_b, stride_t, rows_b, rows_t, k,
-                                                              (float*)dst, kp, relu, zp, zw);
+    k_pack_rows<float, InT><<<grid, 256, 0, (cudaStream_t)stream>>>(src, stride_b, stride_t, rows_b, rows_t, k,
+                                                                   (float*)dst, kp, relu, zp, zw);
   TP_LAUNCH_CHECK();
   return TP_OK;
+}
+
+extern "C" int tp_pack_rows_ex(const float* src, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t,
+                               int k, void* dst, int kp, int dst_precision, int relu, void* zero, size_t zero_bytes, void* stream) {
+  return pack_rows_impl<float>(src, stride_b, stride_t, rows_b, rows_t, k, dst, kp, dst_precision, relu, zero, zero_bytes, stream);
+}
+
+extern "C" int tp_pack_rows_f16(const void* src, int64_t stride_b, int64_t stride_t, int rows_b, int rows_t,
+                                int k, void* dst, int kp, int dst_precision, int relu, void* zero, size_t zero_bytes, void* stream) {
+  return pack_rows_impl<__half>(reinterpret_cast<const __half*>(src), stride_b, stride_t, rows_b, rows_t, k, dst, kp, dst_precision, relu,
+                                zero, zero_bytes, stream);
 }
 
 namespace tp {

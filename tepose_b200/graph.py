@@ -17,11 +17,13 @@ class GraphedTePose:
     g.replay()            # re-run on whatever is in g.static_input
     """
 
-    def __init__(self, model, batch, seqlen, J_regressor=None, is_train=False, warmup=2):
+    def __init__(self, model, batch, seqlen, J_regressor=None, is_train=False, warmup=2, input_dtype=torch.float32):
         p = next(model.parameters())
         nv.require_cuda(p, "model parameters")
         self.model, self.device = model, p.device
-        self.static_input = torch.zeros(batch, seqlen, 2133, device=self.device, dtype=torch.float32)
+        if input_dtype not in (torch.float32, torch.float16):
+            raise ValueError("input_dtype must be torch.float32 or torch.float16")
+        self.static_input = torch.zeros(batch, seqlen, 2133, device=self.device, dtype=input_dtype)
         self.J_regressor = None if J_regressor is None else J_regressor.to(self.device)
         self.is_train = is_train
         side = torch.cuda.Stream(device=self.device)

@@ -16,11 +16,19 @@ from .graph import GraphedTePose, OUTPUT_KEYS
 
 
 class PipelinedTePose:
-    def __init__(self, model, batch, seqlen, depth=3, J_regressor=None):
+    def __init__(self, model, batch, seqlen, depth=3, J_regressor=None, outputs=OUTPUT_KEYS, input_dtype=torch.float32):
+        """outputs: which of the five outputs leave the device (default: all, what the reference's forward returns).  `verts` is
+        97 % of the device -> host bytes; an evaluation that needs the mesh only for MPVPE can keep it on the device
+        (tepose_b200.eval_utils.compute_error_verts) and ask for ("theta", "kp_2d", "kp_3d", "rotmat").
+        input_dtype: torch.float16 accepts the rows the way the reference's datasets store them (lib/dataset/dataset_3d.py:244-248),
+        halving the host -> device bytes; the pack kernel widens them."""
         p = next(model.parameters())
         nv.require_cuda(p, "model parameters")
         self.device, self.depth = p.device, depth
-        self.slots = [GraphedTePose(model, batch, seqlen, J_regressor=J_regressor) for _ in range(depth)]
+        self.outputs = tuple(outputs)
+        if not self.outputs or any(k not in OUTPUT_KEYS for k in self.outputs):
+            raise ValueError(f"outputs must be a non-empty subset of {OUTPUT_KEYS}")
+        self.slots = [GraphedTePose(model, batch, seqlen, J_regressor=J_regressor, input_dtype=input_dtype) for _ in range(depth)]
         # the five outputs of a slot are views of one device allocation (smpl_forward_native): mirror it with one pinned
         # host buffer and move everything with a single D2H copy per step
         self.dev_flat, self.host_flat, self.out_host = [], [], []
@@ -29,17 +37,21 @@ class PipelinedTePose:
             stor = {outs[k].untyped_storage().data_ptr() for k in OUTPUT_KEYS}
             if len(stor) == 1:
                 st = outs[OUTPUT_KEYS[0]].untyped_storage()
-                dflat = torch.empty(0, dtype=torch.uint8, device=self.device).set_(st)
-                hflat = torch.empty(dflat.numel(), dtype=torch.uint8).pin_memory()
+                whole = torch.empty(0, dtype=torch.uint8, device=self.device).set_(st)
+                # one copy over the byte range that covers the requested outputs (they are adjacent pieces of the allocation)
+                lo = min(outs[k].storage_offset() * 4 for k in self.outputs)
+                hi = max(outs[k].storage_offset() * 4 + 4 * outs[k].numel() for k in self.outputs)
+                dflat = whole[lo:hi]
+                hflat = torch.empty(hi - lo, dtype=torch.uint8).pin_memory()
                 views = {}
-                for k in OUTPUT_KEYS:
+                for k in self.outputs:
                     v = outs[k]
-                    o = v.storage_offset() * 4
+                    o = v.storage_offset() * 4 - lo
                     views[k] = hflat[o:o + 4 * v.numel()].view(torch.float32).view(v.shape)
                 self.dev_flat.append(dflat); self.host_flat.append(hflat); self.out_host.append(views)
             else:
                 self.dev_flat.append(None); self.host_flat.append(None)
-                self.out_host.append({k: torch.empty_like(outs[k], device="cpu").pin_memory() for k in OUTPUT_KEYS})
+                self.out_host.append({k: torch.empty_like(outs[k], device="cpu").pin_memory() for k in self.outputs})
         self.compute = torch.cuda.current_stream(self.device)
         self.h2d = torch.cuda.Stream(device=self.device)
         self.d2h = torch.cuda.Stream(device=self.device)
@@ -48,8 +60,9 @@ class PipelinedTePose:
         self.compute_done = [ev() for _ in range(depth)]
         self.d2h_done = [ev() for _ in range(depth)]
         self.count = 0
-        self.h2d_bytes = self.slots[0].static_input.numel() * 4
-        self.d2h_bytes = sum(v.numel() * 4 for v in self.out_host[0].values())
+        self.h2d_bytes = self.slots[0].static_input.numel() * self.slots[0].static_input.element_size()
+        self.d2h_bytes = (self.host_flat[0].numel() if self.host_flat[0] is not None
+                          else sum(v.numel() * 4 for v in self.out_host[0].values()))
 
     @nv.device_guard
     def submit(self, x_host: torch.Tensor) -> int:
@@ -70,7 +83,7 @@ class PipelinedTePose:
             if self.dev_flat[slot] is not None:
                 self.host_flat[slot].copy_(self.dev_flat[slot], non_blocking=True)
             else:
-                for k in OUTPUT_KEYS:
+                for k in self.outputs:
                     self.out_host[slot][k].copy_(s.static_output[k], non_blocking=True)
             self.d2h_done[slot].record(self.d2h)
         self.count += 1

@@ -222,7 +222,9 @@ class TemporalEncoder(nn.Module, GruKernels):
         lp = self.precision == "bf16"
         adt = torch.bfloat16 if lp else torch.float32
         prec = nv.PRECISIONS[self.precision]
-        x = x.detach().float()
+        x = x.detach()
+        if x.dtype != torch.float16 or train_ctx is not None:      # float16 rows (how the reference's datasets store them) are packed as they are
+            x = x.float()
         if x.stride(2) != 1:
             x = x.contiguous()
         if (h0 is not None or return_states) and Ln != 1:
@@ -249,8 +251,9 @@ class TemporalEncoder(nn.Module, GruKernels):
             if l == 0:
                 kp = d["kpf"]
                 xp = torch.empty(T * B, kp, device=dev, dtype=adt)
-                nv.check(L.tp_pack_rows_ex(nv.vp(x.data_ptr()), x.stride(0), x.stride(1), B, T, INPUT_SIZE, nv.ptr(xp), kp,
-                                           prec, 0, nv.ptr(sync), sync.numel() * 4, nv.stream()), "tp_pack_rows")
+                pack_fn = L.tp_pack_rows_f16 if x.dtype == torch.float16 else L.tp_pack_rows_ex
+                nv.check(pack_fn(nv.vp(x.data_ptr()), x.stride(0), x.stride(1), B, T, INPUT_SIZE, nv.ptr(xp), kp,
+                                 prec, 0, nv.ptr(sync), sync.numel() * 4, nv.stream()), "tp_pack_rows")
                 nv.mark("pack")
                 if train_ctx is not None:
                     if lp:      # the weight-gradient GEMM reads the packed input in fp32

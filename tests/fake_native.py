@@ -83,6 +83,19 @@ class FakeLib:
             z.zero_()
         return self.tp_pack_rows(src, stride_b, stride_t, rows_b, rows_t, k, dst, kp, prec, relu, stream)
 
+    def tp_pack_rows_f16(self, src, stride_b, stride_t, rows_b, rows_t, k, dst, kp, prec, relu, zero, zero_bytes, stream):
+        z = _view(zero, zero_bytes, torch.uint8)
+        if z is not None:
+            z.zero_()
+        flat = _view(src, (rows_b - 1) * stride_b + (rows_t - 1) * stride_t + k, torch.float16)
+        s = torch.as_strided(flat, (rows_t, rows_b, k), (stride_t, stride_b, 1)).float()
+        dt = torch.bfloat16 if prec == nv.PRECISION_BF16 else torch.float32
+        d = _mat(dst, rows_t * rows_b, kp, kp, dt)
+        d.zero_()
+        v = s.reshape(rows_t * rows_b, k)
+        d[:, :k] = (v.clamp_min(0) if relu else v).to(dt)
+        return 0
+
     def tp_split3_bf16(self, src, ld_src, rows, k, dst, stream):
         v = _mat(src, rows, k, ld_src).clone()
         hi = v.to(torch.bfloat16)

@@ -254,3 +254,25 @@ def test_forward_on_a_non_current_device():
     for k in want:
         assert got[k].device == want[k].device == torch.device("cuda:1")
         assert torch.equal(got[k], want[k]), k
+
+
+def test_pipeline_float16_rows_and_output_selection():
+    """PipelinedTePose(outputs=..., input_dtype=torch.float16): the float16 rows are widened by the pack kernel (bit-identical to
+    feeding the same values as float32), only the requested outputs reach the host, and they equal the full pipeline's."""
+    from tepose_b200.pipeline import PipelinedTePose
+    from tepose_b200 import synthetic as psynth
+    B, T = 5, 8
+    model, _ = psynth.build_synthetic_model(7, T, 1, 256, "bf16", DEV)
+    x16 = torch.from_numpy(psynth.make_input(7, B, T)).to(torch.float16)
+    x32 = x16.float()
+    full = PipelinedTePose(model, B, T, depth=2)
+    lean = PipelinedTePose(model, B, T, depth=2, outputs=("theta", "kp_3d", "rotmat"), input_dtype=torch.float16)
+    assert lean.h2d_bytes * 2 == full.h2d_bytes and lean.d2h_bytes < full.d2h_bytes // 20
+    with torch.no_grad():
+        a = {k: v.clone() for k, v in full.result(full.submit(x32.pin_memory())).items()}
+        b = {k: v.clone() for k, v in lean.result(lean.submit(x16.pin_memory())).items()}
+        direct = model(x16.to(DEV))[-1]
+    assert set(b) == {"theta", "kp_3d", "rotmat"}
+    for k in b:
+        assert torch.equal(a[k], b[k]), k
+        assert torch.equal(direct[k].cpu().reshape(b[k].shape), b[k]), k
