@@ -291,6 +291,10 @@ typedef struct tp_smpl_model {
    * large-batch path: [vertex tile of 128][plane c 3][K block of 64: 4][row 128][128 B], the eight 16-byte chunks of a row
    * stored at position chunk ^ (row & 7).  NULL: the large-batch path runs the GEMM + skinning pair instead.             */
   const void* blend_um;
+  /* skin_um (optional, with blend_um): the skinning weights as the A operand of the skinning MMA of the large-batch path:
+   * [vertex tile of 128][row 128][128 B] bf16 with k = joint: W_hi = bf16(w) at k 0..23, W_lo = bf16(w - W_hi) at k 32..55, zeros
+   * elsewhere; same chunk swizzle as blend_um.  NULL: the skinning of the large-batch path gathers transforms from shared memory. */
+  const void* skin_um;
 } tp_smpl_model;
 
 TP_API size_t tp_smpl_workspace_bytes(const tp_smpl_model* m, int n, int nreg, int blend_mode);

@@ -57,7 +57,7 @@ class IefWeights(C.Structure):
 class SmplModel(C.Structure):
     _fields_ = [("blend", vp), ("j_template", vp), ("j_shapedirs", vp), ("parents", vp),
                 ("skin_idx", vp), ("skin_w", vp), ("ks", i32), ("n_verts", i32), ("vp", i32),
-                ("blend_tc", vp), ("template_pad", vp), ("blend_km", vp), ("blend_um", vp)]
+                ("blend_tc", vp), ("template_pad", vp), ("blend_km", vp), ("blend_um", vp), ("skin_um", vp)]
 
 
 _SIGNATURES = {

@@ -45,14 +45,23 @@ struct PrepArgs {
   float* rotmat;   // [n][24][9] or null
   float* theta;    // [n][85] or null
   __nv_bfloat16* coef_tc;  // [n][256] bf16: pf(207) | beta_hi(10) | beta_lo(10) | beta_hi(10) | 0   (tensor-core path) or null
-  unsigned char* coef_um;  // the same rows as the tcgen05 B-operand image [group of 32 bodies][K block 4][row 32][128 B, 16-byte chunks
-                           // XOR-swizzled by row & 7] (k_smpl_lbs_um) or null; bodies n..n_pad-1 get zero rows and zero transforms
-  int n_pad;
+  unsigned char* coef_um;  // the same rows as the tcgen05 B-operand image [group of um_rows bodies][K block 4][row][128 B, 16-byte chunks
+                           // XOR-swizzled by row & 7] (k_smpl_lbs_um: 32 rows, k_smpl_lbs_um2: 16) or null; bodies n..n_pad-1 get zero
+                           // rows and zero transforms
+  unsigned char* timg;     // k_smpl_lbs_um2: the joint transforms as the B operand of the skinning MMA: [8 bodies][row (body, e) 96][128 B]
+                           // with k = joint: A_hi at k 0..23, A_lo at k 32..55, zero pads, same chunk swizzle; or null
+  int n_pad, um_rows;
 };
 
 // byte offset of coefficient k of body b inside the tcgen05 B-operand image
-__device__ __forceinline__ size_t coef_um_offset(int b, int k) {
-  return (size_t)(b >> 5) * 16384 + (size_t)(k >> 6) * 4096 + (size_t)(b & 31) * 128 + (size_t)((((k & 63) >> 3) ^ (b & 7)) << 4) + (size_t)(k & 7) * 2;
+__device__ __forceinline__ size_t coef_um_offset(int b, int k, int rows) {
+  const int grp = b / rows, row = b - grp * rows;
+  return (size_t)grp * rows * 512 + (size_t)(k >> 6) * rows * 128 + (size_t)row * 128 + (size_t)((((k & 63) >> 3) ^ (row & 7)) << 4) + (size_t)(k & 7) * 2;
+}
+// byte offset of (entry e of joint j, hi / lo) of body b inside the skinning-MMA operand image
+__device__ __forceinline__ size_t timg_offset(int b, int e, int j, int lo) {
+  const int n = (b & 7) * 12 + e, k = j + 32 * lo;
+  return (size_t)(b >> 3) * 12288 + (size_t)n * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
 }
 
 __global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int n, const PrepArgs a) {
@@ -64,9 +73,12 @@ __global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= n) {                             // whole warp exits together
     if (a.coef_um && b < a.n_pad) {         // padding bodies of the last group: zero operand rows, zero transforms
-      *reinterpret_cast<uint4*>(a.coef_um + (size_t)(b >> 5) * 16384 + (size_t)(lane >> 3) * 4096 + (size_t)(b & 31) * 128 + (size_t)(lane & 7) * 16) =
+      *reinterpret_cast<uint4*>(a.coef_um + coef_um_offset(b, (lane >> 3) * 64, a.um_rows) - (size_t)((b % a.um_rows) & 7) * 16 + (size_t)(lane & 7) * 16) =
           make_uint4(0u, 0u, 0u, 0u);
       for (int i = lane; i < kJ * 12; i += 32) a.A[(int64_t)b * kJ * 12 + i] = 0.0f;
+      if (a.timg)
+        for (int i = lane; i < 96; i += 32)
+          *reinterpret_cast<uint4*>(a.timg + (size_t)(b >> 3) * 12288 + (size_t)((b & 7) * 12) * 128 + (size_t)i * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
     return;
   }
@@ -147,16 +159,36 @@ __global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int
       }
     }
   }
-  if (!active) return;
+  if (!active) {
+    if (a.timg) {                 // lanes 24..31: the zero pads (k 24..31 and 56..63 = chunks 3 and 7) of this body's 12 operand rows
+      for (int i = lane - kJ; i < 24; i += 8) {
+        const int e = i >> 1, n = (b & 7) * 12 + e, chunk = (i & 1) ? 7 : 3;
+        *reinterpret_cast<uint4*>(a.timg + (size_t)(b >> 3) * 12288 + (size_t)n * 128 + (size_t)((chunk ^ (n & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    return;
+  }
 
   float* Ab = a.A + ((int64_t)b * kJ + j) * 12;
+  float Av[12];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    Ab[r * 4 + 0] = WR[r * 3 + 0];
-    Ab[r * 4 + 1] = WR[r * 3 + 1];
-    Ab[r * 4 + 2] = WR[r * 3 + 2];
-    Ab[r * 4 + 3] = Wt[r] - (WR[r * 3 + 0] * Jx[0] + WR[r * 3 + 1] * Jx[1] + WR[r * 3 + 2] * Jx[2]);
+    Av[r * 4 + 0] = WR[r * 3 + 0];
+    Av[r * 4 + 1] = WR[r * 3 + 1];
+    Av[r * 4 + 2] = WR[r * 3 + 2];
+    Av[r * 4 + 3] = Wt[r] - (WR[r * 3 + 0] * Jx[0] + WR[r * 3 + 1] * Jx[1] + WR[r * 3 + 2] * Jx[2]);
     a.posedJ[((int64_t)b * kJ + j) * 3 + r] = Wt[r];
+  }
+#pragma unroll
+  for (int e = 0; e < 12; ++e) Ab[e] = Av[e];
+  if (a.timg) {
+#pragma unroll
+    for (int e = 0; e < 12; ++e) {
+      const float v = Av[e];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      *reinterpret_cast<__nv_bfloat16*>(a.timg + timg_offset(b, e, j, 0)) = hi;
+      *reinterpret_cast<__nv_bfloat16*>(a.timg + timg_offset(b, e, j, 1)) = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
   }
   float* cf = a.coef + (int64_t)b * kCoefLd;
   if (j >= 1) {
@@ -187,18 +219,18 @@ __global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int
     if (j >= 1) {
 #pragma unroll
       for (int k = 0; k < 9; ++k)
-        *reinterpret_cast<__nv_bfloat16*>(a.coef_um + coef_um_offset(b, (j - 1) * 9 + k)) =
+        *reinterpret_cast<__nv_bfloat16*>(a.coef_um + coef_um_offset(b, (j - 1) * 9 + k, a.um_rows)) =
             __float2bfloat16_rn(R[k] - ((k == 0 || k == 4 || k == 8) ? 1.0f : 0.0f));
     } else {
 #pragma unroll
       for (int l = 0; l < 10; ++l) {
         const __nv_bfloat16 hi = __float2bfloat16_rn(beta[l]);
         const __nv_bfloat16 lo = __float2bfloat16_rn(beta[l] - __bfloat162float(hi));
-        *reinterpret_cast<__nv_bfloat16*>(a.coef_um + coef_um_offset(b, 207 + l)) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(a.coef_um + coef_um_offset(b, 217 + l)) = lo;
-        *reinterpret_cast<__nv_bfloat16*>(a.coef_um + coef_um_offset(b, 227 + l)) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(a.coef_um + coef_um_offset(b, 207 + l, a.um_rows)) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(a.coef_um + coef_um_offset(b, 217 + l, a.um_rows)) = lo;
+        *reinterpret_cast<__nv_bfloat16*>(a.coef_um + coef_um_offset(b, 227 + l, a.um_rows)) = hi;
       }
-      for (int k = 237; k < 256; ++k) *reinterpret_cast<__nv_bfloat16*>(a.coef_um + coef_um_offset(b, k)) = __float2bfloat16_rn(0.0f);
+      for (int k = 237; k < 256; ++k) *reinterpret_cast<__nv_bfloat16*>(a.coef_um + coef_um_offset(b, k, a.um_rows)) = __float2bfloat16_rn(0.0f);
     }
   }
   if (a.rotmat) {
@@ -701,6 +733,7 @@ k_smpl_skin(const tp_smpl_model m, int body_lo, int body_hi, int bodies_per_cta,
 }
 
 #include "smpl_um.inl"
+#include "smpl_um2.inl"
 
 __global__ void __launch_bounds__(128) k_smpl_finalize(int n, int n_verts, const float* __restrict__ posedJ,
                                                        const float* __restrict__ jpart, int nsplit, int nreg,
@@ -757,13 +790,15 @@ __global__ void __launch_bounds__(128) k_smpl_finalize(int n, int n_verts, const
 
 static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
-struct SmplPlan { int ntiles, nsplit, tiles_per_split, ngroups; size_t off_A, off_J, off_coef, off_part, off_ctc, off_vposed, off_um, total;
+struct SmplPlan { int ntiles, nsplit, tiles_per_split, ngroups; size_t off_A, off_J, off_coef, off_part, off_ctc, off_vposed, off_um, off_timg, total;
                   int tc, tc_tiles, tc_gsplit, tc_gpc, split, chunk, um, n_pad; };
 
 // large-batch path: from this many bodies on, GEMM + skin over L2-resident chunks replaces the fused kernel
 static int split_min_bodies() { static const int v = getenv("TP_SMPL_SPLIT_MIN") ? atoi(getenv("TP_SMPL_SPLIT_MIN")) : 1024; return v; }
 // fused tcgen05 blend + skinning kernel (k_smpl_lbs_um) for the large-batch path; TP_SMPL_UM=0 falls back to GEMM + k_smpl_skin
-static int um_enabled() { static const int v = getenv("TP_SMPL_UM") ? atoi(getenv("TP_SMPL_UM")) : 1; return v; }
+// TP_SMPL_UM: 2 (default) = both contractions on tcgen05 (k_smpl_lbs_um2), 1 = blend on tcgen05 + shared-memory skinning gathers
+// (k_smpl_lbs_um), 0 = GEMM + k_smpl_skin
+static int um_enabled() { static const int v = getenv("TP_SMPL_UM") ? atoi(getenv("TP_SMPL_UM")) : 2; return v; }
 static int split_chunk_bodies() { static const int v = getenv("TP_SMPL_CHUNK") ? atoi(getenv("TP_SMPL_CHUNK")) : 1024; return v < 16 ? 16 : v; }
 
 static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg, int blend_mode) {
@@ -795,6 +830,7 @@ static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg, int blend_mod
   p.nsplit = (p.ntiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.split = (p.tc && m->blend_km && m->vp % kSkVT == 0 && n >= split_min_bodies()) ? 1 : 0;
   p.um = (p.tc && m->blend_um && m->vp % kUsVT == 0 && nreg <= 16 && n >= split_min_bodies() && um_enabled()) ? 1 : 0;
+  if (p.um && um_enabled() >= 2 && m->skin_um) p.um = 2;
   if (p.um) p.split = 0;
   p.n_pad = p.um ? (n + kUsGB - 1) / kUsGB * kUsGB : n;
   size_t o = 0;
@@ -807,6 +843,7 @@ static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg, int blend_mod
   p.chunk = split_chunk_bodies() < n ? split_chunk_bodies() : n;
   p.off_vposed = o; o += p.split ? al256((size_t)p.chunk * m->vp * 3 * 4) : 0;
   p.off_um = o; o += p.um ? al256((size_t)(p.n_pad / kUsGB) * kUsBBytes) : 0;
+  p.off_timg = o; o += p.um == 2 ? al256((size_t)(p.n_pad / kU2SB) * kU2TimgBytes) : 0;
   p.total = o;
   return p;
 }
@@ -852,7 +889,8 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
   pa.rotmat = rotmat; pa.theta = theta;
   pa.coef_tc = (pl.tc && !pl.um) ? reinterpret_cast<__nv_bfloat16*>(ws + pl.off_ctc) : nullptr;
   pa.coef_um = pl.um ? ws + pl.off_um : nullptr;
-  pa.n_pad = pl.n_pad;
+  pa.timg = pl.um == 2 ? ws + pl.off_timg : nullptr;
+  pa.n_pad = pl.n_pad; pa.um_rows = pl.um == 2 ? kU2GB : kUsGB;
   float* jpart = reinterpret_cast<float*>(ws + pl.off_part);
 
   {
@@ -861,7 +899,17 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
   }
   TP_LAUNCH_CHECK();
   const bool need_verts_pass = verts != nullptr || nreg > 0;
-  if (need_verts_pass && pl.um) {
+  if (need_verts_pass && pl.um == 2) {
+    U2Params up;
+    up.m = *m; up.n = n; up.ngroups = pl.n_pad / kU2GB; up.ntiles = m->vp / kUsVT; up.nreg = nreg;
+    up.coef_img = ws + pl.off_um; up.timg = ws + pl.off_timg; up.jreg = jreg; up.verts = verts; up.jpart = jpart;
+    TP_CUDA(cudaFuncSetAttribute(k_smpl_lbs_um2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kU2Smem));
+    const long long items = (long long)up.ntiles * up.ngroups;
+    const int grid = (int)(items < sm_count() ? items : sm_count());
+    PdlConfig lc(dim3((unsigned)grid), dim3(kU2Threads), kU2Smem, st);
+    TP_CUDA(cudaLaunchKernelEx(&lc.cfg, k_smpl_lbs_um2, up));
+    TP_LAUNCH_CHECK();
+  } else if (need_verts_pass && pl.um) {
     UsParams up;
     up.m = *m; up.n = n; up.ngroups = pl.n_pad / kUsGB; up.ntiles = m->vp / kUsVT; up.nreg = nreg;
     up.coef_img = ws + pl.off_um; up.A = pa.A; up.jreg = jreg; up.verts = verts; up.jpart = jpart;

@@ -146,7 +146,7 @@ class PackedSmpl:
         self.skin_w[:V] = wsel
         self.device = device
         # tensor-core blend tables (bf16 mode): [3*vp, 256] rows ((v//16)*3 + c)*16 + v%16
-        self.blend_tc = self.template_pad = self.blend_km = self.blend_um = None
+        self.blend_tc = self.template_pad = self.blend_km = self.blend_um = self.skin_um = None
         if ks <= 4:
             S = shapedirs.detach().to(device).float()[:, :, :10]                       # [V,3,10]
             S_hi = S.to(torch.bfloat16).float()
@@ -167,10 +167,19 @@ class PackedSmpl:
             img = cols.to(torch.bfloat16).reshape(vp // 128, 128, 3, 4, 8, 8).permute(0, 2, 3, 1, 4, 5)     # t, c, kb, r, q, e
             sw = (torch.arange(8, device=device)[None, :] ^ (torch.arange(128, device=device) % 8)[:, None])   # [r, q'] -> source chunk
             self.blend_um = torch.gather(img, 4, sw[None, None, None, :, :, None].expand(vp // 128, 3, 4, 128, 8, 8)).contiguous()
+            # A operand of the skinning MMA: per vertex row 64 bf16 = W_hi (24 joints) | 0 x 8 | W_lo (24) | 0 x 8, W = hi + lo
+            Wd = torch.zeros(vp, 24, device=device, dtype=torch.float32)
+            Wd[:V] = W
+            w_hi = Wd.to(torch.bfloat16)
+            w_lo = (Wd - w_hi.float()).to(torch.bfloat16)
+            row = torch.zeros(vp, 64, device=device, dtype=torch.bfloat16)
+            row[:, :24], row[:, 32:56] = w_hi, w_lo
+            rimg = row.reshape(vp // 128, 128, 8, 8)
+            self.skin_um = torch.gather(rimg, 2, sw[None, :, :, None].expand(vp // 128, 128, 8, 8)).contiguous()
         self.c_model = nv.SmplModel(nv.ptr(self.blend), nv.ptr(self.j_template), nv.ptr(self.j_shapedirs),
                                     nv.ptr(self.parents), nv.ptr(self.skin_idx), nv.ptr(self.skin_w),
                                     ks, V, vp, nv.ptr(self.blend_tc), nv.ptr(self.template_pad), nv.ptr(self.blend_km),
-                                    nv.ptr(self.blend_um))
+                                    nv.ptr(self.blend_um), nv.ptr(self.skin_um))
 
 
 def smpl_forward_native(packed: PackedSmpl, pose: torch.Tensor, ld_pose: int, pose_kind: int,

@@ -51,4 +51,4 @@ def test_struct_sizes_match_c_layout():
     assert ctypes.sizeof(nv.GemmSeg) == 40
     assert ctypes.sizeof(nv.GruJob) == 108 + 4 + 16
     assert ctypes.sizeof(nv.IefWeights) == 56
-    assert ctypes.sizeof(nv.SmplModel) == 96
+    assert ctypes.sizeof(nv.SmplModel) == 104
