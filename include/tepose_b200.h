@@ -297,6 +297,18 @@ typedef struct tp_smpl_model {
   const void* skin_um;
 } tp_smpl_model;
 
+/* A joint regressor folded through the skinning weights and the blend matrix (optional, large-batch path): with
+ * G[(r,j),v] = jreg[r,v] w[v,j], sum_v jreg[r,v] verts[v] = sum_j ( R_j q[r,j] + t_j g0[r,j] ), q = coef . M^T + q_bias:
+ *   m_km   [2 nq_pad, 256] bf16 row-major: rows [0, nq_pad) = bf16(M), rows [nq_pad, 2 nq_pad) = bf16(M - bf16(M)); row (r*24 + j)*3 + c,
+ *          column k in the coefficient order of blend_tc (M = G . blend_km as stored, i.e. from the bf16 blend matrix)
+ *   q_bias [nq_pad] = G . v_template;   g0 [nreg*24] = sum_v G;   nq_pad = nreg*72 rounded up to a multiple of 16.            */
+typedef struct tp_smpl_regfold {
+  const void* m_km;
+  const float* q_bias;
+  const float* g0;
+  int32_t nreg, nq_pad;
+} tp_smpl_regfold;
+
 TP_API size_t tp_smpl_workspace_bytes(const tp_smpl_model* m, int n, int nreg, int blend_mode);
 /* smplx.SMPL.forward + lbs (restated third-party code), the wrapper
  * lib/models/smpl.py:72-84, the optional H36M regression lib/models/spin.py:275-278, the
@@ -314,6 +326,13 @@ TP_API int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose, int
                     float* verts, float* joints, float* kp2d, float* rotmat, float* theta,
                     int blend_mode /* 0: fp32 FFMA blend (strict); 1: bf16 tensor-core blend (needs blend_tc) */,
                     void* workspace, size_t workspace_bytes, void* stream);
+/* Same with an optional folded form of jreg (NULL = tp_smpl_forward): the large-batch path (>= 1024 bodies, blend_mode 1) then takes
+ * the regressed joints from one small GEMM over all bodies instead of a pass over every body's skinned vertices.             */
+TP_API int tp_smpl_forward_ex(const tp_smpl_model* m, int n, const float* pose, int64_t ld_pose, int pose_kind,
+                       const float* betas, int64_t ld_betas, const float* cam, int64_t ld_cam,
+                       const float* jreg, int nreg, const tp_smpl_regfold* fold, const int32_t* joint_src, int nj,
+                       float* verts, float* joints, float* kp2d, float* rotmat, float* theta, int blend_mode,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ evaluation metrics (lib/utils/eval_utils.py)
  * All take fp32 device arrays; pelvis0 / pelvis1 select the root alignment applied to BOTH point sets first

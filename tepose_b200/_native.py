@@ -29,7 +29,7 @@ EXPORTS = [
     "tp_pack_mma_a_bytes", "tp_pack_mma_a_bf16", "tp_skinny_bf16_workspace_bytes", "tp_skinny_bf16", "tp_skinny_bf16_ex", "tp_gemm_bf16_tc",
     "tp_pack_whh_bf16", "tp_whh_umma_bytes", "tp_pack_whh_umma", "tp_gru_set_trace", "tp_gru_workspace_bytes", "tp_gru_recurrence", "tp_gru_recurrence_ex",
     "tp_encoder_heads_workspace_bytes", "tp_encoder_heads", "tp_encoder_heads_cat", "tp_ief_workspace_bytes", "tp_ief_forward", "tp_heads_ief_forward",
-    "tp_smpl_workspace_bytes", "tp_smpl_forward",
+    "tp_smpl_workspace_bytes", "tp_smpl_forward", "tp_smpl_forward_ex",
     "tp_pose_metrics", "tp_accel_error", "tp_vertex_error",
     "tp_transpose_f32", "tp_colsum_f32", "tp_mask_scale", "tp_relu_backward", "tp_axpby_f32", "tp_gru_cell_backward",
     "tp_rot6d_backward", "tp_rotmat_to_angle_axis_backward", "tp_smpl_backward_workspace_bytes", "tp_smpl_backward",
@@ -58,6 +58,10 @@ class SmplModel(C.Structure):
     _fields_ = [("blend", vp), ("j_template", vp), ("j_shapedirs", vp), ("parents", vp),
                 ("skin_idx", vp), ("skin_w", vp), ("ks", i32), ("n_verts", i32), ("vp", i32),
                 ("blend_tc", vp), ("template_pad", vp), ("blend_km", vp), ("blend_um", vp), ("skin_um", vp)]
+
+
+class SmplRegFold(C.Structure):
+    _fields_ = [("m_km", vp), ("q_bias", vp), ("g0", vp), ("nreg", i32), ("nq_pad", i32)]
 
 
 _SIGNATURES = {
@@ -115,6 +119,8 @@ _SIGNATURES = {
     "tp_smpl_backward": (C.c_int, [C.POINTER(SmplModel), C.c_int, vp, vp, i64, vp, i64, vp, C.c_int, vp, C.c_int, vp,
                                    vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "tp_smpl_workspace_bytes": (sz, [C.POINTER(SmplModel), C.c_int, C.c_int, C.c_int]),
+    "tp_smpl_forward_ex": (C.c_int, [C.POINTER(SmplModel), C.c_int, vp, i64, C.c_int, vp, i64, vp, i64,
+                                     vp, C.c_int, C.POINTER(SmplRegFold), vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, sz, vp]),
     "tp_smpl_forward": (C.c_int, [C.POINTER(SmplModel), C.c_int, vp, i64, C.c_int, vp, i64, vp, i64,
                                   vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, sz, vp]),
 }

@@ -735,18 +735,45 @@ k_smpl_skin(const tp_smpl_model m, int body_lo, int body_hi, int bodies_per_cta,
 #include "smpl_um.inl"
 #include "smpl_um2.inl"
 
+// Folded joint regressors (large-batch path): sum_v J[r,v] verts[v] = sum_j ( R_j q[r,j] + t_j g0[r,j] ) with
+// q[r,j] = sum_v J[r,v] w[v,j] p_v -- linear in the blend coefficients, so it comes out of one small GEMM over all bodies
+// (q = coef . M^T, M = (J (x) w) . Blend folded at pack time, hi / lo bf16 halves in separate column ranges) instead of a pass
+// over the 6890 skinned vertices of every body.
+struct FoldArgs { const float* q; int64_t ldq; int lo_off; const float* A; const float* g0; };
+
 __global__ void __launch_bounds__(128) k_smpl_finalize(int n, int n_verts, const float* __restrict__ posedJ,
                                                        const float* __restrict__ jpart, int nsplit, int nreg,
                                                        const float* __restrict__ verts, const int32_t* __restrict__ joint_src,
                                                        int nj, const float* __restrict__ cam, int64_t ld_cam,
-                                                       float* __restrict__ joints, float* __restrict__ kp2d) {
+                                                       float* __restrict__ joints, float* __restrict__ kp2d, const FoldArgs fold) {
   asm volatile("griddepcontrol.wait;\n" ::: "memory");      // no-op unless launched with programmatic serialization
   __shared__ float Jr[kMaxReg * 3];
   const int b = blockIdx.x, tid = threadIdx.x;
+  if (fold.q) {
+    __shared__ float contrib[kMaxReg * kJ * 3];
+    const float* qb = fold.q + (int64_t)b * fold.ldq;
+    for (int i = tid; i < nreg * kJ; i += blockDim.x) {          // i = r * 24 + j
+      const int j = i % kJ;
+      const float* Aj = fold.A + ((int64_t)b * kJ + j) * 12;
+      const float q0 = qb[i * 3] + qb[fold.lo_off + i * 3], q1 = qb[i * 3 + 1] + qb[fold.lo_off + i * 3 + 1],
+                  q2 = qb[i * 3 + 2] + qb[fold.lo_off + i * 3 + 2];
+      const float g = fold.g0[i];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        contrib[i * 3 + c] = fmaf(Aj[c * 4], q0, fmaf(Aj[c * 4 + 1], q1, fmaf(Aj[c * 4 + 2], q2, Aj[c * 4 + 3] * g)));
+    }
+    __syncthreads();
+    for (int i = tid; i < nreg * 3; i += blockDim.x) {
+      const int r = i / 3, c = i - r * 3;
+      float s = 0.0f;
+      for (int j = 0; j < kJ; ++j) s += contrib[(r * kJ + j) * 3 + c];
+      Jr[i] = s;
+    }
+  } else
   // regressor partials [tile][value]: warp w takes tiles w, w+4, ...; lane = value, so a tile is one contiguous
   // coalesced read and all of a warp's loads are independent (a few L2 round trips in total).  The four warp sums
   // are added in a fixed order -> deterministic.
-  {
+  if (!fold.q) {
     __shared__ float Jw[4][kMaxReg * 3];
     const int warp = tid >> 5, lane = tid & 31, nval = nreg * 3;
     const float* base = jpart + (int64_t)b * nsplit * nval;
@@ -790,8 +817,8 @@ __global__ void __launch_bounds__(128) k_smpl_finalize(int n, int n_verts, const
 
 static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
-struct SmplPlan { int ntiles, nsplit, tiles_per_split, ngroups; size_t off_A, off_J, off_coef, off_part, off_ctc, off_vposed, off_um, off_timg, total;
-                  int tc, tc_tiles, tc_gsplit, tc_gpc, split, chunk, um, n_pad; };
+struct SmplPlan { int ntiles, nsplit, tiles_per_split, ngroups; size_t off_A, off_J, off_coef, off_part, off_ctc, off_vposed, off_um, off_timg, off_q, total;
+                  int tc, tc_tiles, tc_gsplit, tc_gpc, split, chunk, um, n_pad, nq_pad; };
 
 // large-batch path: from this many bodies on, GEMM + skin over L2-resident chunks replaces the fused kernel
 static int split_min_bodies() { static const int v = getenv("TP_SMPL_SPLIT_MIN") ? atoi(getenv("TP_SMPL_SPLIT_MIN")) : 1024; return v; }
@@ -830,7 +857,7 @@ static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg, int blend_mod
   p.nsplit = (p.ntiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.split = (p.tc && m->blend_km && m->vp % kSkVT == 0 && n >= split_min_bodies()) ? 1 : 0;
   p.um = (p.tc && m->blend_um && m->vp % kUsVT == 0 && nreg <= 16 && n >= split_min_bodies() && um_enabled()) ? 1 : 0;
-  if (p.um && um_enabled() >= 2 && m->skin_um) p.um = 2;
+  if (p.tc && m->blend_um && m->vp % kUsVT == 0 && n >= split_min_bodies() && um_enabled() >= 2 && m->skin_um) p.um = 2;   // any nreg <= kMaxReg
   if (p.um) p.split = 0;
   p.n_pad = p.um ? (n + kUsGB - 1) / kUsGB * kUsGB : n;
   size_t o = 0;
@@ -844,6 +871,8 @@ static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg, int blend_mod
   p.off_vposed = o; o += p.split ? al256((size_t)p.chunk * m->vp * 3 * 4) : 0;
   p.off_um = o; o += p.um ? al256((size_t)(p.n_pad / kUsGB) * kUsBBytes) : 0;
   p.off_timg = o; o += p.um == 2 ? al256((size_t)(p.n_pad / kU2SB) * kU2TimgBytes) : 0;
+  p.nq_pad = (nreg * kJ * 3 + 15) / 16 * 16;                  // folded-regressor GEMM output: [n][M_hi part | M_lo part] fp32
+  p.off_q = o; o += (p.um == 2 && nreg > 0) ? al256((size_t)n * 2 * p.nq_pad * 4) : 0;
   p.total = o;
   return p;
 }
@@ -862,6 +891,15 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
                                const float* jreg, int nreg, const int32_t* joint_src, int nj,
                                float* verts, float* joints, float* kp2d, float* rotmat, float* theta, int blend_mode,
                                void* workspace, size_t workspace_bytes, void* stream) {
+  return tp_smpl_forward_ex(m, n, pose, ld_pose, pose_kind, betas, ld_betas, cam, ld_cam, jreg, nreg, nullptr, joint_src, nj, verts, joints,
+                            kp2d, rotmat, theta, blend_mode, workspace, workspace_bytes, stream);
+}
+
+extern "C" int tp_smpl_forward_ex(const tp_smpl_model* m, int n, const float* pose, int64_t ld_pose, int pose_kind,
+                                  const float* betas, int64_t ld_betas, const float* cam, int64_t ld_cam,
+                                  const float* jreg, int nreg, const tp_smpl_regfold* fold, const int32_t* joint_src, int nj,
+                                  float* verts, float* joints, float* kp2d, float* rotmat, float* theta, int blend_mode,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
   TP_CHECK_ARG(m != nullptr, "tp_smpl_forward: null model");
   TP_CHECK_ARG(n >= 0, "tp_smpl_forward: n=%d", n);
   if (n == 0) return TP_OK;
@@ -876,6 +914,12 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
   TP_CHECK_ARG(aligned16(m->blend), "tp_smpl_forward: blend table must be 16-byte aligned");
   TP_CHECK_ARG(blend_mode == 0 || blend_mode == 1, "tp_smpl_forward: bad blend_mode %d", blend_mode);
   SmplPlan pl = make_plan(m, n, nreg, blend_mode);
+  // the folded regressor serves the large-batch tcgen05 path only; it must describe the same nreg rows as jreg
+  const bool use_fold = pl.um == 2 && nreg > 0 && fold && fold->m_km && fold->g0 && fold->nreg == nreg && fold->nq_pad == pl.nq_pad;
+  TP_CHECK_ARG(!fold || fold->nreg == nreg, "tp_smpl_forward_ex: fold->nreg=%d does not match nreg=%d", fold ? fold->nreg : 0, nreg);
+  if (pl.um == 2 && nreg > 16 && !use_fold) {                 // the epilogue regressor handles 16 rows: more need the fold
+    return fail(TP_ERR_UNSUPPORTED, "tp_smpl_forward: the large-batch tcgen05 path needs a folded regressor (tp_smpl_regfold) for nreg=%d > 16", nreg);
+  }
   TP_CHECK_ARG(workspace && workspace_bytes >= pl.total, "tp_smpl_forward: workspace too small (%zu < %zu)", workspace_bytes, pl.total);
   TP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "tp_smpl_forward: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -887,7 +931,7 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
   pa.posedJ = reinterpret_cast<float*>(ws + pl.off_J);
   pa.coef = reinterpret_cast<float*>(ws + pl.off_coef);
   pa.rotmat = rotmat; pa.theta = theta;
-  pa.coef_tc = (pl.tc && !pl.um) ? reinterpret_cast<__nv_bfloat16*>(ws + pl.off_ctc) : nullptr;
+  pa.coef_tc = (pl.tc && (!pl.um || use_fold)) ? reinterpret_cast<__nv_bfloat16*>(ws + pl.off_ctc) : nullptr;   // row-major rows: A operand of the fold GEMM
   pa.coef_um = pl.um ? ws + pl.off_um : nullptr;
   pa.timg = pl.um == 2 ? ws + pl.off_timg : nullptr;
   pa.n_pad = pl.n_pad; pa.um_rows = pl.um == 2 ? kU2GB : kUsGB;
@@ -901,8 +945,16 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
   const bool need_verts_pass = verts != nullptr || nreg > 0;
   if (need_verts_pass && pl.um == 2) {
     U2Params up;
-    up.m = *m; up.n = n; up.ngroups = pl.n_pad / kU2GB; up.ntiles = m->vp / kUsVT; up.nreg = nreg;
+    up.m = *m; up.n = n; up.ngroups = pl.n_pad / kU2GB; up.ntiles = m->vp / kUsVT; up.nreg = use_fold ? 0 : nreg;
     up.coef_img = ws + pl.off_um; up.timg = ws + pl.off_timg; up.jreg = jreg; up.verts = verts; up.jpart = jpart;
+    if (use_fold) {        // q = coef . [M_hi ; M_lo]^T (+ the template part as the bias of the hi columns): one tcgen05 GEMM over all bodies
+      tp_gemm_seg sg[2];
+      float* q = reinterpret_cast<float*>(ws + pl.off_q);
+      sg[0].m_start = 0; sg[0].m_rows = n; sg[0].n_start = 0; sg[0].n_cols = pl.nq_pad; sg[0].out = q; sg[0].ldc = 2 * pl.nq_pad; sg[0].bias = fold->q_bias;
+      sg[1] = sg[0]; sg[1].n_start = pl.nq_pad; sg[1].out = q + pl.nq_pad; sg[1].bias = nullptr;
+      int rc = tp_gemm_bf16_tc(pa.coef_tc, n, fold->m_km, 2 * pl.nq_pad, kTcK, sg, 2, stream);
+      if (rc != TP_OK) return rc;
+    }
     TP_CUDA(cudaFuncSetAttribute(k_smpl_lbs_um2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kU2Smem));
     const long long items = (long long)up.ntiles * up.ngroups;
     const int grid = (int)(items < sm_count() ? items : sm_count());
@@ -975,9 +1027,12 @@ extern "C" int tp_smpl_forward(const tp_smpl_model* m, int n, const float* pose,
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
+      FoldArgs fa;
+      fa.q = use_fold ? reinterpret_cast<const float*>(ws + pl.off_q) : nullptr;
+      fa.ldq = 2 * pl.nq_pad; fa.lo_off = pl.nq_pad; fa.A = pa.A; fa.g0 = use_fold ? fold->g0 : nullptr;
       TP_CUDA(cudaLaunchKernelEx(&cfg, k_smpl_finalize, n, (int)m->n_verts, (const float*)pa.posedJ, (const float*)jpart,
                                  (int)((pl.split || pl.um) ? m->vp / kSkVT : (pl.tc ? pl.tc_tiles : pl.nsplit)), nreg, (const float*)verts,
-                                 joint_src, nj, cam, ld_cam, joints, kp2d));
+                                 joint_src, nj, cam, ld_cam, joints, kp2d, fa));
     }
     TP_LAUNCH_CHECK();
   }

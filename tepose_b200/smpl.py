@@ -15,6 +15,8 @@ import pickle
 from collections import namedtuple
 
 import numpy as np
+import ctypes as C
+
 import torch
 import torch.nn as nn
 
@@ -146,7 +148,8 @@ class PackedSmpl:
         self.skin_w[:V] = wsel
         self.device = device
         # tensor-core blend tables (bf16 mode): [3*vp, 256] rows ((v//16)*3 + c)*16 + v%16
-        self.blend_tc = self.template_pad = self.blend_km = self.blend_um = self.skin_um = None
+        self.blend_tc = self.template_pad = self.blend_km = self.blend_um = self.skin_um = self.w_dense = None
+        self._folds = {}
         if ks <= 4:
             S = shapedirs.detach().to(device).float()[:, :, :10]                       # [V,3,10]
             S_hi = S.to(torch.bfloat16).float()
@@ -170,6 +173,7 @@ class PackedSmpl:
             # A operand of the skinning MMA: per vertex row 64 bf16 = W_hi (24 joints) | 0 x 8 | W_lo (24) | 0 x 8, W = hi + lo
             Wd = torch.zeros(vp, 24, device=device, dtype=torch.float32)
             Wd[:V] = W
+            self.w_dense = Wd
             w_hi = Wd.to(torch.bfloat16)
             w_lo = (Wd - w_hi.float()).to(torch.bfloat16)
             row = torch.zeros(vp, 64, device=device, dtype=torch.bfloat16)
@@ -180,6 +184,42 @@ class PackedSmpl:
                                     nv.ptr(self.parents), nv.ptr(self.skin_idx), nv.ptr(self.skin_w),
                                     ks, V, vp, nv.ptr(self.blend_tc), nv.ptr(self.template_pad), nv.ptr(self.blend_km),
                                     nv.ptr(self.blend_um), nv.ptr(self.skin_um))
+
+
+LARGE_BATCH = 1024          # bodies from which tp_smpl_forward takes the large-batch tcgen05 path (csrc/smpl.cu split_min_bodies)
+
+
+class RegFold:
+    """tp_smpl_regfold of one joint regressor: the regressor folded through the skinning weights and the (bf16) blend matrix in
+    float64 at pack time, so that the large-batch path gets its regressed joints from one small GEMM over all bodies."""
+
+    def __init__(self, packed: "PackedSmpl", jreg: torch.Tensor):
+        R, vp = int(jreg.shape[0]), packed.vp
+        G = (jreg.double()[:, None, :] * packed.w_dense.double().t()[None]).reshape(R * 24, vp)       # [(r, j), v]
+        cols = packed.blend_km.double().reshape(vp, 3 * 256)                                            # [v, (c, k)] as the kernels read it
+        M = (G @ cols).reshape(R * 24 * 3, 256)                                                         # row (r*24 + j)*3 + c
+        self.nreg, self.nq_pad = R, (R * 72 + 15) // 16 * 16
+        hi = M.float().to(torch.bfloat16)
+        lo = (M - hi.double()).float().to(torch.bfloat16)
+        self.m_km = torch.zeros(2 * self.nq_pad, 256, device=jreg.device, dtype=torch.bfloat16)
+        self.m_km[:R * 72], self.m_km[self.nq_pad:self.nq_pad + R * 72] = hi, lo
+        self.q_bias = torch.zeros(self.nq_pad, device=jreg.device, dtype=torch.float32)
+        self.q_bias[:R * 72] = (G @ packed.template_pad.double()).reshape(-1).float()
+        self.g0 = G.sum(dim=1).float().contiguous()
+        self.c_fold = nv.SmplRegFold(nv.ptr(self.m_km), nv.ptr(self.q_bias), nv.ptr(self.g0), self.nreg, self.nq_pad)
+
+
+def _fold_for(packed: "PackedSmpl", jreg):
+    if jreg is None or packed.skin_um is None:
+        return None
+    key = (jreg.data_ptr(), jreg._version, tuple(jreg.shape))
+    hit = packed._folds.get(key)
+    if hit is None:
+        hit = RegFold(packed, jreg)
+        if len(packed._folds) > 4:
+            packed._folds.clear()
+        packed._folds[key] = hit
+    return hit
 
 
 def smpl_forward_native(packed: PackedSmpl, pose: torch.Tensor, ld_pose: int, pose_kind: int,
@@ -215,9 +255,10 @@ def smpl_forward_native(packed: PackedSmpl, pose: torch.Tensor, ld_pose: int, po
     nbytes = L.tp_smpl_workspace_bytes(packed.c_model, n, nreg, blend_mode)
     ws = nv.workspace(nbytes, dev)
     P = lambda t: nv.vp(0) if t is None else nv.vp(t.data_ptr())
-    nv.check(L.tp_smpl_forward(packed.c_model, n, P(pose), ld_pose, pose_kind, P(betas), ld_betas, P(cam), ld_cam,
-                               P(jreg), nreg, P(joint_src), nj, P(verts), P(joints), P(kp2d), P(rotmat), P(theta),
-                               blend_mode, P(ws), ws.numel(), nv.stream()), "tp_smpl_forward")
+    fold = _fold_for(packed, jreg) if (blend_mode == 1 and n >= LARGE_BATCH) else None
+    nv.check(L.tp_smpl_forward_ex(packed.c_model, n, P(pose), ld_pose, pose_kind, P(betas), ld_betas, P(cam), ld_cam,
+                                  P(jreg), nreg, None if fold is None else C.byref(fold.c_fold), P(joint_src), nj, P(verts), P(joints),
+                                  P(kp2d), P(rotmat), P(theta), blend_mode, P(ws), ws.numel(), nv.stream()), "tp_smpl_forward")
     return verts, joints, kp2d, rotmat, theta
 
 

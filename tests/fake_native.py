@@ -260,6 +260,9 @@ class FakeLib:
     def tp_smpl_workspace_bytes(self, m, n, nreg, blend_mode=0):
         return 256
 
+    def tp_smpl_forward_ex(self, m, n, pose, ld_pose, pose_kind, betas, ld_betas, cam, ld_cam, jreg, nreg, fold, joint_src, nj, *rest):
+        return self.tp_smpl_forward(m, n, pose, ld_pose, pose_kind, betas, ld_betas, cam, ld_cam, jreg, nreg, joint_src, nj, *rest)
+
     def tp_smpl_forward(self, m, n, pose, ld_pose, pose_kind, betas, ld_betas, cam, ld_cam, jreg, nreg, joint_src, nj,
                         verts, joints, kp2d, rotmat, theta, blend_mode, ws, ws_bytes, stream):
         m = m.contents if hasattr(m, "contents") else m

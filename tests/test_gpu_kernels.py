@@ -374,6 +374,42 @@ def test_smpl_large_batch_split_path(n):
     assert float((out.joints - torch.cat(fj)).abs().max()) < 2e-5
 
 
+def test_smpl_large_batch_h36m_regressor_folded():
+    """Large-batch tcgen05 path with the 17-row H36M regressor (lib/models/spin.py:275-278 on a big batch): more rows than the
+    in-kernel regressor handles, so the joints come from the folded-regressor GEMM (tp_smpl_regfold).  Against the oracle's
+    J_regressor_h36m . verts and against the small-batch kernel."""
+    n = 2048
+    with base_data_cwd(10):
+        smpl = tepose_b200.SMPL(tepose_b200.SMPL_MODEL_DIR, batch_size=1, create_transl=False).to(DEV)
+    from tepose_b200.smpl import smpl_forward_native
+    m = torch_ref.SmplModel.synthetic(10)
+    p = smpl.packed()
+    jreg, src = smpl.h36m_tables(m.J_regressor_h36m.to(DEV))
+    bodies = synth.make_bodies(12, n)
+    aa, betas = cu(torch.from_numpy(bodies["pose_aa"])), cu(torch.from_numpy(bodies["betas"]))
+    big = smpl_forward_native(p, aa, 72, nv.POSE_AXIS_ANGLE, betas, 10, None, 0, n, jreg, src, want_theta=False, want_rotmat=False, blend_mode=1)
+    pick = torch.tensor([0, 5, 1023, 1024, n - 1])
+    v_ref, _, _ = torch_ref.smpl_forward(m, betas.cpu()[pick], pose_aa=aa.cpu()[pick])
+    j_ref = torch.einsum("jv,bvc->bjc", m.J_regressor_h36m, v_ref)[:, tepose_b200.H36M_TO_J14]
+    assert float((big[0].cpu()[pick] - v_ref).abs().max()) < 1e-4
+    assert float((big[1].cpu()[pick] - j_ref).abs().max()) < 1e-4
+    small = smpl_forward_native(p, aa[:512], 72, nv.POSE_AXIS_ANGLE, betas[:512], 10, None, 0, 512, jreg, src, want_theta=False,
+                                want_rotmat=False, blend_mode=1)
+    assert float((big[1][:512] - small[1]).abs().max()) < 3e-5
+
+
+@pytest.mark.parametrize("um", ["0", "1"])
+def test_smpl_large_batch_older_paths_still_agree(um):
+    """TP_SMPL_UM=1 (tcgen05 blend + shared-memory skinning gathers) and =0 (GEMM + k_smpl_skin) stay selectable; the switch is
+    read once per process, so the split-path test runs in a child process."""
+    import subprocess, sys
+    env = dict(os.environ, TP_SMPL_UM=um)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "--no-header", "-p", "no:cacheprovider",
+                        "-k", "test_smpl_large_batch_split_path"], env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("skinning", ["random", "coherent"])
 def test_smpl_config3_65536_bodies(skinning):
     """BASELINE.json configs[3] at its full size: 65,536 bodies through the fused tcgen05 blend + skinning kernel (k_smpl_lbs_um).
