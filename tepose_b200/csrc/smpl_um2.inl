@@ -11,13 +11,16 @@
 // D2 = W_hi.A_hi + W_lo.A_hi + W_hi.A_lo (6 MMAs of K = 16; the lo.lo term is 2^-18 relative).  The epilogue reads p (3 values)
 // and T (12 values) of its (vertex, body) with tcgen05.ld and does 12 FMAs.
 //
-// TMEM (512 columns): [0,48) D1, [48,144) D2, [144,504) the vertex tile's blend rows (3 planes x K = 240 bf16 = 120 columns each).
+// TMEM (all 512 columns): [0,48) D1, [48,144) + [144,240) D2 of the two 8-body skinning steps of a group (so neither step waits
+// for the epilogue to drain the other: with a single D2 every step cost a full MMA -> epilogue -> MMA round trip, 2.3 ms),
+// [240,272) the tile's skinning-weight operand, [272,512) the x and y planes of the tile's blend rows (K = 240 bf16 = 120 columns
+// each).  The z plane (64 KB) stays in shared memory as a tcgen05 operand image: TMEM has no room for it next to the second D2.
 // Shared memory: ring of {coefficient rows of 16 bodies (8 KB) + transform operands of 2 x 8 bodies (24 KB)} written by
-// k_smpl_prepare as tcgen05 operand images and moved by ONE bulk copy each; the tile's skinning-weight operand (16 KB); per-warp
-// slabs for the coalesced vertex store and the 3xTF32 joint-regressor MMAs (as in the first generation).
+// k_smpl_prepare as tcgen05 operand images and moved by ONE bulk copy each; the z plane; per-warp slabs for the coalesced
+// vertex store and the 3xTF32 joint-regressor MMAs (as in the first generation).
 // Warp roles: 16 epilogue warps (TMEM lane quadrant = warp % 4; body pair = warp / 4 of every 8-body skinning step), a producer
-// warp, an MMA warp.
-constexpr int kU2Threads = 576;
+// warp, three MMA-issuing warps.
+constexpr int kU2Threads = 640;                   // 16 epilogue warps, producer warp, three MMA-issuing warps
 constexpr int kU2EpiWarps = 16;
 constexpr int kU2GB = 16;                          // bodies per blend MMA (N) and per ring stage
 constexpr int kU2SB = 8;                           // bodies per skinning MMA (N = 96)
@@ -30,14 +33,15 @@ constexpr int kU2SlabPitch = 100;
 constexpr int kU2SlabFloats = 4 * kU2SlabPitch;     // 4 bodies per warp and group
 constexpr int kU2ChunkGroups = 256;                 // 4096 bodies per L2-resident chunk
 constexpr size_t kU2OffRing = 0;
-constexpr size_t kU2OffW = kU2OffRing + (size_t)kU2Stages * kU2StageBytes;
-constexpr size_t kU2OffSlab = kU2OffW + kU2WBytes;
+constexpr size_t kU2ZBytes = 4 * 16384;             // z plane of the tile's blend rows: [K block 4][row 128][128 B]
+constexpr size_t kU2OffZ = kU2OffRing + (size_t)kU2Stages * kU2StageBytes;
+constexpr size_t kU2OffSlab = kU2OffZ + kU2ZBytes;
 constexpr size_t kU2OffFrag = kU2OffSlab + (size_t)kU2EpiWarps * kU2SlabFloats * 4;
 constexpr size_t kU2OffBar = kU2OffFrag + kUsFragBytes;
 constexpr size_t kU2Smem = kU2OffBar + 256 + 1024;
 constexpr uint32_t kU2IdescBlend = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kU2GB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 constexpr uint32_t kU2IdescSkin = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((kU2SB * 12) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-constexpr uint32_t kU2ColD1 = 0, kU2ColD2 = 48, kU2ColA = 144;
+constexpr uint32_t kU2ColD1 = 0, kU2ColD2 = 48, kU2ColW = 240, kU2ColA = 272;
 static_assert(kU2Stages * kU2StageBytes >= 4 * 16384, "the TMEM-fill staging area (4 x 16 KB) aliases the ring");
 
 __device__ __forceinline__ void us_tmem_st(uint32_t taddr, const uint32_t* v, int n) {     // n in {32, 16, 8}
@@ -57,6 +61,21 @@ __device__ __forceinline__ void us_tmem_ld2(uint32_t taddr, float& a, float& b) 
   a = __uint_as_float(r0); b = __uint_as_float(r1);
 }
 
+// Busy-polling wait for the TMEM hand-offs between the MMA warp and the epilogue warps: mbarrier.try_wait may suspend the thread
+// for a system-defined time, and the wake-up showed as the dominant cost of every D2 round trip (two per 16 bodies).
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+
 struct U2Params {
   tp_smpl_model m;
   int n, ngroups, ntiles, nreg;
@@ -71,7 +90,7 @@ __global__ void __launch_bounds__(kU2Threads, 1) k_smpl_lbs_um2(const U2Params p
   extern __shared__ __align__(1024) unsigned char u2_raw[];
   unsigned char* smem = u2_raw + ((1024u - (smem_u32(u2_raw) & 1023u)) & 1023u);
   unsigned char* s_ring = smem + kU2OffRing;           // doubles as the TMEM-fill staging area between tiles
-  unsigned char* s_w = smem + kU2OffW;
+  unsigned char* s_z = smem + kU2OffZ;
   float* s_slab = reinterpret_cast<float*>(smem + kU2OffSlab);
   uint32_t* s_frag = reinterpret_cast<uint32_t*>(smem + kU2OffFrag);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kU2OffBar);
@@ -79,19 +98,19 @@ __global__ void __launch_bounds__(kU2Threads, 1) k_smpl_lbs_um2(const U2Params p
   uint64_t* in_empty = bars + 3;           // [3]
   uint64_t* d1_full = bars + 6;
   uint64_t* d1_empty = bars + 7;
-  uint64_t* d2_full = bars + 8;
-  uint64_t* d2_empty = bars + 9;
-  uint64_t* f_full = bars + 10;            // [4]
-  uint64_t* w_full = bars + 14;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* d2_full = bars + 8;            // [2]
+  uint64_t* d2_empty = bars + 10;          // [2]
+  uint64_t* f_full = bars + 12;            // [4]
+  uint64_t* z_full = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < kU2Stages; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
-    mbar_init(d1_full, 1); mbar_init(d1_empty, kU2EpiWarps);
-    mbar_init(d2_full, 1); mbar_init(d2_empty, kU2EpiWarps);
+    for (int i = 0; i < kU2Stages; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 3); }
+    mbar_init(d1_full, 2); mbar_init(d1_empty, kU2EpiWarps);
+    for (int i = 0; i < 2; ++i) { mbar_init(&d2_full[i], 1); mbar_init(&d2_empty[i], kU2EpiWarps); }
     for (int i = 0; i < 4; ++i) mbar_init(&f_full[i], 1);
-    mbar_init(w_full, 1);
+    mbar_init(z_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 16) {
@@ -102,7 +121,7 @@ __global__ void __launch_bounds__(kU2Threads, 1) k_smpl_lbs_um2(const U2Params p
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d1 = tmem_base + kU2ColD1, tmem_d2 = tmem_base + kU2ColD2, tmem_a = tmem_base + kU2ColA;
+  const uint32_t tmem_d1 = tmem_base + kU2ColD1, tmem_d2 = tmem_base + kU2ColD2, tmem_w = tmem_base + kU2ColW, tmem_a = tmem_base + kU2ColA;
 
   pdl_wait();                       // the operand images come from k_smpl_prepare
   pdl_launch_dependents();
@@ -126,10 +145,13 @@ __global__ void __launch_bounds__(kU2Threads, 1) k_smpl_lbs_um2(const U2Params p
     __syncthreads();
     {
       const unsigned char* img = reinterpret_cast<const unsigned char*>(p.m.blend_um) + (size_t)tile * kUsTileImage;
+      // staged blocks 0..7: x and y planes (plane = blk / 4, K block = blk % 4), block 8: the skinning-weight operand
+      const unsigned char* wimg = reinterpret_cast<const unsigned char*>(p.m.skin_um) + (size_t)tile * kU2WBytes;
+      auto blk_src = [&](int blk) { return blk < 8 ? img + (size_t)blk * 16384 : wimg; };
       if (warp == 16 && elect_one()) {
-        for (int i = 0; i < 4; ++i) { mbar_expect_tx(&f_full[i], 16384); us_bulk_g2s(s_ring + i * 16384, img + (size_t)i * 16384, 16384, &f_full[i]); }
-        mbar_expect_tx(w_full, kU2WBytes);
-        us_bulk_g2s(s_w, reinterpret_cast<const unsigned char*>(p.m.skin_um) + (size_t)tile * kU2WBytes, kU2WBytes, w_full);
+        for (int i = 0; i < 4; ++i) { mbar_expect_tx(&f_full[i], 16384); us_bulk_g2s(s_ring + i * 16384, blk_src(i), 16384, &f_full[i]); }
+        mbar_expect_tx(z_full, (uint32_t)kU2ZBytes);
+        us_bulk_g2s(s_z, img + (size_t)8 * 16384, (uint32_t)kU2ZBytes, z_full);             // z plane: straight into place
       }
       for (int i = tid; i < 4 * 4 * 32 * 4; i += kU2Threads) {          // regressor A fragments (m16n8k8, tf32 hi | lo)
         const int e = i & 3, ln = (i >> 2) & 31, ks = (i >> 7) & 3, qq = i >> 9;
@@ -140,10 +162,11 @@ __global__ void __launch_bounds__(kU2Threads, 1) k_smpl_lbs_um2(const U2Params p
         uint32_t* dst = s_frag + ((size_t)(qq * 4 + ks) * 32 + ln) * 8;
         dst[e] = hi; dst[4 + e] = __float_as_uint(lo);
       }
-      for (int blk = 0; blk < 12; ++blk) {                              // block = plane * 4 + K block; K blocks 0..2: 32 columns, block 3: 24 (K = 240)
+      for (int blk = 0; blk < 9; ++blk) {
         const int st = blk & 3;
         if (warp < 4) {
-          mbar_wait(&f_full[st], (nfill * 3 + (uint32_t)(blk >> 2)) & 1u);
+          // stage 0 is used three times per tile set-up (blocks 0, 4, 8), the others twice
+          mbar_wait(&f_full[st], ((st == 0 ? 3u : 2u) * nfill + (uint32_t)(blk >> 2)) & 1u);
           const int row = warp * 32 + lane;
           const unsigned char* rowp = s_ring + (size_t)st * 16384 + (size_t)row * 128;
           uint32_t v[32];
@@ -152,18 +175,22 @@ __global__ void __launch_bounds__(kU2Threads, 1) k_smpl_lbs_um2(const U2Params p
             const uint4 x = *reinterpret_cast<const uint4*>(rowp + ((c ^ (row & 7)) << 4));
             v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
           }
-          const uint32_t dst = tmem_a + (uint32_t)((blk >> 2) * 120 + (blk & 3) * 32) + ((uint32_t)(warp * 32) << 16);
-          if ((blk & 3) < 3) us_tmem_st(dst, v, 32);
-          else { us_tmem_st(dst, v, 16); us_tmem_st(dst + 16, v + 16, 8); }
+          const uint32_t lanes = (uint32_t)(warp * 32) << 16;
+          if (blk == 8) us_tmem_st(tmem_w + lanes, v, 32);
+          else {
+            const uint32_t dst = tmem_a + (uint32_t)((blk >> 2) * 120 + (blk & 3) * 32) + lanes;     // K blocks 0..2: 32 columns, block 3: 24 (K = 240)
+            if ((blk & 3) < 3) us_tmem_st(dst, v, 32);
+            else { us_tmem_st(dst, v, 16); us_tmem_st(dst + 16, v + 16, 8); }
+          }
         }
         __syncthreads();
-        if (warp == 16 && blk + 4 < 12 && elect_one()) {
+        if (warp == 16 && blk + 4 < 9 && elect_one()) {
           mbar_expect_tx(&f_full[st], 16384);
-          us_bulk_g2s(s_ring + st * 16384, img + (size_t)(blk + 4) * 16384, 16384, &f_full[st]);
+          us_bulk_g2s(s_ring + st * 16384, blk_src(blk + 4), 16384, &f_full[st]);
         }
       }
       if (warp < 4) asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-      mbar_wait(w_full, nfill & 1u);
+      mbar_wait(z_full, nfill & 1u);
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncthreads();
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -183,43 +210,62 @@ __global__ void __launch_bounds__(kU2Threads, 1) k_smpl_lbs_um2(const U2Params p
         }
         __syncwarp();
       }
-    } else if (warp == 17) {
-      // ================================================================ MMA issuer
-      const uint64_t dw = umma_desc_sw128(smem_u32(s_w));
+    } else if (warp >= 17) {
+      // ================================================================ MMA issuers: three warps, three independent streams.
+      // A tcgen05.mma with N = 16 occupies the tensor pipe ~17 cycles but costs its issuing thread ~40 (ncu: the single MMA warp
+      // of the first version spent 81 % of its time stalled on UTCHMMA while the pipe was 35 % busy), and the accumulators of
+      // the three streams are disjoint: warp 17 = blend planes x, y (A in TMEM), warp 18 = blend plane z (A in shared memory),
+      // warp 19 = the two skinning steps.  D1 is complete when both blend warps have committed; a ring stage is free when all
+      // three have.
+      const uint32_t role = (uint32_t)warp - 17u;
+      const uint64_t dz = umma_desc_sw128(smem_u32(s_z));
       for (int g = g0; g < g1; ++g, ++ngrp) {
         const uint32_t st = ngrp % kU2Stages, ph = (ngrp / kU2Stages) & 1u;
         mbar_wait(&in_full[st], ph);
-        mbar_wait(d1_empty, (ngrp & 1u) ^ 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const uint64_t dc = umma_desc_sw128(smem_u32(s_ring + (size_t)st * kU2StageBytes));
-        const uint64_t dt = umma_desc_sw128(smem_u32(s_ring + (size_t)st * kU2StageBytes + kU2CoefBytes));
-        if (elect_one()) {
-#pragma unroll
-          for (int pl = 0; pl < 3; ++pl)
-#pragma unroll
-            for (int i = 0; i < 15; ++i)
-              us_umma_ts(tmem_d1 + (uint32_t)(pl * 16), tmem_a + (uint32_t)(pl * 120 + i * 8),
-                         dc + (uint64_t)((i >> 2) * (2048 >> 4) + (i & 3) * 2), kU2IdescBlend, i == 0 ? 0u : 1u);
-          umma_commit(d1_full);
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(d2_empty, ((2u * ngrp + (uint32_t)h) & 1u) ^ 1u);
+        if (role < 2) {
+          mbar_spin(d1_empty, (ngrp & 1u) ^ 1u);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           if (elect_one()) {
-            const uint64_t db = dt + (uint64_t)(h * (kU2TimgBytes >> 4));
-            // (W_hi, A_hi), (W_lo, A_hi), (W_hi, A_lo): two K = 16 steps each; the lo halves sit 64 bytes into the 128-byte rows
-            umma_f16(tmem_d2, dw + 0, db + 0, kU2IdescSkin, 0u);
-            umma_f16(tmem_d2, dw + 2, db + 2, kU2IdescSkin, 1u);
-            umma_f16(tmem_d2, dw + 4, db + 0, kU2IdescSkin, 1u);
-            umma_f16(tmem_d2, dw + 6, db + 2, kU2IdescSkin, 1u);
-            umma_f16(tmem_d2, dw + 0, db + 4, kU2IdescSkin, 1u);
-            umma_f16(tmem_d2, dw + 2, db + 6, kU2IdescSkin, 1u);
-            umma_commit(d2_full);
-            if (h == 1) umma_commit(&in_empty[st]);
+            if (role == 0) {
+#pragma unroll
+              for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                for (int i = 0; i < 15; ++i)
+                  us_umma_ts(tmem_d1 + (uint32_t)(pl * 16), tmem_a + (uint32_t)(pl * 120 + i * 8),
+                             dc + (uint64_t)((i >> 2) * (2048 >> 4) + (i & 3) * 2), kU2IdescBlend, i == 0 ? 0u : 1u);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 15; ++i)
+                umma_f16(tmem_d1 + 32u, dz + (uint64_t)((i >> 2) * (16384 >> 4) + (i & 3) * 2),
+                         dc + (uint64_t)((i >> 2) * (2048 >> 4) + (i & 3) * 2), kU2IdescBlend, i == 0 ? 0u : 1u);
+            }
+            umma_commit(d1_full);
+            umma_commit(&in_empty[st]);
           }
           __syncwarp();
+        } else {
+          const uint64_t dt = dc + (uint64_t)(kU2CoefBytes >> 4);
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            mbar_spin(&d2_empty[h], (ngrp & 1u) ^ 1u);          // buffer h was drained by the epilogue of the PREVIOUS group: no round trip on the critical path
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (elect_one()) {
+              const uint64_t db = dt + (uint64_t)(h * (kU2TimgBytes >> 4));
+              const uint32_t d2 = tmem_d2 + (uint32_t)(h * 96);
+              // (W_hi, A_hi), (W_lo, A_hi), (W_hi, A_lo): two K = 16 steps each.  W in TMEM: hi = columns 0..15, lo = 16..31 (8 columns
+              // per K step); A rows in shared memory: the lo half sits 64 bytes into the 128-byte rows
+              us_umma_ts(d2, tmem_w + 0, db + 0, kU2IdescSkin, 0u);
+              us_umma_ts(d2, tmem_w + 8, db + 2, kU2IdescSkin, 1u);
+              us_umma_ts(d2, tmem_w + 16, db + 0, kU2IdescSkin, 1u);
+              us_umma_ts(d2, tmem_w + 24, db + 2, kU2IdescSkin, 1u);
+              us_umma_ts(d2, tmem_w + 0, db + 4, kU2IdescSkin, 1u);
+              us_umma_ts(d2, tmem_w + 8, db + 6, kU2IdescSkin, 1u);
+              umma_commit(&d2_full[h]);
+              if (h == 1) umma_commit(&in_empty[st]);
+            }
+            __syncwarp();
+          }
         }
       }
     } else {
@@ -237,6 +283,7 @@ __global__ void __launch_bounds__(kU2Threads, 1) k_smpl_lbs_um2(const U2Params p
       const int64_t vrem = nv3 - vbase;
       const bool st_a2 = lane * 2 + 1 < vrem, st_a1 = lane * 2 < vrem;
       const bool st_b2 = lane < 16 && 64 + lane * 2 + 1 < vrem, st_b1 = lane < 16 && 64 + lane * 2 < vrem;
+      const bool tile_full = vrem >= 96;
       // slot bi (0..3) of this warp = body (bi >> 1) * 8 + 2 sset + (bi & 1) of the group
       // partial-sum slots this thread adds up: value i = row * 16 + column, column = slot * 3 + coordinate (12 used of 16)
       int js_off[2]; bool js_ok[2]; int js_body[2];
@@ -251,7 +298,7 @@ __global__ void __launch_bounds__(kU2Threads, 1) k_smpl_lbs_um2(const U2Params p
       }
       for (int g = g0; g < g1; ++g, ++ngrp) {
         float px[4], py[4], pz[4];
-        mbar_wait(d1_full, ngrp & 1u);
+        mbar_spin(d1_full, ngrp & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -266,15 +313,15 @@ __global__ void __launch_bounds__(kU2Threads, 1) k_smpl_lbs_um2(const U2Params p
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           float T[24];
-          mbar_wait(d2_full, (2u * ngrp + (uint32_t)h) & 1u);
+          mbar_spin(&d2_full[h], ngrp & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          us_tmem_ld8(tmem_d2 + t_lane + (uint32_t)(sset * 24), T);
-          us_tmem_ld8(tmem_d2 + t_lane + (uint32_t)(sset * 24 + 8), T + 8);
-          us_tmem_ld8(tmem_d2 + t_lane + (uint32_t)(sset * 24 + 16), T + 16);
+          us_tmem_ld8(tmem_d2 + t_lane + (uint32_t)(h * 96 + sset * 24), T);
+          us_tmem_ld8(tmem_d2 + t_lane + (uint32_t)(h * 96 + sset * 24 + 8), T + 8);
+          us_tmem_ld8(tmem_d2 + t_lane + (uint32_t)(h * 96 + sset * 24 + 16), T + 16);
           asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
           asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
           __syncwarp();
-          if (lane == 0) us_mb_arrive(d2_empty);
+          if (lane == 0) us_mb_arrive(&d2_empty[h]);
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             const int bi = 2 * h + i;
@@ -289,18 +336,23 @@ __global__ void __launch_bounds__(kU2Threads, 1) k_smpl_lbs_um2(const U2Params p
         }
         __syncwarp();
         const int gbody0 = g * kU2GB;
-        // coalesced vertex store: 384 contiguous bytes per (warp, body)
+        // coalesced vertex store: 384 contiguous bytes per (warp, body); one 64-bit address product per group, the ragged last
+        // vertex tile and the ragged last body group take the predicated path
         if (p.verts) {
+          float* d0 = p.verts + (int64_t)(gbody0 + 2 * sset) * nv3 + vbase + lane * 2;
+          const bool full_grp = gbody0 + kU2GB <= p.n;
 #pragma unroll
           for (int bi = 0; bi < 4; ++bi) {
-            const int body = gbody0 + (bi >> 1) * 8 + 2 * sset + (bi & 1);
-            if (body < p.n) {
-              float* dstb = p.verts + (int64_t)body * nv3 + vbase;
-              const float2* src = reinterpret_cast<const float2*>(slab + bi * kU2SlabPitch);
-              if (st_a2) *reinterpret_cast<float2*>(dstb + lane * 2) = src[lane];
-              else if (st_a1) dstb[lane * 2] = src[lane].x;
-              if (st_b2) *reinterpret_cast<float2*>(dstb + 64 + lane * 2) = src[32 + lane];
-              else if (st_b1) dstb[64 + lane * 2] = src[32 + lane].x;
+            float* dstb = d0 + ((bi >> 1) ? nv3 * 8 : 0) + ((bi & 1) ? nv3 : 0);
+            const float2* src = reinterpret_cast<const float2*>(slab + bi * kU2SlabPitch);
+            if (full_grp && tile_full) {
+              *reinterpret_cast<float2*>(dstb) = src[lane];
+              if (lane < 16) *reinterpret_cast<float2*>(dstb + 64) = src[32 + lane];
+            } else if (gbody0 + (bi >> 1) * 8 + 2 * sset + (bi & 1) < p.n) {
+              if (st_a2) *reinterpret_cast<float2*>(dstb) = src[lane];
+              else if (st_a1) dstb[0] = src[lane].x;
+              if (st_b2) *reinterpret_cast<float2*>(dstb + 64) = src[32 + lane];
+              else if (st_b1) dstb[64] = src[32 + lane].x;
             }
           }
         }
