@@ -396,6 +396,19 @@ TP_API int tp_smpl_backward(const tp_smpl_model* m, int n, const float* R, const
                      const float* g_verts, const float* g_joints, const float* g_kp2d, const float* g_R_extra,
                      float* g_R, float* g_betas, float* g_cam, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ generator loss, data terms (lib/core/loss.py:59-171)
+ * Value and gradient of TePoseLoss's data terms in one pass (the reference: ~40 torch ops + autograd):
+ *   losses4 = { e_loss_weight * keypoint_loss (loss.py:179-192), e_3d_loss_weight * keypoint_3d_loss (:194-217),
+ *               e_pose_loss_weight * MSE of quaternion-Rodrigues rotation matrices, e_shape_loss_weight * MSE of betas (:219-231) }
+ *   kp2d [n2,49,2] vs real2d [n2,49,3] (x, y, confidence);  kp3d / real3d [n3,49,3] (rows with 3-D labels; joints 25..38 count);
+ *   theta / real_theta [ns,85] (rows with SMPL labels).  weights6 (HOST array) = { e_loss_weight, e_3d_loss_weight,
+ *   e_pose_loss_weight, e_shape_loss_weight, openpose_weight, gt_weight }.
+ *   g_kp2d / g_kp3d / g_theta: d(sum of the four terms) / d(prediction), same shapes as the predictions.                    */
+TP_API size_t tp_tepose_loss_workspace_bytes(int n2, int n3, int ns);
+TP_API int tp_tepose_loss(const float* kp2d, const float* real2d, int n2, const float* kp3d, const float* real3d, int n3,
+                   const float* theta, const float* real_theta, int ns, const float* weights6,
+                   float* losses4, float* g_kp2d, float* g_kp3d, float* g_theta, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

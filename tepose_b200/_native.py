@@ -33,6 +33,7 @@ EXPORTS = [
     "tp_pose_metrics", "tp_accel_error", "tp_vertex_error",
     "tp_transpose_f32", "tp_colsum_f32", "tp_mask_scale", "tp_relu_backward", "tp_axpby_f32", "tp_gru_cell_backward",
     "tp_rot6d_backward", "tp_rotmat_to_angle_axis_backward", "tp_smpl_backward_workspace_bytes", "tp_smpl_backward",
+    "tp_tepose_loss_workspace_bytes", "tp_tepose_loss",
 ]
 
 vp, i32, i64, f32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -118,6 +119,8 @@ _SIGNATURES = {
     "tp_smpl_backward_workspace_bytes": (sz, [C.POINTER(SmplModel), C.c_int]),
     "tp_smpl_backward": (C.c_int, [C.POINTER(SmplModel), C.c_int, vp, vp, i64, vp, i64, vp, C.c_int, vp, C.c_int, vp,
                                    vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "tp_tepose_loss_workspace_bytes": (sz, [C.c_int, C.c_int, C.c_int]),
+    "tp_tepose_loss": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_int, C.POINTER(f32), vp, vp, vp, vp, vp, sz, vp]),
     "tp_smpl_workspace_bytes": (sz, [C.POINTER(SmplModel), C.c_int, C.c_int, C.c_int]),
     "tp_smpl_forward_ex": (C.c_int, [C.POINTER(SmplModel), C.c_int, vp, i64, C.c_int, vp, i64, vp, i64,
                                      vp, C.c_int, C.POINTER(SmplRegFold), vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, sz, vp]),
