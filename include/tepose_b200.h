@@ -299,8 +299,9 @@ typedef struct tp_smpl_model {
 
 /* A joint regressor folded through the skinning weights and the blend matrix (optional, large-batch path): with
  * G[(r,j),v] = jreg[r,v] w[v,j], sum_v jreg[r,v] verts[v] = sum_j ( R_j q[r,j] + t_j g0[r,j] ), q = coef . M^T + q_bias:
- *   m_km   [2 nq_pad, 256] bf16 row-major: rows [0, nq_pad) = bf16(M), rows [nq_pad, 2 nq_pad) = bf16(M - bf16(M)); row (r*24 + j)*3 + c,
- *          column k in the coefficient order of blend_tc (M = G . blend_km as stored, i.e. from the bf16 blend matrix)
+ *   m_km   [nq_pad, 512] bf16 row-major: columns [0, 256) = bf16(M), [256, 512) = bf16(M - bf16(M)) (contracted with the coefficient
+ *          row twice); row (r*24 + j)*3 + c, column k in the coefficient order of blend_tc (M = G . blend_km as stored, i.e. from
+ *          the bf16 blend matrix)
  *   q_bias [nq_pad] = G . v_template;   g0 [nreg*24] = sum_v G;   nq_pad = nreg*72 rounded up to a multiple of 16.            */
 typedef struct tp_smpl_regfold {
   const void* m_km;

@@ -48,6 +48,7 @@ struct PrepArgs {
   unsigned char* coef_um;  // the same rows as the tcgen05 B-operand image [group of um_rows bodies][K block 4][row][128 B, 16-byte chunks
                            // XOR-swizzled by row & 7] (k_smpl_lbs_um: 32 rows, k_smpl_lbs_um2: 16) or null; bodies n..n_pad-1 get zero
                            // rows and zero transforms
+  __nv_bfloat16* coef_cat; // [n][512] bf16 = [row | row] of coef_tc's rows (the fold GEMM contracts it with [M_hi | M_lo]) or null
   unsigned char* timg;     // k_smpl_lbs_um2: the joint transforms as the B operand of the skinning MMA: [8 bodies][row (body, e) 96][128 B]
                            // with k = joint: A_hi at k 0..23, A_lo at k 32..55, zero pads, same chunk swizzle; or null
   int n_pad, um_rows;
@@ -159,17 +160,6 @@ __global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int
       }
     }
   }
-  if (!active) {
-    if (a.timg) {                 // lanes 24..31: the zero pads (k 24..31 and 56..63 = chunks 3 and 7) of this body's 12 operand rows
-      for (int i = lane - kJ; i < 24; i += 8) {
-        const int e = i >> 1, n = (b & 7) * 12 + e, chunk = (i & 1) ? 7 : 3;
-        *reinterpret_cast<uint4*>(a.timg + (size_t)(b >> 3) * 12288 + (size_t)n * 128 + (size_t)((chunk ^ (n & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
-    return;
-  }
-
-  float* Ab = a.A + ((int64_t)b * kJ + j) * 12;
   float Av[12];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
@@ -177,28 +167,73 @@ __global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int
     Av[r * 4 + 1] = WR[r * 3 + 1];
     Av[r * 4 + 2] = WR[r * 3 + 2];
     Av[r * 4 + 3] = Wt[r] - (WR[r * 3 + 0] * Jx[0] + WR[r * 3 + 1] * Jx[1] + WR[r * 3 + 2] * Jx[2]);
-    a.posedJ[((int64_t)b * kJ + j) * 3 + r] = Wt[r];
   }
-#pragma unroll
-  for (int e = 0; e < 12; ++e) Ab[e] = Av[e];
   if (a.timg) {
+    // ---- large-batch tcgen05 path: the body's operand rows are assembled in shared memory (2-byte stores) and leave as 16-byte
+    // chunks: 32 for the coefficient row (one per K block and chunk position), 96 contiguous ones for the 12 transform rows
+    __shared__ __align__(16) unsigned char stg_all[4][2048];
+    unsigned char* stg = stg_all[threadIdx.x >> 5];
+    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(stg);            // [256] logical order
+    unsigned char* trow = stg + 512;                                         // [12 rows][128 B] in its final (swizzled) layout
+    const int n0 = (b & 7) * 12;
+    if (active) {
+      if (j >= 1) {
 #pragma unroll
-    for (int e = 0; e < 12; ++e) {
-      const float v = Av[e];
-      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-      *reinterpret_cast<__nv_bfloat16*>(a.timg + timg_offset(b, e, j, 0)) = hi;
-      *reinterpret_cast<__nv_bfloat16*>(a.timg + timg_offset(b, e, j, 1)) = __float2bfloat16_rn(v - __bfloat162float(hi));
+        for (int k = 0; k < 9; ++k) crow[(j - 1) * 9 + k] = __float2bfloat16_rn(R[k] - ((k == 0 || k == 4 || k == 8) ? 1.0f : 0.0f));
+      } else {
+#pragma unroll
+        for (int l = 0; l < 10; ++l) {
+          const __nv_bfloat16 hi = __float2bfloat16_rn(beta[l]);
+          crow[207 + l] = hi; crow[217 + l] = __float2bfloat16_rn(beta[l] - __bfloat162float(hi)); crow[227 + l] = hi;
+        }
+        for (int k = 237; k < 256; ++k) crow[k] = __float2bfloat16_rn(0.0f);
+      }
+#pragma unroll
+      for (int e = 0; e < 12; ++e) {
+        const int n = n0 + e;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(Av[e]);
+        unsigned char* row = trow + e * 128;
+        *reinterpret_cast<__nv_bfloat16*>(row + ((((j >> 3)) ^ (n & 7)) << 4) + (j & 7) * 2) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(row + (((4 + (j >> 3)) ^ (n & 7)) << 4) + (j & 7) * 2) = __float2bfloat16_rn(Av[e] - __bfloat162float(hi));
+      }
+    } else {
+      for (int i = lane - kJ; i < 24; i += 8) {            // zero pads: chunks 3 and 7 (k 24..31, 56..63) of the 12 rows
+        const int e = i >> 1, n = n0 + e, chunk = (i & 1) ? 7 : 3;
+        *reinterpret_cast<uint4*>(trow + e * 128 + ((chunk ^ (n & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    __syncwarp();
+    {
+      const int rows = a.um_rows, grp = b / rows, row = b - grp * rows, kb = lane >> 3, c = lane & 7;
+      const uint4 v = *reinterpret_cast<const uint4*>(stg + kb * 128 + c * 16);
+      *reinterpret_cast<uint4*>(a.coef_um + (size_t)grp * rows * 512 + (size_t)kb * rows * 128 + (size_t)row * 128 + (size_t)((c ^ (row & 7)) << 4)) = v;
+      if (a.coef_cat) {                                     // [row | row]: A operand of the folded-regressor GEMM (K = 512)
+        uint4* d = reinterpret_cast<uint4*>(a.coef_cat + (int64_t)b * 512);
+        d[lane] = v; d[32 + lane] = v;
+      }
+      uint4* td = reinterpret_cast<uint4*>(a.timg + (size_t)(b >> 3) * 12288 + (size_t)n0 * 128);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) td[lane + 32 * i] = *reinterpret_cast<const uint4*>(trow + (lane + 32 * i) * 16);
     }
   }
-  float* cf = a.coef + (int64_t)b * kCoefLd;
-  if (j >= 1) {
+  if (!active) return;
+
+  float* Ab = a.A + ((int64_t)b * kJ + j) * 12;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) cf[(j - 1) * 9 + k] = R[k] - ((k == 0 || k == 4 || k == 8) ? 1.0f : 0.0f);
-  } else {
+  for (int e = 0; e < 12; ++e) Ab[e] = Av[e];
 #pragma unroll
-    for (int l = 0; l < 10; ++l) cf[207 + l] = beta[l];
-    cf[217] = 1.0f;
-    for (int k = kCoef; k < kCoefLd; ++k) cf[k] = 0.0f;
+  for (int r = 0; r < 3; ++r) a.posedJ[((int64_t)b * kJ + j) * 3 + r] = Wt[r];
+  if (a.coef) {
+    float* cf = a.coef + (int64_t)b * kCoefLd;
+    if (j >= 1) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) cf[(j - 1) * 9 + k] = R[k] - ((k == 0 || k == 4 || k == 8) ? 1.0f : 0.0f);
+    } else {
+#pragma unroll
+      for (int l = 0; l < 10; ++l) cf[207 + l] = beta[l];
+      cf[217] = 1.0f;
+      for (int k = kCoef; k < kCoefLd; ++k) cf[k] = 0.0f;
+    }
   }
   if (a.coef_tc) {
     __nv_bfloat16* ct = a.coef_tc + (int64_t)b * 256;
@@ -215,7 +250,7 @@ __global__ void __launch_bounds__(128) k_smpl_prepare(const tp_smpl_model m, int
       for (int k = 237; k < 256; ++k) ct[k] = __float2bfloat16_rn(0.0f);
     }
   }
-  if (a.coef_um) {
+  if (a.coef_um && !a.timg) {                               // first-generation tcgen05 path (k_smpl_lbs_um): scattered element stores
     if (j >= 1) {
 #pragma unroll
       for (int k = 0; k < 9; ++k)
@@ -737,7 +772,7 @@ k_smpl_skin(const tp_smpl_model m, int body_lo, int body_hi, int bodies_per_cta,
 
 // Folded joint regressors (large-batch path): sum_v J[r,v] verts[v] = sum_j ( R_j q[r,j] + t_j g0[r,j] ) with
 // q[r,j] = sum_v J[r,v] w[v,j] p_v -- linear in the blend coefficients, so it comes out of one small GEMM over all bodies
-// (q = coef . M^T, M = (J (x) w) . Blend folded at pack time, hi / lo bf16 halves in separate column ranges) instead of a pass
+// (q = [coef | coef] . [M_hi | M_lo]^T, M = (J (x) w) . Blend folded at pack time, split into two bf16 halves) instead of a pass
 // over the 6890 skinned vertices of every body.
 struct FoldArgs { const float* q; int64_t ldq; int lo_off; const float* A; const float* g0; };
 
@@ -755,8 +790,7 @@ __global__ void __launch_bounds__(128) k_smpl_finalize(int n, int n_verts, const
     for (int i = tid; i < nreg * kJ; i += blockDim.x) {          // i = r * 24 + j
       const int j = i % kJ;
       const float* Aj = fold.A + ((int64_t)b * kJ + j) * 12;
-      const float q0 = qb[i * 3] + qb[fold.lo_off + i * 3], q1 = qb[i * 3 + 1] + qb[fold.lo_off + i * 3 + 1],
-                  q2 = qb[i * 3 + 2] + qb[fold.lo_off + i * 3 + 2];
+      const float q0 = qb[i * 3], q1 = qb[i * 3 + 1], q2 = qb[i * 3 + 2];
       const float g = fold.g0[i];
 #pragma unroll
       for (int c = 0; c < 3; ++c)
@@ -866,13 +900,13 @@ static SmplPlan make_plan(const tp_smpl_model* m, int n, int nreg, int blend_mod
   p.off_coef = o; o += al256((size_t)n * kCoefLd * 4);
   const int part_tiles = p.um ? m->vp / kUsVT : (p.tc ? p.tc_tiles : p.nsplit);
   p.off_part = o; o += al256((size_t)n * part_tiles * (nreg > 0 ? nreg : 1) * 3 * 4);
-  p.off_ctc = o; o += p.tc ? al256((size_t)n * kTcK * 2) : 0;
+  p.off_ctc = o; o += p.tc ? al256((size_t)n * kTcK * 2 * 2) : 0;      // x2: the [row | row] form of the fold GEMM
   p.chunk = split_chunk_bodies() < n ? split_chunk_bodies() : n;
   p.off_vposed = o; o += p.split ? al256((size_t)p.chunk * m->vp * 3 * 4) : 0;
   p.off_um = o; o += p.um ? al256((size_t)(p.n_pad / kUsGB) * kUsBBytes) : 0;
   p.off_timg = o; o += p.um == 2 ? al256((size_t)(p.n_pad / kU2SB) * kU2TimgBytes) : 0;
   p.nq_pad = (nreg * kJ * 3 + 15) / 16 * 16;                  // folded-regressor GEMM output: [n][M_hi part | M_lo part] fp32
-  p.off_q = o; o += (p.um == 2 && nreg > 0) ? al256((size_t)n * 2 * p.nq_pad * 4) : 0;
+  p.off_q = o; o += (p.um == 2 && nreg > 0) ? al256((size_t)n * p.nq_pad * 4) : 0;
   p.total = o;
   return p;
 }
@@ -929,9 +963,10 @@ extern "C" int tp_smpl_forward_ex(const tp_smpl_model* m, int n, const float* po
   pa.betas = betas; pa.ld_betas = ld_betas; pa.cam = cam; pa.ld_cam = ld_cam;
   pa.A = reinterpret_cast<float*>(ws + pl.off_A);
   pa.posedJ = reinterpret_cast<float*>(ws + pl.off_J);
-  pa.coef = reinterpret_cast<float*>(ws + pl.off_coef);
+  pa.coef = pl.um ? nullptr : reinterpret_cast<float*>(ws + pl.off_coef);      // the fp32 rows feed the non-tcgen05 vertex kernels only
   pa.rotmat = rotmat; pa.theta = theta;
-  pa.coef_tc = (pl.tc && (!pl.um || use_fold)) ? reinterpret_cast<__nv_bfloat16*>(ws + pl.off_ctc) : nullptr;   // row-major rows: A operand of the fold GEMM
+  pa.coef_tc = (pl.tc && !pl.um) ? reinterpret_cast<__nv_bfloat16*>(ws + pl.off_ctc) : nullptr;
+  pa.coef_cat = use_fold ? reinterpret_cast<__nv_bfloat16*>(ws + pl.off_ctc) : nullptr;
   pa.coef_um = pl.um ? ws + pl.off_um : nullptr;
   pa.timg = pl.um == 2 ? ws + pl.off_timg : nullptr;
   pa.n_pad = pl.n_pad; pa.um_rows = pl.um == 2 ? kU2GB : kUsGB;
@@ -948,11 +983,10 @@ extern "C" int tp_smpl_forward_ex(const tp_smpl_model* m, int n, const float* po
     up.m = *m; up.n = n; up.ngroups = pl.n_pad / kU2GB; up.ntiles = m->vp / kUsVT; up.nreg = use_fold ? 0 : nreg;
     up.coef_img = ws + pl.off_um; up.timg = ws + pl.off_timg; up.jreg = jreg; up.verts = verts; up.jpart = jpart;
     if (use_fold) {        // q = coef . [M_hi ; M_lo]^T (+ the template part as the bias of the hi columns): one tcgen05 GEMM over all bodies
-      tp_gemm_seg sg[2];
-      float* q = reinterpret_cast<float*>(ws + pl.off_q);
-      sg[0].m_start = 0; sg[0].m_rows = n; sg[0].n_start = 0; sg[0].n_cols = pl.nq_pad; sg[0].out = q; sg[0].ldc = 2 * pl.nq_pad; sg[0].bias = fold->q_bias;
-      sg[1] = sg[0]; sg[1].n_start = pl.nq_pad; sg[1].out = q + pl.nq_pad; sg[1].bias = nullptr;
-      int rc = tp_gemm_bf16_tc(pa.coef_tc, n, fold->m_km, 2 * pl.nq_pad, kTcK, sg, 2, stream);
+      tp_gemm_seg sg;
+      sg.m_start = 0; sg.m_rows = n; sg.n_start = 0; sg.n_cols = pl.nq_pad; sg.out = reinterpret_cast<float*>(ws + pl.off_q); sg.ldc = pl.nq_pad;
+      sg.bias = fold->q_bias;
+      int rc = tp_gemm_bf16_tc(pa.coef_cat, n, fold->m_km, pl.nq_pad, 2 * kTcK, &sg, 1, stream);
       if (rc != TP_OK) return rc;
     }
     TP_CUDA(cudaFuncSetAttribute(k_smpl_lbs_um2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kU2Smem));
@@ -1029,7 +1063,7 @@ extern "C" int tp_smpl_forward_ex(const tp_smpl_model* m, int n, const float* po
       cfg.attrs = attr; cfg.numAttrs = 1;
       FoldArgs fa;
       fa.q = use_fold ? reinterpret_cast<const float*>(ws + pl.off_q) : nullptr;
-      fa.ldq = 2 * pl.nq_pad; fa.lo_off = pl.nq_pad; fa.A = pa.A; fa.g0 = use_fold ? fold->g0 : nullptr;
+      fa.ldq = pl.nq_pad; fa.lo_off = 0; fa.A = pa.A; fa.g0 = use_fold ? fold->g0 : nullptr;
       TP_CUDA(cudaLaunchKernelEx(&cfg, k_smpl_finalize, n, (int)m->n_verts, (const float*)pa.posedJ, (const float*)jpart,
                                  (int)((pl.split || pl.um) ? m->vp / kSkVT : (pl.tc ? pl.tc_tiles : pl.nsplit)), nreg, (const float*)verts,
                                  joint_src, nj, cam, ld_cam, joints, kp2d, fa));

@@ -201,8 +201,8 @@ class RegFold:
         self.nreg, self.nq_pad = R, (R * 72 + 15) // 16 * 16
         hi = M.float().to(torch.bfloat16)
         lo = (M - hi.double()).float().to(torch.bfloat16)
-        self.m_km = torch.zeros(2 * self.nq_pad, 256, device=jreg.device, dtype=torch.bfloat16)
-        self.m_km[:R * 72], self.m_km[self.nq_pad:self.nq_pad + R * 72] = hi, lo
+        self.m_km = torch.zeros(self.nq_pad, 512, device=jreg.device, dtype=torch.bfloat16)       # [M_hi | M_lo] against [coef | coef]
+        self.m_km[:R * 72, :256], self.m_km[:R * 72, 256:] = hi, lo
         self.q_bias = torch.zeros(self.nq_pad, device=jreg.device, dtype=torch.float32)
         self.q_bias[:R * 72] = (G @ packed.template_pad.double()).reshape(-1).float()
         self.g0 = G.sum(dim=1).float().contiguous()
