@@ -849,6 +849,69 @@ __global__ void __launch_bounds__(128) k_smpl_finalize(int n, int n_verts, const
   }
 }
 
+// Large-batch form of the finalize step with a folded regressor: ONE WARP per body, no block-wide barrier.  Lane = joint j: for
+// every regressor row r the lane forms R_j q[r,j] + t_j g0[r,j] and the 24 lanes are summed by shuffles (fixed order); then the
+// lanes compose the output joint set and project it.
+__global__ void __launch_bounds__(128) k_smpl_finalize_fold(int n, int n_verts, const float* __restrict__ posedJ, int nreg,
+                                                            const float* __restrict__ verts, const int32_t* __restrict__ joint_src, int nj,
+                                                            const float* __restrict__ cam, int64_t ld_cam, float* __restrict__ joints,
+                                                            float* __restrict__ kp2d, const FoldArgs fold) {
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  __shared__ float Jr_all[4][kMaxReg * 3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + warp;
+  if (b >= n) return;
+  float* Jr = Jr_all[warp];
+  const int j = lane < kJ ? lane : kJ - 1;
+  float Aj[12];
+  {
+    const float4* ap = reinterpret_cast<const float4*>(fold.A + ((int64_t)b * kJ + j) * 12);
+    const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2);
+    Aj[0] = a0.x; Aj[1] = a0.y; Aj[2] = a0.z; Aj[3] = a0.w; Aj[4] = a1.x; Aj[5] = a1.y; Aj[6] = a1.z; Aj[7] = a1.w;
+    Aj[8] = a2.x; Aj[9] = a2.y; Aj[10] = a2.z; Aj[11] = a2.w;
+  }
+  const float* qb = fold.q + (int64_t)b * fold.ldq;
+  for (int r = 0; r < nreg; ++r) {
+    const int i = r * kJ + j;
+    const float q0 = __ldcg(qb + i * 3), q1 = __ldcg(qb + i * 3 + 1), q2 = __ldcg(qb + i * 3 + 2), g = __ldg(fold.g0 + i);
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    if (lane < kJ) {
+      c0 = fmaf(Aj[0], q0, fmaf(Aj[1], q1, fmaf(Aj[2], q2, Aj[3] * g)));
+      c1 = fmaf(Aj[4], q0, fmaf(Aj[5], q1, fmaf(Aj[6], q2, Aj[7] * g)));
+      c2 = fmaf(Aj[8], q0, fmaf(Aj[9], q1, fmaf(Aj[10], q2, Aj[11] * g)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o); c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    }
+    if (lane == 0) { Jr[r * 3] = c0; Jr[r * 3 + 1] = c1; Jr[r * 3 + 2] = c2; }
+  }
+  __syncwarp();
+  for (int o = lane; o < nj; o += 32) {
+    const int code = joint_src[o];
+    float X[3];
+    if (code >= 1000) {
+      const float* p = verts + ((int64_t)b * n_verts + (code - 1000)) * 3;
+      X[0] = p[0]; X[1] = p[1]; X[2] = p[2];
+    } else if (code >= 100) {
+      X[0] = Jr[(code - 100) * 3]; X[1] = Jr[(code - 100) * 3 + 1]; X[2] = Jr[(code - 100) * 3 + 2];
+    } else {
+      const float* p = posedJ + ((int64_t)b * kJ + code) * 3;
+      X[0] = p[0]; X[1] = p[1]; X[2] = p[2];
+    }
+    if (joints) {
+      float* d = joints + ((int64_t)b * nj + o) * 3;
+      d[0] = X[0]; d[1] = X[1]; d[2] = X[2];
+    }
+    if (kp2d && cam) {
+      float c[3] = {cam[(int64_t)b * ld_cam], cam[(int64_t)b * ld_cam + 1], cam[(int64_t)b * ld_cam + 2]}, kp[2];
+      project_point_(X, c, kp);
+      kp2d[((int64_t)b * nj + o) * 2] = kp[0];
+      kp2d[((int64_t)b * nj + o) * 2 + 1] = kp[1];
+    }
+  }
+}
+
 static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct SmplPlan { int ntiles, nsplit, tiles_per_split, ngroups; size_t off_A, off_J, off_coef, off_part, off_ctc, off_vposed, off_um, off_timg, off_q, total;
@@ -1064,6 +1127,11 @@ extern "C" int tp_smpl_forward_ex(const tp_smpl_model* m, int n, const float* po
       FoldArgs fa;
       fa.q = use_fold ? reinterpret_cast<const float*>(ws + pl.off_q) : nullptr;
       fa.ldq = pl.nq_pad; fa.lo_off = 0; fa.A = pa.A; fa.g0 = use_fold ? fold->g0 : nullptr;
+      if (use_fold) {
+        cfg.gridDim = dim3((unsigned)ceil_div(n, 4));
+        TP_CUDA(cudaLaunchKernelEx(&cfg, k_smpl_finalize_fold, n, (int)m->n_verts, (const float*)pa.posedJ, nreg, (const float*)verts,
+                                   joint_src, nj, cam, ld_cam, joints, kp2d, fa));
+      } else
       TP_CUDA(cudaLaunchKernelEx(&cfg, k_smpl_finalize, n, (int)m->n_verts, (const float*)pa.posedJ, (const float*)jpart,
                                  (int)((pl.split || pl.um) ? m->vp / kSkVT : (pl.tc ? pl.tc_tiles : pl.nsplit)), nreg, (const float*)verts,
                                  joint_src, nj, cam, ld_cam, joints, kp2d, fa));
