@@ -12,7 +12,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtepose_b200.so")
+# TEPOSE_B200_LIB selects another build of the same sources (tests: the -DTP_BARRIER_ACQUIRE_FENCE twin, tepose_b200/build.py)
+LIB_PATH = os.environ.get("TEPOSE_B200_LIB") or os.path.join(_HERE, "libtepose_b200.so")
 
 PRECISION_FP32, PRECISION_BF16, PRECISION_BF16X3 = 0, 1, 2
 POSE_ROTMAT, POSE_AXIS_ANGLE, POSE_ROT6D = 0, 1, 2

@@ -31,17 +31,27 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
+    """variant="fence": the same sources with -DTP_BARRIER_ACQUIRE_FENCE (every grid barrier executes the formal acquire fence after
+    its relaxed polls) -> libtepose_b200_fence.so; tests/test_gpu_e2e.py checks that its outputs are bit-identical to the default
+    build's (the default relies on every post-barrier read of other CTAs' data being an L2-coherent access)."""
     nvcc = _nvcc()
-    os.makedirs(OBJ, exist_ok=True)
+    flags = list(NVCC_FLAGS)
+    obj_dir, lib_path = OBJ, LIB
+    if variant == "fence":
+        flags.append("-DTP_BARRIER_ACQUIRE_FENCE")
+        obj_dir, lib_path = os.path.join(HERE, "build_fence"), os.path.join(HERE, "libtepose_b200_fence.so")
+    elif variant:
+        raise ValueError(f"unknown build variant {variant!r}")
+    os.makedirs(obj_dir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".inl"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "tepose_b200.h"))
 
     def compile_one(src):
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ, src[:-3] + ".o")
+        o = os.path.join(obj_dir, src[:-3] + ".o")
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
+            cmd = [nvcc] + flags + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             r = subprocess.run(cmd, capture_output=True, text=True)
@@ -51,13 +61,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    if force or _stale(lib_path, objs):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, variant="fence" if "--fence" in sys.argv else ""))

@@ -228,6 +228,9 @@ __global__ void __launch_bounds__(kDualThreads, 1) k_gru_bf16_dual(const GruPara
         do {
           asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(counter) : "memory");
         } while (seen < target);
+#ifdef TP_BARRIER_ACQUIRE_FENCE
+        asm volatile("fence.acq_rel.gpu;\n" ::: "memory");     // the formal acquire (see common.cuh grid_barrier); off by default
+#endif
       }
       bar_sync(1 + d, 160);
       TP_TRACE(5);

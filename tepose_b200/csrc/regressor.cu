@@ -131,7 +131,7 @@ struct IefFusedParams {
   int nlayers, M;
   unsigned int* barrier; int barrier_shards;
   int narrow_from, narrow_ctas;   // layers >= narrow_from need only the first narrow_ctas CTAs: the others leave, and the
-                                  // barriers of that phase count narrow_ctas arrivals on a second counter (barrier + 32)
+                                  // barriers of that phase count narrow_ctas arrivals on a second counter (word 240 of the slot)
   int direct_kb;      // layers with at most this many 32-column blocks load their B fragments straight into registers (0 = never)
   const float* feat; const __nv_bfloat16* feat_lp; __nv_bfloat16* feat_cvt;   // feat_cvt: kIefRep bf16 replicas of feat
   const float* init; int init_rows; float* psc; __nv_bfloat16* psc_lp;
@@ -193,13 +193,16 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
   auto barrier_narrow = [&]() {          // grid_barrier() among the first narrow_ctas CTAs
     __syncthreads();
     if (tid == 0) {
-      unsigned int* ctr = p.barrier + 32;
+      unsigned int* ctr = p.barrier + 32 * (kBarrierShards - 1) + 16;      // word 240 of the 1 KB slot: not one of grid_barrier_sh's shard counters (base + 32 k)
       const unsigned int target = ++epoch2 * (unsigned int)p.narrow_ctas;
       unsigned int seen;
       asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(ctr) : "memory");
       do {
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(ctr) : "memory");
       } while (seen < target);
+#ifdef TP_BARRIER_ACQUIRE_FENCE
+      asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+#endif
     }
     __syncthreads();
   };
@@ -405,7 +408,7 @@ static int ief_fused(const tp_ief_weights* w, const float* feat, const void* fea
     add(u2_lp, 1024, 1024, n1024, w->wdec, 160, w->bdec, psc, 160, psc, 160, psc_lp, 160, n160);
   }
   p.nlayers = n;
-  if (!barrier) TP_CUDA(cudaMemsetAsync(sc, 0, 256, st));
+  if (!barrier) TP_CUDA(cudaMemsetAsync(sc, 0, 1024, st));
   const int nb = N <= 8 ? 8 : 32;
   const size_t smem = (size_t)nb * (2048 + 32) * 2 + (size_t)8 * nb * 17 * 4;
   if (nb == 8) {

@@ -277,15 +277,14 @@ extern "C" size_t tp_skinny_bf16_workspace_bytes(int M, int N, int splits) {
 
 template <typename KernelT>
 static int launch_pdl(KernelT kfn, dim3 grid, size_t smem, cudaStream_t st, const SkArgs& a) {
-  static const bool no_pdl = getenv("TP_NO_PDL") != nullptr;
   TP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = dim3(kSkThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;      // tp_set_pdl(): the one switch of every PDL launch
+  cfg.attrs = attr; cfg.numAttrs = 1;
   TP_CUDA(cudaLaunchKernelEx(&cfg, kfn, a));
   count_launch();
   return TP_OK;

@@ -1101,7 +1101,7 @@ extern "C" int tp_smpl_forward_ex(const tp_smpl_model* m, int n, const float* po
     cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = kTcSmem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     TP_CUDA(cudaLaunchKernelEx(&cfg, k_smpl_verts_tc, *m, n, (const __nv_bfloat16*)pa.coef_tc, (const float*)pa.A, jreg, nreg, verts,
                                jpart, pl.tc_tiles, pl.tc_gpc));
@@ -1122,7 +1122,7 @@ extern "C" int tp_smpl_forward_ex(const tp_smpl_model* m, int n, const float* po
       cfg.gridDim = dim3((unsigned)n); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = st;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
       cfg.attrs = attr; cfg.numAttrs = 1;
       FoldArgs fa;
       fa.q = use_fold ? reinterpret_cast<const float*>(ws + pl.off_q) : nullptr;

@@ -276,3 +276,45 @@ def test_pipeline_float16_rows_and_output_selection():
     for k in b:
         assert torch.equal(a[k], b[k]), k
         assert torch.equal(direct[k].cpu().reshape(b[k].shape), b[k]), k
+
+
+def test_acquire_fence_build_is_bit_identical():
+    """VERDICT r1 / ADVICE r1: the grid barriers of the persistent kernels poll with relaxed loads and skip the formal acquire fence
+    (every post-barrier read of another CTA's data is an L2-coherent access).  The same sources built with -DTP_BARRIER_ACQUIRE_FENCE
+    (tepose_b200/build.py variant 'fence') must give bit-identical outputs at the headline shape, with and without CUDA graph + PDL."""
+    import hashlib
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fence = os.path.join(root, "tepose_b200", "libtepose_b200_fence.so")
+    if not os.path.isfile(fence):
+        pytest.skip("libtepose_b200_fence.so not built (python -m tepose_b200.build --fence)")
+    prog = (
+        "import sys, hashlib, torch; sys.path.insert(0, %r)\n"
+        "from tepose_b200 import synthetic as s\n"
+        "from tepose_b200.graph import GraphedTePose\n"
+        "import tepose_b200._native as nv\n"
+        "h = hashlib.sha256()\n"
+        "for prec, B, T, L, H in (('bf16', 32, 16, 1, 2048), ('bf16', 5, 6, 2, 256), ('fp32', 4, 8, 1, 128)):\n"
+        "    m, _ = s.build_synthetic_model(3, T, L, H, prec, 'cuda:0')\n"
+        "    x = torch.from_numpy(s.make_input(3, B, T)).cuda()\n"
+        "    with torch.no_grad():\n"
+        "        o = m(x)[-1]\n"
+        "        g = GraphedTePose(m, B, T); g.static_input.copy_(x); og = g.replay()\n"
+        "    torch.cuda.synchronize()\n"
+        "    for k in sorted(o):\n"
+        "        assert torch.equal(o[k], og[k].reshape(o[k].shape)), k\n"
+        "        h.update(o[k].cpu().numpy().tobytes())\n"
+        "print('DIGEST', h.hexdigest(), nv.LIB_PATH)\n") % root
+    digests = []
+    for lib in (None, fence):
+        env = dict(os.environ)
+        env.pop("TEPOSE_B200_LIB", None)
+        if lib:
+            env["TEPOSE_B200_LIB"] = lib
+        r = subprocess.run([sys.executable, "-c", prog], env=env, capture_output=True, text=True, timeout=900, cwd=root)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][-1].split()
+        assert (lib or "libtepose_b200.so") in line[2]
+        digests.append(line[1])
+    assert digests[0] == digests[1], digests
