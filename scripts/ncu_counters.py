@@ -29,7 +29,7 @@ def main():
             v = float(r[i].replace(",", ""))
             u = units[i].lower()
             return v * {"kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "byte": 1.0, "ms": 1e3, "us": 1.0, "ns": 1e-3, "second": 1e6}.get(u, 1.0)
-        name = r[h.index("Kernel Name")].split("(")[0]
+        name = r[h.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0].strip()
         e = {"shape": tag, "csrc_sha": csrc_hash(), "report": os.path.basename(rep),
              "dram_read_bytes": val("dram__bytes_read.sum"), "dram_write_bytes": val("dram__bytes_write.sum"),
              "l2_to_sm_read_bytes": 32.0 * val("lts__t_sectors_srcunit_tex_op_read.sum"),
