@@ -67,6 +67,10 @@ TP_API unsigned long long tp_launch_count(void);
  * predecessor).  On by default; profiling passes that bracket single kernels with events switch it off.  Returns the
  * previous setting. */
 TP_API int tp_set_pdl(int enable);
+/* The iterations of the fused IEF loop (lib/models/spin.py:250-261) as ONE 16-CTA thread-block cluster with the weights
+ * on chip (csrc/ief_cluster.inl), instead of one grid barrier per layer.  On by default where the device can host the
+ * cluster; 0 keeps the iterations inside the grid-barrier kernel (A/B tests).  Returns the previous setting. */
+TP_API int tp_set_ief_cluster(int enable);
 /* host out-params; any may be NULL */
 TP_API int tp_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_per_block_optin);
 

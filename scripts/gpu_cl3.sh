@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+timeout -s KILL 90 python scripts/heads_hang_debug.py > gpurun_out/hang_debug.txt 2>&1
+tail -5 gpurun_out/hang_debug.txt | cut -c1-300
+grep -q completed gpurun_out/hang_debug.txt || exit 1
+timeout -s KILL 120 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "ief_cluster" 2>&1 | tail -3
+timeout -s KILL 400 python -m pytest tests/test_gpu_e2e.py -m gpu -q 2>&1 | tail -6
+scripts/gpu_cl1.sh
+head -12 gpurun_out/cl_trace_b1.txt

@@ -24,7 +24,7 @@ PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16, "fp32_tc": PRECISI
 
 # every symbol include/tepose_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "tp_version", "tp_last_error", "tp_launch_count", "tp_set_pdl", "tp_device_info",
+    "tp_version", "tp_last_error", "tp_launch_count", "tp_set_pdl", "tp_set_ief_cluster", "tp_device_info",
     "tp_rot6d_to_rotmat", "tp_rotmat_to_angle_axis", "tp_batch_rodrigues", "tp_projection",
     "tp_pack_rows", "tp_pack_rows_ex", "tp_pack_rows_f16", "tp_split3_bf16", "tp_unpack_rows_residual", "tp_gemm_f32", "tp_gemm_f32_splitk_workspace_bytes", "tp_gemm_f32_splitk",
     "tp_pack_mma_a_bytes", "tp_pack_mma_a_bf16", "tp_skinny_bf16_workspace_bytes", "tp_skinny_bf16", "tp_skinny_bf16_ex", "tp_gemm_bf16_tc",
@@ -71,6 +71,7 @@ _SIGNATURES = {
     "tp_last_error": (C.c_char_p, []),
     "tp_launch_count": (C.c_ulonglong, []),
     "tp_set_pdl": (C.c_int, [C.c_int]),
+    "tp_set_ief_cluster": (C.c_int, [C.c_int]),
     "tp_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(sz)]),
     "tp_rot6d_to_rotmat": (C.c_int, [vp, vp, i64, vp]),
     "tp_rotmat_to_angle_axis": (C.c_int, [vp, vp, i64, vp]),

@@ -3,6 +3,8 @@
 // stream (graph-capturable); fc1 is evaluated as  x.W1x^T (once)  +  [pose|shape|cam].W1p^T
 // (per iteration) -- algebraically identical to fc1(cat[x, pose, shape, cam]).
 #include "skinny.cuh"
+#include "ief_cluster.inl"
+#include "ief_heads.inl"
 #include <stdlib.h>
 
 namespace tp {
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
   pdl_launch_dependents();
 
   // prologue: IEF state <- init (fp32 + bf16 copy), optional feat conversion
+  if (p.psc)           // (null: the iterations, and their state, belong to k_ief_cluster)
   for (int i = blockIdx.x * kSkThreads + tid; i < p.M * 160; i += gridDim.x * kSkThreads) {
     const float v = p.init_rows == 1 ? p.init[i % 160] : p.init[i];
     p.psc[i] = v;
@@ -345,6 +348,82 @@ __global__ void __launch_bounds__(kSkThreads, 1) k_ief_fused(const IefFusedParam
 
 struct HeadsArgs { const void* w_cat; const float* b_cat; const float* h_cat; int64_t ld_h; int H; };
 
+// The iterations of the IEF loop as one 16-CTA cluster with the weights on chip (ief_cluster.inl).  Needs a GPC with 16 free SMs
+// and 223 KB of shared memory per CTA; TP_IEF_NO_CLUSTER=1 keeps the iterations inside the grid-barrier kernel.
+static int g_ief_cluster = 1;       // tp_set_ief_cluster()
+extern "C" int tp_set_ief_cluster(int enable) { const int was = g_ief_cluster; g_ief_cluster = enable ? 1 : 0; return was; }
+
+static bool ief_cluster_available() {
+  if (!g_ief_cluster) return false;
+  static const int ok = [] {
+    if (getenv("TP_IEF_NO_CLUSTER")) return 0;
+    if (cudaFuncSetAttribute(tp::k_ief_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+        cudaFuncSetAttribute(tp::k_ief_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp::kClSmemBytes) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+    cudaLaunchAttribute at[1];
+    cfg.gridDim = dim3(tp::kClCtas); cfg.blockDim = dim3(tp::kClThreads); cfg.dynamicSmemBytes = tp::kClSmemBytes;
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = tp::kClCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, tp::k_ief_cluster, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n >= 1 ? 1 : 0;
+  }();
+  return ok != 0;
+}
+
+// heads + fc1's feature part as the split-K kernel (ief_heads.inl); the caller has checked ief_cluster_available().
+// scratch: >= 4 MB (two partial-sum areas of kHbPartBytes)
+static int heads_base_launch(const tp_ief_weights* w, const HeadsArgs* hd, const float* feat, const void* feat_bf16, int N,
+                             __nv_bfloat16* feat_rep, float* base, unsigned char* scratch, unsigned int* barrier, int barrier_shards,
+                             cudaStream_t st) {
+  tp::HeadsBaseParams q;
+  memset(&q, 0, sizeof(q));
+  int pitch = 256 + 32;
+  if (hd) {
+    q.hcat = hd->h_cat; q.ld_h = hd->ld_h; q.KH = 3 * hd->H;
+    q.w_cat = reinterpret_cast<const uint4*>(hd->w_cat); q.b_cat = hd->b_cat;
+    if (q.KH / 8 + 32 > pitch) pitch = q.KH / 8 + 32;
+  } else {
+    q.feat = feat; q.feat_lp = reinterpret_cast<const __nv_bfloat16*>(feat_bf16);
+  }
+  q.feat_rep = feat_rep; q.w1x = reinterpret_cast<const uint4*>(w->w1x); q.b1 = w->b1; q.base = base; q.M = N;
+  q.part1 = reinterpret_cast<float*>(scratch); q.part2 = reinterpret_cast<float*>(scratch + tp::kHbPartBytes);
+  q.barrier = barrier; q.barrier_shards = barrier_shards; q.trace = tp::trace_ptr();
+  const size_t smem = tp::kHbOffAs + (size_t)32 * pitch * 2;
+  TP_CUDA(cudaFuncSetAttribute(tp::k_heads_base, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tp::PdlConfig lc(dim3(tp::kHbGrid), dim3(tp::kHbThreads), smem, st, /*cooperative=*/true);   // the CTAs of a group wait for each other
+  TP_CUDA(cudaLaunchKernelEx(&lc.cfg, tp::k_heads_base, q));
+  tp::count_launch();
+  return TP_OK;
+}
+
+static int ief_cluster_launch(const tp_ief_weights* w, const float* base, int N, const float* init, int init_rows, int n_iter,
+                              float* psc, cudaStream_t st) {
+  tp::IefClParams q;
+  memset(&q, 0, sizeof(q));
+  q.base = base; q.w1p = reinterpret_cast<const uint4*>(w->w1p); q.w2 = reinterpret_cast<const uint4*>(w->w2);
+  q.wdec = reinterpret_cast<const uint4*>(w->wdec); q.b2 = w->b2; q.bdec = w->bdec;
+  q.init = init; q.init_rows = init_rows; q.psc = psc; q.M = N; q.n_iter = n_iter;
+  q.trace = tp::trace_ptr();
+  TP_CUDA(cudaFuncSetAttribute(tp::k_ief_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  TP_CUDA(cudaFuncSetAttribute(tp::k_ief_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp::kClSmemBytes));
+  cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+  cudaLaunchAttribute at[2];
+  cfg.gridDim = dim3(tp::kClCtas); cfg.blockDim = dim3(tp::kClThreads); cfg.dynamicSmemBytes = tp::kClSmemBytes; cfg.stream = st;
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = tp::kClCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = tp::pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 2;
+  TP_CUDA(cudaLaunchKernelEx(&cfg, tp::k_ief_cluster, q));
+  tp::count_launch();
+  return TP_OK;
+}
+
 static int ief_fused(const tp_ief_weights* w, const float* feat, const void* feat_bf16, int N, const float* init,
                      int init_rows, int n_iter, float* psc, unsigned char* ws, cudaStream_t st, const HeadsArgs* hd = nullptr,
                      void* barrier = nullptr) {
@@ -368,7 +447,8 @@ static int ief_fused(const tp_ief_weights* w, const float* feat, const void* fea
   static const int shards_env = getenv("TP_BARRIER_SHARDS") ? atoi(getenv("TP_BARRIER_SHARDS")) : 1;
   p.barrier_shards = barrier ? (shards_env >= 1 && shards_env <= tp::kBarrierShards ? shards_env : 1) : 1;
   p.feat = feat; p.feat_lp = reinterpret_cast<const __nv_bfloat16*>(feat_bf16); p.feat_cvt = feat_rep;
-  p.init = init; p.init_rows = init_rows; p.psc = psc; p.psc_lp = psc_lp;
+  const bool cluster_tail = n_iter <= tp::kClMaxIter && ief_cluster_available();
+  p.init = init; p.init_rows = init_rows; p.psc = cluster_tail ? nullptr : psc; p.psc_lp = psc_lp;
   p.trace = tp::trace_ptr();
   static const bool no_direct = getenv("TP_IEF_NO_DIRECT") != nullptr;
   static const int direct_env = getenv("TP_IEF_DIRECT_KB") ? atoi(getenv("TP_IEF_DIRECT_KB")) : 32;
@@ -402,13 +482,19 @@ static int ief_fused(const tp_ief_weights* w, const float* feat, const void* fea
     if (no_narrow) p.narrow_ctas = 128;
   }
   add(feat_rep, 2048, 2048, n2048, w->w1x, 1024, w->b1, nullptr, 0, base, 1024, nullptr, 0, 0);
-  for (int it = 0; it < n_iter; ++it) {
+  for (int it = 0; it < (cluster_tail ? 0 : n_iter); ++it) {
     add(psc_lp, 160, 160, n160, w->w1p, 1024, nullptr, base, 1024, nullptr, 0, u1_lp, 1024, n1024);
     add(u1_lp, 1024, 1024, n1024, w->w2, 1024, w->b2, nullptr, 0, nullptr, 0, u2_lp, 1024, n1024);
     add(u2_lp, 1024, 1024, n1024, w->wdec, 160, w->bdec, psc, 160, psc, 160, psc_lp, 160, n160);
   }
   p.nlayers = n;
   if (!barrier) TP_CUDA(cudaMemsetAsync(sc, 0, 1024, st));
+  static const bool no_splitk = getenv("TP_IEF_NO_SPLITK") != nullptr;
+  if (cluster_tail && !no_splitk && tp::sm_count() >= tp::kHbGrid && (!hd || ((3 * hd->H) % 1024 == 0 && 3 * hd->H <= 8192))) {
+    // (scratch: the replica buffers end below 4 MB -- see the check in tp_heads_ief_forward -- the partial sums take [4 MB, 8 MB))
+    TP_TRY(heads_base_launch(w, hd, feat, feat_bf16, N, feat_rep, base, sc + ((size_t)4 << 20), p.barrier, p.barrier_shards, st));
+    return ief_cluster_launch(w, base, N, init, init_rows, n_iter, psc, st);
+  }
   const int nb = N <= 8 ? 8 : 32;
   const size_t smem = (size_t)nb * (2048 + 32) * 2 + (size_t)8 * nb * 17 * 4;
   if (nb == 8) {
@@ -421,6 +507,7 @@ static int ief_fused(const tp_ief_weights* w, const float* feat, const void* fea
     TP_CUDA(cudaLaunchKernelEx(&lc.cfg, tp::k_ief_fused<4>, p));
   }
   tp::count_launch();
+  if (cluster_tail) return ief_cluster_launch(w, base, N, init, init_rows, n_iter, psc, st);
   return TP_OK;
 }
 
@@ -486,7 +573,7 @@ extern "C" int tp_heads_ief_forward(const void* w_cat, const float* b_cat, const
   TP_CHECK_ARG(w->w1x && w->b1 && w->w1p && w->w2 && w->b2 && w->wdec && w->bdec, "tp_heads_ief_forward: null weight");
   TP_CHECK_ARG(workspace && workspace_bytes >= tp_ief_workspace_bytes(n_rows), "tp_heads_ief_forward: workspace too small");
   TP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "tp_heads_ief_forward: workspace must be 256-byte aligned");
-  TP_CHECK_ARG((size_t)4096 + (size_t)n_rows * (2 * 1024 + 160 + 2048 + 3 * (size_t)H) * 2 <= kSplitScratch, "tp_heads_ief_forward: H too large for the scratch region");
+  TP_CHECK_ARG((size_t)4096 + (size_t)n_rows * (2 * 1024 + 160 + 2048 + 3 * (size_t)H) * 2 <= ((size_t)4 << 20), "tp_heads_ief_forward: H too large for the scratch region");
   if (sm_count() < 128) return fail(TP_ERR_UNSUPPORTED, "tp_heads_ief_forward needs 128 co-resident CTAs");
   HeadsArgs hd{w_cat, b_cat, h_cat, ld_h, H};
   return ief_fused(w, nullptr, nullptr, n_rows, init, init_rows, n_iter, psc, reinterpret_cast<unsigned char*>(workspace),

@@ -532,3 +532,65 @@ def test_gru_recurrence_umma(B, steps, H):
             assert float((d["hf"][:, H:].cpu().double() - hT).abs().max()) < 2e-4
             assert float(d["hf"][:, :H].abs().max()) == 0.0
             assert float((d["ylp"].float().cpu().double() - ys).abs().max()) < 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,n_iter,per_row_init", [(32, 3, False), (1, 3, False), (5, 1, True), (32, 4, True), (17, 0, False), (8, 3, True)])
+def test_ief_cluster_kernel(N, n_iter, per_row_init):
+    """k_ief_cluster (the IEF iterations of lib/models/spin.py:250-261 on one 16-CTA cluster, weights on chip) against
+    (a) the same iterations inside the grid-barrier kernel (same bf16 operands, another summation order) and
+    (b) a float64 evaluation of the loop whose inter-layer activations are rounded to bf16 like the kernels' are.  The decoder
+    weights are made large so that the state really moves between iterations."""
+    from tepose_b200 import _native as nv
+    from tepose_b200.spin import PSC
+    from tepose_b200.synthetic import build_synthetic_model
+    model, _ = build_synthetic_model(77, 4, 1, 128, "bf16", DEV)
+    reg = model.regressor
+    g = torch.Generator().manual_seed(N * 10 + n_iter)
+    with torch.no_grad():
+        for lin, s in ((reg.decpose, 0.02), (reg.decshape, 0.02), (reg.deccam, 0.02)):
+            lin.weight.copy_((torch.randn(lin.weight.shape, generator=g) * s).to(DEV))
+            lin.bias.copy_((torch.randn(lin.bias.shape, generator=g) * 0.1).to(DEV))
+        reg.fc2.bias.copy_((torch.randn(1024, generator=g) * 0.1).to(DEV))
+    pk = reg.packed()
+    feat = (torch.randn(N, 2048, generator=g)).to(DEV)
+    init = pk["init"]
+    if per_row_init:
+        init = (pk["init"].cpu() + 0.2 * torch.randn(N, PSC, generator=g)).to(DEV).contiguous()
+        init[:, 157:] = 0
+    L = nv.lib()
+
+    def run(cluster):
+        was = L.tp_set_ief_cluster(1 if cluster else 0)
+        try:
+            psc = torch.full((N, PSC), float("nan"), device=DEV)
+            ws = nv.workspace(L.tp_ief_workspace_bytes(N), torch.device(DEV))
+            nv.check(L.tp_ief_forward(nv.PRECISIONS["bf16"], pk["c"], nv.ptr(feat), None, N, nv.ptr(init), init.shape[0], n_iter, nv.ptr(psc),
+                                      nv.ptr(ws), ws.numel(), nv.stream()), "tp_ief_forward")
+            torch.cuda.synchronize()
+            return psc.cpu()
+        finally:
+            L.tp_set_ief_cluster(was)
+
+    got, grid = run(True), run(False)
+    bf = lambda t: t.to(torch.bfloat16).double()
+    W1 = bf(reg.fc1.weight.detach().cpu()); W2 = bf(reg.fc2.weight.detach().cpu())
+    Wd = bf(torch.cat([reg.decpose.weight, reg.decshape.weight, reg.deccam.weight]).detach().cpu())
+    bd = torch.cat([reg.decpose.bias, reg.decshape.bias, reg.deccam.bias]).detach().cpu().double()
+    st = init.cpu().double().expand(N, PSC)[:, :157].clone()
+    base = bf(feat.cpu()) @ W1[:, :2048].T + reg.fc1.bias.detach().cpu().double()
+    for _ in range(n_iter):
+        u1 = bf((base + bf(st.float()) @ W1[:, 2048:].T).float())
+        u2 = bf((u1 @ W2.T + reg.fc2.bias.detach().cpu().double()).float())
+        st = st + u2 @ Wd.T + bd
+    assert torch.isfinite(got).all()
+    err_ref = float((got[:, :157].double() - st).abs().max())
+    err_grid = float((got[:, :157] - grid[:, :157]).abs().max())
+    moved = float((st - init.cpu().double().expand(N, PSC)[:, :157]).abs().max())
+    if n_iter:
+        assert moved > 0.05, moved                      # the test would be vacuous otherwise
+    # a bf16 rounding of u1 / u2 / the state may flip on a last-bit difference of the fp32 sums: 2^-9 relative on values ~1, times |Wd| row sums
+    assert err_ref < 5e-3, (err_ref, err_grid)
+    assert err_grid < 5e-3, (err_ref, err_grid)
+    if n_iter == 0:
+        assert torch.equal(got[:, :157], init.cpu().expand(N, PSC)[:, :157])
