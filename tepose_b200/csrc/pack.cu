@@ -20,11 +20,26 @@ __global__ void k_pack_rows(const InT* __restrict__ src, int64_t stride_b, int64
   const InT* s = src + (int64_t)b * stride_b + (int64_t)t * stride_t;
   OutT* d = dst + (int64_t)row * kp;
   if constexpr (sizeof(OutT) == 2) {
-    // two columns per thread: one 4-byte store instead of two 2-byte stores (kp is even)
-    for (int c = 2 * threadIdx.x; c < kp; c += 2 * blockDim.x) {
-      float v0 = (c < k) ? in_f32(s[c]) : 0.0f, v1 = (c + 1 < k) ? in_f32(s[c + 1]) : 0.0f;
-      if (relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
-      *reinterpret_cast<__nv_bfloat162*>(d + c) = __floats2bfloat162_rn(v0, v1);
+    // two columns per thread and store (kp is even); the loads of five column pairs are issued before the first store, so a
+    // 2176-wide row is ONE memory round trip per thread instead of five dependent ones
+    constexpr int U = 5;
+    for (int c0 = 2 * threadIdx.x; c0 < kp; c0 += U * 2 * blockDim.x) {
+      float v0[U], v1[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int c = c0 + u * 2 * blockDim.x;
+        v0[u] = (c < k) ? in_f32(s[c]) : 0.0f;
+        v1[u] = (c + 1 < k) ? in_f32(s[c + 1]) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int c = c0 + u * 2 * blockDim.x;
+        if (c < kp) {
+          float a = v0[u], b = v1[u];
+          if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+          *reinterpret_cast<__nv_bfloat162*>(d + c) = __floats2bfloat162_rn(a, b);
+        }
+      }
     }
   } else {
     for (int c = threadIdx.x; c < kp; c += blockDim.x) {

@@ -174,7 +174,8 @@ def test_unpack_rows_residual():
 
 
 @pytest.mark.parametrize("rows,wrows,kp", [(8, 192, 128), (512, 768, 2176), (130, 384, 64), (32, 96, 192),
-                                            (512, 9216, 256), (768, 9216, 128), (300, 9216, 64)])   # > 1 wave: 192-wide, 256-row tiles
+                                            (512, 9216, 256), (768, 9216, 128), (300, 9216, 64),    # > 1 wave: 192-wide tiles, CTA pairs sharing W / A / nothing
+                                            (544, 18432, 2176), (512, 1152, 192)])
 def test_gemm_bf16_tcgen05(rows, wrows, kp):
     g = torch.Generator().manual_seed(rows + wrows)
     A = torch.randn(rows, kp, generator=g).to(torch.bfloat16)
