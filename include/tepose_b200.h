@@ -151,13 +151,21 @@ TP_API int tp_skinny_bf16_ex(const float* A, int64_t lda, const void* A_bf16, in
                       int splits, int mode, void* workspace, size_t workspace_bytes, void* stream);
 
 /* One segment of a tensor-core GEMM launch: rows [m_start, m_start+m_rows) of A against rows
- * [n_start, n_start+n_cols) of W;  out[(m-m_start)*ldc + (n-n_start)] = dot + bias[n-n_start]. */
+ * [n_start, n_start+n_cols) of W;  out[(m-m_start)*ldc + (n-n_start)] = dot + bias[n-n_start].
+ * Epilogue options (flags; 0 = the plain fp32 output above): TP_GEMM_RELU clamps at zero, TP_GEMM_OUT_BF16 makes `out` a bf16
+ * matrix (ldc in elements, ldc % 8 == 0), and a non-NULL `residual` (bf16 [m_rows, ldr], ldr % 8 == 0) is added before the clamp
+ * -- the conv + folded BatchNorm (+ shortcut) + ReLU of a ResNet bottleneck (lib/models/spin.py:35-54) as one GEMM.          */
+#define TP_GEMM_RELU 1
+#define TP_GEMM_OUT_BF16 2
 typedef struct tp_gemm_seg {
   int32_t m_start, m_rows;
   int32_t n_start, n_cols; /* n_cols % 16 == 0 */
   float* out;
   int64_t ldc;
   const float* bias; /* [n_cols] or NULL */
+  int32_t flags;
+  int32_t ldr;
+  const void* residual;
 } tp_gemm_seg;
 
 /* tcgen05 / TMEM GEMM fed by TMA (GRU input projection over all timesteps, K1):
@@ -165,6 +173,21 @@ typedef struct tp_gemm_seg {
  * `segs` is a HOST array (nseg <= 8).  Requires an sm_100 device.                        */
 TP_API int tp_gemm_bf16_tc(const void* A, int a_rows, const void* W, int w_rows, int kp,
                     const tp_gemm_seg* segs, int nseg, void* stream);
+
+/* ------------------------------------------------------------------ HMR ResNet-50 feature extractor
+ * Data movement around tp_gemm_bf16_tc for lib/models/spin.py:59-141 (feature_extractor; caller demo.py:183-198).
+ * Activations are NHWC bf16; a convolution is  im2col rows x [Cout, kh*kw*Cin (padded to KP)]  with BatchNorm folded into
+ * the weights / bias (eval mode) and ReLU / shortcut in the GEMM epilogue (TP_GEMM_RELU, TP_GEMM_OUT_BF16, residual).     */
+/* x [N,C,H,W] fp32 -> y [N,H,W,CP] bf16, channels C..CP-1 zero */
+TP_API int tp_nchw_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, int CP, void* stream);
+/* in [N,H,W,C] bf16 -> out [N*Ho*Wo, KP] bf16, column (ky*kw + kx)*C + c, zero outside the image and beyond kh*kw*C;
+ * Ho = (H + 2 pad - kh) / stride + 1 (nn.Conv2d); C % 4 == 0, KP % 8 == 0 */
+TP_API int tp_im2col_nhwc_bf16(const void* in, void* out, int N, int H, int W, int C, int kh, int kw, int stride, int pad,
+                        int KP, void* stream);
+/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NHWC bf16 (lib/models/spin.py:70); C % 8 == 0 */
+TP_API int tp_maxpool3x3s2_nhwc_bf16(const void* in, void* out, int N, int H, int W, int C, void* stream);
+/* mean over the HW positions of [N, HW, C] bf16 -> [N, C] fp32 (nn.AvgPool2d(7) on the 7x7 map + view, spin.py:75,139-140) */
+TP_API int tp_avgpool_nhwc_bf16(const void* in, float* out, int N, int HW, int C, void* stream);
 
 /* ------------------------------------------------------------------ GRU recurrence (K2)
  * One direction of one torch.nn.GRU layer (lib/models/tepose.py:53-64,73,76) given the

@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("TEPOSE_B200_LIB") or os.path.join(_HERE, "libtepose_b
 PRECISION_FP32, PRECISION_BF16, PRECISION_BF16X3 = 0, 1, 2
 POSE_ROTMAT, POSE_AXIS_ANGLE, POSE_ROT6D = 0, 1, 2
 RODRIGUES_SMPLX, RODRIGUES_QUAT = 0, 1
+GEMM_RELU, GEMM_OUT_BF16 = 1, 2            # tp_gemm_seg.flags
 # "fp32_tc": fp32-grade results with the two big contractions (K1 input projection, K2 recurrence) on tensor cores as 3-term bf16
 # splits (TP_PRECISION_BF16X3); every other stage runs exactly as in "fp32", which is the code the C ABI sees for them
 PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16, "fp32_tc": PRECISION_FP32}
@@ -35,6 +36,7 @@ EXPORTS = [
     "tp_transpose_f32", "tp_colsum_f32", "tp_mask_scale", "tp_relu_backward", "tp_axpby_f32", "tp_gru_cell_backward",
     "tp_rot6d_backward", "tp_rotmat_to_angle_axis_backward", "tp_smpl_backward_workspace_bytes", "tp_smpl_backward",
     "tp_tepose_loss_workspace_bytes", "tp_tepose_loss",
+    "tp_nchw_to_nhwc_bf16", "tp_im2col_nhwc_bf16", "tp_maxpool3x3s2_nhwc_bf16", "tp_avgpool_nhwc_bf16",
 ]
 
 vp, i32, i64, f32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -42,7 +44,7 @@ vp, i32, i64, f32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
 class GemmSeg(C.Structure):
     _fields_ = [("m_start", i32), ("m_rows", i32), ("n_start", i32), ("n_cols", i32),
-                ("out", vp), ("ldc", i64), ("bias", vp)]
+                ("out", vp), ("ldc", i64), ("bias", vp), ("flags", i32), ("ldr", i32), ("residual", vp)]
 
 
 class GruJob(C.Structure):
@@ -72,6 +74,10 @@ _SIGNATURES = {
     "tp_launch_count": (C.c_ulonglong, []),
     "tp_set_pdl": (C.c_int, [C.c_int]),
     "tp_set_ief_cluster": (C.c_int, [C.c_int]),
+    "tp_nchw_to_nhwc_bf16": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "tp_im2col_nhwc_bf16": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "tp_maxpool3x3s2_nhwc_bf16": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "tp_avgpool_nhwc_bf16": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "tp_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(sz)]),
     "tp_rot6d_to_rotmat": (C.c_int, [vp, vp, i64, vp]),
     "tp_rotmat_to_angle_axis": (C.c_int, [vp, vp, i64, vp]),

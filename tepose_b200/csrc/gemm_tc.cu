@@ -153,8 +153,11 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const int row = t.m0 + lg * 32 + lane;             // segment-local output row of this thread (= its TMEM lane)
       const bool row_ok = row < t.sg.m_rows;
+      const bool relu = (t.sg.flags & TP_GEMM_RELU) != 0, out_lp = (t.sg.flags & TP_GEMM_OUT_BF16) != 0;
       const bool vec_ok = ((t.sg.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(t.sg.out) & 15) == 0);
       float* orow = t.sg.out + (int64_t)row * t.sg.ldc + t.n0;
+      __nv_bfloat16* orow_lp = reinterpret_cast<__nv_bfloat16*>(t.sg.out) + (int64_t)row * t.sg.ldc + t.n0;
+      const __nv_bfloat16* rrow = t.sg.residual ? reinterpret_cast<const __nv_bfloat16*>(t.sg.residual) + (int64_t)row * t.sg.ldr + t.n0 : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -162,18 +165,42 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
         if (row_ok) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 bb = *reinterpret_cast<const float4*>(&s_bias[acc][c0 + q * 4]);
-            float4 o;
-            o.x = __uint_as_float(v[q * 4 + 0]) + bb.x; o.y = __uint_as_float(v[q * 4 + 1]) + bb.y;
-            o.z = __uint_as_float(v[q * 4 + 2]) + bb.z; o.w = __uint_as_float(v[q * 4 + 3]) + bb.w;
-            const int n = t.n0 + c0 + q * 4;
-            if (n + 3 < t.sg.n_cols && vec_ok) {
-              *reinterpret_cast<float4*>(orow + c0 + q * 4) = o;      // a thread writes 128 contiguous bytes of its row per chunk
+          for (int q = 0; q < 4; ++q) {                   // 8 columns at a time
+            const int n = t.n0 + c0 + q * 8;
+            if (n >= t.sg.n_cols) break;
+            float o[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) o[u] = __uint_as_float(v[q * 8 + u]) + s_bias[acc][c0 + q * 8 + u];
+            const bool full = n + 7 < t.sg.n_cols;
+            if (rrow && full) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + q * 8);
+              const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) { const float2 f = __bfloat1622float2(rh[u]); o[2 * u] += f.x; o[2 * u + 1] += f.y; }
+            } else if (rrow) {
+              for (int u = 0; u < 8; ++u)
+                if (n + u < t.sg.n_cols) o[u] += __bfloat162float(rrow[c0 + q * 8 + u]);
+            }
+            if (relu) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) o[u] = fmaxf(o[u], 0.0f);
+            }
+            if (out_lp) {
+              if (full) {
+                __nv_bfloat162 h[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(o[2 * u], o[2 * u + 1]);
+                *reinterpret_cast<uint4*>(orow_lp + c0 + q * 8) = *reinterpret_cast<const uint4*>(h);
+              } else {
+                for (int u = 0; u < 8; ++u)
+                  if (n + u < t.sg.n_cols) orow_lp[c0 + q * 8 + u] = __float2bfloat16_rn(o[u]);
+              }
+            } else if (full && vec_ok) {
+              *reinterpret_cast<float4*>(orow + c0 + q * 8) = make_float4(o[0], o[1], o[2], o[3]);      // a thread writes 128 contiguous bytes of its row per chunk
+              *reinterpret_cast<float4*>(orow + c0 + q * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
             } else {
-              const float e[4] = {o.x, o.y, o.z, o.w};
-              for (int u = 0; u < 4; ++u)
-                if (n + u < t.sg.n_cols) orow[c0 + q * 4 + u] = e[u];
+              for (int u = 0; u < 8; ++u)
+                if (n + u < t.sg.n_cols) orow[c0 + q * 8 + u] = o[u];
             }
           }
         }
@@ -252,6 +279,8 @@ extern "C" int tp_gemm_bf16_tc(const void* A, int a_rows, const void* W, int w_r
     TP_CHECK_ARG(sg.out && sg.m_rows > 0 && sg.n_cols > 0, "tp_gemm_bf16_tc: segment %d is empty / has no output", i);
     TP_CHECK_ARG(sg.m_start >= 0 && sg.m_start + sg.m_rows <= a_rows, "tp_gemm_bf16_tc: segment %d rows out of range", i);
     TP_CHECK_ARG(sg.n_start >= 0 && sg.n_start + sg.n_cols <= w_rows, "tp_gemm_bf16_tc: segment %d cols out of range", i);
+    TP_CHECK_ARG(!(sg.flags & TP_GEMM_OUT_BF16) || (sg.ldc % 8 == 0 && aligned16(sg.out)), "tp_gemm_bf16_tc: segment %d: bf16 output needs ldc %% 8 == 0 and 16-byte alignment", i);
+    TP_CHECK_ARG(!sg.residual || (sg.ldr % 8 == 0 && aligned16(sg.residual)), "tp_gemm_bf16_tc: segment %d: residual needs ldr %% 8 == 0 and 16-byte alignment", i);
     p.seg[i] = sg;
     p.tile_begin[i] = tiles;
     tiles += (int)(ceil_div(sg.m_rows, TC_BM) * ceil_div(sg.n_cols, bn));

@@ -308,3 +308,65 @@ def build_synthetic_vibe(seed: int, seqlen: int, n_layers: int, hidden: int, add
         own[k] = torch.as_tensor(v)
     model.load_state_dict(own, strict=True)
     return model.eval().to(device), sd
+
+
+def make_hmr_state(shapes: dict, seed: int) -> dict:
+    """Deterministic synthetic parameters / BatchNorm statistics for an HMR-shaped model (lib/models/spin.py:59-204): `shapes` maps
+    state_dict keys to shapes (smpl.* and init_* keys are skipped -- they come from the synthetic base data).  The same function
+    fills the unmodified reference model (oracle/make_golden_hmr.py) and tepose_b200.HMR, so the ~25 M weights never have to be stored."""
+    out = {}
+    for idx, k in enumerate(sorted(shapes)):
+        if k.startswith("smpl.") or k.startswith("init_"):
+            continue
+        shp = tuple(shapes[k])
+        rs = np.random.RandomState((seed * 1000003 + idx * 7919) % (2 ** 31 - 1))
+        if k.endswith("num_batches_tracked"):
+            out[k] = np.zeros(shp, np.int64)
+        elif len(shp) == 4:                                   # conv weight: He init, as the reference's constructor draws it
+            n = shp[2] * shp[3] * shp[0]
+            out[k] = (rs.standard_normal(shp) * np.sqrt(2.0 / n)).astype(np.float32)
+        elif len(shp) == 2:                                   # nn.Linear weight
+            gain = 0.01 if k.startswith("dec") else 1.0
+            out[k] = ((rs.random_sample(shp) * 2 - 1) * gain / np.sqrt(shp[1])).astype(np.float32)
+        elif k.endswith("running_var"):
+            out[k] = (0.6 + 0.8 * rs.random_sample(shp)).astype(np.float32)
+        elif k.endswith("running_mean"):
+            out[k] = (0.05 * rs.standard_normal(shp)).astype(np.float32)
+        elif k.split(".")[-2].startswith("bn") or k.split(".")[-2] == "1":     # BatchNorm affine (bnX.* / downsample.1.*)
+            out[k] = ((0.6 + 0.4 * rs.random_sample(shp)) if k.endswith("weight") else 0.05 * rs.standard_normal(shp)).astype(np.float32)
+        else:                                                 # nn.Linear bias
+            out[k] = (0.02 * rs.standard_normal(shp)).astype(np.float32)
+    return out
+
+
+def make_image_batch(seed: int, n: int, size: int = 224) -> np.ndarray:
+    """[n,3,size,size] fp32 crops, normalised-image-like (zero mean, unit scale, smooth + noise)."""
+    rs = np.random.RandomState(seed + 4242)
+    yy, xx = np.meshgrid(np.linspace(-1, 1, size), np.linspace(-1, 1, size), indexing="ij")
+    imgs = []
+    for i in range(n):
+        a, b, c = rs.standard_normal(3)
+        base = np.stack([np.sin(3 * a * xx + b) * np.cos(2 * c * yy), xx * a - yy * b, np.cos(4 * (xx * yy) + c)], 0)
+        imgs.append(base + 0.5 * rs.standard_normal((3, size, size)))
+    return np.stack(imgs).astype(np.float32)
+
+
+def build_synthetic_hmr(seed: int, device="cpu"):
+    """tepose_b200.HMR (ResNet-50 + regressor) with make_hmr_state(seed) loaded, on `device`, in eval mode."""
+    import tempfile
+    import torch
+    from .hmr import hmr
+    old = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        write_base_data(os.path.join(tmp, "data", "base_data"), seed)      # asset paths are cwd-relative
+        os.chdir(tmp)
+        try:
+            model = hmr(pretrained=False)
+        finally:
+            os.chdir(old)
+    own = model.state_dict()
+    sd = make_hmr_state({k: v.shape for k, v in own.items()}, seed)
+    for k, v in sd.items():
+        own[k] = torch.as_tensor(v)
+    model.load_state_dict(own, strict=True)
+    return model.to(device).eval()

@@ -48,7 +48,7 @@ def test_sass_contains_blackwell_tensor_path():
 
 def test_struct_sizes_match_c_layout():
     # natural alignment, no packing pragmas in the header
-    assert ctypes.sizeof(nv.GemmSeg) == 40
+    assert ctypes.sizeof(nv.GemmSeg) == 56          # + flags, ldr, residual (epilogue options)
     assert ctypes.sizeof(nv.GruJob) == 108 + 4 + 16
     assert ctypes.sizeof(nv.IefWeights) == 56
     assert ctypes.sizeof(nv.SmplModel) == 104
