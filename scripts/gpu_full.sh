@@ -1,15 +1,12 @@
 #!/bin/bash
-# full GPU regression: parity suites + default bench line (+ the same without the tcgen05 recurrence, for the A/B)
-mkdir -p gpurun_out
-bash scripts/gpu_check.sh 2>&1 | tail -8
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "bench exit=$?"
-python - <<'PY'
+cd "$(dirname "$0")/.."
+timeout -s KILL 90 python scripts/heads_hang_debug.py > gpurun_out/hang_debug.txt 2>&1
+grep -q completed gpurun_out/hang_debug.txt || { tail -5 gpurun_out/hang_debug.txt | cut -c1-300; exit 1; }
+timeout -s KILL 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+timeout -s KILL 400 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -c 300 gpurun_out/bench_full.err
+python - <<'P'
 import json
 d = json.loads(open("gpurun_out/bench_full.json").read().strip().splitlines()[-1])
-print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"])
-print("stages", d.get("stages_ms"))
-print("live", d.get("live"))
-print("released", d.get("released_config"))
-print("folded", d.get("folded", {}).get("ms_per_step"))
-print("smpl", d.get("smpl_standalone"))
-PY
+print(d["ms_per_step"], d["value"], d["e2e"]["value"], d["stages_ms"])
+print(d["live"]["p50_ms"], d["live"]["windowed"]["p50_ms"], d["released_config"]["ms_per_step"], d["folded"]["ms_per_step"], d["fp32"]["fp32_tc"]["ms_per_step"])
+P

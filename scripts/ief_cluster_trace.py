@@ -43,7 +43,7 @@ for cta in (0, 7, 64, 127):
     row = [f"{hn[i]} +{hb[cta, i] - hb[cta, i - 1]:.0f}" for i in range(1, 8)]
     print(f"k_heads_base cta {cta}: total {hb[cta, 7] - hb[cta, 0]:.0f} | " + " | ".join(row))
 cl = tr[16384:16384 + 16 * 64].reshape(16, 64).astype(np.float64)
-names = {1: "S wait done", 2: "fc1p + push", 3: "fc2 2 slices", 4: "fc2 done", 5: "dec pushed", 6: "P wait done", 7: "owner done"}
+names = {1: "S wait done", 2: "fc1p + push", 3: "fc2 first 4 slices in", 4: "fc2 done", 5: "dec pushed", 6: "P wait done", 7: "owner done"}
 for c in (0, 9, 15):
     print(f"k_ief_cluster cta {c}: total {cl[c,63]-cl[c,0]:.0f} cycles")
     for it in range(3):

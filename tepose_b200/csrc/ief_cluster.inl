@@ -9,7 +9,7 @@
 //
 //   CTA c owns output rows [64c, 64c+64) of fc1 and fc2 (4 weight tiles of 16 rows) and the K slice [64c, 64c+64) of dec.
 //   fc1p : warp = (tile, half of the batch), W1p fragments in registers, B operand = bf16 state PS [32,160] (every CTA has a copy);
-//          the CTA's [32,64] slice of u1 goes to all 16 CTAs as ONE bulk copy each (two per warp, nearest rank first), and each
+//          the CTA's [32,64] slice of u1 goes to all 16 CTAs as 16-byte st.async stores (nearest rank first), and each
 //          slice completes ITS OWN barrier U[s] in the receiver, so
 //   fc2  : (warp = tile x parity of the arrival order) starts on a slice as soon as it has landed: the all-gather of u1 (64 KB into
 //          every SM at the 16 B/clk of distributed shared memory = 4K cycles) runs under the MMAs instead of before them.
@@ -18,7 +18,7 @@
 //   dec  : split-K over the cluster -- CTA c multiplies ITS u2 slice with Wdec[:, 64c:64c+64] (20 KB) and sends the fp32 partial sums
 //          of output tile j (16 columns) to CTA j (st.async, 2 KB per (source, tile), completing barrier P of the owner).
 //   owner: CTAs 0..9 add the 16 partials to the fp32 state they keep in registers, and broadcast the bf16 copy of their 16 columns
-//          (1 KB bulk copy per peer, barrier S); the last iteration writes the fp32 state to global memory instead.
+//          (1 KB of st.async stores per peer, barrier S); the last iteration writes the fp32 state to global memory instead.
 //
 // Batches below 25 rows move and multiply only the 8-row groups in use.  The barriers are re-armed per iteration (phase = it & 1).
 // Ordering argument for buffer re-use: a CTA sends its u1 slice of iteration i+1 only after S(i) completed, i.e. after every
@@ -38,7 +38,7 @@ constexpr uint32_t kClOffU1 = kClOffWd + 10 * 2048;        // u1: [16 slices][32
 constexpr uint32_t kClPsTile = 1088;                       // state tile [32 rows][16 cols] bf16 = 1 KB, +64 B so that tiles 2k, 2k+1 sit in different banks
 constexpr uint32_t kClOffPs = kClOffU1 + 65536;            // 10 state tiles
 constexpr uint32_t kClOffPart = kClOffPs + 10 * kClPsTile; // owner's inbox: [16 sources][4 n][32 lanes][4] fp32
-constexpr uint32_t kClOffStage = kClOffPart + 16 * 2048;   // this CTA's u1 slice, source of the 16 bulk copies (never aliased: the copies read it asynchronously)
+constexpr uint32_t kClOffStage = kClOffPart + 16 * 2048;   // this CTA's u1 slice: transposes the MMA fragments into the 16-byte chunks that are sent
 constexpr uint32_t kClOffBar = kClOffStage + 4096;         // mbarriers: weights, U[16 slices], P, S
 constexpr uint32_t kClSmemBytes = kClOffBar + 8 * 19;
 static_assert(kClSmemBytes <= 232448, "k_ief_cluster: shared memory");
@@ -53,6 +53,9 @@ struct IefClParams {
   const float* init; int init_rows;
   float* psc;               // [M,160] out
   int M, n_iter;
+  int rows_per_cluster;     // the batch is cut into independent clusters of this many rows (a multiple of 8, <= 32): the hand-offs between
+                            // the layers are bound by distributed-shared-memory bandwidth (2 KB per row and CTA), so fewer rows per cluster
+                            // is faster as long as SMs are free -- 4 clusters of 8 rows at B = 32
   long long* trace;
 };
 
@@ -78,6 +81,10 @@ __device__ __forceinline__ void cl_st_async_f4(uint32_t dst_cluster, const float
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];\n" ::
                    "r"(dst_cluster), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "r"(bar_cluster) : "memory");
 }
+__device__ __forceinline__ void cl_st_async_u4(uint32_t dst_cluster, const uint4& v, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::
+                   "r"(dst_cluster), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar_cluster) : "memory");
+}
 __device__ __forceinline__ void cl_wait(uint32_t bar_cta, uint32_t parity) {
   uint32_t done = 0;
   do {
@@ -90,10 +97,20 @@ __device__ __forceinline__ uint4 lds16(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
-#define CL_TRACE(slot) do { if (p.trace && tid == 0) p.trace[16384 + (size_t)c * 64 + (slot)] = clock64(); } while (0)
+#define CL_TRACE(slot) do { if (trace && tid == 0) trace[16384 + (size_t)c * 64 + (slot)] = clock64(); } while (0)
 
-__global__ void __launch_bounds__(kClThreads, 1) k_ief_cluster(const IefClParams p) {
+__global__ void __launch_bounds__(kClThreads, 1) k_ief_cluster(const IefClParams pp) {
   extern __shared__ __align__(128) unsigned char cl_smem[];
+  // this cluster's rows of the batch
+  IefClParams p = pp;
+  {
+    const int row0 = (int)(blockIdx.x / kClCtas) * pp.rows_per_cluster;
+    p.M = min(pp.rows_per_cluster, pp.M - row0);
+    p.base += (size_t)row0 * 1024;
+    p.psc += (size_t)row0 * 160;
+    if (pp.init_rows != 1) p.init += (size_t)row0 * 160;
+  }
+  long long* const trace = blockIdx.x < kClCtas ? pp.trace : nullptr;      // (stamps of the first cluster only)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int tile = warp & 3, hh = warp >> 2;      // hh: half of the batch (fc1p) / K half (fc2)
   const uint32_t c = cl_rank();
@@ -210,48 +227,59 @@ __global__ void __launch_bounds__(kClThreads, 1) k_ief_cluster(const IefClParams
           const int b = (2 * hh + nn) * 8 + 2 * t + (j & 1), u = tile * 16 + g + 8 * (j >> 1);
           *reinterpret_cast<__nv_bfloat16*>(mine + slice_off(b, u)) = __float2bfloat16_rn(a1[nn][j]);
         }
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       __syncthreads();
-      if (lane < 2) {                            // 16 copies (this CTA's own u1 included), two per warp, nearest rank first
-        const uint32_t peer = (c + 2 * warp + lane) & 15;
-        cl_bulk_to_peer(cl_map(sm + kClOffU1 + c * 4096, peer), sm + kClOffStage, ntc * 1024, cl_map(bar_u(c), peer));
+      // the slice leaves as 16-byte st.async stores straight from registers, one per (thread, CTA of the cluster): the bulk-copy
+      // engine of an SM works through its copies one after the other (~280 cycles each, 16 B/clk), the store path does not queue
+      if (tid < ntc * 64) {
+        const uint4 v = lds16(sm + kClOffStage + tid * 16);
+#pragma unroll 4
+        for (int kk = 0; kk < kClCtas; ++kk) {
+          const uint32_t peer = (c + kk) & 15;   // nearest rank first: the order in which the receivers consume
+          cl_st_async_u4(cl_map(sm + kClOffU1 + c * 4096 + tid * 16, peer), v, cl_map(bar_u(c), peer));
+        }
       }
     }
     CL_TRACE(2 + it * 8);
     if (it == 0) cl_wait(bar_w, 0);
     // ---- fc2: u2 slice = W2[64c:64c+64, :] . u1^T + b2     (warp: tile x parity of the slice order; a slice is used as it lands)
     {
-      float a2[4][4];
+      float a2[4][4], a2b[4][4];                 // two accumulator sets (the k-blocks of a slice alternate): half the dependent-MMA chain
 #pragma unroll
-      for (int n = 0; n < 4; ++n) a2[n][0] = a2[n][1] = a2[n][2] = a2[n][3] = 0.0f;
+      for (int n = 0; n < 4; ++n) a2[n][0] = a2[n][1] = a2[n][2] = a2[n][3] = a2b[n][0] = a2b[n][1] = a2b[n][2] = a2b[n][3] = 0.0f;
       auto step = [&](int sl, int kk, const uint4& wa, const uint4& wb) {
         const uint32_t rowbase = sm + kClOffU1 + sl * 4096 + g * 128 + (((kk * 4 + t) ^ ((g & 1) << 2)) << 4);
 #pragma unroll
         for (int n = 0; n < 4; ++n)
           if (n < ntc) {
             const uint4 bv = lds16(rowbase + n * 1024);
-            mma16816(a2[n], wa, bv.x, bv.y);
-            mma16816(a2[n], wb, bv.z, bv.w);
+            mma16816(kk ? a2b[n] : a2[n], wa, bv.x, bv.y);
+            mma16816(kk ? a2b[n] : a2[n], wb, bv.z, bv.w);
           }
       };
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int sl = slice_of(i);
-        cl_wait(bar_u(sl), par);
-        step(sl, 0, w2r[2 * i][0], w2r[2 * i][1]);
-        step(sl, 1, w2r[2 * i + 1][0], w2r[2 * i + 1][1]);
-      }
-      CL_TRACE(3 + it * 8);
+      // the warp's 8 slices in two groups of 4 (nearest ranks first): ONE round of barrier waits per group, then four steps whose
+      // shared-memory loads the scheduler may overlap freely (a wait per slice made every step a ~460-cycle dependent round)
       const uint32_t wsm = sm + kClOffW2 + (tile * 2 + hh) * kClW2Chunk + lane * 16;
-#pragma unroll 2
-      for (int i = 2; i < 8; ++i) {
-        const int sl = slice_of(i);
-        const uint4 wa0 = lds16(wsm + (i - 2) * 2048), wb0 = lds16(wsm + (i - 2) * 2048 + 512);
-        const uint4 wa1 = lds16(wsm + (i - 2) * 2048 + 1024), wb1 = lds16(wsm + (i - 2) * 2048 + 1536);
-        cl_wait(bar_u(sl), par);
-        step(sl, 0, wa0, wb0);
-        step(sl, 1, wa1, wb1);
+#pragma unroll
+      for (int grp = 0; grp < 2; ++grp) {
+#pragma unroll
+        for (int i = 4 * grp; i < 4 * grp + 4; ++i) cl_wait(bar_u(slice_of(i)), par);
+        if (grp == 0) CL_TRACE(3 + it * 8);
+#pragma unroll
+        for (int i = 4 * grp; i < 4 * grp + 4; ++i) {
+          const int sl = slice_of(i);
+          if (i < 2) {
+            step(sl, 0, w2r[2 * i][0], w2r[2 * i][1]);
+            step(sl, 1, w2r[2 * i + 1][0], w2r[2 * i + 1][1]);
+          } else {
+            const uint4 wa0 = lds16(wsm + (i - 2) * 2048), wb0 = lds16(wsm + (i - 2) * 2048 + 512);
+            const uint4 wa1 = lds16(wsm + (i - 2) * 2048 + 1024), wb1 = lds16(wsm + (i - 2) * 2048 + 1536);
+            step(sl, 0, wa0, wb0);
+            step(sl, 1, wa1, wb1);
+          }
+        }
       }
+#pragma unroll
+      for (int n = 0; n < 4; ++n) { a2[n][0] += a2b[n][0]; a2[n][1] += a2b[n][1]; a2[n][2] += a2b[n][2]; a2[n][3] += a2b[n][3]; }
       __syncthreads();                            // u1 is consumed: its space takes the parity exchange and the u2 slice
       float* red = reinterpret_cast<float*>(cl_smem + kClOffU1);                 // [4 tiles][4 n][32 lanes][4]
       unsigned char* u2s = cl_smem + kClOffU1 + 8192;
@@ -321,11 +349,14 @@ __global__ void __launch_bounds__(kClThreads, 1) k_ief_cluster(const IefClParams
         }
       }
       if (!last) {
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncthreads();
-        if (lane < 2 && 2 * warp + lane < 15) {
-          const uint32_t peer = (c + 1 + 2 * warp + lane) & 15;
-          cl_bulk_to_peer(cl_map(sm + kClOffPs + c * kClPsTile, peer), sm + kClOffPs + c * kClPsTile, ntc * 256, cl_map(bar_s, peer));
+        if (tid < ntc * 16) {                    // the tile's [8 ntc rows][32 B] as 16-byte chunks, to the 15 other CTAs
+          const uint4 v = lds16(sm + kClOffPs + c * kClPsTile + tid * 16);
+#pragma unroll 5
+          for (int kk = 1; kk < kClCtas; ++kk) {
+            const uint32_t peer = (c + kk) & 15;
+            cl_st_async_u4(cl_map(sm + kClOffPs + c * kClPsTile + tid * 16, peer), v, cl_map(bar_s, peer));
+          }
         }
       }
       CL_TRACE(7 + it * 8);

@@ -408,12 +408,15 @@ static int ief_cluster_launch(const tp_ief_weights* w, const float* base, int N,
   q.base = base; q.w1p = reinterpret_cast<const uint4*>(w->w1p); q.w2 = reinterpret_cast<const uint4*>(w->w2);
   q.wdec = reinterpret_cast<const uint4*>(w->wdec); q.b2 = w->b2; q.bdec = w->bdec;
   q.init = init; q.init_rows = init_rows; q.psc = psc; q.M = N; q.n_iter = n_iter;
+  static const int rpc_env = getenv("TP_IEF_CLUSTER_ROWS") ? atoi(getenv("TP_IEF_CLUSTER_ROWS")) : 8;
+  q.rows_per_cluster = (rpc_env == 8 || rpc_env == 16 || rpc_env == 32) ? rpc_env : 8;
+  const int nclusters = (N + q.rows_per_cluster - 1) / q.rows_per_cluster;
   q.trace = tp::trace_ptr();
   TP_CUDA(cudaFuncSetAttribute(tp::k_ief_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   TP_CUDA(cudaFuncSetAttribute(tp::k_ief_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp::kClSmemBytes));
   cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
   cudaLaunchAttribute at[2];
-  cfg.gridDim = dim3(tp::kClCtas); cfg.blockDim = dim3(tp::kClThreads); cfg.dynamicSmemBytes = tp::kClSmemBytes; cfg.stream = st;
+  cfg.gridDim = dim3(tp::kClCtas * nclusters); cfg.blockDim = dim3(tp::kClThreads); cfg.dynamicSmemBytes = tp::kClSmemBytes; cfg.stream = st;
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = tp::kClCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;

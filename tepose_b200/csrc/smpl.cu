@@ -1046,7 +1046,7 @@ extern "C" int tp_smpl_forward_ex(const tp_smpl_model* m, int n, const float* po
     up.m = *m; up.n = n; up.ngroups = pl.n_pad / kU2GB; up.ntiles = m->vp / kUsVT; up.nreg = use_fold ? 0 : nreg;
     up.coef_img = ws + pl.off_um; up.timg = ws + pl.off_timg; up.jreg = jreg; up.verts = verts; up.jpart = jpart;
     if (use_fold) {        // q = coef . [M_hi ; M_lo]^T (+ the template part as the bias of the hi columns): one tcgen05 GEMM over all bodies
-      tp_gemm_seg sg;
+      tp_gemm_seg sg = tp_gemm_seg{};
       sg.m_start = 0; sg.m_rows = n; sg.n_start = 0; sg.n_cols = pl.nq_pad; sg.out = reinterpret_cast<float*>(ws + pl.off_q); sg.ldc = pl.nq_pad;
       sg.bias = fold->q_bias;
       int rc = tp_gemm_bf16_tc(pa.coef_cat, n, fold->m_km, pl.nq_pad, 2 * kTcK, &sg, 1, stream);
@@ -1079,7 +1079,7 @@ extern "C" int tp_smpl_forward_ex(const tp_smpl_model* m, int n, const float* po
     const int vt = m->vp / kSkVT, slots = (per_sm > 0 ? per_sm : 1) * sm_count();
     for (int c0 = 0; c0 < n; c0 += pl.chunk) {
       const int cb = n - c0 < pl.chunk ? n - c0 : pl.chunk;
-      tp_gemm_seg sg;
+      tp_gemm_seg sg = tp_gemm_seg{};
       sg.m_start = c0; sg.m_rows = cb; sg.n_start = 0; sg.n_cols = m->vp * 3;
       sg.out = vposed; sg.ldc = ldv; sg.bias = m->template_pad;
       int rc = tp_gemm_bf16_tc(pa.coef_tc, n, m->blend_km, m->vp * 3, kTcK, &sg, 1, stream);
