@@ -17,8 +17,8 @@
 
 namespace tp {
 
-// Tile 128 x BN, BN = 192 or 128 (chosen per launch): every k-step a CTA pulls (128 + BN) x 64 bf16 through the L2 -> SM path,
-// so a wider tile raises the MACs per byte; BN = 192 also turns the 2.92 waves of the B=32,T=16 input projection (432 tiles
+// Tile 128 x BN, BN = 192 or 128 (chosen per launch): every k-step a CTA pulls (128 + BN) x 64 bf16 through the L2 -> SM path
+// (the kernel's bound, see the note at k_gemm_bf16_tc2), so a wider tile raises the MACs per byte; BN = 192 also turns the 2.92 waves of the B=32,T=16 input projection (432 tiles
 // of 128 x 128) into 1.95 (288 tiles).  Skinny launches (one wave or less of 128-wide tiles, e.g. the B = 1 live window)
 // stay at BN = 128: they stream weights and want more CTAs.
 constexpr int TC_BM = 128, TC_BK = 64;
@@ -217,6 +217,222 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// CTA-PAIR variant (tcgen05.mma.cta_group::2, M = 256) -- OPT-IN (TP_TC_2CTA=1): measured 47 us against the 43 us of the
+// one-CTA kernel above on the B=32,T=16 input projection.
+// What bounds the one-CTA kernel (ncu, profiles/): tensor pipe 49 % active, DRAM 29 %, and 5.4 TB/s leaving the L2 towards the
+// SMs averaged over the whole kernel (200 MB: the L2 merges concurrent requests for the same line, the CTAs ask for 392 MB) --
+// the L2 -> SM side runs at the ~6.9 TB/s scripts/micro/l2bw.cu measures as its ceiling while the mainloop is active.  Neither
+// multicasting the shared operand inside a cluster of 2 (no change: the merging already did that) nor a contiguous, pre-swizzled
+// copy of W fetched with plain bulk copies (no change: HBM is not the limit) moved it.  A CTA pair computes a 256 x 256 tile with
+// each CTA holding its own 128 rows of A and only HALF of the W tile -- the tensor core reads the other half out of the peer's
+// shared memory -- 0.60x the operand bytes per MAC; the pair's cross-CTA barrier hops and the 120 pair tiles on 74 pairs (1.62
+// waves, the 32-row segment wasting half of its pair tiles) cost more than that saves at this size.
+//   * both CTAs run a TMA producer (own A rows, own half of W); every load completes the LEADER's full barrier
+//     (cp.async.bulk.tensor ... cta_group::2), and only the leader issues the MMAs;
+//   * tcgen05.commit multicasts to both CTAs' empty barriers (a slot is free in BOTH rings once the pair's MMAs have read
+//     it) and to both CTAs' accumulator-full barriers; the epilogue warps of both CTAs drain their own 128 TMEM lanes and
+//     arrive on the leader's accumulator-empty barrier (8 arrivals);
+//   * persistent pairs, double-buffered accumulator (2 x 256 TMEM columns), as above.
+constexpr int TC2_BN = 256, TC2_STAGE_BYTES = TC_BM * TC_BK * 2 + (TC2_BN / 2) * TC_BK * 2, TC2_STAGES = 6;
+constexpr uint32_t TC2_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC2_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+struct Tc2Params {
+  tp_gemm_seg seg[TC_MAX_SEGS];
+  int tile_begin[TC_MAX_SEGS + 1];     // in pair tiles (256 x 256)
+  int nseg, kblocks;
+};
+
+__device__ __forceinline__ TcTile tc2_decode(const Tc2Params& p, int tile) {
+  int s = 0;
+#pragma unroll
+  for (int q = 1; q < TC_MAX_SEGS; ++q)
+    if (q < p.nseg && tile >= p.tile_begin[q]) s = q;
+  TcTile t;
+  t.sg = p.seg[0];
+  int tile0 = p.tile_begin[0];
+#pragma unroll
+  for (int q = 1; q < TC_MAX_SEGS; ++q)
+    if (q == s) { t.sg = p.seg[q]; tile0 = p.tile_begin[q]; }
+  const int local = tile - tile0;
+  const int m_pairs = (t.sg.m_rows + 2 * TC_BM - 1) / (2 * TC_BM);
+  const int n_tile = local / m_pairs, m_pair = local - n_tile * m_pairs;
+  t.m0 = m_pair * 2 * TC_BM; t.n0 = n_tile * TC2_BN;
+  return t;
+}
+
+__device__ __forceinline__ uint32_t tc2_map(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tc2_tma_load(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+          "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc2_commit(uint64_t* bar) {      // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::
+                   "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_bf16_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Tc2Params p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC2_STAGES * TC2_STAGE_BYTES);     // used in the leader
+  uint64_t* empty_bar = full_bar + TC2_STAGES;                                              // per CTA
+  uint64_t* tmem_full_bar = empty_bar + TC2_STAGES;      // [2], per CTA
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2], used in the leader: 8 arrivals (4 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  __shared__ float s_bias[2][TC2_BN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
+  const int total = p.tile_begin[TC_MAX_SEGS];
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  constexpr int A_BYTES = TC_BM * TC_BK * 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC2_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (elect_one()) {  // ===== TMA producer (both CTAs): own 128 rows of A, own half of the W tile; completion on the LEADER's barrier =====
+      int it = 0;
+      for (int tile = pair_id; tile < total; tile += n_pairs) {
+        const TcTile t = tc2_decode(p, tile);
+        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const int st = it % TC2_STAGES;
+          const uint32_t ph = (it / TC2_STAGES) & 1;
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          unsigned char* a_dst = smem + st * TC2_STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[st], (uint32_t)(2 * TC2_STAGE_BYTES));
+          const uint32_t lead_bar = tc2_map(smem_u32(&full_bar[st]), 0);
+          tc2_tma_load(a_dst, &map_a, lead_bar, kb * TC_BK, t.sg.m_start + t.m0 + (int)rank * TC_BM);
+          tc2_tma_load(a_dst + A_BYTES, &map_w, lead_bar, kb * TC_BK, t.sg.n_start + t.n0 + (int)rank * (TC2_BN / 2));
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {  // ===== MMA issuer: the leader CTA only =====
+      int it = 0, i = 0;
+      for (int tile = pair_id; tile < total; tile += n_pairs, ++i) {
+        const int acc = i & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((i >> 1) & 1) ^ 1);     // both CTAs' epilogues have drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const int st = it % TC2_STAGES;
+          const uint32_t ph = (it / TC2_STAGES) & 1;
+          mbar_wait(&full_bar[st], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          const uint32_t a_addr = smem_u32(smem + st * TC2_STAGE_BYTES);
+          const uint64_t da = umma_desc_sw128(a_addr), db = umma_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            tc2_umma(tmem_base + (uint32_t)(acc * TC2_BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), TC2_IDESC, (kb | k) != 0 ? 1u : 0u);
+          tc2_commit(&empty_bar[st]);
+        }
+        tc2_commit(&tmem_full_bar[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue (both CTAs): warps 2..5, TMEM lane group = warp % 4; this CTA's rows are m0 + 128 rank + lane group * 32 + lane =====
+    const int lg = warp & 3, et = threadIdx.x - 64;
+    const uint32_t lead_empty0 = tc2_map(smem_u32(&tmem_empty_bar[0]), 0);
+    int i = 0;
+    for (int tile = pair_id; tile < total; tile += n_pairs, ++i) {
+      const TcTile t = tc2_decode(p, tile);
+      const int acc = i & 1;
+      for (int c = et; c < TC2_BN; c += 128) s_bias[acc][c] = (t.sg.bias && t.n0 + c < t.sg.n_cols) ? t.sg.bias[t.n0 + c] : 0.0f;
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      mbar_wait(&tmem_full_bar[acc], (i >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const int row = t.m0 + (int)rank * TC_BM + lg * 32 + lane;
+      const bool row_ok = row < t.sg.m_rows;
+      const bool relu = (t.sg.flags & TP_GEMM_RELU) != 0, out_lp = (t.sg.flags & TP_GEMM_OUT_BF16) != 0;
+      const bool vec_ok = ((t.sg.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(t.sg.out) & 15) == 0);
+      float* orow = t.sg.out + (int64_t)row * t.sg.ldc + t.n0;
+      __nv_bfloat16* orow_lp = reinterpret_cast<__nv_bfloat16*>(t.sg.out) + (int64_t)row * t.sg.ldc + t.n0;
+      const __nv_bfloat16* rrow = t.sg.residual ? reinterpret_cast<const __nv_bfloat16*>(t.sg.residual) + (int64_t)row * t.sg.ldr + t.n0 : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TC2_BN; c0 += 32) {
+        if (t.n0 + c0 >= t.sg.n_cols) break;             // (warp-uniform) nothing left in this tile's ragged tail
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * TC2_BN + c0), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (row_ok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int n = t.n0 + c0 + q * 8;
+            if (n >= t.sg.n_cols) break;
+            float o[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) o[u] = __uint_as_float(v[q * 8 + u]) + s_bias[acc][c0 + q * 8 + u];
+            const bool full = n + 7 < t.sg.n_cols;
+            if (rrow) {
+              for (int u = 0; u < 8; ++u)
+                if (n + u < t.sg.n_cols) o[u] += __bfloat162float(rrow[c0 + q * 8 + u]);
+            }
+            if (relu) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) o[u] = fmaxf(o[u], 0.0f);
+            }
+            if (out_lp) {
+              for (int u = 0; u < 8; ++u)
+                if (n + u < t.sg.n_cols) orow_lp[c0 + q * 8 + u] = __float2bfloat16_rn(o[u]);
+            } else if (full && vec_ok) {
+              *reinterpret_cast<float4*>(orow + c0 + q * 8) = make_float4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<float4*>(orow + c0 + q * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            } else {
+              for (int u = 0; u < 8; ++u)
+                if (n + u < t.sg.n_cols) orow[c0 + q * 8 + u] = o[u];
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(lead_empty0 + 8u * acc) : "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
 // ---- host side: tensor maps through the driver entry point (no libcuda link dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -291,6 +507,35 @@ extern "C" int tp_gemm_bf16_tc(const void* A, int a_rows, const void* W, int w_r
   if (rc != TP_OK) return rc;
   rc = make_map(&map_w, W, w_rows, kp, bn);
   if (rc != TP_OK) return rc;
+  static const bool use_2cta = getenv("TP_TC_2CTA") != nullptr;
+  if (use_2cta && tiles128 > sm_count() && kp % TC_BK == 0) {
+    // CTA pairs on 256 x 256 tiles (k_gemm_bf16_tc2): measured 47 us against 43 us on the B=32,T=16 input projection -- opt-in
+    Tc2Params q;
+    memset(&q, 0, sizeof(q));
+    q.nseg = nseg; q.kblocks = kp / TC_BK;
+    int ptiles = 0;
+    for (int i = 0; i < nseg; ++i) {
+      q.seg[i] = segs[i];
+      q.tile_begin[i] = ptiles;
+      ptiles += (int)(ceil_div(segs[i].m_rows, 2 * TC_BM) * ceil_div(segs[i].n_cols, TC2_BN));
+    }
+    for (int i = nseg; i <= TC_MAX_SEGS; ++i) q.tile_begin[i] = ptiles;
+    CUtensorMap map_w2;
+    rc = make_map(&map_w2, W, w_rows, kp, TC2_BN / 2);
+    if (rc != TP_OK) return rc;
+    const size_t smem = (size_t)TC2_STAGES * TC2_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    TP_CUDA(cudaFuncSetAttribute(k_gemm_bf16_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int pairs = ptiles < sm_count() / 2 ? ptiles : sm_count() / 2;
+    PdlConfig lc(dim3((unsigned)(2 * pairs)), dim3(TC_THREADS), smem, (cudaStream_t)stream);
+    cudaLaunchAttribute at[2];
+    at[0] = lc.attr[0];
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = 2; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    lc.cfg.attrs = at; lc.cfg.numAttrs = 2;
+    TP_CUDA(cudaLaunchKernelEx(&lc.cfg, k_gemm_bf16_tc2, map_a, map_w2, q));
+    TP_LAUNCH_CHECK();
+    return TP_OK;
+  }
   const int grid = tiles < sm_count() ? tiles : sm_count();      // persistent: CTA c takes tiles c, c + grid, ...
   if (bn == 192) {
     using Cfg = TcCfg<192>;

@@ -198,6 +198,17 @@ def test_gemm_bf16_tcgen05(rows, wrows, kp):
         assert err < 1e-4, (err, (m0, mr, n0, nc))       # exact bf16 products, fp32 accumulation order only
 
 
+def test_gemm_bf16_tcgen05_cta_pairs():
+    """TP_TC_2CTA=1: the same GEMM cases on the tcgen05.mma.cta_group::2 kernel (k_gemm_bf16_tc2, opt-in: slower at these sizes).
+    The switch is read once per process, so the cases run in a child process."""
+    import subprocess, sys
+    env = dict(os.environ, TP_TC_2CTA="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "--no-header", "-p", "no:cacheprovider",
+                        "-k", "test_gemm_bf16_tcgen05 and not cta_pairs"], env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 # ------------------------------------------------------------------ GRU recurrence
 def _gru_case(B, T, H, precision, seed, with_h0=False, reverse=False):
     g = torch.Generator().manual_seed(seed)
