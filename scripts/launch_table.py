@@ -7,6 +7,8 @@ rows = list(csv.DictReader(lines))
 names = [r["Kernel Name"] for r in rows]
 starts = [i for i, n in enumerate(names) if "k_pack_rows" in n]
 start = starts[-1]
+if not any("k_smpl_finalize" in n for n in names[start:]) and len(starts) > 1:      # the capture stopped inside the last forward
+    start = starts[-2]
 end = len(rows)
 tot = 0.0
 for r in rows[start:end]:
