@@ -23,9 +23,12 @@
 // arrives on the direction's grid barrier.
 //
 // Warp roles: warps 0-7 epilogue / gate math (warps 0-3 read tile 1's accumulator, warps 4-7 tile 2's; TMEM lane quadrant =
-// warp % 4), warp 8 producer (grid-barrier wait + h bulk copies), warp 9 MMA issuer.  Directions never synchronise with
+// warp % 4), warp 8 producer (grid-barrier wait + h bulk copies), warps 9 and 10 MMA issuers -- ONE PER TILE: a single thread
+// issuing all 128 tcgen05.mma of a step needed 4.4K cycles (35 per MMA: descriptor arithmetic and uniform-register moves of the
+// issuing thread, not the tensor pipe, whose 17 + 25 cycles per tile-1 / tile-2 pair add up to 2.7K); the two chains are
+// independent (own accumulator, own A operand), so two threads issue them side by side.  Directions never synchronise with
 // each other.
-constexpr int kUmThreads = 320;                   // 8 epilogue / gate warps, producer warp, MMA warp
+constexpr int kUmThreads = 352;                   // 8 epilogue / gate warps, producer warp, two MMA warps (one per tile)
 constexpr int kUmEpiThreads = 256;
 constexpr int kUmStages = 3;                      // h ring: stages of up to FOUR 64-column K blocks (32 rows x 128 B = 4 KB each)
 constexpr int kUmBlockBytes = 32 * 128;
@@ -247,8 +250,8 @@ __global__ void __launch_bounds__(kUmThreads, 1) k_gru_umma(const UmParams up) {
   for (int i = tid; i < (int)(sizeof(tp_gru_job) * kMaxJobs / 4); i += kUmThreads)
     reinterpret_cast<int*>(sjobs)[i] = reinterpret_cast<const int*>(p.jobs)[i];
   if (tid == 0) {
-    for (int i = 0; i < kUmStages; ++i) { mb_init(&full[i], 1); mb_init(&empty[i], 1); mb_init(&tfull[i], 1); mb_init(&tempty[i], 4); }
-    mb_init(wres, 1); mb_init(acc_full, 1); mb_init(xbar, 1);      // xbar: one local arrive.expect_tx + the peer's 12 KB bulk copy
+    for (int i = 0; i < kUmStages; ++i) { mb_init(&full[i], 1); mb_init(&empty[i], 2); mb_init(&tfull[i], 1); mb_init(&tempty[i], 4); }   // empty / acc_full: one commit per MMA warp
+    mb_init(wres, 1); mb_init(acc_full, 2); mb_init(xbar, 1);      // xbar: one local arrive.expect_tx + the peer's 12 KB bulk copy
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -357,11 +360,13 @@ __global__ void __launch_bounds__(kUmThreads, 1) k_gru_umma(const UmParams up) {
         if (++st == kUmStages) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 9) {
-    // ===================== MMA issuer (warp-uniform loop, one elected lane issues)
+  } else if (warp == 9 || warp == 10) {
+    // ===================== MMA issuers (warp-uniform loops, one elected lane issues): warp 9 tile 1 (A in TMEM / rest in shared
+    // memory), warp 10 tile 2 (A in shared memory).  Both wait on the same full barriers and both commit to empty / acc_full.
+    const bool t1 = warp == 9;
     if (steps > 1) {
       mb_wait(wres, 0);
-      if (lane == 0) UM_TRACE(0, 6);
+      if (lane == 0 && t1) UM_TRACE(0, 6);
       uint32_t st = 0, ph = 0;
       const uint64_t d_ring = umma_desc_sw128(sm_u32(s_ring)), d_t2 = umma_desc_sw128(sm_u32(s_t2)), d_rest = umma_desc_sw128(sm_u32(s_rest));
       const int total_stages = (steps - 1) * (geo.nkb / bps);
@@ -378,53 +383,56 @@ __global__ void __launch_bounds__(kUmThreads, 1) k_gru_umma(const UmParams up) {
           if (elect_one()) {
             if (!landed) mb_wait(&full[st], ph);
             landed = false;
-            if (up.trace_set == 2 && kb0 / bps < 4) UM_TRACE(s, 2 * (kb0 / bps));
-            if (kb0 == 0 && !up.trace_set) UM_TRACE(s, 3);
+            if (t1 && up.trace_set == 2 && kb0 / bps < 4) UM_TRACE(s, 2 * (kb0 / bps));
+            if (t1 && kb0 == 0 && !up.trace_set) UM_TRACE(s, 3);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             // descriptor start addresses are in 16-byte units: a 4 KB h block = 256, an 8 KB tile-2 block = 512, a 16 KB rest block = 1024
             if (bps == 4 && kb0 + 4 <= geo.ntm) {
-              // the common case as straight-line code: 4 K blocks x 4 k-steps x (tile 1 from TMEM, tile 2 from shared memory).
-              // The wait for the NEXT stage sits before the last quarter, while the tensor pipe still has queued work.
+              // the common case as straight-line code: 4 K blocks x 4 k-steps.  The wait for the NEXT stage sits before the
+              // last quarter, while the tensor pipe still has queued work.
+              if (t1) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                if (i == 12 && has_next) { mb_wait(&full[nst], nph); landed = true; }
-                const uint64_t db = db0 + (uint64_t)((i >> 2) * 256 + (i & 3) * 2);
-                umma_f16_ts(tmem_d1, ta0 + (uint32_t)(i * 8), db, kUmIdesc128, i == 0 ? acc0 : 1u);
-                umma_f16(tmem_d2, da20 + (uint64_t)((i >> 2) * 512 + (i & 3) * 2), db, kUmIdesc64, i == 0 ? acc0 : 1u);
+                for (int i = 0; i < 16; ++i) {
+                  if (i == 12 && has_next) { mb_wait(&full[nst], nph); landed = true; }
+                  umma_f16_ts(tmem_d1, ta0 + (uint32_t)(i * 8), db0 + (uint64_t)((i >> 2) * 256 + (i & 3) * 2), kUmIdesc128, i == 0 ? acc0 : 1u);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  if (i == 12 && has_next) { mb_wait(&full[nst], nph); landed = true; }
+                  umma_f16(tmem_d2, da20 + (uint64_t)((i >> 2) * 512 + (i & 3) * 2), db0 + (uint64_t)((i >> 2) * 256 + (i & 3) * 2), kUmIdesc64, i == 0 ? acc0 : 1u);
+                }
               }
             } else {
               for (int j = 0; j < bps; ++j) {
                 const int kb = kb0 + j;
                 const uint64_t db = db0 + (uint64_t)(j * 256);
-                const uint64_t da2 = da20 + (uint64_t)(j * 512);
-                if (kb < geo.ntm) {
+                if (!t1) {
+                  const uint64_t da2 = da20 + (uint64_t)(j * 512);
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_d2, da2 + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), kUmIdesc64, (kb | ks) != 0 ? 1u : 0u);
+                } else if (kb < geo.ntm) {
                   const uint32_t ta = ta0 + (uint32_t)(j * 32);
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
-                    umma_f16_ts(tmem_d1, ta + (uint32_t)(ks * 8), db + (uint64_t)(ks * 2), kUmIdesc128, (kb | ks) != 0 ? 1u : 0u);
-                    umma_f16(tmem_d2, da2 + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), kUmIdesc64, (kb | ks) != 0 ? 1u : 0u);
-                  }
+                  for (int ks = 0; ks < 4; ++ks) umma_f16_ts(tmem_d1, ta + (uint32_t)(ks * 8), db + (uint64_t)(ks * 2), kUmIdesc128, (kb | ks) != 0 ? 1u : 0u);
                 } else {
                   const uint64_t da1 = d_rest + (uint64_t)((kb - geo.ntm) * 1024);
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
-                    umma_f16(tmem_d1, da1 + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), kUmIdesc128, (kb | ks) != 0 ? 1u : 0u);
-                    umma_f16(tmem_d2, da2 + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), kUmIdesc64, (kb | ks) != 0 ? 1u : 0u);
-                  }
+                  for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_d1, da1 + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), kUmIdesc128, (kb | ks) != 0 ? 1u : 0u);
                 }
               }
             }
             umma_commit(&empty[st]);
             if (kb0 + bps >= geo.nkb) umma_commit(acc_full);
-            if (up.trace_set == 2 && kb0 / bps < 4) UM_TRACE(s, 2 * (kb0 / bps) + 1);
+            if (t1 && up.trace_set == 2 && kb0 / bps < 4) UM_TRACE(s, 2 * (kb0 / bps) + 1);
           }
           __syncwarp();
           st = nst; ph = nph;
         }
-        if (lane == 0 && !up.trace_set) UM_TRACE(s, 4);
+        if (lane == 0 && t1 && !up.trace_set) UM_TRACE(s, 4);
       }
     }
-  } else {
+  } else if (warp < 8) {
     // ===================== epilogue / gate math (8 warps)
     // single-step jobs from a zero state have no matmul: plain gate math, grid-strided over the epilogue threads
     for (int je = p.n_item_jobs; je < p.njobs; ++je) {
