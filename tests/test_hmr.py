@@ -117,5 +117,8 @@ def test_hmr_against_reference_golden():
     for k, tol in (("verts", 2e-3), ("kp_3d", 2e-3), ("kp_2d", 2e-2)):
         err = float((out[0][k].cpu() - torch.from_numpy(z[k])).abs().max())
         assert err < tol, (k, err)
+    from tepose_b200.graph import GraphedHMRFeatures
+    g = GraphedHMRFeatures(model, 2)
+    assert torch.equal(g(x), xf) and g.launches_per_replay > 50
     with pytest.raises(NotImplementedError):
         model.train().feature_extractor(x)
