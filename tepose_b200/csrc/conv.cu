@@ -17,28 +17,35 @@ __global__ void k_nchw_to_nhwc(const float* __restrict__ x, __nv_bfloat16* __res
 }
 
 // in [N,H,W,C] bf16 -> out [N*Ho*Wo, KP] bf16, column (ky*kw + kx)*C + c; taps outside the image and columns >= kh*kw*C are zero.
-// VEC channels (16 or 8 bytes) per thread and copy.
-template <int VEC>
+// VEC channels (16 or 8 bytes) per thread and copy.  IdxT = unsigned int whenever the vector count fits 31 bits: the index
+// arithmetic (five divisions per copy) in 64 bits made the kernel compute-bound (1.8 TB/s of stores, 0.95 TB/s for the stem).
+template <int VEC, typename IdxT>
 __global__ void k_im2col(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int N, int H, int W, int C,
                          int kh, int kw, int stride, int pad, int Ho, int Wo, int KP) {
-  const int kv = KP / VEC;                                    // vectors per output row
-  const int64_t total = (int64_t)N * Ho * Wo * kv;
-  const int K = kh * kw * C;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / kv;
-    const int col = (int)(i - row * kv) * VEC;
-    const int wo = (int)(row % Wo), ho = (int)((row / Wo) % Ho), n = (int)(row / ((int64_t)Wo * Ho));
-    const int tap = col / C, c = col - tap * C;
-    const int ky = tap / kw, kx = tap - ky * kw;
+  const IdxT kv = (IdxT)(KP / VEC);                           // vectors per output row
+  const IdxT total = (IdxT)N * (IdxT)Ho * (IdxT)Wo * kv;
+  const unsigned K = (unsigned)(kh * kw * C), cv = (unsigned)(C / VEC);      // vectors per tap
+  for (IdxT i = blockIdx.x * (IdxT)blockDim.x + threadIdx.x; i < total; i += (IdxT)gridDim.x * blockDim.x) {
+    const IdxT row = i / kv;
+    const unsigned v = (unsigned)(i - row * kv);
+    const unsigned col = v * VEC;
+    const IdxT t1 = row / (IdxT)Wo;
+    const int wo = (int)(row - t1 * (IdxT)Wo);
+    const IdxT n = t1 / (IdxT)Ho;
+    const int ho = (int)(t1 - n * (IdxT)Ho);
+    const unsigned tap = v / cv, c = (v - tap * cv) * VEC;
+    const int ky = (int)(tap / (unsigned)kw), kx = (int)(tap - (unsigned)ky * (unsigned)kw);
     const int hi = ho * stride - pad + ky, wi = wo * stride - pad + kx;
+    const bool ok = col < K && hi >= 0 && hi < H && wi >= 0 && wi < W;
+    const size_t src = (((size_t)n * H + hi) * W + wi) * C + c;
     if (VEC == 8) {
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (col < K && hi >= 0 && hi < H && wi >= 0 && wi < W) v = *reinterpret_cast<const uint4*>(in + (((int64_t)n * H + hi) * W + wi) * C + c);
-      *reinterpret_cast<uint4*>(out + row * KP + col) = v;
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if (ok) val = *reinterpret_cast<const uint4*>(in + src);
+      *reinterpret_cast<uint4*>(out + (size_t)row * KP + col) = val;
     } else {
-      uint2 v = make_uint2(0u, 0u);
-      if (col < K && hi >= 0 && hi < H && wi >= 0 && wi < W) v = *reinterpret_cast<const uint2*>(in + (((int64_t)n * H + hi) * W + wi) * C + c);
-      *reinterpret_cast<uint2*>(out + row * KP + col) = v;
+      uint2 val = make_uint2(0u, 0u);
+      if (ok) val = *reinterpret_cast<const uint2*>(in + src);
+      *reinterpret_cast<uint2*>(out + (size_t)row * KP + col) = val;
     }
   }
 }
@@ -108,10 +115,15 @@ extern "C" int tp_im2col_nhwc_bf16(const void* in, void* out, int N, int H, int 
   TP_CHECK_ARG(Ho > 0 && Wo > 0, "tp_im2col_nhwc_bf16: empty output");
   const __nv_bfloat16* i = reinterpret_cast<const __nv_bfloat16*>(in);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  if (C % 8 == 0)
-    k_im2col<8><<<grid_for((int64_t)N * Ho * Wo * (KP / 8)), 256, 0, (cudaStream_t)stream>>>(i, o, N, H, W, C, kh, kw, stride, pad, Ho, Wo, KP);
-  else
-    k_im2col<4><<<grid_for((int64_t)N * Ho * Wo * (KP / 4)), 256, 0, (cudaStream_t)stream>>>(i, o, N, H, W, C, kh, kw, stride, pad, Ho, Wo, KP);
+  const int vec = C % 8 == 0 ? 8 : 4;
+  const int64_t nvec = (int64_t)N * Ho * Wo * (KP / vec);
+  const bool small = nvec < ((int64_t)1 << 31) - ((int64_t)1 << 24);       // 32-bit indices (with room for the grid stride)
+  const unsigned grid = grid_for(nvec);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec == 8 && small) k_im2col<8, unsigned int><<<grid, 256, 0, st>>>(i, o, N, H, W, C, kh, kw, stride, pad, Ho, Wo, KP);
+  else if (vec == 8) k_im2col<8, unsigned long long><<<grid, 256, 0, st>>>(i, o, N, H, W, C, kh, kw, stride, pad, Ho, Wo, KP);
+  else if (small) k_im2col<4, unsigned int><<<grid, 256, 0, st>>>(i, o, N, H, W, C, kh, kw, stride, pad, Ho, Wo, KP);
+  else k_im2col<4, unsigned long long><<<grid, 256, 0, st>>>(i, o, N, H, W, C, kh, kw, stride, pad, Ho, Wo, KP);
   TP_LAUNCH_CHECK();
   return TP_OK;
 }

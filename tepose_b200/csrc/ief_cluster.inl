@@ -69,10 +69,6 @@ __device__ __forceinline__ void cl_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
-__device__ __forceinline__ void cl_bulk_to_peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
-  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
-                   "r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
-}
 __device__ __forceinline__ void cl_bulk_g2s(uint32_t dst_cta, const void* src, uint32_t bytes, uint32_t bar_cta) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
                    "r"(dst_cta), "l"(src), "r"(bytes), "r"(bar_cta) : "memory");
