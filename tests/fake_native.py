@@ -145,8 +145,45 @@ class FakeLib:
             v = a[sg.m_start:sg.m_start + sg.m_rows] @ w[sg.n_start:sg.n_start + sg.n_cols].t()
             if sg.bias:
                 v = v + _view(sg.bias, sg.n_cols, torch.float32)
-            _mat(sg.out, sg.m_rows, sg.n_cols, sg.ldc).copy_(v)
+            if sg.residual:
+                v = v + _mat(sg.residual, sg.m_rows, sg.n_cols, sg.ldr, torch.bfloat16).float()
+            if sg.flags & nv.GEMM_RELU:
+                v = v.clamp_min(0)
+            if sg.flags & nv.GEMM_OUT_BF16:
+                _mat(sg.out, sg.m_rows, sg.n_cols, sg.ldc, torch.bfloat16).copy_(v.to(torch.bfloat16))
+            else:
+                _mat(sg.out, sg.m_rows, sg.n_cols, sg.ldc).copy_(v)
         self.calls.append(("gemm_bf16_tc", a_rows, w_rows, kp, nseg))
+        return 0
+
+    # ---- HMR data movement (NHWC bf16)
+    def tp_nchw_to_nhwc_bf16(self, x, y, N, Cc, H, W, CP, stream):
+        xin = _view(x, N * Cc * H * W, torch.float32).reshape(N, Cc, H, W)
+        out = torch.zeros(N, H, W, CP, dtype=torch.bfloat16)
+        out[..., :Cc] = xin.permute(0, 2, 3, 1).to(torch.bfloat16)
+        _view(y, N * H * W * CP, torch.bfloat16).copy_(out.reshape(-1))
+        return 0
+
+    def tp_im2col_nhwc_bf16(self, inp, out, N, H, W, Cc, kh, kw, stride, pad, KP, stream):
+        a = _view(inp, N * H * W * Cc, torch.bfloat16).reshape(N, H, W, Cc).float().permute(0, 3, 1, 2)
+        Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+        cols = torch.nn.functional.unfold(a, (kh, kw), padding=pad, stride=stride)              # [N, C*kh*kw, L], (c, ky, kx) order
+        cols = cols.view(N, Cc, kh * kw, Ho * Wo).permute(0, 3, 2, 1).reshape(N * Ho * Wo, kh * kw * Cc)
+        o = torch.zeros(N * Ho * Wo, KP, dtype=torch.bfloat16)
+        o[:, :kh * kw * Cc] = cols.to(torch.bfloat16)
+        _view(out, N * Ho * Wo * KP, torch.bfloat16).copy_(o.reshape(-1))
+        self.calls.append(("im2col", N, H, W, Cc, kh, stride))
+        return 0
+
+    def tp_maxpool3x3s2_nhwc_bf16(self, inp, out, N, H, W, Cc, stream):
+        a = _view(inp, N * H * W * Cc, torch.bfloat16).reshape(N, H, W, Cc).float().permute(0, 3, 1, 2)
+        o = torch.nn.functional.max_pool2d(a, 3, 2, 1).permute(0, 2, 3, 1).contiguous()
+        _view(out, o.numel(), torch.bfloat16).copy_(o.to(torch.bfloat16).reshape(-1))
+        return 0
+
+    def tp_avgpool_nhwc_bf16(self, inp, out, N, HW, Cc, stream):
+        a = _view(inp, N * HW * Cc, torch.bfloat16).reshape(N, HW, Cc).float()
+        _view(out, N * Cc, torch.float32).copy_(a.mean(1).reshape(-1))
         return 0
 
     # ---- recurrence

@@ -40,6 +40,22 @@ def test_batchnorm_fold_matches_conv_then_bn():
     assert w.shape == (16, 128) and float(w[:, 72:].abs().max()) == 0.0
 
 
+def test_hmr_host_schedule_against_reference_golden_on_cpu():
+    """The Python layer of HMR.feature_extractor (BatchNorm fold, weight column order, block wiring, shortcut / stride handling)
+    with the native calls emulated on CPU (tests/fake_native.py: bf16 activations, fp32 accumulation) against the unmodified
+    reference's features for the first golden crop."""
+    from tests import fake_native
+    z = np.load(GOLD)
+    model = psynth.build_synthetic_hmr(11, "cpu")
+    x = torch.from_numpy(psynth.make_image_batch(11, 2))[:1]
+    with fake_native.install() as fake, torch.no_grad():
+        xf = model.feature_extractor(x)
+    ref = torch.from_numpy(z["xf"])[:1]
+    rel = float((xf - ref).norm() / ref.norm())
+    assert xf.shape == (1, 2048) and rel < 3e-2, rel
+    assert sum(1 for c in fake.calls if c[0] == "gemm_bf16_tc") == 53 and sum(1 for c in fake.calls if c[0] == "im2col") == 20
+
+
 @pytest.mark.gpu
 def test_conv_data_movement_kernels_are_exact():
     from tepose_b200 import _native as nv
