@@ -40,6 +40,17 @@ def test_batchnorm_fold_matches_conv_then_bn():
     assert w.shape == (16, 128) and float(w[:, 72:].abs().max()) == 0.0
 
 
+def test_hmr_oracle_restatement_matches_the_reference_golden():
+    """oracle/hmr_ref.py (functional fp32 restatement of lib/models/spin.py:16-141) against the unmodified reference's features."""
+    from oracle import hmr_ref
+    z = np.load(GOLD)
+    model = psynth.build_synthetic_hmr(11, "cpu")
+    sd = {k: v.float() for k, v in model.state_dict().items() if v.is_floating_point()}
+    with torch.no_grad():
+        xf = hmr_ref.feature_extractor(sd, torch.from_numpy(psynth.make_image_batch(11, 2)))
+    assert float((xf - torch.from_numpy(z["xf"])).abs().max()) < 1e-4 * float(np.abs(z["xf"]).max())
+
+
 def test_hmr_host_schedule_against_reference_golden_on_cpu():
     """The Python layer of HMR.feature_extractor (BatchNorm fold, weight column order, block wiring, shortcut / stride handling)
     with the native calls emulated on CPU (tests/fake_native.py: bf16 activations, fp32 accumulation) against the unmodified
@@ -133,6 +144,14 @@ def test_hmr_against_reference_golden():
     for k, tol in (("verts", 2e-3), ("kp_3d", 2e-3), ("kp_2d", 2e-2)):
         err = float((out[0][k].cpu() - torch.from_numpy(z[k])).abs().max())
         assert err < tol, (k, err)
+    # another batch size / other crops: against the oracle restatement (pinned to the same golden on CPU)
+    from oracle import hmr_ref
+    x5 = torch.from_numpy(psynth.make_image_batch(5, 5))
+    sd = {k: v.float().cpu() for k, v in model.state_dict().items() if v.is_floating_point()}
+    with torch.no_grad():
+        want5 = hmr_ref.feature_extractor(sd, x5)
+        got5 = model.feature_extractor(x5.to(DEV)).cpu()
+    assert float((got5 - want5).norm() / want5.norm()) < 3e-2
     from tepose_b200.graph import GraphedHMRFeatures
     g = GraphedHMRFeatures(model, 2)
     assert torch.equal(g(x), xf) and g.launches_per_replay > 50
